@@ -1,0 +1,216 @@
+/*
+ * b200ka.h -- C ABI of libb200ka.so, the native runtime behind `B200Backend <: KA.GPU`.
+ *
+ * This header is the drop-in boundary for the KernelAbstractions.jl hot path.  It plays the
+ * role that the 23 `@ccall libpocl.POcl*` symbols play for the in-tree POCL backend
+ * (reference: src/pocl/nanoOpenCL.jl:492-682): plain `extern "C"`, raw pointers and sizes,
+ * every function returns an int32 status (0 == OK, negative == error) exactly like the
+ * `cl_int` returned by the OpenCL entry points that `@checked` wraps
+ * (src/pocl/nanoOpenCL.jl:22-52, CLError at :392-408).
+ *
+ * Conventions
+ *   - arrays are column-major, dims[0] is the fastest dimension (Julia layout,
+ *     reference src/pocl/device/array.jl:167-189);
+ *   - all indices crossing this ABI are 0-based (the host layers translate Julia's 1-based ids);
+ *   - all work is enqueued on the calling thread's current stream (one non-blocking stream per
+ *     (host thread, device), see b200_get_stream); nothing blocks unless documented;
+ *   - the library never frees or retains caller memory.
+ *
+ * There is NO CPU fallback anywhere in this library: without a CUDA device every compute
+ * entry point returns B200_ERR_NO_DEVICE.
+ */
+#ifndef B200KA_H
+#define B200KA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200KA_VERSION 100 /* 0.1.0 */
+#define B200_MAX_NDIM 4
+
+/* ---- status codes -------------------------------------------------------------------------
+ * Mapping to the exception types the reference testsuite asserts:
+ *   B200_ERR_PARTITION       -> ErrorException (src/KernelAbstractions.jl:768,773,780; test/test.jl:29,41)
+ *   B200_ERR_LAUNCH_DIMS     -> ArgumentError  (src/intrinsics.jl:182-188; test/intrinsics.jl:79-80)
+ *   B200_ERR_BAD_DEVICE      -> ArgumentError  (src/KernelAbstractions.jl:686-691; test/devices.jl:10-11)
+ *   B200_ERR_LENGTH_MISMATCH -> error("Arrays must match in length") (src/pocl/backend.jl:42-44)
+ *   B200_ERR_ALIAS           -> error("Arrays may not alias")        (src/pocl/backend.jl:45-47)
+ *   B200_ERR_CUDA            -> error("Kernel execution failed")     (src/pocl/nanoOpenCL.jl:1423-1432)
+ */
+typedef int32_t b200_status;
+enum {
+    B200_OK = 0,
+    B200_NOT_READY = 1,            /* b200_stream_query: work still in flight */
+    B200_ERR_CUDA = -1,            /* a CUDA runtime call failed; see b200_last_error() */
+    B200_ERR_INVALID_VALUE = -2,
+    B200_ERR_UNKNOWN_KERNEL = -3,  /* b200_launch: no precompiled kernel of that name/arity */
+    B200_ERR_BAD_ARGS = -4,        /* kernel exists but argument kinds/eltypes/shapes do not fit */
+    B200_ERR_LAUNCH_DIMS = -5,     /* more than 3 launch dims, or workgroup > 1024 items */
+    B200_ERR_LENGTH_MISMATCH = -6,
+    B200_ERR_ALIAS = -7,
+    B200_ERR_UNSUPPORTED = -8,
+    B200_ERR_NO_DEVICE = -9,
+    B200_ERR_OOM = -10,
+    B200_ERR_PARTITION = -11,
+    B200_ERR_BAD_DEVICE = -12,
+    B200_ERR_NCCL = -13
+};
+
+/* Thread-local, human readable description of the last non-OK status on this thread. */
+const char *b200_last_error(void);
+const char *b200_status_name(int32_t status);
+int32_t b200_version(void);
+
+/* ---- device management (KA.ndevices/device/device!, src/KernelAbstractions.jl:670-691;
+ *      KI.multiprocessor_count / KI.max_work_group_size, src/pocl/backend.jl:174-179) -------- */
+b200_status b200_init(void);
+b200_status b200_device_count(int32_t *count);
+b200_status b200_set_device(int32_t device);       /* 0-based; out of range -> B200_ERR_BAD_DEVICE */
+b200_status b200_get_device(int32_t *device);
+b200_status b200_sm_count(int32_t *count);
+b200_status b200_max_threads_per_block(int32_t *count);
+b200_status b200_mem_info(size_t *free_bytes, size_t *total_bytes);
+b200_status b200_device_name(char *buf, size_t buflen);
+
+/* ---- memory (KA.allocate / unsafe_free! / pagelock!, src/pocl/backend.jl:25,57;
+ *      src/KernelAbstractions.jl:166,193-195,574-583) ---------------------------------------- */
+b200_status b200_malloc(void **ptr, size_t bytes, int32_t unified); /* bytes==0 -> *ptr = NULL, OK */
+b200_status b200_free(void *ptr);
+b200_status b200_host_alloc(void **ptr, size_t bytes);   /* pinned host memory */
+b200_status b200_host_free(void *ptr);
+b200_status b200_host_register(void *ptr, size_t bytes); /* KA.pagelock! */
+b200_status b200_host_unregister(void *ptr);
+
+/* KA.copyto! legs that cross the host/device boundary (src/pocl/backend.jl:52 -> Base.copyto!).
+ * Asynchronous and stream ordered: the caller keeps `src` alive until b200_synchronize
+ * (contract: src/KernelAbstractions.jl:118-151). */
+b200_status b200_memcpy_h2d_async(void *dst, const void *src, size_t bytes);
+b200_status b200_memcpy_d2h_async(void *dst, const void *src, size_t bytes);
+b200_status b200_memcpy_d2d_async(void *dst, const void *src, size_t bytes);
+b200_status b200_memset_async(void *dst, int32_t byte, size_t bytes);
+
+/* ---- streams / synchronisation (KA.synchronize, KA.priority!; src/pocl/backend.jl:67,
+ *      src/KernelAbstractions.jl:176,658-663; docs/src/implementations.md:3-11) --------------- */
+b200_status b200_stream_query(void);  /* B200_OK when idle, B200_NOT_READY otherwise: yield-loop for Julia */
+b200_status b200_synchronize(void);   /* blocking wait on the calling thread's stream */
+b200_status b200_device_synchronize(void);
+b200_status b200_set_priority(int32_t priority); /* -1 :low, 0 :normal, 1 :high */
+b200_status b200_get_stream(void **cuda_stream);
+b200_status b200_set_stream(void *cuda_stream);  /* adopt an external cudaStream_t (NULL = back to own) */
+
+/* CUDA events on the calling thread's stream (device-side timing for bench.py). */
+b200_status b200_event_create(void **event);
+b200_status b200_event_record(void *event);
+b200_status b200_event_synchronize(void *event);
+b200_status b200_event_elapsed_ms(void *start, void *stop, float *ms);
+b200_status b200_event_destroy(void *event);
+
+/* ---- generic kernel launch ----------------------------------------------------------------
+ * Replaces  clSetKernelArg* + clEnqueueNDRangeKernel  (src/pocl/nanoOpenCL.jl:1161-1283) for
+ *   (obj::KA.Kernel{B})(args...; ndrange, workgroupsize)      src/pocl/backend.jl:117-147  (kind 0)
+ *   (obj::KI.Kernel{B})(args...; numworkgroups, workgroupsize) src/pocl/backend.jl:156-168  (kind 1)
+ * There is no JIT: `name` selects one of the precompiled sm_100a kernels (b200_kernel_name).
+ * b200_launch_desc is the flattened CompilerMetadata/NDRange (src/compiler.jl:1-33,
+ * src/nditeration.jl:49-60) that the host obtains from the unchanged KA.partition. */
+enum { B200_LAUNCH_KA = 0, B200_LAUNCH_KI = 1 };
+
+typedef struct b200_launch_desc {
+    int32_t kind;                    /* B200_LAUNCH_KA or B200_LAUNCH_KI */
+    int32_t ndim;                    /* KA: N of the ndrange (1..4); KI: number of given dims (1..3) */
+    int64_t ndrange[B200_MAX_NDIM];  /* KA only: size(ndrange) */
+    int64_t wgs[B200_MAX_NDIM];      /* work-items per group, padded with 1 */
+    int64_t blocks[B200_MAX_NDIM];   /* groups per dimension, padded with 1 */
+    int32_t dynamic_check;           /* KA: __validindex does the `I in ndrange` test */
+    int32_t flags;                   /* bit0 static ndrange, bit1 static workgroupsize (informational) */
+} b200_launch_desc;
+
+enum { /* b200_arg.kind */
+    B200_ARG_ARRAY = 0,   /* device array: ptr, eltype, elsize, ndim, dims */
+    B200_ARG_SCALAR = 1,  /* by-value bits in .scalar (i64) / .fscalar (f64), eltype says which */
+    B200_ARG_VAL = 2      /* Julia Val{N}() / type argument: value in .scalar */
+};
+
+enum { /* b200_arg.eltype */
+    B200_T_OPAQUE = 0,
+    B200_T_I8 = 1, B200_T_U8 = 2, B200_T_I16 = 3, B200_T_U16 = 4,
+    B200_T_I32 = 5, B200_T_U32 = 6, B200_T_I64 = 7, B200_T_U64 = 8,
+    B200_T_F16 = 9, B200_T_BF16 = 10, B200_T_F32 = 11, B200_T_F64 = 12, B200_T_BOOL = 13
+};
+
+typedef struct b200_arg {
+    int32_t kind;
+    int32_t eltype;
+    int32_t elsize;                 /* bytes per element */
+    int32_t ndim;
+    int64_t dims[B200_MAX_NDIM];
+    void *ptr;
+    int64_t scalar;
+    double fscalar;
+} b200_arg;
+
+b200_status b200_launch(const char *name, const b200_launch_desc *desc, const b200_arg *args, int32_t nargs);
+b200_status b200_kernel_count(int32_t *count);
+const char *b200_kernel_name(int32_t index); /* NULL when out of range */
+/* KI.kernel_max_work_group_size (src/pocl/backend.jl:170-173; test/intrinsics.jl:95-96) */
+b200_status b200_kernel_max_work_group_size(const char *name, int64_t max_work_items, int64_t *out);
+/* number of device kernels this thread has launched since the last reset (bench.py gpu_launches) */
+b200_status b200_launch_counter(int64_t *count, int32_t reset);
+
+/* ---- typed fast paths (what b200_launch routes the north-star kernels to) ------------------- */
+
+/* copy_kernel / copy_kernel! : A[I] = B[I]  (src/KernelAbstractions.jl:874-877,
+ * examples/memcopy.jl:4-7).  Byte-exact, dtype agnostic. Overlap -> B200_ERR_ALIAS. */
+b200_status b200_copy(void *dst, const void *src, size_t bytes);
+/* init_kernel: arr[I] = f(T) (src/KernelAbstractions.jl:869-872); value = elsize bytes, elsize in {1,2,4,8,16}. */
+b200_status b200_fill(void *dst, size_t count, int32_t elsize, const void *value);
+
+/* naive_transpose_kernel!: a[i,j] = b[j,i]  (examples/naive_transpose.jl:4-7).
+ * a is m x n (leading dim lda >= m), b is n x m (ldb >= n), column-major, elsize 4 or 8. */
+b200_status b200_transpose(void *a, const void *b, int64_t m, int64_t n, int64_t lda, int64_t ldb,
+                           int32_t elsize);
+
+/* histogram_kernel!: bins[v-1] += #{t : input[t] == v}, v in 1..nbins (values outside are ignored)
+ * (examples/histogram.jl:18-58).  Accumulates into `bins` like the reference's atomic +=. */
+b200_status b200_histogram_i32(int32_t *bins, int64_t nbins, const int32_t *input, int64_t n);
+
+/* matmul_kernel! / coalesced_matmul_kernel!: C(MxN) = A(MxK) * B(KxN), column-major
+ * (examples/matmul.jl:5-15, examples/performant_matmul.jl:15-77).
+ * mode 0: FP32 SIMT, summation order of the reference tiled kernel (16-wide k partials, k ascending,
+ *         fused multiply-add) -> bit-identical to the oracle;
+ * mode 1: FP32 SIMT, single running accumulator per output (k ascending). */
+enum { B200_MATMUL_TILE16 = 0, B200_MATMUL_RUNNING = 1 };
+b200_status b200_matmul_f32(float *C, const float *A, const float *B, int64_t M, int64_t K, int64_t N,
+                            int64_t lda, int64_t ldb, int64_t ldc, int32_t mode);
+
+/* Opt-in tensor-core paths (tcgen05 + TMEM + TMA).  No reference implementation exists for these
+ * ("parity unpinned"): defined as the FP32 oracle on BF16/TF32-rounded inputs, rtol 1e-2.
+ * Abf: M x K bf16 with K contiguous (row-major, ld = K); Bbf: N x K bf16 with K contiguous
+ * (i.e. the column-major K x N matrix B as stored); C: M x N float32 column-major, ldc >= M. */
+b200_status b200_matmul_bf16(float *C, const uint16_t *Abf, const uint16_t *Bbf, int64_t M, int64_t K,
+                             int64_t N, int64_t ldc);
+/* float32 column-major (rows x cols, ld) -> bf16; transpose!=0 writes the cols x rows... see DESIGN.md:
+ * out is K-contiguous storage for the GEMM above: for A (M x K col-major) use transpose=1,
+ * for B (K x N col-major) use transpose=0. Round-to-nearest-even. */
+b200_status b200_convert_f32_bf16(uint16_t *out, const float *in, int64_t rows, int64_t cols, int64_t ld,
+                                  int32_t transpose);
+/* C = A*B with FP32 storage, BF16 tensor-core arithmetic: converts then calls b200_matmul_bf16.
+ * `workspace` must hold (M*K + K*N) * 2 bytes. */
+b200_status b200_matmul_f32_via_bf16(float *C, const float *A, const float *B, int64_t M, int64_t K,
+                                     int64_t N, int64_t lda, int64_t ldb, int64_t ldc, void *workspace);
+
+/* ---- multi-GPU plumbing (pattern: examples/mpi.jl:24-39; NCCL over NVLink) ------------------ */
+#define B200_UNIQUE_ID_BYTES 128
+b200_status b200_comm_unique_id(void *id128);
+b200_status b200_comm_init_rank(void **comm, int32_t nranks, int32_t rank, const void *id128);
+b200_status b200_comm_destroy(void *comm);
+b200_status b200_allreduce_sum_i32(void *comm, int32_t *buf, int64_t count);
+b200_status b200_broadcast(void *comm, void *buf, size_t bytes, int32_t root);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200KA_H */
