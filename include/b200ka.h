@@ -160,6 +160,11 @@ b200_status b200_kernel_max_work_group_size(const char *name, int64_t max_work_i
 /* number of device kernels this thread has launched since the last reset (bench.py gpu_launches) */
 b200_status b200_launch_counter(int64_t *count, int32_t reset);
 
+/* Tuning knobs (kernel variant / grid sizing sweeps; defaults are the measured best). Not part of the
+ * reference-facing surface. */
+b200_status b200_tune_set(const char *key, int32_t value);
+b200_status b200_tune_get(const char *key, int32_t dflt, int32_t *value);
+
 /* ---- typed fast paths (what b200_launch routes the north-star kernels to) ------------------- */
 
 /* copy_kernel / copy_kernel! : A[I] = B[I]  (src/KernelAbstractions.jl:874-877,

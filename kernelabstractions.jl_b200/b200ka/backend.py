@@ -1,0 +1,326 @@
+"""B200Backend and B200Array: the Python mirror of `struct B200Backend <: KA.GPU` (julia/B200Backend).
+
+Method-for-method twin of the in-tree backend glue (reference src/pocl/backend.jl:19-69) on top of the C ABI.
+Julia's `f!` is spelled `f_` here.  All device work is asynchronous and ordered on the calling thread's stream;
+`synchronize` is cooperative (it polls and yields instead of blocking in the driver), as the reference requires
+of GPU backends (docs/src/implementations.md:3-11).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import time
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+from ._lib import ArgumentError, ErrorException, MethodError, call, lib
+
+_DTYPE_CODES = {
+    np.dtype(np.int8): _lib.B200_T_I8, np.dtype(np.uint8): _lib.B200_T_U8,
+    np.dtype(np.int16): _lib.B200_T_I16, np.dtype(np.uint16): _lib.B200_T_U16,
+    np.dtype(np.int32): _lib.B200_T_I32, np.dtype(np.uint32): _lib.B200_T_U32,
+    np.dtype(np.int64): _lib.B200_T_I64, np.dtype(np.uint64): _lib.B200_T_U64,
+    np.dtype(np.float16): _lib.B200_T_F16, np.dtype(np.float32): _lib.B200_T_F32,
+    np.dtype(np.float64): _lib.B200_T_F64, np.dtype(np.bool_): _lib.B200_T_BOOL,
+}
+
+
+def eltype_code(dtype) -> int:
+    return _DTYPE_CODES.get(np.dtype(dtype), _lib.B200_T_OPAQUE)
+
+
+def CartesianIndex(n: int) -> np.dtype:
+    """eltype of an array of CartesianIndex{n}: n consecutive Int64 (reference test/test.jl:131-139)."""
+    return np.dtype([("I", np.int64, (n,))])
+
+
+KernelData = np.dtype([(k, np.int64) for k in
+                       ("global_size", "global_id", "local_size", "local_id", "num_groups", "group_id")])
+"""reference test/intrinsics.jl:3-10"""
+
+
+class B200Backend:
+    """`struct B200Backend <: KA.GPU end` -- stateless, all instances compare equal (reference src/pocl/backend.jl:19-20)."""
+
+    def __eq__(self, other):
+        return isinstance(other, B200Backend)
+
+    def __hash__(self):
+        return hash("B200Backend")
+
+    def __repr__(self):
+        return "B200Backend()"
+
+
+class CPU:
+    """Stand-in for KA.CPU() used only as the target of `adapt(CPU(), x)` (reference test/test.jl:107-113)."""
+
+    def __eq__(self, other):
+        return isinstance(other, CPU)
+
+    def __hash__(self):
+        return hash("CPU")
+
+
+_pending_host_refs = []  # host buffers of in-flight async copies (caller-preserve rule, KernelAbstractions.jl:127-142)
+
+
+class B200Array:
+    """Device array: pointer + dims (column-major) + eltype, owner of its allocation (finalizer -> b200_free).
+
+    The Julia twin is `mutable struct B200Array{T,N} <: AbstractArray{T,N}`."""
+
+    __slots__ = ("ptr", "shape", "dtype", "unified", "_owner", "_freed")
+
+    def __init__(self, dtype, shape: Sequence[int], unified: bool = False, _ptr: Optional[int] = None, _owner=None):
+        self.dtype = np.dtype(dtype)
+        self.shape = tuple(int(s) for s in shape)
+        if any(s < 0 for s in self.shape):
+            raise ArgumentError("invalid Array dimensions")
+        self.unified = bool(unified)
+        self._owner = _owner
+        self._freed = False
+        if _ptr is not None:
+            self.ptr = _ptr
+        else:
+            p = C.c_void_p()
+            call("b200_malloc", C.byref(p), C.c_size_t(self.nbytes), C.c_int32(1 if unified else 0))
+            self.ptr = p.value or 0
+
+    # -- Base array interface -------------------------------------------------------------------
+    @property
+    def size(self) -> int:  # length(A)
+        n = 1
+        for s in self.shape:
+            n *= s
+        return n
+
+    def __len__(self) -> int:
+        return self.size
+
+    @property
+    def ndim(self) -> int:
+        return len(self.shape)
+
+    @property
+    def nbytes(self) -> int:
+        return self.size * self.dtype.itemsize
+
+    def __getitem__(self, idx):
+        """Scalar indexing: ErrorException unless the array is unified memory (reference test/test.jl:82-87)."""
+        if not self.unified:
+            raise ErrorException("Scalar indexing of a B200Array is disallowed; copy it to the host with Array(A)")
+        synchronize(B200Backend())
+        return Array(self)[idx]
+
+    def __del__(self):
+        try:
+            unsafe_free_(self)
+        except Exception:
+            pass
+
+    def __repr__(self):
+        return f"B200Array({self.dtype}, {self.shape}, ptr=0x{self.ptr:x})"
+
+    def view(self, offset_elems: int, shape: Sequence[int]) -> "B200Array":
+        """A contiguous sub-array sharing memory (keeps the parent alive), e.g. one slab of a sharded matrix."""
+        v = B200Array(self.dtype, shape, self.unified, _ptr=self.ptr + offset_elems * self.dtype.itemsize, _owner=self)
+        assert offset_elems + v.size <= self.size
+        return v
+
+    def fill_(self, value) -> "B200Array":
+        """fill!(A, x) / `A .= x` (reference test/private.jl:75), on the device."""
+        v = np.array([value], dtype=self.dtype)
+        if self.size:
+            call("b200_fill", C.c_void_p(self.ptr), C.c_size_t(self.size), C.c_int32(self.dtype.itemsize),
+                 v.ctypes.data_as(C.c_void_p))
+        return self
+
+
+def unsafe_free_(A: B200Array) -> None:
+    """KA.unsafe_free! (reference src/KernelAbstractions.jl:193-195)"""
+    if isinstance(A, B200Array) and not A._freed and A._owner is None and A.ptr:
+        A._freed = True
+        lib().b200_free(C.c_void_p(A.ptr))
+        A.ptr = 0
+
+
+# ---- memory operations (reference src/pocl/backend.jl:25-57) ---------------------------------------
+def _dims(dims) -> Tuple[int, ...]:
+    if isinstance(dims, (int, np.integer)):
+        return (int(dims),)
+    return tuple(int(d) for d in dims)
+
+
+def allocate(backend, T, *dims, unified: bool = False) -> B200Array:
+    """KA.allocate(::B200Backend, T, dims; unified) (reference src/pocl/backend.jl:25).
+    A non-type first argument is a MethodError (reference test/test.jl:300-305)."""
+    if not isinstance(backend, B200Backend):
+        raise MethodError(f"no method matching allocate(::{type(backend).__name__}, ...)")
+    try:
+        dt = np.dtype(T)
+    except TypeError as e:
+        raise MethodError(f"no method matching allocate(::B200Backend, ::{type(T).__name__}, ...)") from e
+    if isinstance(T, (np.ndarray, B200Array, list, tuple)) and not isinstance(T, type):
+        raise MethodError("allocate: eltype must be a type")
+    shape = _dims(dims[0]) if len(dims) == 1 and not isinstance(dims[0], (int, np.integer)) else _dims(dims)
+    return B200Array(dt, shape, unified=unified)
+
+
+def zeros(backend, T, *dims, **kw) -> B200Array:
+    """KA.zeros = allocate + init_kernel(arr, zero, T) (reference src/pocl/backend.jl:27-32)."""
+    return allocate(backend, T, *dims, **kw).fill_(0)
+
+
+def ones(backend, T, *dims, **kw) -> B200Array:
+    """KA.ones (reference src/pocl/backend.jl:33-38)."""
+    return allocate(backend, T, *dims, **kw).fill_(1)
+
+
+def _host_ptr(a: np.ndarray):
+    if not (a.flags.f_contiguous or a.flags.c_contiguous):
+        raise ArgumentError("host arrays must be contiguous")
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def copyto_(backend, A, B):
+    """KA.copyto!(backend, A, B) (reference src/pocl/backend.jl:40-54): device<-device through the copy kernel
+    (with the length and alias checks), host<->device as stream-ordered async copies.  Returns A."""
+    a_dev, b_dev = isinstance(A, B200Array), isinstance(B, B200Array)
+    if a_dev and b_dev:
+        if A.size != B.size:
+            raise ErrorException("Arrays must match in length")
+        if A.dtype.itemsize != B.dtype.itemsize:
+            raise ErrorException("Arrays must match in element size")
+        try:
+            call("b200_copy", C.c_void_p(A.ptr), C.c_void_p(B.ptr), C.c_size_t(A.nbytes))
+        except _lib.B200Error as e:
+            if e.status == _lib.B200_ERR_ALIAS:
+                raise ErrorException("Arrays may not alias") from e
+            raise
+        return A
+    if a_dev and isinstance(B, np.ndarray):
+        if A.size != B.size:
+            raise ErrorException("Arrays must match in length")
+        src = B if B.dtype == A.dtype else B.astype(A.dtype)
+        call("b200_memcpy_h2d_async", C.c_void_p(A.ptr), _host_ptr(src), C.c_size_t(A.nbytes))
+        _pending_host_refs.append(src)
+        return A
+    if isinstance(A, np.ndarray) and b_dev:
+        if A.size != B.size:
+            raise ErrorException("Arrays must match in length")
+        if A.dtype != B.dtype:
+            raise ErrorException("copyto!: host destination must have the device array's eltype")
+        call("b200_memcpy_d2h_async", _host_ptr(A), C.c_void_p(B.ptr), C.c_size_t(B.nbytes))
+        _pending_host_refs.append(A)
+        return A
+    raise MethodError("copyto!(::B200Backend, A, B): at least one side must be a B200Array")
+
+
+def synchronize(backend) -> None:
+    """KA.synchronize (reference src/KernelAbstractions.jl:176): cooperative wait -- poll b200_stream_query and yield
+    to other host threads, never block inside the driver (docs/src/implementations.md:3-11)."""
+    if not isinstance(backend, B200Backend):
+        raise MethodError(f"no method matching synchronize(::{type(backend).__name__})")
+    spins = 0
+    while True:
+        st = lib().b200_stream_query()
+        if st == _lib.B200_OK:
+            break
+        if st != _lib.B200_NOT_READY:
+            _lib.check(st)
+        spins += 1
+        time.sleep(0 if spins < 2000 else 50e-6)
+    _pending_host_refs.clear()
+
+
+def get_backend(A):
+    """KA.get_backend (reference src/KernelAbstractions.jl:548-557, src/pocl/backend.jl:59)."""
+    if isinstance(A, B200Array):
+        return B200Backend()
+    if isinstance(A, np.ndarray):
+        return CPU()
+    raise ArgumentError(f"Implement KernelAbstractions.get_backend(::{type(A).__name__})")
+
+
+def functional(backend) -> bool:
+    n = C.c_int32(0)
+    return lib().b200_device_count(C.byref(n)) == 0 and n.value > 0
+
+
+def pagelock_(backend, x: np.ndarray) -> None:
+    """KA.pagelock! (reference src/KernelAbstractions.jl:166)"""
+    call("b200_host_register", _host_ptr(x), C.c_size_t(x.nbytes))
+
+
+def supports_float64(backend) -> bool:
+    return True
+
+
+def supports_atomics(backend) -> bool:
+    return True
+
+
+def supports_unified(backend) -> bool:
+    return True
+
+
+def priority_(backend, prio: str) -> None:
+    """KA.priority!(backend, :high | :normal | :low) (reference src/KernelAbstractions.jl:658-663)."""
+    if prio not in ("high", "normal", "low"):
+        raise ErrorException(f"priority must be one of :high, :normal, :low (got {prio!r})")
+    call("b200_set_priority", C.c_int32({"low": -1, "normal": 0, "high": 1}[prio]))
+
+
+def ndevices(backend) -> int:
+    n = C.c_int32(0)
+    call("b200_device_count", C.byref(n))
+    return n.value
+
+
+def device(backend) -> int:
+    """1-based like KA.device (reference src/KernelAbstractions.jl:670-680)."""
+    d = C.c_int32(0)
+    call("b200_get_device", C.byref(d))
+    return d.value + 1
+
+
+def device_(backend, id: int) -> None:
+    """KA.device!(backend, id): ArgumentError when out of range (reference src/KernelAbstractions.jl:686-691)."""
+    if id < 1 or id > ndevices(backend):
+        raise ArgumentError(f"Device id {id} out of bounds.")
+    call("b200_set_device", C.c_int32(id - 1))
+
+
+# ---- conversions the testsuite relies on (reference test/test.jl:107-113, test/private.jl:75-91) -----------
+def Array(A: B200Array) -> np.ndarray:
+    """Array(::B200Array): synchronous device->host copy, column-major numpy array."""
+    out = np.empty(A.shape, dtype=A.dtype, order="F")
+    if A.size:
+        call("b200_memcpy_d2h_async", out.ctypes.data_as(C.c_void_p), C.c_void_p(A.ptr), C.c_size_t(A.nbytes))
+        call("b200_synchronize")
+    return out
+
+
+def to_device(host: np.ndarray, unified: bool = False) -> B200Array:
+    """B200Array(::Array): synchronous host->device copy (column-major)."""
+    h = np.asfortranarray(host)
+    A = B200Array(h.dtype, h.shape, unified=unified)
+    if A.size:
+        call("b200_memcpy_h2d_async", C.c_void_p(A.ptr), h.ctypes.data_as(C.c_void_p), C.c_size_t(A.nbytes))
+        call("b200_synchronize")
+    return A
+
+
+def similar(A: B200Array, dtype=None, shape=None) -> B200Array:
+    return B200Array(A.dtype if dtype is None else dtype, A.shape if shape is None else shape, unified=A.unified)
+
+
+def adapt(backend, x):
+    """Adapt.adapt_storage for the three cases the testsuite uses (reference test/test.jl:107-113)."""
+    if isinstance(backend, CPU):
+        return Array(x) if isinstance(x, B200Array) else x
+    if isinstance(backend, B200Backend):
+        return x if isinstance(x, B200Array) else to_device(x)
+    raise MethodError("adapt: unknown backend")

@@ -1,0 +1,303 @@
+// histogram.cu -- b200_histogram_i32: bins[v-1] += #{t : input[t] == v} for v in 1..nbins.
+//
+// Reference: histogram_kernel! (examples/histogram.jl:18-58).  The reference algorithm gives every
+// 256-item group a shared histogram and merges all `gs` bins of every group into global memory with one
+// atomic per bin (:52-54): for 2^30 inputs that is 2^30 shared + 2^30 global atomics.  Counts are integer
+// sums, so ANY regrouping of the additions gives the same bits; this file regroups them so the kernel is
+// bound by the 4 bytes/element it must read from HBM:
+//
+//   impl 0 "bytes" (nbins <= 256): every THREAD owns a private column of 256 one-byte counters in shared
+//       memory (256*T bytes per CTA).  The byte for (bin, thread) sits at bin*T + (warp/4)*128 + lane*4 + warp%4,
+//       i.e. lane l always hits bank l: increments are plain LDS.U8/IADD/STS.U8 with zero bank conflicts and
+//       no atomics, independent of the input distribution (all-equal inputs cost the same as uniform ones).
+//       Counters are flushed (dp4a byte sums, rotated 16-byte chunks, conflict-free) into per-thread 32-bit
+//       accumulators before any of them can reach 256; one red.global.add per (bin, part) per CTA at the end.
+//   impl 1 "atomics": per-warp private 32-bit shared histograms updated with shared-memory atomics
+//       (also the path for 256 < nbins <= 14336).
+//   larger nbins: one red.global.add per in-range element.
+// Values outside 1..nbins are ignored, exactly like the reference's range test (:45-46).
+#include "../common.cuh"
+#include "../tune.h"
+
+namespace b200 {
+
+__device__ __forceinline__ int4 ldg_stream_i4(const int4 *p) {
+    int4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// impl 0: thread-private byte counters
+// ---------------------------------------------------------------------------------------------
+template <int T>
+__device__ __forceinline__ void bump1(unsigned char *cnt, uint32_t base, int v, uint32_t nbins) {
+    uint32_t b = (uint32_t)(v - 1);
+    if (b < nbins) {
+        unsigned char *p = cnt + b * T + base;
+        *p = (unsigned char)(*p + 1);
+    }
+}
+template <int T>
+__device__ __forceinline__ void bump2(unsigned char *cnt, uint32_t base, int v1, int v2, uint32_t nbins) {
+    uint32_t b1 = (uint32_t)(v1 - 1), b2 = (uint32_t)(v2 - 1);
+    bool ok1 = b1 < nbins, ok2 = b2 < nbins;
+    unsigned char *p1 = cnt + (ok1 ? b1 : 0u) * T + base;
+    unsigned char *p2 = cnt + (ok2 ? b2 : 0u) * T + base;
+    uint32_t c1 = *p1, c2 = *p2;  // both loads issue before either store
+    bool same = ok1 && ok2 && (b1 == b2);
+    if (ok1) *p1 = (unsigned char)(c1 + 1 + (same ? 1 : 0));
+    if (ok2 && !same) *p2 = (unsigned char)(c2 + 1);
+}
+
+template <int T, int ILP>
+__device__ __forceinline__ void bump4(unsigned char *cnt, uint32_t base, const int4 &v, uint32_t nbins) {
+    if (ILP == 2) {
+        bump2<T>(cnt, base, v.x, v.y, nbins);
+        bump2<T>(cnt, base, v.z, v.w, nbins);
+    } else {
+        bump1<T>(cnt, base, v.x, nbins);
+        bump1<T>(cnt, base, v.y, nbins);
+        bump1<T>(cnt, base, v.z, nbins);
+        bump1<T>(cnt, base, v.w, nbins);
+    }
+}
+
+// Sum this thread's slice (256 bytes of row `bin`) of the byte counters into acc and clear it.
+template <int T>
+__device__ __forceinline__ void flush_bytes(unsigned char *cnt, uint32_t &acc) {
+    const int t = threadIdx.x, lane = t & 31;
+    const int bin = t & 255, part = t >> 8;
+    uint4 *row = reinterpret_cast<uint4 *>(cnt + bin * T + part * 256);
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        const int c = (k + lane) & 15;
+        uint4 x = row[c];
+        s = __dp4a(x.x, 0x01010101u, s);
+        s = __dp4a(x.y, 0x01010101u, s);
+        s = __dp4a(x.z, 0x01010101u, s);
+        s = __dp4a(x.w, 0x01010101u, s);
+        row[c] = make_uint4(0, 0, 0, 0);
+    }
+    acc += s;
+}
+
+// in4: 16-byte aligned input viewed as int4 units; the CTA owns units [u0, u1).
+// P = int4 loads in flight per thread per batch (double buffered); a flush happens every PERIOD batches
+// with PERIOD * P * 4 <= 255 so no byte counter can wrap.
+template <int T, int P, int ILP>
+__global__ void __launch_bounds__(T, 1) hist256_bytes_kernel(int32_t *__restrict__ bins, uint32_t nbins,
+                                                             const int4 *__restrict__ in4, int64_t n4,
+                                                             const int32_t *__restrict__ tail, int ntail) {
+    static_assert(T % 256 == 0, "flush mapping needs T multiple of 256");
+    constexpr int PERIOD = 255 / (P * 4);
+    extern __shared__ __align__(16) unsigned char cnt[];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    for (int i = t; i < 256 * T / 16; i += T) reinterpret_cast<uint4 *>(cnt)[i] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    const uint32_t base = (uint32_t)((warp >> 2) * 128 + lane * 4 + (warp & 3));
+    uint32_t acc = 0;
+
+    const int64_t u0 = n4 * (int64_t)blockIdx.x / gridDim.x;
+    const int64_t u1 = n4 * (int64_t)(blockIdx.x + 1) / gridDim.x;
+    // batch k covers units u0 + k*P*T + p*T + t, p = 0..P-1
+    const int64_t nbatch = (u1 - u0 + (int64_t)P * T - 1) / ((int64_t)P * T);
+    int4 cur[P], nxt[P];
+    auto load_batch = [&](int64_t k, int4 *buf) {
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            int64_t u = u0 + (k * P + p) * (int64_t)T + t;
+            buf[p] = u < u1 ? ldg_stream_i4(in4 + u) : make_int4(0, 0, 0, 0);  // 0 is outside 1..nbins
+        }
+    };
+    if (nbatch > 0) load_batch(0, cur);
+    int since_flush = 0;
+    for (int64_t k = 0; k < nbatch; ++k) {
+        if (k + 1 < nbatch) load_batch(k + 1, nxt);
+#pragma unroll
+        for (int p = 0; p < P; ++p) bump4<T, ILP>(cnt, base, cur[p], nbins);
+#pragma unroll
+        for (int p = 0; p < P; ++p) cur[p] = nxt[p];
+        if (++since_flush == PERIOD) {
+            __syncthreads();
+            flush_bytes<T>(cnt, acc);
+            __syncthreads();
+            since_flush = 0;
+        }
+    }
+    // scalar tail (n % 4 elements and/or an unaligned head), done by CTA 0
+    if (blockIdx.x == 0 && t < ntail) bump1<T>(cnt, base, tail[t], nbins);
+    __syncthreads();
+    flush_bytes<T>(cnt, acc);
+    const uint32_t bin = t & 255;
+    if (acc != 0 && bin < nbins) atomicAdd(reinterpret_cast<unsigned int *>(bins) + bin, acc);
+}
+
+// ---------------------------------------------------------------------------------------------
+// impl 1: shared-memory atomics on `copies` private 32-bit histograms per CTA
+// ---------------------------------------------------------------------------------------------
+template <int T, int P>
+__global__ void __launch_bounds__(T) hist_atomic_kernel(int32_t *__restrict__ bins, uint32_t nbins,
+                                                        const int4 *__restrict__ in4, int64_t n4,
+                                                        const int32_t *__restrict__ tail, int ntail, int copies) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t *sh = reinterpret_cast<uint32_t *>(smem_raw);
+    const int t = threadIdx.x, warp = t >> 5;
+    for (uint32_t i = t; i < nbins * (uint32_t)copies; i += T) sh[i] = 0;
+    __syncthreads();
+    uint32_t *mine = sh + (uint32_t)(warp % copies) * nbins;
+    auto bump = [&](int v) {
+        uint32_t b = (uint32_t)(v - 1);
+        if (b < nbins) atomicAdd(mine + b, 1u);
+    };
+    const int64_t u0 = n4 * (int64_t)blockIdx.x / gridDim.x;
+    const int64_t u1 = n4 * (int64_t)(blockIdx.x + 1) / gridDim.x;
+    const int64_t nbatch = (u1 - u0 + (int64_t)P * T - 1) / ((int64_t)P * T);
+    int4 cur[P], nxt[P];
+    auto load_batch = [&](int64_t k, int4 *buf) {
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            int64_t u = u0 + (k * P + p) * (int64_t)T + t;
+            buf[p] = u < u1 ? ldg_stream_i4(in4 + u) : make_int4(0, 0, 0, 0);
+        }
+    };
+    if (nbatch > 0) load_batch(0, cur);
+    for (int64_t k = 0; k < nbatch; ++k) {
+        if (k + 1 < nbatch) load_batch(k + 1, nxt);
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            bump(cur[p].x);
+            bump(cur[p].y);
+            bump(cur[p].z);
+            bump(cur[p].w);
+        }
+#pragma unroll
+        for (int p = 0; p < P; ++p) cur[p] = nxt[p];
+    }
+    if (blockIdx.x == 0 && t < ntail) bump(tail[t]);
+    __syncthreads();
+    for (uint32_t b = t; b < nbins; b += T) {
+        uint32_t s = 0;
+        for (int c = 0; c < copies; ++c) s += sh[(uint32_t)c * nbins + b];
+        if (s) atomicAdd(reinterpret_cast<unsigned int *>(bins) + b, s);
+    }
+}
+
+// nbins too large for shared memory: one global reduction per in-range element.
+__global__ void hist_global_kernel(int32_t *__restrict__ bins, uint64_t nbins, const int32_t *__restrict__ in,
+                                   int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        uint64_t b = (uint64_t)(uint32_t)(in[i] - 1);
+        if (in[i] >= 1 && b < nbins) atomicAdd(reinterpret_cast<unsigned int *>(bins) + b, 1u);
+    }
+}
+
+template <int T, int P, int ILP>
+static int launch_bytes(int32_t *bins, uint32_t nbins, const int4 *in4, int64_t n4, const int32_t *tail, int ntail,
+                        int grid, cudaStream_t st) {
+    size_t smem = (size_t)256 * T;
+    B200_CUDA(cudaFuncSetAttribute(hist256_bytes_kernel<T, P, ILP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)smem));
+    hist256_bytes_kernel<T, P, ILP><<<grid, T, smem, st>>>(bins, nbins, in4, n4, tail, ntail);
+    B200_CHECK_LAUNCH("hist256_bytes_kernel");
+    return B200_OK;
+}
+
+template <int T, int P>
+static int launch_atomic(int32_t *bins, uint32_t nbins, const int4 *in4, int64_t n4, const int32_t *tail, int ntail,
+                         int grid, int copies, cudaStream_t st) {
+    size_t smem = (size_t)nbins * copies * 4;
+    if (smem > 48 * 1024)
+        B200_CUDA(cudaFuncSetAttribute(hist_atomic_kernel<T, P>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem));
+    hist_atomic_kernel<T, P><<<grid, T, smem, st>>>(bins, nbins, in4, n4, tail, ntail, copies);
+    B200_CHECK_LAUNCH("hist_atomic_kernel");
+    return B200_OK;
+}
+
+int histogram_launch(int32_t *bins, int64_t nbins, const int32_t *input, int64_t n, cudaStream_t st) {
+    if (n == 0 || nbins == 0) return B200_OK;
+    const int sms = sm_count();
+    if (nbins > 14336) {
+        int grid = sms * 8;
+        hist_global_kernel<<<grid, 256, 0, st>>>(bins, (uint64_t)nbins, input, n);
+        B200_CHECK_LAUNCH("hist_global_kernel");
+        return B200_OK;
+    }
+    // split into [unaligned head | 16-byte aligned int4 body | tail]; head+tail (< 8 elements) go through `tail`
+    // by launching the scalar pieces as a separate tiny range handled by CTA 0.
+    int64_t head = 0;
+    uintptr_t addr = (uintptr_t)input;
+    if (addr & 15) head = (int64_t)((16 - (addr & 15)) / 4);
+    if (head > n) head = n;
+    const int32_t *body = input + head;
+    int64_t n4 = (n - head) / 4;
+    int64_t tail_n = (n - head) - n4 * 4;
+    const int4 *in4 = reinterpret_cast<const int4 *>(body);
+    const int32_t *tailp = body + n4 * 4;
+    int impl = tune_get("hist.impl", 0);
+    if (nbins > 256) impl = 1;
+    if (head > 0) {
+        // rare: unaligned input.  Count the (< 4) head elements with the global kernel first.
+        hist_global_kernel<<<1, 32, 0, st>>>(bins, (uint64_t)nbins, input, head);
+        B200_CHECK_LAUNCH("hist_global_kernel");
+    }
+    int grid = sms * tune_get("hist.ctas_per_sm", 1);
+    if (impl == 0) {
+        int T = tune_get("hist.threads", 512), P = tune_get("hist.batch", 8), ILP = tune_get("hist.ilp", 2);
+        int64_t min_units = (int64_t)T;  // do not launch more CTAs than there is work
+        if ((int64_t)grid > (n4 + min_units - 1) / min_units) grid = (int)((n4 + min_units - 1) / min_units);
+        if (grid < 1) grid = 1;
+#define B200_HB(TT, PP, II)                                                                                      \
+    if (T == TT && P == PP && ILP == II)                                                                         \
+        return launch_bytes<TT, PP, II>(bins, (uint32_t)nbins, in4, n4, tailp, (int)tail_n, grid, st);
+        B200_HB(512, 8, 2)
+        B200_HB(512, 8, 1)
+        B200_HB(512, 4, 2)
+        B200_HB(512, 4, 1)
+        B200_HB(768, 4, 2)
+        B200_HB(768, 4, 1)
+        B200_HB(768, 8, 2)
+        B200_HB(256, 8, 2)
+        B200_HB(256, 8, 1)
+#undef B200_HB
+        return set_error(B200_ERR_INVALID_VALUE, "hist: unsupported (threads=%d, batch=%d, ilp=%d)", T, P, ILP);
+    }
+    {
+        int T = tune_get("hist.atomic_threads", 512), P = tune_get("hist.atomic_batch", 4);
+        int warps = T / 32;
+        int copies = (int)((48 * 1024) / (nbins * 4));
+        if (copies > warps) copies = warps;
+        if (copies < 1) copies = 1;
+        int cps = tune_get("hist.atomic_ctas_per_sm", 4);
+        grid = sms * cps;
+        if ((int64_t)grid > (n4 + T - 1) / T) grid = (int)((n4 + T - 1) / T);
+        if (grid < 1) grid = 1;
+#define B200_HA(TT, PP)                                                                                          \
+    if (T == TT && P == PP)                                                                                      \
+        return launch_atomic<TT, PP>(bins, (uint32_t)nbins, in4, n4, tailp, (int)tail_n, grid, copies, st);
+        B200_HA(512, 4)
+        B200_HA(512, 8)
+        B200_HA(256, 4)
+        B200_HA(256, 8)
+        B200_HA(1024, 4)
+#undef B200_HA
+        return set_error(B200_ERR_INVALID_VALUE, "hist: unsupported atomic config (threads=%d, batch=%d)", T, P);
+    }
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" b200_status b200_histogram_i32(int32_t *bins, int64_t nbins, const int32_t *input, int64_t n) {
+    if (nbins < 0 || n < 0) return set_error(B200_ERR_INVALID_VALUE, "b200_histogram_i32: negative size");
+    if (n == 0 || nbins == 0) return B200_OK;
+    if (!bins || !input) return set_error(B200_ERR_INVALID_VALUE, "b200_histogram_i32: NULL pointer");
+    cudaStream_t st;
+    B200_TRY(current_stream(&st));
+    return histogram_launch(bins, nbins, input, n, st);
+}

@@ -1,0 +1,147 @@
+// transpose.cu -- b200_transpose: a[i,j] = b[j,i]  (reference examples/naive_transpose.jl:4-7).
+//
+// The reference kernel is "naive": with workgroup (256,1) the stores to `a` are coalesced and the loads
+// of `b` are strided by a whole column (64 KiB at 16384^2), i.e. one 32-byte sector per 4-byte element.
+// This file computes exactly the same result (a pure permutation of 4/8-byte words: bit-exact) with a
+// shared-memory tile so that BOTH sides move 128-bit, fully coalesced:
+//
+//   fast path (4-byte elements, m,n multiples of 64, 16-byte aligned rows):
+//     64x64 tile per CTA, 256 threads.  Each thread loads four float4 along b's contiguous dimension from
+//     four consecutive columns -> a 4x4 block in registers, transposed for free by renaming registers,
+//     written as four float4 into a [64][64] shared tile whose 16-byte chunks are XOR-swizzled by (row>>2)
+//     (conflict-free for both the write and the read pattern), then read back as float4 along a's
+//     contiguous dimension and stored.  Per 16 bytes moved: 1 LDG.128 + 1 STS.128 + 1 LDS.128 + 1 STG.128.
+//   generic path (any m,n, leading dims, 4- or 8-byte elements): 32x32 padded tile, predicated edges.
+//
+// HBM bound: 2*elsize bytes of traffic per element; algorithmic bytes for 16384^2 F32 = 2^31.
+#include "../common.cuh"
+#include "../tune.h"
+
+namespace b200 {
+
+__device__ __forceinline__ float4 ldg_stream_f4(const float *p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void stg_stream_f4(float *p, const float4 &v) {
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+                 "f"(v.w)
+                 : "memory");
+}
+
+// a: m x n (lda), b: n x m (ldb).  Tile (ti, tj) covers i in [64 ti, 64 ti + 64), j in [64 tj, 64 tj + 64).
+// ORDER 0: consecutive CTAs walk j (b's contiguous dimension) first; ORDER 1: i (a's contiguous dim) first.
+template <int ORDER>
+__global__ void __launch_bounds__(256) transpose64_f32_kernel(float *__restrict__ a, const float *__restrict__ b,
+                                                              int tiles_i, int tiles_j, int64_t lda, int64_t ldb) {
+    __shared__ __align__(16) float tile[64 * 64];  // [j][i], 16-byte chunk index XOR ((j >> 2) & 15)
+    const int t = threadIdx.x;
+    int ti, tj;
+    if (ORDER == 0) {
+        tj = blockIdx.x % tiles_j;
+        ti = blockIdx.x / tiles_j;
+    } else {
+        ti = blockIdx.x % tiles_i;
+        tj = blockIdx.x / tiles_i;
+    }
+    const int64_t i0 = (int64_t)ti * 64, j0 = (int64_t)tj * 64;
+
+    // ---- load: thread owns j = 4*jq .. 4*jq+3 and i = 4*iq .. 4*iq+3
+    const int jq = t & 15, iq = t >> 4;
+    const float *src = b + (j0 + 4 * jq) + (i0 + 4 * iq) * ldb;
+    float4 v0 = ldg_stream_f4(src);
+    float4 v1 = ldg_stream_f4(src + ldb);
+    float4 v2 = ldg_stream_f4(src + 2 * ldb);
+    float4 v3 = ldg_stream_f4(src + 3 * ldb);
+    // v_r.{x,y,z,w} = b[j+{0,1,2,3}, i+r]  ->  row (j+c) of the tile gets (v0.c, v1.c, v2.c, v3.c)
+    float4 *tile4 = reinterpret_cast<float4 *>(tile);
+    const int chunk = iq ^ jq;  // (row >> 2) == jq for the four rows 4*jq + c
+    tile4[(4 * jq + 0) * 16 + chunk] = make_float4(v0.x, v1.x, v2.x, v3.x);
+    tile4[(4 * jq + 1) * 16 + chunk] = make_float4(v0.y, v1.y, v2.y, v3.y);
+    tile4[(4 * jq + 2) * 16 + chunk] = make_float4(v0.z, v1.z, v2.z, v3.z);
+    tile4[(4 * jq + 3) * 16 + chunk] = make_float4(v0.w, v1.w, v2.w, v3.w);
+    __syncthreads();
+    // ---- store: thread owns i-chunk ic (i = 4*ic..4*ic+3) of rows j = jr, jr+16, jr+32, jr+48
+    const int ic = t & 15, jr = t >> 4;
+    float *dst = a + (i0 + 4 * ic) + (j0 + jr) * lda;
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        const int j = jr + 16 * s;
+        float4 w = tile4[j * 16 + (ic ^ ((j >> 2) & 15))];
+        stg_stream_f4(dst + (int64_t)(16 * s) * lda, w);
+    }
+}
+
+// Generic tile transpose with bounds checks; T is a 4- or 8-byte word type.
+template <typename T>
+__global__ void __launch_bounds__(256) transpose32_generic_kernel(T *__restrict__ a, const T *__restrict__ b,
+                                                                  int64_t m, int64_t n, int64_t lda, int64_t ldb,
+                                                                  int64_t tiles_j) {
+    __shared__ T tile[32][33];
+    const int64_t tj = blockIdx.x % tiles_j, ti = blockIdx.x / tiles_j;
+    const int64_t i0 = ti * 32, j0 = tj * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+#pragma unroll
+    for (int r = 0; r < 32; r += 8) {
+        int64_t j = j0 + tx, i = i0 + ty + r;
+        if (j < n && i < m) tile[ty + r][tx] = b[j + i * ldb];  // tile[i_local][j_local]
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 32; r += 8) {
+        int64_t i = i0 + tx, j = j0 + ty + r;
+        if (i < m && j < n) a[i + j * lda] = tile[tx][ty + r];
+    }
+}
+
+int transpose_launch(void *a, const void *b, int64_t m, int64_t n, int64_t lda, int64_t ldb, int elsize,
+                     cudaStream_t st) {
+    if (m == 0 || n == 0) return B200_OK;
+    const bool fast = elsize == 4 && (m % 64 == 0) && (n % 64 == 0) && (lda % 4 == 0) && (ldb % 4 == 0) &&
+                      (((uintptr_t)a | (uintptr_t)b) & 15) == 0 && (m / 64) * (n / 64) < (int64_t)INT32_MAX &&
+                      tune_get("transpose.force_generic", 0) == 0;
+    if (fast) {
+        int tiles_i = (int)(m / 64), tiles_j = (int)(n / 64);
+        unsigned grid = (unsigned)((int64_t)tiles_i * tiles_j);
+        if (tune_get("transpose.order", 0) == 0)
+            transpose64_f32_kernel<0><<<grid, 256, 0, st>>>((float *)a, (const float *)b, tiles_i, tiles_j, lda, ldb);
+        else
+            transpose64_f32_kernel<1><<<grid, 256, 0, st>>>((float *)a, (const float *)b, tiles_i, tiles_j, lda, ldb);
+        B200_CHECK_LAUNCH("transpose64_f32_kernel");
+        return B200_OK;
+    }
+    int64_t tiles_i = cdiv(m, 32), tiles_j = cdiv(n, 32);
+    if (tiles_i * tiles_j >= (int64_t)INT32_MAX)
+        return set_error(B200_ERR_UNSUPPORTED, "transpose: %lld x %lld too large for the generic path", (long long)m,
+                         (long long)n);
+    unsigned grid = (unsigned)(tiles_i * tiles_j);
+    if (elsize == 4)
+        transpose32_generic_kernel<uint32_t>
+            <<<grid, 256, 0, st>>>((uint32_t *)a, (const uint32_t *)b, m, n, lda, ldb, tiles_j);
+    else if (elsize == 8)
+        transpose32_generic_kernel<uint64_t>
+            <<<grid, 256, 0, st>>>((uint64_t *)a, (const uint64_t *)b, m, n, lda, ldb, tiles_j);
+    else
+        return set_error(B200_ERR_UNSUPPORTED, "transpose: element size %d not in {4,8}", elsize);
+    B200_CHECK_LAUNCH("transpose32_generic_kernel");
+    return B200_OK;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" b200_status b200_transpose(void *a, const void *b, int64_t m, int64_t n, int64_t lda, int64_t ldb,
+                                      int32_t elsize) {
+    if (m < 0 || n < 0 || lda < m || ldb < n)
+        return set_error(B200_ERR_INVALID_VALUE, "b200_transpose: bad shape m=%lld n=%lld lda=%lld ldb=%lld",
+                         (long long)m, (long long)n, (long long)lda, (long long)ldb);
+    if (m == 0 || n == 0) return B200_OK;
+    if (!a || !b) return set_error(B200_ERR_INVALID_VALUE, "b200_transpose: NULL pointer");
+    cudaStream_t st;
+    B200_TRY(current_stream(&st));
+    return transpose_launch(a, b, m, n, lda, ldb, elsize, st);
+}

@@ -1,0 +1,481 @@
+// twins.cu -- literal CUDA twins of every kernel the reference defines on the hot path.
+//
+// There is no JIT in this backend, so each `@kernel` / KI kernel of the reference's examples and testsuite
+// exists here as a precompiled sm_100a kernel that follows the lowering `transform_gpu!`/`split`/`emit`
+// produce (reference src/macros.jl:55-88,113-196): `active = __validindex(ctx)`,
+// hoisted @localmem/@private/@uniform allocations, `if active` regions separated by unguarded barriers.
+// They honour ANY ndrange / workgroupsize the host passes.  The registry (registry.cu) routes the
+// north-star shapes to the tuned kernels in copy.cu / transpose.cu / histogram.cu / matmul_f32.cu and
+// everything else here, so results never depend on which one ran.
+#include "twins.h"
+
+#include "../common.cuh"
+
+namespace b200 {
+
+#define KA_LAUNCH_1D(ctx, groups, items)                                                               \
+    long long groups = 1, items = 1;                                                                   \
+    for (int d = 0; d < (ctx).ndim; ++d) {                                                             \
+        groups *= (ctx).blocks[d];                                                                     \
+        items *= (ctx).wgs[d];                                                                         \
+    }                                                                                                  \
+    if (groups == 0) return B200_OK; /* reference src/pocl/backend.jl:136-138 */                       \
+    if (items > 1024 || items < 1)                                                                     \
+        return set_error(B200_ERR_LAUNCH_DIMS, "workgroup of %lld items exceeds 1024", items);         \
+    if (groups > 2147483647LL) return set_error(B200_ERR_LAUNCH_DIMS, "%lld groups exceed 2^31-1", groups);
+
+// ---- copy_kernel / copy_kernel!  (src/KernelAbstractions.jl:874-877, examples/memcopy.jl:4-7) ----
+template <typename T>
+__global__ void copy_twin_kernel(KaCtx c, T *__restrict__ A, const T *__restrict__ B) {
+    const bool active = ka_valid(c);
+    if (active) {
+        const long long I = ka_global_linear();
+        A[I - 1] = B[I - 1];
+    }
+}
+int twin_copy(const KaCtx &c, void *A, const void *B, int elsize, cudaStream_t st) {
+    KA_LAUNCH_1D(c, groups, items);
+    switch (elsize) {
+        case 1: copy_twin_kernel<uint8_t><<<(unsigned)groups, (unsigned)items, 0, st>>>(c, (uint8_t *)A, (const uint8_t *)B); break;
+        case 2: copy_twin_kernel<uint16_t><<<(unsigned)groups, (unsigned)items, 0, st>>>(c, (uint16_t *)A, (const uint16_t *)B); break;
+        case 4: copy_twin_kernel<uint32_t><<<(unsigned)groups, (unsigned)items, 0, st>>>(c, (uint32_t *)A, (const uint32_t *)B); break;
+        case 8: copy_twin_kernel<uint64_t><<<(unsigned)groups, (unsigned)items, 0, st>>>(c, (uint64_t *)A, (const uint64_t *)B); break;
+        case 16: copy_twin_kernel<uint4><<<(unsigned)groups, (unsigned)items, 0, st>>>(c, (uint4 *)A, (const uint4 *)B); break;
+        default: return set_error(B200_ERR_UNSUPPORTED, "copy_kernel: element size %d", elsize);
+    }
+    B200_CHECK_LAUNCH("copy_twin_kernel");
+    return B200_OK;
+}
+
+// ---- init_kernel  (src/KernelAbstractions.jl:869-872) ----
+template <typename T>
+__global__ void init_twin_kernel(KaCtx c, T *__restrict__ arr, T value) {
+    if (ka_valid(c)) arr[ka_global_linear() - 1] = value;
+}
+int twin_init(const KaCtx &c, void *arr, const void *value, int elsize, cudaStream_t st) {
+    KA_LAUNCH_1D(c, groups, items);
+    switch (elsize) {
+        case 1: init_twin_kernel<uint8_t><<<(unsigned)groups, (unsigned)items, 0, st>>>(c, (uint8_t *)arr, *(const uint8_t *)value); break;
+        case 2: init_twin_kernel<uint16_t><<<(unsigned)groups, (unsigned)items, 0, st>>>(c, (uint16_t *)arr, *(const uint16_t *)value); break;
+        case 4: init_twin_kernel<uint32_t><<<(unsigned)groups, (unsigned)items, 0, st>>>(c, (uint32_t *)arr, *(const uint32_t *)value); break;
+        case 8: init_twin_kernel<uint64_t><<<(unsigned)groups, (unsigned)items, 0, st>>>(c, (uint64_t *)arr, *(const uint64_t *)value); break;
+        default: return set_error(B200_ERR_UNSUPPORTED, "init_kernel: element size %d", elsize);
+    }
+    B200_CHECK_LAUNCH("init_twin_kernel");
+    return B200_OK;
+}
+
+// ---- naive_transpose_kernel!  (examples/naive_transpose.jl:4-7) ----
+template <typename T>
+__global__ void transpose_twin_kernel(KaCtx c, T *__restrict__ a, const T *__restrict__ b, long long rows_a,
+                                      long long rows_b) {
+    if (ka_valid(c)) {
+        long long I[KA_MAX_NDIM];
+        ka_expand(c, I);
+        const long long i = I[0], j = I[1];
+        a[(i - 1) + (j - 1) * rows_a] = b[(j - 1) + (i - 1) * rows_b];
+    }
+}
+int twin_transpose(const KaCtx &c, void *a, const void *b, long long rows_a, long long rows_b, int elsize,
+                   cudaStream_t st) {
+    KA_LAUNCH_1D(c, groups, items);
+    if (elsize == 4)
+        transpose_twin_kernel<uint32_t><<<(unsigned)groups, (unsigned)items, 0, st>>>(c, (uint32_t *)a, (const uint32_t *)b, rows_a, rows_b);
+    else if (elsize == 8)
+        transpose_twin_kernel<uint64_t><<<(unsigned)groups, (unsigned)items, 0, st>>>(c, (uint64_t *)a, (const uint64_t *)b, rows_a, rows_b);
+    else
+        return set_error(B200_ERR_UNSUPPORTED, "naive_transpose_kernel!: element size %d", elsize);
+    B200_CHECK_LAUNCH("transpose_twin_kernel");
+    return B200_OK;
+}
+
+// ---- matmul_kernel!  (examples/matmul.jl:5-15): separate multiply and add roundings, k ascending ----
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+template <typename T>
+__global__ void matmul_naive_twin_kernel(KaCtx c, T *__restrict__ out, const T *__restrict__ a,
+                                         const T *__restrict__ b, long long M, long long K) {
+    if (ka_valid(c)) {
+        long long I[KA_MAX_NDIM];
+        ka_expand(c, I);
+        const long long i = I[0], j = I[1];
+        T tmp = (T)0;
+        for (long long k = 1; k <= K; ++k) tmp = add_rn(tmp, mul_rn(a[(i - 1) + (k - 1) * M], b[(k - 1) + (j - 1) * K]));
+        out[(i - 1) + (j - 1) * M] = tmp;
+    }
+}
+int twin_matmul_naive(const KaCtx &c, void *out, const void *a, const void *b, long long M, long long K, int is_f64,
+                      cudaStream_t st) {
+    KA_LAUNCH_1D(c, groups, items);
+    if (is_f64)
+        matmul_naive_twin_kernel<double><<<(unsigned)groups, (unsigned)items, 0, st>>>(c, (double *)out, (const double *)a, (const double *)b, M, K);
+    else
+        matmul_naive_twin_kernel<float><<<(unsigned)groups, (unsigned)items, 0, st>>>(c, (float *)out, (const float *)a, (const float *)b, M, K);
+    B200_CHECK_LAUNCH("matmul_naive_twin_kernel");
+    return B200_OK;
+}
+
+// ---- test/localmem.jl:4-65 ----
+__global__ void localmem_twin_kernel(KaCtx c, int variant, long long *__restrict__ A, long long lenA) {
+    extern __shared__ __align__(16) long long lmem[];  // @localmem Int (N,)  [x2 for many_localmem]
+    const long long N = ka_groupsize_prod(c);           // N = @uniform prod(@groupsize()); N2 likewise
+    const long long i = ka_local_linear();
+    if (variant == 2) {  // unsafe_indices = true: no guard, no region splitting (test/localmem.jl:37-48)
+        const long long gI = ka_group_linear();
+        lmem[i - 1] = i;
+        __syncthreads();
+        const long long I = (gI - 1) * N + i;
+        if (I <= lenA) A[I - 1] = lmem[N - i + 1 - 1];
+        return;
+    }
+    const bool active = ka_valid(c);
+    const long long I = ka_global_linear();
+    if (variant == 0) {
+        if (active) lmem[i - 1] = i;
+        __syncthreads();
+        if (active) A[I - 1] = lmem[N - i + 1 - 1];
+    } else if (variant == 1) {
+        if (active) lmem[i - 1] = i + 3;
+        for (long long j = 1; j <= 2; ++j) {  // loop header on all lanes
+            if (active) lmem[i - 1] -= j;
+            __syncthreads();
+        }
+        if (active) A[I - 1] = lmem[N - i + 1 - 1];
+    } else {
+        long long *lmem2 = lmem + N;
+        if (active) {
+            lmem[i - 1] = i - 1;
+            lmem2[i - 1] = 1;
+        }
+        __syncthreads();
+        if (active) A[I - 1] = lmem[N - i + 1 - 1] + lmem2[N - i + 1 - 1];
+    }
+}
+int twin_localmem(const KaCtx &c, int variant, long long *A, long long lenA, cudaStream_t st) {
+    KA_LAUNCH_1D(c, groups, items);
+    size_t smem = (size_t)items * 8 * (variant == 3 ? 2 : 1);
+    localmem_twin_kernel<<<(unsigned)groups, (unsigned)items, smem, st>>>(c, variant, A, lenA);
+    B200_CHECK_LAUNCH("localmem_twin_kernel");
+    return B200_OK;
+}
+
+// ---- test/private.jl:4-59 ----
+__global__ void stmt_form_twin_kernel(KaCtx c) {
+    const long long bs = c.wgs[0];   // @uniform bs = @groupsize()[1]
+    volatile long long s = bs / 2;   // @private s = bs / 2
+    (void)s;
+    __syncthreads();
+}
+__global__ void private_twin_kernel(KaCtx c, long long *__restrict__ A) {
+    const long long N = ka_groupsize_prod(c);
+    const bool active = ka_valid(c);
+    long long priv[1];
+    const long long I = ka_global_linear(), i = ka_local_linear();
+    if (active) priv[0] = N - i + 1;
+    __syncthreads();
+    if (active) A[I - 1] = priv[0];
+}
+__global__ void typetest_twin_kernel(KaCtx c, uint8_t *__restrict__ B) {
+    if (ka_valid(c)) B[ka_global_linear() - 1] = 1;  // eltype(priv) === eltype(A)
+}
+constexpr int FORLOOP_MAX_N = 128;
+__global__ void forloop_twin_kernel(KaCtx c, long long *__restrict__ A, long long rowsA, int N) {
+    const bool active = ka_valid(c);
+    const long long I = ka_global_linear(), i = ka_local_linear();
+    long long priv[FORLOOP_MAX_N];  // @private Int (N,)
+    if (active) {
+        for (int j = 1; j <= N; ++j) priv[j - 1] = A[(I - 1) + (long long)(j - 1) * rowsA];
+        A[I - 1] = 0;
+    }
+    __syncthreads();
+    for (int j = 1; j <= N; ++j) {
+        if (active) {
+            const long long k = (j + i - 1 - 1) % N + 1;  // mod1(j + i - 1, N)
+            A[k - 1] += priv[j - 1];
+        }
+        __syncthreads();
+    }
+}
+template <typename T>
+__global__ void reduce_private_twin_kernel(KaCtx c, T *__restrict__ out, const T *__restrict__ A, long long n,
+                                           long long K) {
+    if (ka_valid(c)) {
+        long long I[KA_MAX_NDIM];
+        ka_expand(c, I);
+        T priv = (T)0;
+        for (long long k = 1; k <= K; ++k) priv = add_rn(priv, A[(I[0] - 1) + (k - 1) * n]);
+        out[I[0] - 1] = priv;
+    }
+}
+int twin_stmt_form(const KaCtx &c, cudaStream_t st) {
+    KA_LAUNCH_1D(c, groups, items);
+    stmt_form_twin_kernel<<<(unsigned)groups, (unsigned)items, 0, st>>>(c);
+    B200_CHECK_LAUNCH("stmt_form_twin_kernel");
+    return B200_OK;
+}
+int twin_private(const KaCtx &c, long long *A, cudaStream_t st) {
+    KA_LAUNCH_1D(c, groups, items);
+    private_twin_kernel<<<(unsigned)groups, (unsigned)items, 0, st>>>(c, A);
+    B200_CHECK_LAUNCH("private_twin_kernel");
+    return B200_OK;
+}
+int twin_typetest(const KaCtx &c, uint8_t *B, cudaStream_t st) {
+    KA_LAUNCH_1D(c, groups, items);
+    typetest_twin_kernel<<<(unsigned)groups, (unsigned)items, 0, st>>>(c, B);
+    B200_CHECK_LAUNCH("typetest_twin_kernel");
+    return B200_OK;
+}
+int twin_forloop(const KaCtx &c, long long *A, long long rowsA, long long N, cudaStream_t st) {
+    KA_LAUNCH_1D(c, groups, items);
+    if (N < 0 || N > FORLOOP_MAX_N)
+        return set_error(B200_ERR_UNSUPPORTED, "forloop: Val(N) with N=%lld > %d private slots", N, FORLOOP_MAX_N);
+    forloop_twin_kernel<<<(unsigned)groups, (unsigned)items, 0, st>>>(c, A, rowsA, (int)N);
+    B200_CHECK_LAUNCH("forloop_twin_kernel");
+    return B200_OK;
+}
+int twin_reduce_private(const KaCtx &c, void *out, const void *A, long long n, long long K, int is_f64,
+                        cudaStream_t st) {
+    KA_LAUNCH_1D(c, groups, items);
+    if (is_f64)
+        reduce_private_twin_kernel<double><<<(unsigned)groups, (unsigned)items, 0, st>>>(c, (double *)out, (const double *)A, n, K);
+    else
+        reduce_private_twin_kernel<float><<<(unsigned)groups, (unsigned)items, 0, st>>>(c, (float *)out, (const float *)A, n, K);
+    B200_CHECK_LAUNCH("reduce_private_twin_kernel");
+    return B200_OK;
+}
+
+// ---- test/unroll.jl:5-37 ----
+__global__ void unroll_twin_kernel(KaCtx c, int variant, float *__restrict__ a, int N) {
+    const bool active = ka_valid(c);
+    if (variant == 0) {
+        if (active) {
+#pragma unroll
+            for (int i = 1; i <= 5; ++i) a[i - 1] = (float)i;
+        }
+    } else if (variant == 1) {
+        if (active) {
+            const int M = N + 5;
+#pragma unroll 4
+            for (int i = 6; i <= M; ++i) a[i - 5 - 1] = (float)i;
+        }
+        __syncthreads();
+    } else {
+        const float va[3] = {1.f, 2.f, 3.f}, vb[3] = {3.f, 2.f, 1.f};  // @uniform MVectors
+        float vc[9];
+        const long long I = ka_global_linear();
+        for (int m = 1; m <= 3; ++m) {
+            if (active) {
+#pragma unroll
+                for (int j = 1; j <= 3; ++j)
+#pragma unroll
+                    for (int i = 1; i <= 3; ++i) vc[(j - 1) * 3] = (float)m * va[0] * vb[j - 1];
+                a[I - 1] = vc[0];
+            }
+            __syncthreads();  // @synchronize(m % 2 == 0): the condition is ignored (src/KernelAbstractions.jl:319-345)
+        }
+    }
+}
+int twin_unroll(const KaCtx &c, int variant, float *a, long long N, cudaStream_t st) {
+    KA_LAUNCH_1D(c, groups, items);
+    unroll_twin_kernel<<<(unsigned)groups, (unsigned)items, 0, st>>>(c, variant, a, (int)N);
+    B200_CHECK_LAUNCH("unroll_twin_kernel");
+    return B200_OK;
+}
+
+// ---- test/test.jl:46-73 index kernels, :216-230 kernel_val!/kernel_empty ----
+__global__ void index_linear_twin_kernel(KaCtx c, int which, long long *__restrict__ A) {
+    if (ka_valid(c)) {
+        const long long I = ka_global_linear();
+        A[I - 1] = which == 0 ? I : (which == 1 ? ka_local_linear() : ka_group_linear());
+    }
+}
+__global__ void index_cartesian_twin_kernel(KaCtx c, int which, long long *__restrict__ A, int ndimA, long long d0,
+                                            long long d1, long long d2) {
+    if (ka_valid(c)) {
+        long long I[KA_MAX_NDIM], v[KA_MAX_NDIM];
+        ka_expand(c, I);
+        if (which == 0) {
+            for (int d = 0; d < c.ndim; ++d) v[d] = I[d];
+        } else if (which == 1) {
+            ka_local_cartesian(c, v);
+        } else {
+            ka_group_cartesian(c, v);
+        }
+        const long long dims[3] = {d0, d1, d2};
+        long long lin;
+        if (c.ndim == ndimA) {
+            lin = 0;
+            long long stride = 1;
+            for (int d = 0; d < c.ndim; ++d) {
+                lin += (I[d] - 1) * stride;
+                stride *= dims[d < 3 ? d : 2];
+            }
+        } else {
+            lin = I[0] - 1;
+        }
+        for (int d = 0; d < c.ndim; ++d) A[lin * c.ndim + d] = v[d];
+    }
+}
+__global__ void kernel_val_twin_kernel(KaCtx c, long long *__restrict__ a, long long m) {
+    if (ka_valid(c)) a[ka_global_linear() - 1] = m;
+}
+__global__ void kernel_empty_twin_kernel(KaCtx c) { (void)ka_valid(c); }
+int twin_index_linear(const KaCtx &c, int which, long long *A, cudaStream_t st) {
+    KA_LAUNCH_1D(c, groups, items);
+    index_linear_twin_kernel<<<(unsigned)groups, (unsigned)items, 0, st>>>(c, which, A);
+    B200_CHECK_LAUNCH("index_linear_twin_kernel");
+    return B200_OK;
+}
+int twin_index_cartesian(const KaCtx &c, int which, long long *A, int ndimA, const long long *dimsA, cudaStream_t st) {
+    KA_LAUNCH_1D(c, groups, items);
+    if (c.ndim > 3) return set_error(B200_ERR_UNSUPPORTED, "index_cartesian: more than 3 dims");
+    index_cartesian_twin_kernel<<<(unsigned)groups, (unsigned)items, 0, st>>>(
+        c, which, A, ndimA, ndimA > 0 ? dimsA[0] : 1, ndimA > 1 ? dimsA[1] : 1, ndimA > 2 ? dimsA[2] : 1);
+    B200_CHECK_LAUNCH("index_cartesian_twin_kernel");
+    return B200_OK;
+}
+int twin_kernel_val(const KaCtx &c, long long *a, long long m, cudaStream_t st) {
+    KA_LAUNCH_1D(c, groups, items);
+    kernel_val_twin_kernel<<<(unsigned)groups, (unsigned)items, 0, st>>>(c, a, m);
+    B200_CHECK_LAUNCH("kernel_val_twin_kernel");
+    return B200_OK;
+}
+int twin_kernel_empty(const KaCtx &c, cudaStream_t st) {
+    KA_LAUNCH_1D(c, groups, items);
+    kernel_empty_twin_kernel<<<(unsigned)groups, (unsigned)items, 0, st>>>(c);
+    B200_CHECK_LAUNCH("kernel_empty_twin_kernel");
+    return B200_OK;
+}
+
+// ---- saxpy_kernel!  (benchmark/benchmarks.jl:29-32, examples/numa_aware.jl:10-13): Z = a*X + Y, unfused ----
+template <typename T>
+__global__ void saxpy_twin_kernel(KaCtx c, T *__restrict__ Z, T a, const T *__restrict__ X, const T *__restrict__ Y) {
+    if (ka_valid(c)) {
+        const long long I = ka_global_linear();
+        Z[I - 1] = add_rn(mul_rn(a, X[I - 1]), Y[I - 1]);
+    }
+}
+int twin_saxpy(const KaCtx &c, void *Z, double a, const void *X, const void *Y, int is_f64, cudaStream_t st) {
+    KA_LAUNCH_1D(c, groups, items);
+    if (is_f64)
+        saxpy_twin_kernel<double><<<(unsigned)groups, (unsigned)items, 0, st>>>(c, (double *)Z, a, (const double *)X, (const double *)Y);
+    else
+        saxpy_twin_kernel<float><<<(unsigned)groups, (unsigned)items, 0, st>>>(c, (float *)Z, (float)a, (const float *)X, (const float *)Y);
+    B200_CHECK_LAUNCH("saxpy_twin_kernel");
+    return B200_OK;
+}
+
+// ==================================================================================================
+// KI twins: true <=3-D launches, no implicit bounds check (src/intrinsics.jl:300-373, pocl/backend.jl:156-205)
+// ==================================================================================================
+
+// histogram_kernel!  (examples/histogram.jl:18-58), literal: multi-pass over bins when N > gs
+__global__ void histogram_twin_kernel(int32_t *__restrict__ histogram_output, long long N,
+                                      const int32_t *__restrict__ input, long long len, int gs) {
+    extern __shared__ int32_t shared_histogram[];  // KI.localmemory(eltype(input), gs)
+    const long long gid = (long long)blockIdx.x + 1, lid = (long long)threadIdx.x + 1;
+    const long long tid = (gid - 1) * gs + lid;
+    for (long long min_element = 1; min_element <= N; min_element += gs) {
+        shared_histogram[lid - 1] = 0;
+        __syncthreads();
+        long long max_element = min_element + gs;
+        if (max_element > N) max_element = N + 1;
+        long long bin = tid <= len ? (long long)input[tid - 1] : 0;
+        if (bin >= min_element && bin < max_element) {
+            bin -= min_element - 1;
+            atomicAdd(&shared_histogram[bin - 1], 1);
+        }
+        __syncthreads();
+        if (lid + min_element - 1 <= N) atomicAdd(&histogram_output[lid + min_element - 1 - 1], shared_histogram[lid - 1]);
+    }
+}
+int twin_histogram(int32_t *out, long long N, const int32_t *input, long long len, long long gs, long long groups,
+                   cudaStream_t st) {
+    if (groups == 0) return B200_OK;
+    if (gs < 1 || gs > 1024) return set_error(B200_ERR_LAUNCH_DIMS, "workgroup of %lld items exceeds 1024", gs);
+    if (groups > 2147483647LL) return set_error(B200_ERR_LAUNCH_DIMS, "too many groups");
+    histogram_twin_kernel<<<(unsigned)groups, (unsigned)gs, (size_t)gs * 4, st>>>(out, N, input, len, (int)gs);
+    B200_CHECK_LAUNCH("histogram_twin_kernel");
+    return B200_OK;
+}
+
+// coalesced_matmul_kernel!  (examples/performant_matmul.jl:15-77), literal 16x16-tile version (TDIM <= 32)
+__global__ void coalesced_matmul_twin_kernel(float *__restrict__ output, const float *__restrict__ input1,
+                                             const float *__restrict__ input2, long long N, long long R, long long M,
+                                             int TDIM) {
+    extern __shared__ float tiles[];  // two (TDIM+1, TDIM) column-major tiles
+    float *tile1 = tiles, *tile2 = tiles + (TDIM + 1) * TDIM;
+    const long long gi = blockIdx.x + 1, gj = blockIdx.y + 1;
+    const int i = threadIdx.x + 1, j = threadIdx.y + 1;
+    float outval = -0.0f;
+    const long long NUM_TILES = (R + TDIM - 1) / TDIM;
+    const long long I = (gi - 1) * TDIM + i, J = (gj - 1) * TDIM + j;
+    for (long long t = 0; t < NUM_TILES; ++t) {
+        tile1[(i - 1) + (j - 1) * (TDIM + 1)] =
+            (I <= N && t * TDIM + j <= R) ? input1[(I - 1) + (t * TDIM + j - 1) * N] : 0.0f;
+        tile2[(i - 1) + (j - 1) * (TDIM + 1)] =
+            (t * TDIM + i <= R && J <= M) ? input2[(t * TDIM + i - 1) + (J - 1) * R] : 0.0f;
+        __syncthreads();
+        float out = 0.0f;
+        for (int k = 1; k <= TDIM; ++k)
+            out = fmaf(tile1[(i - 1) + (k - 1) * (TDIM + 1)], tile2[(k - 1) + (j - 1) * (TDIM + 1)], out);
+        outval += out;
+        __syncthreads();
+    }
+    if (I <= N && J <= M) output[(I - 1) + (J - 1) * N] = outval;
+}
+int twin_coalesced_matmul(float *output, const float *in1, const float *in2, long long N, long long R, long long M,
+                          int TDIM, long long groups_x, long long groups_y, cudaStream_t st) {
+    if (groups_x == 0 || groups_y == 0) return B200_OK;
+    if (TDIM < 1 || TDIM > 32) return set_error(B200_ERR_LAUNCH_DIMS, "coalesced_matmul_kernel!: TDIM %d not in 1..32", TDIM);
+    if (groups_y > 65535 || groups_x > 2147483647LL) return set_error(B200_ERR_LAUNCH_DIMS, "too many groups");
+    dim3 grid((unsigned)groups_x, (unsigned)groups_y), block(TDIM, TDIM);
+    size_t smem = (size_t)2 * (TDIM + 1) * TDIM * sizeof(float);
+    coalesced_matmul_twin_kernel<<<grid, block, smem, st>>>(output, in1, in2, N, R, M, TDIM);
+    B200_CHECK_LAUNCH("coalesced_matmul_twin_kernel");
+    return B200_OK;
+}
+
+// test_intrinsics_kernel  (test/intrinsics.jl:11-25): six Int64 per element, .x components, 1-based
+__global__ void test_intrinsics_twin_kernel(long long *__restrict__ results, long long len) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x + 1;
+    if (i <= len) {
+        long long *r = results + (i - 1) * 6;
+        r[0] = (long long)gridDim.x * blockDim.x;
+        r[1] = i;
+        r[2] = blockDim.x;
+        r[3] = threadIdx.x + 1;
+        r[4] = gridDim.x;
+        r[5] = blockIdx.x + 1;
+    }
+}
+// launch_kernel1d/2d/3d  (test/intrinsics.jl:31-72)
+__global__ void launch_kernel_nd_twin_kernel(float *__restrict__ arr, long long d0, long long d1) {
+    const long long i = threadIdx.x + 1, j = threadIdx.y + 1, k = threadIdx.z + 1;
+    const long long gi = blockIdx.x + 1, gj = blockIdx.y + 1, gk = blockIdx.z + 1;
+    const long long ngi = gridDim.x, ngj = gridDim.y, ngk = gridDim.z;
+    const long long x = (gi - 1) * ngi + i, y = (gj - 1) * ngj + j, z = (gk - 1) * ngk + k;
+    arr[(x - 1) + (y - 1) * d0 + (z - 1) * d0 * d1] = 1.0f;
+}
+int twin_test_intrinsics(long long *results, long long len, const long long *groups, const long long *wgs,
+                         cudaStream_t st) {
+    if (groups[0] * groups[1] * groups[2] == 0) return B200_OK;
+    dim3 grid((unsigned)groups[0], (unsigned)groups[1], (unsigned)groups[2]);
+    dim3 block((unsigned)wgs[0], (unsigned)wgs[1], (unsigned)wgs[2]);
+    test_intrinsics_twin_kernel<<<grid, block, 0, st>>>(results, len);
+    B200_CHECK_LAUNCH("test_intrinsics_twin_kernel");
+    return B200_OK;
+}
+int twin_launch_kernel_nd(float *arr, const long long *dims, const long long *groups, const long long *wgs,
+                          cudaStream_t st) {
+    if (groups[0] * groups[1] * groups[2] == 0) return B200_OK;
+    dim3 grid((unsigned)groups[0], (unsigned)groups[1], (unsigned)groups[2]);
+    dim3 block((unsigned)wgs[0], (unsigned)wgs[1], (unsigned)wgs[2]);
+    launch_kernel_nd_twin_kernel<<<grid, block, 0, st>>>(arr, dims[0], dims[1]);
+    B200_CHECK_LAUNCH("launch_kernel_nd_twin_kernel");
+    return B200_OK;
+}
+
+}  // namespace b200

@@ -1,0 +1,421 @@
+// registry.cu -- b200_launch: name -> precompiled sm_100a kernel.
+//
+// Replaces the reference's JIT path  @opencl launch=false obj.f(ctx, args...)  -> clfunction ->
+// cached_compilation -> clEnqueueNDRangeKernel  (src/pocl/backend.jl:117-168,
+// src/pocl/compiler/execution.jl:149-217, src/pocl/nanoOpenCL.jl:1228-1283).  The host layer computes the
+// iteration space with the UNCHANGED KA.partition and hands it over flattened (b200_launch_desc); `name` is
+// nameof(obj.f) for `@kernel`s ("gpu_" * name, src/macros.jl:32) or the function name for KI.@kernel.
+//
+// Routing rule: a north-star kernel whose launch covers a contiguous / rectangular region goes to the tuned
+// kernel (copy.cu, transpose.cu, histogram.cu, matmul_f32.cu); every other shape, and every testsuite kernel,
+// runs its literal twin (kernels/twins.cu).  Both produce the same bits, so the choice is invisible.
+#include <cstring>
+
+#include "common.cuh"
+#include "kernels/twins.h"
+#include "tune.h"
+
+namespace b200 {
+
+struct Launch {
+    const b200_launch_desc *desc;
+    KaCtx ctx;            // KA launches
+    long long groups[3];  // KI launches (padded)
+    long long wgs[3];
+    const b200_arg *args;
+    int nargs;
+    cudaStream_t st;
+};
+
+typedef int (*Handler)(const Launch &);
+
+static inline bool is_array(const b200_arg &a) { return a.kind == B200_ARG_ARRAY; }
+static inline bool is_value(const b200_arg &a) { return a.kind == B200_ARG_SCALAR || a.kind == B200_ARG_VAL; }
+static inline long long numel(const b200_arg &a) {
+    long long n = 1;
+    for (int d = 0; d < a.ndim; ++d) n *= a.dims[d];
+    return n;
+}
+static inline long long dim(const b200_arg &a, int d) { return d < a.ndim ? a.dims[d] : 1; }
+
+#define REQUIRE(cond, ...)                                            \
+    do {                                                              \
+        if (!(cond)) return set_error(B200_ERR_BAD_ARGS, __VA_ARGS__); \
+    } while (0)
+
+// largest @index(Global, Linear) among the valid work-items of a KA launch (0 when nothing runs)
+static long long ka_max_global_linear(const KaCtx &c) {
+    long long groups = 1, items = 1;
+    for (int d = 0; d < c.ndim; ++d) {
+        groups *= c.blocks[d];
+        items *= c.wgs[d];
+    }
+    if (groups == 0) return 0;
+    if (!c.dynamic_check) return groups * items;
+    long long l_lin = 0, stride = 1;
+    for (int d = 0; d < c.ndim; ++d) {
+        long long in_last = c.ndrange[d] - (c.blocks[d] - 1) * c.wgs[d];
+        if (in_last > c.wgs[d]) in_last = c.wgs[d];
+        if (in_last < 1) return 0;
+        l_lin += (in_last - 1) * stride;
+        stride *= c.wgs[d];
+    }
+    return (groups - 1) * items + l_lin + 1;
+}
+// do the valid lanes cover exactly I = 1..prod(ndrange), each once?
+static bool ka_covers_linear_prefix(const KaCtx &c) {
+    if (c.ndim == 1) return true;
+    for (int d = 0; d < c.ndim; ++d)
+        if (c.ndrange[d] % c.wgs[d] != 0) return false;
+    return true;
+}
+static long long ka_ndrange_prod(const KaCtx &c) {
+    long long n = 1;
+    for (int d = 0; d < c.ndim; ++d) n *= c.ndrange[d];
+    return n;
+}
+static bool force_twins() { return tune_get("registry.force_twins", 0) != 0; }
+
+// ------------------------------------------------------------------------------------------------
+static int h_copy(const Launch &L) {
+    REQUIRE(L.nargs == 2 && is_array(L.args[0]) && is_array(L.args[1]), "copy_kernel(A, B): two arrays expected");
+    const b200_arg &A = L.args[0], &B = L.args[1];
+    REQUIRE(A.elsize == B.elsize && A.elsize > 0, "copy_kernel: element sizes differ (%d vs %d)", A.elsize, B.elsize);
+    long long maxI = ka_max_global_linear(L.ctx);
+    REQUIRE(maxI <= numel(A) && maxI <= numel(B), "copy_kernel: ndrange reaches index %lld beyond the arrays", maxI);
+    if (maxI == 0) return B200_OK;
+    if (!force_twins() && ka_covers_linear_prefix(L.ctx)) {
+        size_t bytes = (size_t)ka_ndrange_prod(L.ctx) * A.elsize;
+        const char *d = (const char *)A.ptr, *s = (const char *)B.ptr;
+        if (!(d < s + bytes && s < d + bytes)) return copy_bytes(A.ptr, B.ptr, bytes, L.st);
+    }
+    return twin_copy(L.ctx, A.ptr, B.ptr, A.elsize, L.st);
+}
+
+static int h_init(const Launch &L) {
+    REQUIRE(L.nargs >= 2 && is_array(L.args[0]) && is_value(L.args[1]), "init_kernel(arr, value[, T])");
+    const b200_arg &A = L.args[0], &V = L.args[1];
+    long long maxI = ka_max_global_linear(L.ctx);
+    REQUIRE(maxI <= numel(A), "init_kernel: ndrange reaches index %lld beyond the array", maxI);
+    if (maxI == 0) return B200_OK;
+    unsigned char value[16] = {0};
+    // the host passes f(T) already converted to the array's eltype: integers in .scalar, floats in .fscalar
+    switch (A.eltype) {
+        case B200_T_F32: { float f = (float)V.fscalar; memcpy(value, &f, 4); break; }
+        case B200_T_F64: { double f = V.fscalar; memcpy(value, &f, 8); break; }
+        case B200_T_F16: case B200_T_BF16: case B200_T_OPAQUE:
+            REQUIRE(A.elsize <= 8, "init_kernel: opaque element wider than 8 bytes");
+            memcpy(value, &V.scalar, (size_t)A.elsize);  // raw bits supplied by the host
+            break;
+        default: memcpy(value, &V.scalar, (size_t)(A.elsize <= 8 ? A.elsize : 8)); break;  // little endian
+    }
+    if (!force_twins() && ka_covers_linear_prefix(L.ctx))
+        return fill_elems(A.ptr, (size_t)ka_ndrange_prod(L.ctx), A.elsize, value, L.st);
+    return twin_init(L.ctx, A.ptr, value, A.elsize, L.st);
+}
+
+static int h_transpose(const Launch &L) {
+    REQUIRE(L.nargs == 2 && is_array(L.args[0]) && is_array(L.args[1]), "naive_transpose_kernel!(a, b)");
+    const b200_arg &a = L.args[0], &b = L.args[1];
+    REQUIRE(L.ctx.ndim == 2, "naive_transpose_kernel!: a 2-d ndrange is required (got %d-d)", L.ctx.ndim);
+    REQUIRE(a.elsize == b.elsize, "naive_transpose_kernel!: element sizes differ");
+    const long long r0 = L.ctx.ndrange[0], r1 = L.ctx.ndrange[1];
+    if (r0 == 0 || r1 == 0) return B200_OK;
+    REQUIRE(r0 <= dim(a, 0) && r1 <= dim(a, 1) && r1 <= dim(b, 0) && r0 <= dim(b, 1),
+            "naive_transpose_kernel!: ndrange (%lld,%lld) exceeds size(a)=(%lld,%lld) / size(b)=(%lld,%lld)", r0, r1,
+            dim(a, 0), dim(a, 1), dim(b, 0), dim(b, 1));
+    if (!force_twins()) return transpose_launch(a.ptr, b.ptr, r0, r1, dim(a, 0), dim(b, 0), a.elsize, L.st);
+    return twin_transpose(L.ctx, a.ptr, b.ptr, dim(a, 0), dim(b, 0), a.elsize, L.st);
+}
+
+static int h_matmul_naive(const Launch &L) {
+    REQUIRE(L.nargs == 3 && is_array(L.args[0]) && is_array(L.args[1]) && is_array(L.args[2]),
+            "matmul_kernel!(output, a, b)");
+    const b200_arg &o = L.args[0], &a = L.args[1], &b = L.args[2];
+    REQUIRE(L.ctx.ndim == 2, "matmul_kernel!: a 2-d ndrange is required");
+    REQUIRE((o.eltype == B200_T_F32 || o.eltype == B200_T_F64) && a.eltype == o.eltype && b.eltype == o.eltype,
+            "matmul_kernel!: Float32 or Float64 arrays of one type expected");
+    const long long M = dim(a, 0), K = dim(a, 1);
+    REQUIRE(dim(b, 0) >= K, "matmul_kernel!: size(b,1) < size(a,2)");
+    REQUIRE(L.ctx.ndrange[0] <= dim(o, 0) && L.ctx.ndrange[0] <= M && L.ctx.ndrange[1] <= dim(o, 1) &&
+                L.ctx.ndrange[1] <= dim(b, 1) && dim(o, 0) == M && dim(b, 0) == K,
+            "matmul_kernel!: ndrange/shape mismatch");
+    return twin_matmul_naive(L.ctx, o.ptr, a.ptr, b.ptr, M, K, o.eltype == B200_T_F64, L.st);
+}
+
+template <int VARIANT>
+static int h_localmem(const Launch &L) {
+    REQUIRE(L.nargs == 1 && is_array(L.args[0]) && L.args[0].elsize == 8, "localmem(A::Array{Int64})");
+    if (VARIANT != 2)
+        REQUIRE(ka_max_global_linear(L.ctx) <= numel(L.args[0]), "localmem: ndrange exceeds length(A)");
+    return twin_localmem(L.ctx, VARIANT, (long long *)L.args[0].ptr, numel(L.args[0]), L.st);
+}
+static int h_stmt_form(const Launch &L) {
+    REQUIRE(L.nargs == 0, "stmt_form()");
+    return twin_stmt_form(L.ctx, L.st);
+}
+static int h_private(const Launch &L) {
+    REQUIRE(L.nargs == 1 && is_array(L.args[0]) && L.args[0].elsize == 8, "private(A::Array{Int64})");
+    REQUIRE(ka_max_global_linear(L.ctx) <= numel(L.args[0]), "private: ndrange exceeds length(A)");
+    return twin_private(L.ctx, (long long *)L.args[0].ptr, L.st);
+}
+static int h_typetest(const Launch &L) {
+    REQUIRE(L.nargs == 2 && is_array(L.args[0]) && is_array(L.args[1]) && L.args[1].elsize == 1,
+            "typetest(A, B::Array{Bool})");
+    REQUIRE(ka_max_global_linear(L.ctx) <= numel(L.args[1]), "typetest: ndrange exceeds length(B)");
+    return twin_typetest(L.ctx, (uint8_t *)L.args[1].ptr, L.st);
+}
+static int h_forloop(const Launch &L) {
+    REQUIRE(L.nargs == 2 && is_array(L.args[0]) && L.args[0].elsize == 8 && is_value(L.args[1]),
+            "forloop(A::Matrix{Int64}, Val(N))");
+    const b200_arg &A = L.args[0];
+    const long long N = L.args[1].scalar;
+    REQUIRE(N <= dim(A, 1) && N >= 1, "forloop: Val(N)=%lld exceeds size(A,2)=%lld", N, dim(A, 1));
+    REQUIRE(ka_max_global_linear(L.ctx) <= dim(A, 0) && N <= dim(A, 0), "forloop: ndrange exceeds size(A,1)");
+    return twin_forloop(L.ctx, (long long *)A.ptr, dim(A, 0), N, L.st);
+}
+static int h_reduce_private(const Launch &L) {
+    REQUIRE(L.nargs == 2 && is_array(L.args[0]) && is_array(L.args[1]), "reduce_private(out, A)");
+    const b200_arg &o = L.args[0], &A = L.args[1];
+    REQUIRE((o.eltype == B200_T_F32 || o.eltype == B200_T_F64) && A.eltype == o.eltype, "reduce_private: Float32/64");
+    REQUIRE(L.ctx.ndim == 1 && A.ndim == 2, "reduce_private: 1-d ndrange over a matrix");
+    REQUIRE(L.ctx.ndrange[0] <= numel(o) && L.ctx.ndrange[0] <= dim(A, 0), "reduce_private: ndrange exceeds arrays");
+    return twin_reduce_private(L.ctx, o.ptr, A.ptr, dim(A, 0), dim(A, 1), o.eltype == B200_T_F64, L.st);
+}
+static int h_unroll(const Launch &L) {  // two methods of one gpu_ function (test/unroll.jl:5-18): keyed on arity
+    REQUIRE((L.nargs == 1 || L.nargs == 2) && is_array(L.args[0]) && L.args[0].eltype == B200_T_F32,
+            "kernel_unroll!(a::Array{Float32}[, Val(N)])");
+    if (L.nargs == 1) {
+        REQUIRE(numel(L.args[0]) >= 5, "kernel_unroll!: length(a) < 5");
+        return twin_unroll(L.ctx, 0, (float *)L.args[0].ptr, 5, L.st);
+    }
+    REQUIRE(is_value(L.args[1]) && L.args[1].scalar >= 0 && L.args[1].scalar <= numel(L.args[0]),
+            "kernel_unroll!: Val(N) exceeds length(a)");
+    return twin_unroll(L.ctx, 1, (float *)L.args[0].ptr, L.args[1].scalar, L.st);
+}
+static int h_unroll2(const Launch &L) {
+    REQUIRE(L.nargs == 1 && is_array(L.args[0]) && L.args[0].eltype == B200_T_F32, "kernel_unroll2!(A::Array{Float32})");
+    REQUIRE(ka_max_global_linear(L.ctx) <= numel(L.args[0]), "kernel_unroll2!: ndrange exceeds length(A)");
+    return twin_unroll(L.ctx, 2, (float *)L.args[0].ptr, 0, L.st);
+}
+template <int WHICH>
+static int h_index_linear(const Launch &L) {
+    REQUIRE(L.nargs == 1 && is_array(L.args[0]) && L.args[0].elsize == 8, "index_linear_*(A::Array{Int64})");
+    REQUIRE(ka_max_global_linear(L.ctx) <= numel(L.args[0]), "index kernel: ndrange exceeds length(A)");
+    return twin_index_linear(L.ctx, WHICH, (long long *)L.args[0].ptr, L.st);
+}
+template <int WHICH>
+static int h_index_cartesian(const Launch &L) {
+    REQUIRE(L.nargs == 1 && is_array(L.args[0]), "index_cartesian_*(A::Array{CartesianIndex{N}})");
+    const b200_arg &A = L.args[0];
+    REQUIRE(A.elsize == 8 * L.ctx.ndim, "index_cartesian: eltype must be CartesianIndex{%d} (%d bytes), got %d bytes",
+            L.ctx.ndim, 8 * L.ctx.ndim, A.elsize);
+    REQUIRE(L.ctx.ndim == A.ndim || L.ctx.ndim == 1, "index_cartesian: ndrange rank must equal ndims(A) or be 1");
+    if (L.ctx.ndim == A.ndim) {
+        for (int d = 0; d < A.ndim; ++d) REQUIRE(L.ctx.ndrange[d] <= A.dims[d], "index_cartesian: ndrange exceeds size(A)");
+    } else {
+        REQUIRE(L.ctx.ndrange[0] <= numel(A), "index_cartesian: ndrange exceeds length(A)");
+    }
+    long long dims[B200_MAX_NDIM];
+    for (int d = 0; d < B200_MAX_NDIM; ++d) dims[d] = dim(A, d);
+    return twin_index_cartesian(L.ctx, WHICH, (long long *)A.ptr, A.ndim, dims, L.st);
+}
+static int h_kernel_val(const Launch &L) {
+    REQUIRE(L.nargs == 2 && is_array(L.args[0]) && L.args[0].elsize == 8 && is_value(L.args[1]),
+            "kernel_val!(a::Array{Int64}, Val(m))");
+    REQUIRE(ka_max_global_linear(L.ctx) <= numel(L.args[0]), "kernel_val!: ndrange exceeds length(a)");
+    return twin_kernel_val(L.ctx, (long long *)L.args[0].ptr, L.args[1].scalar, L.st);
+}
+static int h_kernel_empty(const Launch &L) { return twin_kernel_empty(L.ctx, L.st); }
+static int h_saxpy(const Launch &L) {
+    REQUIRE(L.nargs == 4 && is_array(L.args[0]) && is_value(L.args[1]) && is_array(L.args[2]) && is_array(L.args[3]),
+            "saxpy_kernel!(Z, a, X, Y)");
+    const b200_arg &Z = L.args[0], &X = L.args[2], &Y = L.args[3];
+    REQUIRE((Z.eltype == B200_T_F32 || Z.eltype == B200_T_F64) && X.eltype == Z.eltype && Y.eltype == Z.eltype,
+            "saxpy_kernel!: Float32/Float64 arrays of one type");
+    long long maxI = ka_max_global_linear(L.ctx);
+    REQUIRE(maxI <= numel(Z) && maxI <= numel(X) && maxI <= numel(Y), "saxpy_kernel!: ndrange exceeds arrays");
+    return twin_saxpy(L.ctx, Z.ptr, L.args[1].fscalar, X.ptr, Y.ptr, Z.eltype == B200_T_F64, L.st);
+}
+
+// ---- KI kernels ----------------------------------------------------------------------------------
+static int h_histogram(const Launch &L) {
+    REQUIRE(L.nargs == 3 && is_array(L.args[0]) && is_array(L.args[1]) && is_value(L.args[2]),
+            "histogram_kernel!(histogram_output, input, Val(gs))");
+    const b200_arg &out = L.args[0], &in = L.args[1];
+    REQUIRE(out.eltype == B200_T_I32 && in.eltype == B200_T_I32,
+            "histogram_kernel!: only Int32 bins/inputs are precompiled (examples/histogram.jl:75)");
+    const long long gs = L.args[2].scalar;
+    REQUIRE(L.wgs[1] == 1 && L.wgs[2] == 1 && L.groups[1] == 1 && L.groups[2] == 1, "histogram_kernel!: 1-d launch");
+    REQUIRE(L.wgs[0] == gs, "histogram_kernel!: workgroupsize %lld must equal Val(gs)=%lld", L.wgs[0], gs);
+    const long long N = numel(out), len = numel(in);
+    if (L.groups[0] == 0 || N == 0) return B200_OK;
+    if (!force_twins()) {
+        long long covered = L.groups[0] * gs;
+        return histogram_launch((int32_t *)out.ptr, N, (const int32_t *)in.ptr, covered < len ? covered : len, L.st);
+    }
+    return twin_histogram((int32_t *)out.ptr, N, (const int32_t *)in.ptr, len, gs, L.groups[0], L.st);
+}
+
+static int h_coalesced_matmul(const Launch &L) {
+    REQUIRE((L.nargs == 7 || L.nargs == 8) && is_array(L.args[0]) && is_array(L.args[1]) && is_array(L.args[2]) &&
+                is_value(L.args[3]) && is_value(L.args[4]) && is_value(L.args[5]) && is_value(L.args[6]),
+            "coalesced_matmul_kernel!(output, input1, input2, N, R, M, Val(TDIM)[, Val(BANK)])");
+    const b200_arg &o = L.args[0], &a = L.args[1], &b = L.args[2];
+    REQUIRE(o.eltype == B200_T_F32 && a.eltype == B200_T_F32 && b.eltype == B200_T_F32,
+            "coalesced_matmul_kernel!: only Float32 is precompiled");
+    const long long N = dim(o, 0);  // `N = size(output, 1)` (examples/performant_matmul.jl:29)
+    const long long R = L.args[4].scalar, M = L.args[5].scalar, TDIM = L.args[6].scalar;
+    REQUIRE(dim(a, 0) == N && dim(a, 1) >= R && dim(b, 0) == R && dim(b, 1) >= M && dim(o, 1) >= M && R >= 0 && M >= 0,
+            "coalesced_matmul_kernel!: shapes output %lldx%lld, input1 %lldx%lld, input2 %lldx%lld vs R=%lld M=%lld",
+            dim(o, 0), dim(o, 1), dim(a, 0), dim(a, 1), dim(b, 0), dim(b, 1), R, M);
+    REQUIRE(L.wgs[0] == TDIM && L.wgs[1] == TDIM && L.wgs[2] == 1 && L.groups[2] == 1,
+            "coalesced_matmul_kernel!: workgroupsize must be (TDIM, TDIM)");
+    if (L.groups[0] == 0 || L.groups[1] == 0) return B200_OK;
+    const bool full = L.groups[0] >= cdiv(N, TDIM) && L.groups[1] >= cdiv(M, TDIM);
+    if (!force_twins() && TDIM == 16 && full)
+        return sgemm_launch((float *)o.ptr, (const float *)a.ptr, (const float *)b.ptr, N, R, M, N, R, N,
+                            B200_MATMUL_TILE16, L.st);
+    return twin_coalesced_matmul((float *)o.ptr, (const float *)a.ptr, (const float *)b.ptr, N, R, M, (int)TDIM,
+                                 L.groups[0], L.groups[1], L.st);
+}
+
+static int h_test_intrinsics(const Launch &L) {
+    REQUIRE(L.nargs == 1 && is_array(L.args[0]) && L.args[0].elsize == 48, "test_intrinsics_kernel(results::Array{KernelData})");
+    return twin_test_intrinsics((long long *)L.args[0].ptr, numel(L.args[0]), L.groups, L.wgs, L.st);
+}
+static int h_launch_kernel_nd(const Launch &L) {
+    REQUIRE(L.nargs == 1 && is_array(L.args[0]) && L.args[0].eltype == B200_T_F32, "launch_kernelNd(arr::Array{Float32})");
+    const b200_arg &A = L.args[0];
+    long long dims[3] = {dim(A, 0), dim(A, 1), dim(A, 2)};
+    for (int d = 0; d < 3; ++d)
+        REQUIRE((L.groups[d] - 1) * L.groups[d] + L.wgs[d] <= dims[d], "launch_kernel: index exceeds size(arr, %d)", d + 1);
+    return twin_launch_kernel_nd((float *)A.ptr, dims, L.groups, L.wgs, L.st);
+}
+
+struct Entry {
+    const char *name;
+    int kind;
+    Handler fn;
+};
+
+static const Entry kTable[] = {
+    // KA `@kernel`s: name = "gpu_" * function name (src/macros.jl:32)
+    {"gpu_copy_kernel", B200_LAUNCH_KA, h_copy},                    // src/KernelAbstractions.jl:874-877
+    {"gpu_copy_kernel!", B200_LAUNCH_KA, h_copy},                   // examples/memcopy.jl, memcopy_static.jl
+    {"gpu_constarg", B200_LAUNCH_KA, h_copy},                       // test/test.jl:162-165
+    {"gpu_init_kernel", B200_LAUNCH_KA, h_init},                    // src/KernelAbstractions.jl:869-872
+    {"gpu_naive_transpose_kernel!", B200_LAUNCH_KA, h_transpose},   // examples/naive_transpose.jl:4-7
+    {"gpu_matmul_kernel!", B200_LAUNCH_KA, h_matmul_naive},         // examples/matmul.jl:5-15
+    {"gpu_localmem", B200_LAUNCH_KA, h_localmem<0>},                // test/localmem.jl:4-17
+    {"gpu_localmem2", B200_LAUNCH_KA, h_localmem<1>},               // test/localmem.jl:19-35
+    {"gpu_localmem_unsafe_indices", B200_LAUNCH_KA, h_localmem<2>}, // test/localmem.jl:37-48
+    {"gpu_many_localmem", B200_LAUNCH_KA, h_localmem<3>},           // test/localmem.jl:50-65
+    {"gpu_stmt_form", B200_LAUNCH_KA, h_stmt_form},                 // test/private.jl:4-8
+    {"gpu_typetest", B200_LAUNCH_KA, h_typetest},                   // test/private.jl:10-16
+    {"gpu_private", B200_LAUNCH_KA, h_private},                     // test/private.jl:18-28
+    {"gpu_forloop", B200_LAUNCH_KA, h_forloop},                     // test/private.jl:31-45
+    {"gpu_reduce_private", B200_LAUNCH_KA, h_reduce_private},       // test/private.jl:47-59
+    {"gpu_kernel_unroll!", B200_LAUNCH_KA, h_unroll},               // test/unroll.jl:5-18
+    {"gpu_kernel_unroll2!", B200_LAUNCH_KA, h_unroll2},             // test/unroll.jl:21-37
+    {"gpu_index_linear_global", B200_LAUNCH_KA, h_index_linear<0>}, // test/test.jl:46-49
+    {"gpu_index_linear_local", B200_LAUNCH_KA, h_index_linear<1>},
+    {"gpu_index_linear_group", B200_LAUNCH_KA, h_index_linear<2>},
+    {"gpu_index_cartesian_global", B200_LAUNCH_KA, h_index_cartesian<0>},
+    {"gpu_index_cartesian_local", B200_LAUNCH_KA, h_index_cartesian<1>},
+    {"gpu_index_cartesian_group", B200_LAUNCH_KA, h_index_cartesian<2>},
+    {"gpu_kernel_val!", B200_LAUNCH_KA, h_kernel_val},              // test/test.jl:216-224
+    {"gpu_kernel_empty", B200_LAUNCH_KA, h_kernel_empty},           // test/test.jl:226-228
+    {"gpu_saxpy_kernel!", B200_LAUNCH_KA, h_saxpy},                 // benchmark/benchmarks.jl:29-32
+    {"gpu_saxpy_kernel", B200_LAUNCH_KA, h_saxpy},                  // examples/numa_aware.jl:10-13
+    // KI.@kernel launches: name = function name
+    {"histogram_kernel!", B200_LAUNCH_KI, h_histogram},             // examples/histogram.jl:18-58
+    {"coalesced_matmul_kernel!", B200_LAUNCH_KI, h_coalesced_matmul}, // examples/performant_matmul.jl:15-77
+    {"test_intrinsics_kernel", B200_LAUNCH_KI, h_test_intrinsics},  // test/intrinsics.jl:11-25
+    {"launch_kernel1d", B200_LAUNCH_KI, h_launch_kernel_nd},        // test/intrinsics.jl:31-38
+    {"launch_kernel2d", B200_LAUNCH_KI, h_launch_kernel_nd},        // test/intrinsics.jl:47-54
+    {"launch_kernel3d", B200_LAUNCH_KI, h_launch_kernel_nd},        // test/intrinsics.jl:61-68
+};
+constexpr int kNumEntries = (int)(sizeof(kTable) / sizeof(kTable[0]));
+
+static const Entry *find_entry(const char *name) {
+    for (int i = 0; i < kNumEntries; ++i)
+        if (strcmp(kTable[i].name, name) == 0) return &kTable[i];
+    return nullptr;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" b200_status b200_kernel_count(int32_t *count) {
+    if (!count) return set_error(B200_ERR_INVALID_VALUE, "count is NULL");
+    *count = kNumEntries;
+    return B200_OK;
+}
+
+extern "C" const char *b200_kernel_name(int32_t index) {
+    return (index >= 0 && index < kNumEntries) ? kTable[index].name : nullptr;
+}
+
+extern "C" b200_status b200_kernel_max_work_group_size(const char *name, int64_t max_work_items, int64_t *out) {
+    if (!name || !out) return set_error(B200_ERR_INVALID_VALUE, "NULL argument");
+    if (!find_entry(name)) return set_error(B200_ERR_UNKNOWN_KERNEL, "no precompiled kernel named '%s'", name);
+    *out = max_work_items < 1024 ? max_work_items : 1024;  // reference src/pocl/backend.jl:170-173
+    return B200_OK;
+}
+
+extern "C" b200_status b200_launch(const char *name, const b200_launch_desc *desc, const b200_arg *args,
+                                   int32_t nargs) {
+    if (!name || !desc || nargs < 0 || (nargs > 0 && !args))
+        return set_error(B200_ERR_INVALID_VALUE, "b200_launch: NULL argument");
+    Launch L;
+    memset(&L, 0, sizeof(L));
+    L.desc = desc;
+    L.args = args;
+    L.nargs = nargs;
+    if (desc->kind == B200_LAUNCH_KA) {
+        if (desc->ndim < 1 || desc->ndim > KA_MAX_NDIM)
+            return set_error(B200_ERR_LAUNCH_DIMS, "ndrange of %d dimensions (1..%d supported)", desc->ndim, KA_MAX_NDIM);
+        L.ctx.ndim = desc->ndim;
+        L.ctx.dynamic_check = desc->dynamic_check;
+        for (int d = 0; d < KA_MAX_NDIM; ++d) {
+            bool in = d < desc->ndim;
+            L.ctx.ndrange[d] = in ? desc->ndrange[d] : 1;
+            L.ctx.wgs[d] = in ? desc->wgs[d] : 1;
+            L.ctx.blocks[d] = in ? desc->blocks[d] : 1;
+            if (in && (desc->ndrange[d] < 0 || desc->wgs[d] < 1 || desc->blocks[d] < 0))
+                return set_error(B200_ERR_PARTITION, "invalid iteration space in dimension %d", d + 1);
+        }
+    } else if (desc->kind == B200_LAUNCH_KI) {
+        // KI.check_launch_args (reference src/intrinsics.jl:182-188): at most 3 dimensions -> ArgumentError
+        if (desc->ndim < 1 || desc->ndim > 3)
+            return set_error(B200_ERR_LAUNCH_DIMS, "`numworkgroups`/`workgroupsize` only accept up to 3 dimensions");
+        long long items = 1;
+        for (int d = 0; d < 3; ++d) {
+            bool in = d < desc->ndim;
+            L.groups[d] = in ? desc->blocks[d] : 1;
+            L.wgs[d] = in ? desc->wgs[d] : 1;
+            if (L.groups[d] < 0 || L.wgs[d] < 1) return set_error(B200_ERR_LAUNCH_DIMS, "invalid launch size");
+            items *= L.wgs[d];
+        }
+        if (items > 1024 || L.wgs[2] > 64)
+            return set_error(B200_ERR_LAUNCH_DIMS, "workgroup of %lld items exceeds the device limit", items);
+        if (L.groups[1] > 65535 || L.groups[2] > 65535 || L.groups[0] > 2147483647LL)
+            return set_error(B200_ERR_LAUNCH_DIMS, "too many workgroups");
+    } else {
+        return set_error(B200_ERR_INVALID_VALUE, "b200_launch: unknown launch kind %d", desc->kind);
+    }
+    const Entry *e = find_entry(name);
+    if (!e)
+        return set_error(B200_ERR_UNKNOWN_KERNEL,
+                         "no precompiled sm_100a kernel named '%s' (B200Backend has no JIT; see b200_kernel_name)", name);
+    if (e->kind != desc->kind)
+        return set_error(B200_ERR_BAD_ARGS, "kernel '%s' is a %s kernel", name,
+                         e->kind == B200_LAUNCH_KA ? "KA @kernel" : "KI.@kernel");
+    for (int i = 0; i < nargs; ++i)
+        if (args[i].kind == B200_ARG_ARRAY && args[i].ptr == nullptr && numel(args[i]) > 0)
+            return set_error(B200_ERR_BAD_ARGS, "argument %d: NULL pointer for a non-empty array", i + 1);
+    B200_TRY(current_stream(&L.st));
+    return e->fn(L);
+}

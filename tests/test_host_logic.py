@@ -1,0 +1,132 @@
+"""CPU-only: the host-side mirror of KA's launch logic against the reference's known answers and the oracle."""
+import numpy as np
+import pytest
+
+import b200ka as KA
+from b200ka.kernel import Kernel, check_launch_args
+from b200ka.ndrange import DYNAMIC, StaticSize
+
+
+# ---- test/test.jl:14-44 "partition" ---------------------------------------------------------------
+def test_partition_static_wgs_dynamic_ndrange():
+    ws, nd = StaticSize(64), DYNAMIC
+    it, dyn = KA.ka_partition(nd, ws, (128,), None)
+    assert len(it) == 2 and isinstance(dyn, KA.NoDynamicCheck)
+    it, dyn = KA.ka_partition(nd, ws, (129,), None)
+    assert len(it) == 3 and isinstance(dyn, KA.DynamicCheck)
+    it, dyn = KA.ka_partition(nd, ws, (129,), (64,))
+    assert len(it) == 3 and isinstance(dyn, KA.DynamicCheck)
+    with pytest.raises(KA.ErrorException):
+        KA.ka_partition(nd, ws, (129,), (65,))
+
+
+def test_partition_static_both():
+    ws, nd = StaticSize(64), StaticSize(128)
+    it, dyn = KA.ka_partition(nd, ws, (128,), None)
+    assert len(it) == 2 and isinstance(dyn, KA.NoDynamicCheck)
+    it, dyn = KA.ka_partition(nd, ws, None, None)
+    assert len(it) == 2 and isinstance(dyn, KA.NoDynamicCheck)
+    with pytest.raises(KA.ErrorException):
+        KA.ka_partition(nd, ws, (129,), None)
+
+
+def test_partition_missing_runtime_sizes():
+    with pytest.raises(KA.ErrorException):
+        KA.ka_partition(DYNAMIC, DYNAMIC, None, (8,))
+    with pytest.raises(KA.ErrorException):
+        KA.ka_partition(DYNAMIC, DYNAMIC, (8,), None)
+
+
+@pytest.mark.parametrize("ndrange,wgs", [((128,), (64,)), ((129,), (64,)), ((16384, 16384), (256,)), ((10, 7), (0, 2)),
+                                         ((7, 7, 3), (4, 2)), ((0,), (1,)), ((5, 9), (8, 8))])
+def test_nd_partition_matches_oracle(orc, ndrange, wgs):
+    blocks, w, dyn = KA.nd_partition(ndrange, wgs)
+    ob, ow, od = orc.partition(ndrange, wgs)
+    assert blocks == ob and w == ow and isinstance(dyn, KA.DynamicCheck) == od
+
+
+def test_expand_matches_oracle(orc):
+    for blocks, items in [((4, 4), (32, 32)), ((4, 128), (32, 1)), ((128, 4), (1, 32)), ((3, 2, 2), (4, 2, 3))]:
+        nd = KA.NDRange(len(blocks), blocks, items)
+        ctx = orc.raw_ctx(blocks, items)
+        G, L = len(nd), nd.nitems()
+        rng = np.random.default_rng(0)
+        for g, l in zip(rng.integers(1, G + 1, 200), rng.integers(1, L + 1, 200)):
+            assert KA.expand(nd, int(g), int(l)) == orc.expand(ctx, int(g), int(l))
+
+
+def test_threads_to_workgroupsize(orc):
+    for threads, nd in [(1024, (256, 45)), (1024, (4096,)), (1024, (8, 8, 100)), (256, (16384, 16384))]:
+        assert KA.threads_to_workgroupsize(threads, nd) == orc.threads_to_workgroupsize(threads, nd)
+
+
+def test_static_size_indexing():
+    s = StaticSize(32, 4)
+    assert s[1] == 32 and s[2] == 4 and s[3] == 1 and len(s) == 128 and s.ndims() == 2
+
+
+def test_launch_config_like_reference():
+    be = KA.B200Backend()
+    # memcopy_static: copy_kernel!(backend, 32, size(A)) called with ndrange=size(A)
+    k = KA.kernels.copy_kernel_(be, 32, (128, 128))
+    nd, wgs, it, dyn = k.launch_config((128, 128), None)
+    assert nd is None and it.blocks == (4, 128) and it.workitems == (32, 1)
+    with pytest.raises(KA.ErrorException):
+        k.launch_config((128, 129), None)
+    # naive_transpose: static wgs 256, dynamic ndrange
+    k = KA.kernels.naive_transpose_kernel_(be, 256)
+    nd, wgs, it, dyn = k.launch_config((16384, 16384), None)
+    assert it.workitems == (256, 1) and it.blocks == (64, 16384) and len(it) == 2 ** 20
+    desc = k.mkcontext(nd, it)
+    assert desc.kind == 0 and desc.ndim == 2 and desc.dynamic_check == 1
+    assert list(desc.ndrange)[:2] == [16384, 16384] and list(desc.blocks)[:2] == [64, 16384]
+    # fully dynamic kernel without ndrange -> error
+    with pytest.raises(KA.ErrorException):
+        KA.kernels.copy_kernel_(be).launch_config(None, None)
+
+
+def test_check_launch_args():
+    check_launch_args((2, 2, 2), (2, 2, 2))
+    with pytest.raises(KA.ArgumentError):
+        check_launch_args((2, 2, 2, 2), (2, 2, 2))
+    with pytest.raises(KA.ArgumentError):
+        check_launch_args((2, 2, 2), (2, 2, 2, 2))
+
+
+def test_backend_traits():
+    be = KA.B200Backend()
+    assert be == KA.B200Backend()
+    assert KA.supports_float64(be) and KA.supports_atomics(be) and KA.supports_unified(be) in (True, False)
+    with pytest.raises(KA.ErrorException):
+        KA.priority_(be, "urgent")
+    with pytest.raises(KA.MethodError):
+        KA.synchronize(object())
+    with pytest.raises(KA.ArgumentError):
+        KA.get_backend(object())
+
+
+def test_argconvert_records():
+    from b200ka import _lib
+    from b200ka.kernel import argconvert
+
+    a = argconvert(KA.Val(16))
+    assert a.kind == _lib.B200_ARG_VAL and a.scalar == 16
+    a = argconvert(2.5)
+    assert a.kind == _lib.B200_ARG_SCALAR and a.fscalar == 2.5 and a.eltype == _lib.B200_T_F64
+    a = argconvert(np.float32(2.5))
+    assert a.eltype == _lib.B200_T_F32
+    with pytest.raises(KA.ErrorException):
+        argconvert(np.zeros(3))
+
+
+# ---- multi-GPU partitioning -------------------------------------------------------------------------------
+@pytest.mark.parametrize("ws", [1, 2, 4, 8])
+def test_slabs_tile_the_range(ws):
+    from b200ka import multigpu as mg
+
+    for n, fn in [(2 ** 26, mg.copy_shard), (16384, mg.transpose_shard), (2 ** 30, mg.histogram_shard),
+                  (8192, mg.matmul_shard), (1000003, mg.histogram_shard)]:
+        edges = [fn(n, ws, r) for r in range(ws)]
+        assert edges[0][0] == 0 and edges[-1][1] == n
+        for (a0, a1), (b0, b1) in zip(edges, edges[1:]):
+            assert a1 == b0 and a1 > a0
