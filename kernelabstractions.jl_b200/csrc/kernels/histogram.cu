@@ -34,7 +34,7 @@ __device__ __forceinline__ int4 ldg_stream_i4(const int4 *p) {
 // ---------------------------------------------------------------------------------------------
 template <int T>
 __device__ __forceinline__ void bump1(unsigned char *cnt, uint32_t base, int v, uint32_t nbins) {
-    uint32_t b = (uint32_t)(v - 1);
+    uint32_t b = (uint32_t)v - 1u;
     if (b < nbins) {
         unsigned char *p = cnt + b * T + base;
         *p = (unsigned char)(*p + 1);
@@ -42,7 +42,7 @@ __device__ __forceinline__ void bump1(unsigned char *cnt, uint32_t base, int v, 
 }
 template <int T>
 __device__ __forceinline__ void bump2(unsigned char *cnt, uint32_t base, int v1, int v2, uint32_t nbins) {
-    uint32_t b1 = (uint32_t)(v1 - 1), b2 = (uint32_t)(v2 - 1);
+    uint32_t b1 = (uint32_t)v1 - 1u, b2 = (uint32_t)v2 - 1u;
     bool ok1 = b1 < nbins, ok2 = b2 < nbins;
     unsigned char *p1 = cnt + (ok1 ? b1 : 0u) * T + base;
     unsigned char *p2 = cnt + (ok2 ? b2 : 0u) * T + base;
@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(T) hist_atomic_kernel(int32_t *__restrict__ bi
     __syncthreads();
     uint32_t *mine = sh + (uint32_t)(warp % copies) * nbins;
     auto bump = [&](int v) {
-        uint32_t b = (uint32_t)(v - 1);
+        uint32_t b = (uint32_t)v - 1u;
         if (b < nbins) atomicAdd(mine + b, 1u);
     };
     const int64_t u0 = n4 * (int64_t)blockIdx.x / gridDim.x;
@@ -190,8 +190,9 @@ __global__ void __launch_bounds__(T) hist_atomic_kernel(int32_t *__restrict__ bi
 __global__ void hist_global_kernel(int32_t *__restrict__ bins, uint64_t nbins, const int32_t *__restrict__ in,
                                    int64_t n) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        uint64_t b = (uint64_t)(uint32_t)(in[i] - 1);
-        if (in[i] >= 1 && b < nbins) atomicAdd(reinterpret_cast<unsigned int *>(bins) + b, 1u);
+        const int32_t v = in[i];
+        const uint64_t b = (uint64_t)((uint32_t)v - 1u);
+        if (v >= 1 && b < nbins) atomicAdd(reinterpret_cast<unsigned int *>(bins) + b, 1u);
     }
 }
 

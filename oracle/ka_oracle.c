@@ -179,6 +179,29 @@ void orc_naive_transpose(const ka_ctx *c, void *a, const void *b, Int rows_a, In
         }
 }
 
+/* Same kernel, as a work-group-vectorising CPU compiler (PoCL's work-item loops) would run it: the group's
+ * Cartesian index is computed once per group, the work-items of the group become the inner loops.  Identical
+ * results to orc_naive_transpose (tests/test_oracle_golden.py checks it); used as the timed CPU baseline so the
+ * baseline is not slowed down by this file's generic per-item div/mod. 4-byte elements, 2-d ndrange. */
+void orc_naive_transpose_wg_f32(const ka_ctx *c, float *a, const float *b, Int rows_a, Int rows_b) {
+    Int G = ka_num_groups(c);
+    const Int W0 = c->wgs[0], W1 = c->wgs[1], N0 = c->ndrange[0], N1 = c->ndrange[1];
+#pragma omp parallel for schedule(static)
+    for (Int g = 1; g <= G; ++g) {
+        Int gI[KA_MAX_NDIM];
+        ka_group_cartesian(c, g, gI);
+        const Int i0 = (gI[0] - 1) * W0, j0 = (gI[1] - 1) * W1;
+        for (Int lj = 1; lj <= W1; ++lj) {
+            const Int j = j0 + lj;
+            if (j > N1) continue;
+            const Int imax = (i0 + W0 <= N0) ? W0 : N0 - i0;
+            float *arow = a + (j - 1) * rows_a + i0;
+            const float *bcol = b + (j - 1) + i0 * rows_b;
+            for (Int li = 0; li < imax; ++li) arow[li] = bcol[li * rows_b];
+        }
+    }
+}
+
 /* matmul_kernel!: tmp = zero(T); for k: tmp += a[i,k]*b[k,j]; output[i,j] = tmp
  * (reference examples/matmul.jl:5-15).  No @simd / @fastmath: separate multiply and add roundings,
  * so this file must be compiled with -ffp-contract=off. */

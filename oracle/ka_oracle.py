@@ -174,6 +174,13 @@ def naive_transpose(a: np.ndarray, b: np.ndarray, ndrange=None, workgroupsize=25
                               C.c_int64(a.dtype.itemsize))
 
 
+def naive_transpose_wg(a: np.ndarray, b: np.ndarray, workgroupsize=256) -> None:
+    """Work-group-vectorised execution of the same kernel (the timed CPU baseline); float32 only."""
+    assert a.dtype == np.float32 and b.dtype == np.float32
+    ctx = make_ctx(a.shape, workgroupsize)
+    lib().orc_naive_transpose_wg_f32(C.byref(ctx), _p(_F(a)), _p(_F(b)), C.c_int64(a.shape[0]), C.c_int64(b.shape[0]))
+
+
 def matmul_naive(out: np.ndarray, a: np.ndarray, b: np.ndarray, workgroupsize=None, max_threads=1024) -> None:
     """reference examples/matmul.jl:5-27 (dynamic workgroup -> threads_to_workgroupsize)"""
     ndrange = out.shape

@@ -1,0 +1,50 @@
+"""Child process of test_gpu_parity.test_matmul_bf16_tensor_core (and of bench.py's opt-in BF16 line).
+
+Checks the tcgen05/TMEM BF16 GEMM against the oracle: FP32-oracle GEMM (reference summation structure) on
+BF16-rounded inputs, rtol 1e-2 as north_star states; additionally reports the distance to FP64 truth on the
+rounded inputs, which for FP32 accumulation should be ~1e-6.  Exit code 0 == pass.
+"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "kernelabstractions.jl_b200"))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+import b200ka as KA  # noqa: E402
+import ka_oracle as orc  # noqa: E402
+from b200ka import _lib  # noqa: E402
+
+be = KA.B200Backend()
+ok = True
+for (M, K, N) in [(128, 64, 256), (128, 256, 256), (256, 512, 512), (1024, 2048, 1024), (384, 4096, 768)]:
+    A = orc.gen_uniform_f32((M, K), 1237) - 0.5
+    B = orc.gen_uniform_f32((K, N), 1238) - 0.5
+    dA, dB = KA.to_device(A), KA.to_device(B)
+    dC = KA.zeros(be, np.float32, M, N)
+    ws = KA.allocate(be, np.uint16, M * K + K * N)
+    _lib.call("b200_matmul_f32_via_bf16", C.c_void_p(dC.ptr), C.c_void_p(dA.ptr), C.c_void_p(dB.ptr), M, K, N, M, K, M,
+              C.c_void_p(ws.ptr))
+    KA.synchronize(be)
+    got = KA.Array(dC)
+    # operand conversion kernels: bit-exact against round-to-nearest-even
+    wsh = KA.Array(ws)
+    a_bits = wsh[:M * K].reshape(M, K)            # M rows of K (row-major)
+    b_bits = wsh[M * K:].reshape(N, K)            # N rows of K == column-major K x N
+    conv_ok = np.array_equal(a_bits, orc.to_bf16_bits(A)) and np.array_equal(b_bits, orc.to_bf16_bits(B).T)
+    Ar = np.asfortranarray(orc.round_bf16(A))
+    Br = np.asfortranarray(orc.round_bf16(B))
+    ref = np.zeros((M, N), dtype=np.float32, order="F")
+    orc.coalesced_matmul(ref, Ar, Br)
+    truth = orc.matmul_f64_truth(Ar, Br)
+    scale = np.abs(truth).max()
+    err_oracle = np.abs(got - ref).max() / scale
+    err_truth = np.abs(got - truth).max() / scale
+    close = np.allclose(got, ref, rtol=1e-2, atol=1e-2 * scale * 1e-2)
+    print(f"bf16 gemm {M}x{K}x{N}: convert_bit_exact={conv_ok} max_rel_err_vs_oracle={err_oracle:.3e} "
+          f"vs_fp64_truth={err_truth:.3e} allclose_rtol1e-2={close}", flush=True)
+    ok = ok and conv_ok and close and err_truth < 1e-4
+sys.exit(0 if ok else 1)

@@ -1,0 +1,387 @@
+"""GPU parity: the CUDA hot path (through the C ABI / host mirror) against the CPU oracle on the same seeded inputs.
+
+Bar: bit-exact for copy / fill / transpose / histogram (integer, byte and index work) and for the FP32 GEMM in the
+reference's summation order; rtol 1e-2 for the opt-in BF16 tensor-core GEMM (tolerance stated in the test).
+Full BASELINE sizes are covered through size-independent properties plus sampled oracle blocks.
+"""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import b200ka as KA
+from b200ka import _lib
+from b200ka import examples as EX
+from b200ka import kernels as K
+from b200ka.kernel import Val, ki_kernel
+
+pytestmark = pytest.mark.gpu
+be = KA.B200Backend()
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def tune(**kv):
+    for k, v in kv.items():
+        _lib.call("b200_tune_set", k.replace("__", ".").encode(), int(v))
+
+
+@pytest.fixture(autouse=True)
+def _reset_tuning():
+    yield
+    for k in ["registry.force_twins", "copy.impl", "transpose.order", "transpose.force_generic", "hist.impl"]:
+        _lib.call("b200_tune_set", k.encode(), 0)
+    for k, v in [("hist.threads", 512), ("hist.batch", 8), ("hist.ilp", 2), ("copy.unroll", 4), ("copy.ctas_per_sm", 8)]:
+        _lib.call("b200_tune_set", k.encode(), v)
+
+
+def F(shape, dtype):
+    return np.zeros(shape, dtype=dtype, order="F")
+
+
+# =====================================================================================================
+# copy / fill
+# =====================================================================================================
+@pytest.mark.parametrize("n", [1, 3, 17, 1000, 4097, (1 << 20) + 3, 1 << 22])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64, np.uint8])
+def test_memcopy_matches_oracle(orc, n, dtype):
+    src = (orc.gen_uniform_f32((n,), 1234) * 255).astype(dtype)
+    B = KA.to_device(src)
+    A = KA.zeros(be, dtype, n)
+    EX.mycopy_(A, B)
+    KA.synchronize(be)
+    ref = np.zeros(n, dtype=dtype)
+    orc.copy_kernel(ref, src, n, KA.threads_to_workgroupsize(1024, (n,)))
+    assert np.array_equal(KA.Array(A).view(np.uint8), ref.view(np.uint8))
+
+
+@pytest.mark.parametrize("force_twins", [0, 1])
+def test_memcopy_examples(orc, force_twins):
+    # examples/memcopy.jl:19-23 and memcopy_static.jl:19-23
+    tune(registry__force_twins=force_twins)
+    for fn in (EX.mycopy_, EX.mycopy_static_):
+        A = KA.zeros(be, np.float64, 128, 128)
+        B = KA.ones(be, np.float64, 128, 128)
+        fn(A, B)
+        KA.synchronize(be)
+        assert np.array_equal(KA.Array(A), KA.Array(B))
+        assert np.all(KA.Array(A) == 1.0)
+
+
+def test_copy_partial_ndrange_and_unaligned(orc):
+    src = orc.gen_uniform_f32((5000,), 7)
+    B = KA.to_device(src)
+    for force in (0, 1):
+        tune(registry__force_twins=force)
+        # only the first 1234 elements are in the ndrange: the rest of A must stay untouched
+        A = KA.allocate(be, np.float32, 5000).fill_(-1.0)
+        K.copy_kernel_(be, 64)(A, B, ndrange=1234)
+        ref = np.full(5000, -1.0, dtype=np.float32)
+        orc.copy_kernel(ref, src, 1234, 64)
+        assert np.array_equal(KA.Array(A), ref)
+        # misaligned views (offset by 1 and 3 elements: 4- and 12-byte misalignment)
+        A = KA.allocate(be, np.float32, 5000).fill_(-1.0)
+        K.copy_kernel_(be, 256)(A.view(1, (4000,)), B.view(3, (4000,)), ndrange=4000)
+        ref = np.full(5000, -1.0, dtype=np.float32)
+        ref[1:4001] = src[3:4003]
+        assert np.array_equal(KA.Array(A), ref)
+    # N-d ndrange that is not a multiple of the workgroup: literal twin semantics (padded linear ids)
+    A = KA.allocate(be, np.float32, 64).fill_(-1.0)
+    K.copy_kernel_(be, (4, 2))(A, B, ndrange=(6, 5))
+    ref = np.full(64, -1.0, dtype=np.float32)
+    orc.copy_kernel(ref, src[:64].copy(), (6, 5), (4, 2))
+    assert np.array_equal(KA.Array(A), ref)
+
+
+@pytest.mark.parametrize("impl,knobs", [(0, dict(copy__unroll=1)), (0, dict(copy__unroll=2)), (0, dict(copy__unroll=8)),
+                                        (1, dict(copy__bulk_stages=2)), (1, dict(copy__bulk_stages=4)),
+                                        (1, dict(copy__bulk_stages=8, copy__bulk_stage_kb=16))])
+def test_copy_implementations_bit_exact(orc, impl, knobs):
+    tune(copy__impl=impl, **knobs)
+    for n in [(1 << 22), (1 << 22) + 1028, (3 << 20) + 4]:
+        src = orc.gen_uniform_f32((n,), 99)
+        B = KA.to_device(src)
+        A = KA.zeros(be, np.float32, n)
+        KA.copyto_(be, A, B)
+        KA.synchronize(be)
+        assert np.array_equal(KA.Array(A), src)
+    tune(copy__bulk_stage_kb=32, copy__bulk_stages=4)
+
+
+def test_copy_c1_size_property(orc):
+    # BASELINE config: 2^26 Float32.  Property: copy is the identity on bytes (compare checksums and samples).
+    n = 1 << 26
+    src = orc.gen_uniform_f32((n,), 1234)
+    B = KA.to_device(src)
+    A = KA.zeros(be, np.float32, n)
+    EX.mycopy_(A, B)
+    KA.synchronize(be)
+    got = KA.Array(A)
+    assert np.array_equal(got.view(np.uint32), src.view(np.uint32))
+
+
+@pytest.mark.parametrize("dtype,shape", [(np.float32, (7, 5)), (np.float64, (1000,)), (np.int64, (64, 64)), (np.uint8, (12345,)),
+                                         (np.int32, (1 << 20,)), (np.float32, (3, 1))])
+def test_zeros_ones_fill(orc, dtype, shape):
+    Z = KA.zeros(be, dtype, shape)
+    O = KA.ones(be, dtype, shape)
+    KA.synchronize(be)
+    assert np.array_equal(KA.Array(Z), np.zeros(shape, dtype))
+    assert np.array_equal(KA.Array(O), np.ones(shape, dtype))
+    # init_kernel through the generic launch, fast path and literal twin
+    for force in (0, 1):
+        tune(registry__force_twins=force)
+        A = KA.allocate(be, dtype, shape).fill_(5)
+        n = A.size
+        K.init_kernel(be)(A, dtype(1), dtype, ndrange=n)
+        ref = np.full(shape, 5, dtype=dtype, order="F")
+        orc.init_kernel(ref, 1, n, KA.threads_to_workgroupsize(1024, (n,)))
+        assert np.array_equal(KA.Array(A), ref)
+    # unaligned fill (views)
+    A = KA.allocate(be, dtype, 100).fill_(9)
+    A.view(3, (90,)).fill_(2)
+    ref = np.full(100, 9, dtype=dtype)
+    ref[3:93] = 2
+    assert np.array_equal(KA.Array(A), ref)
+
+
+# =====================================================================================================
+# transpose
+# =====================================================================================================
+@pytest.mark.parametrize("shape", [(1024, 1024), (64, 128), (128, 64), (2048, 512), (37, 300), (1, 1), (65, 63), (1000, 1000)])
+@pytest.mark.parametrize("order", [0, 1])
+def test_transpose_matches_oracle(orc, shape, order):
+    tune(transpose__order=order)
+    m, n = shape  # a is m x n, b is n x m
+    b = orc.gen_uniform_f32((n, m), 1235)
+    a_ref = F((m, n), np.float32)
+    orc.naive_transpose(a_ref, b)
+    dA = KA.zeros(be, np.float32, m, n)
+    EX.naive_transpose_(dA, KA.to_device(b))
+    KA.synchronize(be)
+    assert np.array_equal(KA.Array(dA).view(np.uint32), a_ref.view(np.uint32))
+
+
+def test_transpose_variants(orc):
+    b = orc.gen_uniform_f32((256, 192), 5)
+    a_ref = F((192, 256), np.float32)
+    orc.naive_transpose(a_ref, b)
+    for knobs in (dict(registry__force_twins=1), dict(transpose__force_generic=1)):
+        tune(**knobs)
+        dA = KA.zeros(be, np.float32, 192, 256)
+        EX.naive_transpose_(dA, KA.to_device(b))
+        assert np.array_equal(KA.Array(dA), a_ref)
+        tune(registry__force_twins=0, transpose__force_generic=0)
+    # Float64 (the example's f_type when supports_float64) goes through the generic tile kernel
+    b64 = np.asfortranarray(np.random.default_rng(1).random((96, 130)))
+    dA = KA.zeros(be, np.float64, 130, 96)
+    EX.naive_transpose_(dA, KA.to_device(b64))
+    assert np.array_equal(KA.Array(dA), b64.T)
+    # size mismatch: prints and returns nothing, `a` untouched (examples/naive_transpose.jl:12-15)
+    dA = KA.zeros(be, np.float32, 10, 10)
+    assert EX.naive_transpose_(dA, KA.to_device(b)) is None
+    assert np.all(KA.Array(dA) == 0)
+    # partial ndrange: only the top-left block is written
+    dA = KA.allocate(be, np.float32, 192, 256).fill_(-1)
+    K.naive_transpose_kernel_(be, 256)(dA, KA.to_device(b), ndrange=(100, 70))
+    ref = np.full((192, 256), -1, dtype=np.float32, order="F")
+    orc.naive_transpose(ref, b, ndrange=(100, 70))
+    assert np.array_equal(KA.Array(dA), ref)
+
+
+def test_transpose_c2_size_properties(orc):
+    # BASELINE config: 16384 x 16384 Float32.  Properties: (1) involution, (2) sampled rows against the definition.
+    n = 16384
+    b = orc.gen_uniform_f32((n, n), 1235)
+    dB = KA.to_device(b)
+    dA = KA.zeros(be, np.float32, n, n)
+    EX.naive_transpose_(dA, dB)
+    dB2 = KA.zeros(be, np.float32, n, n)
+    EX.naive_transpose_(dB2, dA)
+    KA.synchronize(be)
+    assert np.array_equal(KA.Array(dB2).view(np.uint32), b.view(np.uint32))
+    a = KA.Array(dA)
+    for i in [0, 1, 63, 64, 4097, n - 1]:
+        assert np.array_equal(a[i, :], b[:, i])
+        assert np.array_equal(a[:, i], b[i, :])
+
+
+# =====================================================================================================
+# histogram
+# =====================================================================================================
+def _hist_check(orc, inp, nbins, gs=256):
+    base = np.zeros(nbins, dtype=np.int32)
+    orc.histogram(base, inp, gs)
+    out = KA.zeros(be, np.int32, nbins)
+    EX.histogram_(out, EX.move(be, inp), gs)
+    KA.synchronize(be)
+    got = KA.Array(out)
+    assert np.array_equal(got, base), f"max |diff| = {np.abs(got.astype(np.int64) - base).max()}"
+    return got
+
+
+def test_histogram_examples(orc):
+    # examples/histogram.jl:74-100
+    rng = np.random.default_rng(1236)
+    rand_input = rng.integers(1, 129, size=1000).astype(np.int32)
+    linear_input = np.arange(1, 1025, dtype=np.int32)
+    all_two = np.full(512, 2, dtype=np.int32)
+    for force in (0, 1):
+        tune(registry__force_twins=force)
+        for inp, gs in ((rand_input, 6), (linear_input, 256), (all_two, 256)):
+            got = _hist_check(orc, inp, int(inp.max()), gs)
+            assert np.array_equal(got, orc.create_histogram(inp))
+
+
+@pytest.mark.parametrize("cfg", [dict(hist__impl=0, hist__threads=512, hist__batch=8, hist__ilp=2),
+                                 dict(hist__impl=0, hist__threads=512, hist__batch=8, hist__ilp=1),
+                                 dict(hist__impl=0, hist__threads=512, hist__batch=4, hist__ilp=2),
+                                 dict(hist__impl=0, hist__threads=768, hist__batch=4, hist__ilp=2),
+                                 dict(hist__impl=0, hist__threads=256, hist__batch=8, hist__ilp=2),
+                                 dict(hist__impl=1)])
+@pytest.mark.parametrize("dist", ["uniform", "all_equal", "ramp", "out_of_range"])
+def test_histogram_variants_and_distributions(orc, cfg, dist):
+    tune(**cfg)
+    n = (1 << 22) + 3  # not a multiple of 4: exercises the scalar tail
+    if dist == "uniform":
+        inp = orc.gen_bins_i32(n, 1236, 256)
+    elif dist == "all_equal":
+        inp = np.full(n, 2, dtype=np.int32)  # examples/histogram.jl:78 at scale: worst case for atomics
+    elif dist == "ramp":
+        inp = (np.arange(n, dtype=np.int64) * 256 // n + 1).astype(np.int32)  # sorted: long equal runs
+    else:
+        inp = orc.gen_bins_i32(n, 5, 256)
+        inp[::7] = 0
+        inp[1::11] = -5
+        inp[2::13] = 300
+        inp[3::17] = np.iinfo(np.int32).min
+    _hist_check(orc, inp, 256)
+
+
+def test_histogram_accumulates_and_other_bin_counts(orc):
+    inp = orc.gen_bins_i32(100000, 3, 100)
+    # `+=` semantics: a second launch adds to the existing bins (examples/histogram.jl:53)
+    out = KA.zeros(be, np.int32, 100)
+    dinp = EX.move(be, inp)
+    EX.histogram_(out, dinp)
+    EX.histogram_(out, dinp)
+    KA.synchronize(be)
+    assert np.array_equal(KA.Array(out), 2 * np.bincount(inp, minlength=101)[1:])
+    for nbins in (1, 37, 255, 257, 1000, 5000, 20000):
+        inp = orc.gen_bins_i32(50000, nbins, nbins)
+        _hist_check(orc, inp, nbins)
+    # unaligned input pointer
+    inp = orc.gen_bins_i32(10001, 9, 256)
+    d = EX.move(be, inp)
+    out = KA.zeros(be, np.int32, 256)
+    v = d.view(1, (10000,))
+    EX.histogram_(out, v)
+    assert np.array_equal(KA.Array(out), np.bincount(inp[1:], minlength=257)[1:])
+
+
+def test_histogram_c3_full_size(orc):
+    # BASELINE config: 2^30 Int32 into 256 bins.  Checked against the serial reference baseline on the whole input.
+    n = 1 << 30
+    inp = orc.gen_bins_i32(n, 1236, 256)
+    want = orc.create_histogram(inp)  # the reference's serial baseline (examples/histogram.jl:9-15)
+    d = EX.move(be, inp)
+    out = KA.zeros(be, np.int32, 256)
+    EX.histogram_(out, d)
+    KA.synchronize(be)
+    got = KA.Array(out)
+    assert int(got.astype(np.int64).sum()) == n  # conservation
+    assert np.array_equal(got, want)
+
+
+# =====================================================================================================
+# matmul
+# =====================================================================================================
+def test_matmul_example_bit_exact(orc):
+    # examples/matmul.jl:29-36
+    a = orc.gen_uniform_f32((256, 123), 1237)
+    b = orc.gen_uniform_f32((123, 45), 1238)
+    out = KA.zeros(be, np.float32, 256, 45)
+    EX.matmul_(out, KA.to_device(a), KA.to_device(b))
+    KA.synchronize(be)
+    ref = F((256, 45), np.float32)
+    orc.matmul_naive(ref, a, b)
+    assert np.array_equal(KA.Array(out).view(np.uint32), ref.view(np.uint32))
+    # Float64 variant
+    a64, b64 = a.astype(np.float64), b.astype(np.float64)
+    out64 = KA.zeros(be, np.float64, 256, 45)
+    EX.matmul_(out64, KA.to_device(a64), KA.to_device(b64))
+    ref64 = F((256, 45), np.float64)
+    orc.matmul_naive(ref64, np.asfortranarray(a64), np.asfortranarray(b64))
+    assert np.array_equal(KA.Array(out64), ref64)
+
+
+@pytest.mark.parametrize("shape", [(1024, 512, 2048), (128, 16, 128), (256, 123, 45), (37, 29, 21), (130, 17, 129), (16, 16, 16)])
+@pytest.mark.parametrize("force_twins", [0, 1])
+def test_performant_matmul_bit_exact(orc, shape, force_twins):
+    # examples/performant_matmul.jl:79-92 (first shape) + ragged shapes; FP32 parity: bit-identical to the oracle,
+    # and within rtol 1e-5 of FP64 truth for the example's uniform [0,1) inputs
+    tune(registry__force_twins=force_twins)
+    N, R, M = shape
+    A = orc.gen_uniform_f32((N, R), 1237)
+    B = orc.gen_uniform_f32((R, M), 1238)
+    dC = KA.zeros(be, np.float32, N, M)
+    EX.performant_matmul_(dC, KA.to_device(A), KA.to_device(B))
+    KA.synchronize(be)
+    ref = F((N, M), np.float32)
+    orc.coalesced_matmul(ref, A, B)
+    got = KA.Array(dC)
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+    assert np.allclose(got, orc.matmul_f64_truth(A, B), rtol=1e-5, atol=0)
+
+
+def test_matmul_signed_and_running_mode(orc):
+    rng = np.random.default_rng(8)
+    A = np.asfortranarray(rng.standard_normal((256, 200)).astype(np.float32))
+    B = np.asfortranarray(rng.standard_normal((200, 384)).astype(np.float32))
+    dA, dB = KA.to_device(A), KA.to_device(B)
+    dC = KA.zeros(be, np.float32, 256, 384)
+    EX.performant_matmul_(dC, dA, dB)
+    ref = F((256, 384), np.float32)
+    orc.coalesced_matmul(ref, A, B)
+    assert np.array_equal(KA.Array(dC).view(np.uint32), ref.view(np.uint32))
+    # typed entry point, running-accumulator mode, aligned and ragged
+    for (M, Kd, N) in [(256, 200, 384), (256, 192, 384), (100, 50, 70)]:
+        A2 = np.asfortranarray(A[:M, :Kd]); B2 = np.asfortranarray(B[:Kd, :N])
+        dC2 = KA.zeros(be, np.float32, M, N)
+        dA2, dB2 = KA.to_device(A2), KA.to_device(B2)
+        _lib.call("b200_matmul_f32", C.c_void_p(dC2.ptr), C.c_void_p(dA2.ptr), C.c_void_p(dB2.ptr),
+                  M, Kd, N, M, Kd, M, _lib.B200_MATMUL_RUNNING)
+        ref2 = F((M, N), np.float32)
+        orc.matmul_running(ref2, A2, B2)
+        assert np.array_equal(KA.Array(dC2).view(np.uint32), ref2.view(np.uint32))
+
+
+def test_matmul_c4_size_sampled_blocks(orc):
+    # BASELINE config: 8192^3 FP32.  The oracle cannot run 1.1 TFLOP in seconds, so bit-exactness is checked on
+    # three 128x128 output blocks (each needs only a row panel of A and a column panel of B) and rtol 1e-5 vs FP64.
+    n = 8192
+    A = orc.gen_uniform_f32((n, n), 1237)
+    B = orc.gen_uniform_f32((n, n), 1238)
+    dC = KA.zeros(be, np.float32, n, n)
+    EX.performant_matmul_(dC, KA.to_device(A), KA.to_device(B))
+    KA.synchronize(be)
+    got = KA.Array(dC)
+    for (r0, c0) in [(0, 0), (4096 - 64, 4096 + 64), (n - 128, n - 128)]:
+        Ap = np.asfortranarray(A[r0:r0 + 128, :])
+        Bp = np.asfortranarray(B[:, c0:c0 + 128])
+        ref = F((128, 128), np.float32)
+        orc.coalesced_matmul(ref, Ap, Bp)
+        blk = got[r0:r0 + 128, c0:c0 + 128]
+        assert np.array_equal(blk.view(np.uint32), ref.view(np.uint32))
+        assert np.allclose(blk, orc.matmul_f64_truth(Ap, Bp), rtol=1e-5, atol=0)
+
+
+def test_matmul_bf16_tensor_core():
+    # Runs in a child process with a hard timeout: a mis-synchronised tcgen05 pipeline must not hang the suite.
+    script = os.path.join(ROOT, "tests", "gpu_tc_check.py")
+    r = subprocess.run([sys.executable, script], capture_output=True, text=True, timeout=300)
+    sys.stdout.write(r.stdout[-4000:])
+    sys.stderr.write(r.stderr[-4000:])
+    assert r.returncode == 0, "tensor-core GEMM check failed:\n" + r.stdout[-2000:] + r.stderr[-2000:]

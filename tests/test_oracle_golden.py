@@ -174,6 +174,15 @@ def test_naive_transpose_example(orc):
     assert np.array_equal(a, b.T)
 
 
+def test_naive_transpose_wg_equals_generic(orc):
+    for shape in [(300, 37), (512, 256), (1, 5)]:
+        b = orc.gen_uniform_f32((shape[1], shape[0]), 3)
+        a1, a2 = F(shape, np.float32), F(shape, np.float32)
+        orc.naive_transpose(a1, b)
+        orc.naive_transpose_wg(a2, b)
+        assert np.array_equal(a1, a2) and np.array_equal(a1, b.T)
+
+
 def test_naive_transpose_rect_and_ragged(orc):
     rng = np.random.default_rng(7)
     b = np.asfortranarray(rng.random((37, 300), dtype=np.float32))
