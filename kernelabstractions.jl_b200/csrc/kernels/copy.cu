@@ -202,7 +202,7 @@ static int launch_vec16(unsigned char *d, const unsigned char *s, size_t n16, in
 }
 
 static int launch_bulk(unsigned char *d, const unsigned char *s, size_t bytes16, cudaStream_t st) {
-    int stage_kb = tune_get("copy.bulk_stage_kb", 32);
+    int stage_kb = tune_get("copy.bulk_stage_kb", 16);
     int stages = tune_get("copy.bulk_stages", 4);
     int ctas_per_sm = tune_get("copy.bulk_ctas_per_sm", 1);
     uint32_t stage_bytes = (uint32_t)stage_kb * 1024u;
@@ -220,10 +220,11 @@ static int launch_bulk(unsigned char *d, const unsigned char *s, size_t bytes16,
         B200_BULK_CASE(2)
         B200_BULK_CASE(3)
         B200_BULK_CASE(4)
+        B200_BULK_CASE(5)
         B200_BULK_CASE(6)
         B200_BULK_CASE(8)
         default:
-            return set_error(B200_ERR_INVALID_VALUE, "copy.bulk_stages must be 2,3,4,6 or 8");
+            return set_error(B200_ERR_INVALID_VALUE, "copy.bulk_stages must be 2,3,4,5,6 or 8");
     }
 #undef B200_BULK_CASE
     B200_CHECK_LAUNCH("copy_bulk_kernel");
@@ -247,12 +248,12 @@ int copy_bytes(void *dst, const void *src, size_t bytes, cudaStream_t st) {
     }
     size_t body = bytes & ~(size_t)15;
     if (body) {
-        int impl = tune_get("copy.impl", 0);
+        int impl = tune_get("copy.impl", 1);  // measured: TMA bulk ring (16 KiB x 4) >= LDG/STG at every size >= 1 MiB
         if (impl == 1 && body >= (size_t)1 << 20) {
             B200_TRY(launch_bulk(d, s, body, st));
         } else {
-            int unroll = tune_get("copy.unroll", 4);
-            int cps = tune_get("copy.ctas_per_sm", 8);
+            int unroll = tune_get("copy.unroll", 8);
+            int cps = tune_get("copy.ctas_per_sm", 32);
             size_t n16 = body / 16;
             switch (unroll) {
                 case 1: B200_TRY(launch_vec16<1>(d, s, n16, cps, st)); break;

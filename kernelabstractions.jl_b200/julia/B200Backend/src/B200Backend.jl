@@ -1,0 +1,405 @@
+# B200Backend.jl -- the Julia host layer: `struct B200Backend <: KA.GPU` over libb200ka.so (`ccall`).
+#
+# This file is the twin of the in-tree backend glue, reference src/pocl/backend.jl (all 244 lines), with the
+# OpenCL runtime (src/pocl/nanoOpenCL.jl) replaced by the C ABI declared in include/b200ka.h.  KA's front end
+# (`@kernel`, `@index`, `@localmem`, `@private`, `@synchronize`, `@Const`), `KA.partition` and NDIteration are
+# reused UNCHANGED; only the methods a backend must provide are defined here.
+#
+# NOTE: there is no Julia toolchain in the build environment of this repository, so this file is verified by
+# reading, not by execution; its behaviour is pinned through the Python mirror (kernelabstractions.jl_b200/b200ka),
+# which implements the same methods over the same C ABI and runs the ported testsuite on a B200.
+#
+# There is no JIT.  A `@kernel` launched on B200Backend is dispatched BY NAME (`nameof(obj.f)`, i.e.
+# `:gpu_<kernel name>`, reference src/macros.jl:32) to a precompiled sm_100a kernel inside the library; an
+# unknown name raises an ErrorException.  The catalogue is `B200Backend.registered_kernels()`.
+module B200BackendModule
+
+import KernelAbstractions as KA
+import KernelAbstractions.KernelIntrinsics as KI
+import Adapt
+
+export B200Backend, B200Array
+
+# ---------------------------------------------------------------------------------------------------------
+# library handle + checked calls (twin of `@checked`, reference src/pocl/nanoOpenCL.jl:22-52,392-408)
+# ---------------------------------------------------------------------------------------------------------
+const libb200ka = get(ENV, "B200KA_LIB", joinpath(@__DIR__, "..", "..", "..", "libb200ka.so"))
+
+const B200_OK = Int32(0)
+const B200_NOT_READY = Int32(1)
+const B200_ERR_UNKNOWN_KERNEL = Int32(-3)
+const B200_ERR_LAUNCH_DIMS = Int32(-5)
+const B200_ERR_LENGTH_MISMATCH = Int32(-6)
+const B200_ERR_ALIAS = Int32(-7)
+const B200_ERR_BAD_DEVICE = Int32(-12)
+
+struct B200Error <: Exception
+    code::Int32
+    msg::String
+end
+Base.showerror(io::IO, e::B200Error) = print(io, "B200Error($(e.code)): ", e.msg)
+
+last_error() = unsafe_string(ccall((:b200_last_error, libb200ka), Cstring, ()))
+
+function check(status::Int32)
+    status == B200_OK && return nothing
+    msg = last_error()
+    # same exception *types* as the reference (tests assert them: test/intrinsics.jl:79-80, test/devices.jl:10-11)
+    (status == B200_ERR_LAUNCH_DIMS || status == B200_ERR_BAD_DEVICE) && throw(ArgumentError(msg))
+    (status == B200_ERR_UNKNOWN_KERNEL || status == B200_ERR_LENGTH_MISMATCH || status == B200_ERR_ALIAS) && error(msg)
+    throw(B200Error(status, msg))
+end
+
+macro b200(name, argtypes, args...)
+    return quote
+        check(ccall(($(QuoteNode(name)), libb200ka), Int32, $(esc(argtypes)), $(map(esc, args)...)))
+    end
+end
+
+# ---------------------------------------------------------------------------------------------------------
+# Back-end definition (reference src/pocl/backend.jl:19-20)
+# ---------------------------------------------------------------------------------------------------------
+struct B200Backend <: KA.GPU end
+
+# ---------------------------------------------------------------------------------------------------------
+# Device array: pointer + dims, column-major, owner of its allocation (SURVEY.md Appendix C)
+# ---------------------------------------------------------------------------------------------------------
+mutable struct B200Array{T, N} <: AbstractArray{T, N}
+    ptr::Ptr{T}
+    dims::Dims{N}
+    unified::Bool
+    parent::Any           # keeps the owner alive for views
+    function B200Array{T, N}(::UndefInitializer, dims::Dims{N}; unified::Bool = false) where {T, N}
+        p = Ref{Ptr{Cvoid}}(C_NULL)
+        @b200 b200_malloc (Ptr{Ptr{Cvoid}}, Csize_t, Int32) p (prod(dims) * sizeof(T)) Int32(unified)
+        A = new{T, N}(convert(Ptr{T}, p[]), dims, unified, nothing)
+        finalizer(KA.unsafe_free!, A)
+        return A
+    end
+    B200Array{T, N}(ptr::Ptr{T}, dims::Dims{N}, unified::Bool, parent) where {T, N} = new{T, N}(ptr, dims, unified, parent)
+end
+B200Array{T}(::UndefInitializer, dims::Integer...) where {T} = B200Array{T, length(dims)}(undef, Dims(dims))
+B200Array{T}(::UndefInitializer, dims::Dims{N}) where {T, N} = B200Array{T, N}(undef, dims)
+function B200Array(h::Array{T, N}) where {T, N}
+    A = B200Array{T, N}(undef, size(h))
+    copyto!(A, h)
+    return A
+end
+
+Base.size(A::B200Array) = A.dims
+Base.length(A::B200Array) = prod(A.dims)
+Base.eltype(::B200Array{T}) where {T} = T
+Base.elsize(::Type{<:B200Array{T}}) where {T} = sizeof(T)
+Base.pointer(A::B200Array) = A.ptr
+Base.similar(A::B200Array{T}, ::Type{S} = T, dims::Dims = size(A)) where {T, S} = B200Array{S}(undef, dims)
+Base.unsafe_convert(::Type{Ptr{T}}, A::B200Array{T}) where {T} = A.ptr
+Base.dataids(A::B200Array) = (UInt(A.ptr),)
+
+# scalar getindex throws unless the memory is unified (reference test/test.jl:82-87)
+function Base.getindex(A::B200Array{T}, i::Int) where {T}
+    A.unified || error("Scalar indexing of a B200Array is disallowed; copy it to the host with Array(A)")
+    KA.synchronize(B200Backend())
+    return unsafe_load(A.ptr, i)
+end
+Base.getindex(A::B200Array, I::Int...) = A[LinearIndices(A.dims)[I...]]
+
+function Base.Array(A::B200Array{T, N}) where {T, N}
+    h = Array{T, N}(undef, A.dims)
+    copyto!(h, A)
+    return h
+end
+function Base.copyto!(dst::B200Array{T}, src::Array{T}) where {T}   # synchronous host -> device
+    length(dst) == length(src) || error("Arrays must match in length")
+    GC.@preserve src begin
+        @b200 b200_memcpy_h2d_async (Ptr{Cvoid}, Ptr{Cvoid}, Csize_t) dst.ptr pointer(src) sizeof(src)
+        @b200 b200_synchronize ()
+    end
+    return dst
+end
+function Base.copyto!(dst::Array{T}, src::B200Array{T}) where {T}   # synchronous device -> host
+    length(dst) == length(src) || error("Arrays must match in length")
+    GC.@preserve dst begin
+        @b200 b200_memcpy_d2h_async (Ptr{Cvoid}, Ptr{Cvoid}, Csize_t) pointer(dst) src.ptr sizeof(dst)
+        @b200 b200_synchronize ()
+    end
+    return dst
+end
+function Base.fill!(A::B200Array{T}, x) where {T}                 # also `A .= x` via the broadcast fallback below
+    v = Ref(convert(T, x))
+    GC.@preserve v @b200 b200_fill (Ptr{Cvoid}, Csize_t, Int32, Ptr{Cvoid}) A.ptr length(A) Int32(sizeof(T)) Base.unsafe_convert(Ptr{Cvoid}, v)
+    return A
+end
+Base.Broadcast.materialize!(A::B200Array, bc::Base.Broadcast.Broadcasted{<:Any, <:Any, typeof(identity), <:Tuple{Number}}) =
+    fill!(A, bc.args[1])
+# verification-only operations of the examples/tests: host round trip (documented in DESIGN.md)
+Base.:(==)(A::B200Array, B::AbstractArray) = Array(A) == (B isa B200Array ? Array(B) : collect(B))
+Base.:(==)(A::AbstractArray, B::B200Array) = B == A
+Base.isapprox(A::B200Array, B::AbstractArray; kw...) = isapprox(Array(A), B isa B200Array ? Array(B) : collect(B); kw...)
+Base.isapprox(A::AbstractArray, B::B200Array; kw...) = isapprox(B, A; kw...)
+Base.maximum(A::B200Array) = maximum(Array(A))
+Base.:*(A::B200Array{Float32, 2}, B::B200Array{Float32, 2}) = Array(A) * Array(B)
+Base.view(A::B200Array{T}, r::UnitRange{Int}) where {T} =
+    B200Array{T, 1}(A.ptr + (first(r) - 1) * sizeof(T), (length(r),), A.unified, A)
+
+# ---------------------------------------------------------------------------------------------------------
+# Memory operations (reference src/pocl/backend.jl:25-57)
+# ---------------------------------------------------------------------------------------------------------
+KA.allocate(::B200Backend, ::Type{T}, dims::Tuple; unified::Bool = false) where {T} =
+    B200Array{T, length(dims)}(undef, Dims(dims); unified)
+
+function KA.zeros(backend::B200Backend, ::Type{T}, dims::Tuple; kwargs...) where {T}
+    return fill!(KA.allocate(backend, T, dims; kwargs...), zero(T))      # init_kernel(arr, zero, T) -> b200_fill
+end
+function KA.ones(backend::B200Backend, ::Type{T}, dims::Tuple; kwargs...) where {T}
+    return fill!(KA.allocate(backend, T, dims; kwargs...), one(T))
+end
+
+function KA.unsafe_free!(A::B200Array)
+    if A.parent === nothing && A.ptr != C_NULL
+        ccall((:b200_free, libb200ka), Int32, (Ptr{Cvoid},), A.ptr)
+        A.ptr = C_NULL
+    end
+    return nothing
+end
+
+# KA.copyto! is asynchronous and stream ordered; the caller keeps host buffers alive until synchronize
+# (contract: reference src/KernelAbstractions.jl:118-151).
+function KA.copyto!(::B200Backend, A::B200Array{T}, B::B200Array{T}) where {T}
+    length(A) == length(B) || error("Arrays must match in length")              # :42-44
+    # the alias check (Base.mightalias, :45-47) is done in the library on the byte ranges -> B200_ERR_ALIAS
+    @b200 b200_copy (Ptr{Cvoid}, Ptr{Cvoid}, Csize_t) A.ptr B.ptr (length(A) * sizeof(T))
+    return A
+end
+function KA.copyto!(::B200Backend, A::B200Array{T}, B::Array{T}) where {T}
+    length(A) == length(B) || error("Arrays must match in length")
+    @b200 b200_memcpy_h2d_async (Ptr{Cvoid}, Ptr{Cvoid}, Csize_t) A.ptr pointer(B) sizeof(B)
+    return A
+end
+function KA.copyto!(::B200Backend, A::Array{T}, B::B200Array{T}) where {T}
+    length(A) == length(B) || error("Arrays must match in length")
+    @b200 b200_memcpy_d2h_async (Ptr{Cvoid}, Ptr{Cvoid}, Csize_t) pointer(A) B.ptr sizeof(A)
+    return A
+end
+
+KA.functional(::B200Backend) = begin
+    n = Ref{Int32}(0)
+    ccall((:b200_device_count, libb200ka), Int32, (Ptr{Int32},), n) == B200_OK && n[] > 0
+end
+KA.pagelock!(::B200Backend, x::Array) = (@b200 b200_host_register (Ptr{Cvoid}, Csize_t) pointer(x) sizeof(x); nothing)
+KA.get_backend(::B200Array) = B200Backend()
+KA.supports_float64(::B200Backend) = true
+KA.supports_atomics(::B200Backend) = true
+KA.supports_unified(::B200Backend) = true
+
+# Cooperative synchronize: never block inside the driver, yield to the Julia scheduler
+# (reference docs/src/implementations.md:3-11; examples/mpi.jl:30 relies on it).
+function KA.synchronize(::B200Backend)
+    while true
+        st = ccall((:b200_stream_query, libb200ka), Int32, ())
+        st == B200_OK && break
+        st == B200_NOT_READY || check(st)
+        yield()
+    end
+    return nothing
+end
+
+function KA.priority!(::B200Backend, prio::Symbol)
+    prio in (:high, :normal, :low) || error("priority must be one of :high, :normal, :low")   # KernelAbstractions.jl:658-663
+    @b200 b200_set_priority (Int32,) Int32(prio === :high ? 1 : (prio === :low ? -1 : 0))
+    return nothing
+end
+
+function KA.ndevices(::B200Backend)
+    n = Ref{Int32}(0)
+    @b200 b200_device_count (Ptr{Int32},) n
+    return Int(n[])
+end
+function KA.device(::B200Backend)
+    d = Ref{Int32}(0)
+    @b200 b200_get_device (Ptr{Int32},) d
+    return Int(d[]) + 1
+end
+function KA.device!(backend::B200Backend, id::Int)
+    (1 <= id <= KA.ndevices(backend)) || throw(ArgumentError("Device id $id out of bounds."))   # KernelAbstractions.jl:686-691
+    @b200 b200_set_device (Int32,) Int32(id - 1)
+    return nothing
+end
+
+Adapt.adapt_storage(::B200Backend, a::Array) = B200Array(a)
+Adapt.adapt_storage(::B200Backend, a::B200Array) = a
+Adapt.adapt_storage(::KA.CPU, a::B200Array) = Array(a)
+
+# ---------------------------------------------------------------------------------------------------------
+# Argument marshalling: the C records of include/b200ka.h
+# ---------------------------------------------------------------------------------------------------------
+const B200_MAX_NDIM = 4
+
+struct LaunchDesc            # b200_launch_desc
+    kind::Int32
+    ndim::Int32
+    ndrange::NTuple{4, Int64}
+    wgs::NTuple{4, Int64}
+    blocks::NTuple{4, Int64}
+    dynamic_check::Int32
+    flags::Int32
+end
+
+struct CArg                  # b200_arg
+    kind::Int32
+    eltype::Int32
+    elsize::Int32
+    ndim::Int32
+    dims::NTuple{4, Int64}
+    ptr::Ptr{Cvoid}
+    scalar::Int64
+    fscalar::Float64
+end
+
+eltype_code(::Type{Int8}) = Int32(1);  eltype_code(::Type{UInt8}) = Int32(2)
+eltype_code(::Type{Int16}) = Int32(3); eltype_code(::Type{UInt16}) = Int32(4)
+eltype_code(::Type{Int32}) = Int32(5); eltype_code(::Type{UInt32}) = Int32(6)
+eltype_code(::Type{Int64}) = Int32(7); eltype_code(::Type{UInt64}) = Int32(8)
+eltype_code(::Type{Float16}) = Int32(9); eltype_code(::Type{Float32}) = Int32(11)
+eltype_code(::Type{Float64}) = Int32(12); eltype_code(::Type{Bool}) = Int32(13)
+eltype_code(::Type) = Int32(0)       # opaque isbits element (CartesianIndex{N}, KernelData, ...)
+
+pad4(t::Tuple) = ntuple(i -> i <= length(t) ? Int64(t[i]) : Int64(1), 4)
+
+# KA.argconvert / KI.argconvert (reference src/pocl/backend.jl:149,242)
+carg(A::B200Array{T, N}) where {T, N} = CArg(0, eltype_code(T), sizeof(T), N, pad4(size(A)), convert(Ptr{Cvoid}, A.ptr), 0, 0.0)
+carg(x::Integer) = CArg(1, eltype_code(Int64), 8, 0, pad4(()), C_NULL, Int64(x), Float64(x))
+carg(x::AbstractFloat) = CArg(1, eltype_code(typeof(x)), sizeof(x), 0, pad4(()), C_NULL, isinteger(x) ? Int64(x) : 0, Float64(x))
+carg(::Val{x}) where {x} = CArg(2, eltype_code(Int64), 8, 0, pad4(()), C_NULL, Int64(x), Float64(x))
+carg(::Type{T}) where {T} = CArg(2, eltype_code(T), sizeof(T), 0, pad4(()), C_NULL, Int64(eltype_code(T)), 0.0)
+carg(f::Function) = f === zero ? carg(0) : f === one ? carg(1) : error("Don't know how to convert function $f for Kernel{B200Backend}")
+carg(x) = error("Don't know how to convert arguments of type $(typeof(x)) for Kernel{B200Backend}")
+KA.argconvert(::KA.Kernel{B200Backend}, arg) = carg(arg)
+KI.argconvert(::B200Backend, arg) = carg(arg)
+
+function launch(name::String, desc::LaunchDesc, args)
+    cargs = CArg[carg(a) for a in args]
+    GC.@preserve args cargs begin
+        st = ccall((:b200_launch, libb200ka), Int32, (Cstring, Ref{LaunchDesc}, Ptr{CArg}, Int32),
+                   name, Ref(desc), cargs, Int32(length(cargs)))
+        check(st)
+    end
+    return nothing
+end
+
+function registered_kernels()
+    n = Ref{Int32}(0)
+    @b200 b200_kernel_count (Ptr{Int32},) n
+    return [unsafe_string(ccall((:b200_kernel_name, libb200ka), Cstring, (Int32,), Int32(i))) for i in 0:(n[] - 1)]
+end
+
+# ---------------------------------------------------------------------------------------------------------
+# Kernel launch (reference src/pocl/backend.jl:74-147)
+# ---------------------------------------------------------------------------------------------------------
+function KA.mkcontext(kernel::KA.Kernel{B200Backend}, _ndrange, iterspace)
+    return KA.CompilerMetadata{KA.ndrange(kernel), KA.DynamicCheck}(_ndrange, iterspace)
+end
+function KA.mkcontext(kernel::KA.Kernel{B200Backend}, I, _ndrange, iterspace, ::Dynamic) where {Dynamic}
+    return KA.CompilerMetadata{KA.ndrange(kernel), Dynamic}(I, _ndrange, iterspace)
+end
+
+function KA.launch_config(kernel::KA.Kernel{B200Backend}, ndrange, workgroupsize)
+    if ndrange isa Integer
+        ndrange = (ndrange,)
+    end
+    if workgroupsize isa Integer
+        workgroupsize = (workgroupsize,)
+    end
+    # partition checked that the ndrange's agreed
+    if KA.ndrange(kernel) <: KA.StaticSize
+        ndrange = nothing
+    end
+    iterspace, dynamic = if KA.workgroupsize(kernel) <: KA.DynamicSize && workgroupsize === nothing
+        KA.partition(kernel, ndrange, ndrange)          # use ndrange as preliminary workgroupsize
+    else
+        KA.partition(kernel, ndrange, workgroupsize)
+    end
+    return ndrange, workgroupsize, iterspace, dynamic
+end
+
+function threads_to_workgroupsize(threads, ndrange)       # reference src/pocl/backend.jl:108-115
+    total = 1
+    return map(ndrange) do n
+        x = min(div(threads, total), n)
+        total *= x
+        return x
+    end
+end
+
+const MAX_WORK_GROUP_SIZE = 1024
+
+function (obj::KA.Kernel{B200Backend})(args...; ndrange = nothing, workgroupsize = nothing)
+    ndrange, workgroupsize, iterspace, dynamic = KA.launch_config(obj, ndrange, workgroupsize)
+    ctx = KA.mkcontext(obj, ndrange, iterspace)
+
+    # figure out the workgroupsize automatically: greedy fill of the device maximum (:126-131)
+    if KA.workgroupsize(obj) <: KA.DynamicSize && workgroupsize === nothing
+        wg_size_nd = threads_to_workgroupsize(MAX_WORK_GROUP_SIZE, ndrange)
+        iterspace, dynamic = KA.partition(obj, ndrange, wg_size_nd)
+        ctx = KA.mkcontext(obj, ndrange, iterspace)
+    end
+
+    blocks = size(KA.blocks(iterspace))
+    items = size(KA.workitems(iterspace))
+    prod(blocks) == 0 && return nothing                    # groups == 0 (:136-138)
+    N = length(blocks)
+    N <= B200_MAX_NDIM || throw(ArgumentError("ndranges of more than $B200_MAX_NDIM dimensions are not supported"))
+    prod(items) <= MAX_WORK_GROUP_SIZE || throw(ArgumentError("workgroupsize $items exceeds $MAX_WORK_GROUP_SIZE work-items"))
+
+    full_ndrange = size(KA.__ndrange(ctx))
+    flags = Int32((KA.ndrange(obj) <: KA.StaticSize ? 1 : 0) | (KA.workgroupsize(obj) <: KA.StaticSize ? 2 : 0))
+    # the flattened CompilerMetadata; DynamicCheck always, like the in-tree backend (:74-76)
+    desc = LaunchDesc(0, N, pad4(full_ndrange), pad4(items), pad4(blocks), 1, flags)
+    launch(String(nameof(obj.f)), desc, args)               # "gpu_<kernel name>" (src/macros.jl:32)
+    return nothing
+end
+
+# ---------------------------------------------------------------------------------------------------------
+# KernelIntrinsics (reference src/pocl/backend.jl:149-179)
+# ---------------------------------------------------------------------------------------------------------
+struct B200Function
+    name::String
+end
+
+function KI.kernel_function(::B200Backend, f::F, tt::TT = Tuple{}; name = nothing, kwargs...) where {F, TT}
+    kname = name === nothing ? String(nameof(f)) : String(name)
+    out = Ref{Int64}(0)
+    @b200 b200_kernel_max_work_group_size (Cstring, Int64, Ptr{Int64}) kname Int64(MAX_WORK_GROUP_SIZE) out   # existence check
+    return KI.Kernel{B200Backend, B200Function}(B200Backend(), B200Function(kname))
+end
+
+function (obj::KI.Kernel{B200Backend})(args...; numworkgroups = 1, workgroupsize = 1)
+    KI.check_launch_args(numworkgroups, workgroupsize)       # ArgumentError for > 3 dims (src/intrinsics.jl:182-188)
+    ng = Tuple(numworkgroups)
+    ws = Tuple(workgroupsize)
+    nd = max(length(ng), length(ws))
+    desc = LaunchDesc(1, nd, pad4(ntuple(i -> (i <= length(ng) ? ng[i] : 1) * (i <= length(ws) ? ws[i] : 1), nd)),
+                      pad4(ws), pad4(ng), 0, 0)
+    launch(obj.kern.name, desc, args)
+    return nothing
+end
+
+function KI.kernel_max_work_group_size(kernel::KI.Kernel{<:B200Backend}; max_work_items::Int = typemax(Int))::Int
+    out = Ref{Int64}(0)
+    @b200 b200_kernel_max_work_group_size (Cstring, Int64, Ptr{Int64}) kernel.kern.name Int64(max_work_items) out
+    return Int(out[])
+end
+function KI.max_work_group_size(::B200Backend)::Int
+    v = Ref{Int32}(0)
+    @b200 b200_max_threads_per_block (Ptr{Int32},) v
+    return Int(v[])
+end
+function KI.multiprocessor_count(::B200Backend)::Int
+    v = Ref{Int32}(0)
+    @b200 b200_sm_count (Ptr{Int32},) v
+    return Int(v[])
+end
+
+# Device-side overrides (KI.get_*_id, KI.localmemory, KI.barrier, KA.__validindex, KA.Scratchpad; reference
+# src/pocl/backend.jl:183-237) have no Julia twin: they live in csrc/ka_device.cuh inside the library.
+
+end # module

@@ -31,9 +31,10 @@ def tune(**kv):
 @pytest.fixture(autouse=True)
 def _reset_tuning():
     yield
-    for k in ["registry.force_twins", "copy.impl", "transpose.order", "transpose.force_generic", "hist.impl"]:
+    for k in ["registry.force_twins", "transpose.order", "transpose.force_generic"]:
         _lib.call("b200_tune_set", k.encode(), 0)
-    for k, v in [("hist.threads", 512), ("hist.batch", 8), ("hist.ilp", 2), ("copy.unroll", 4), ("copy.ctas_per_sm", 8)]:
+    for k, v in [("hist.impl", 1), ("copy.impl", 1), ("hist.threads", 512), ("hist.batch", 8), ("hist.ilp", 2), ("copy.unroll", 8),
+                 ("copy.ctas_per_sm", 32), ("copy.bulk_stage_kb", 16), ("copy.bulk_stages", 4)]:
         _lib.call("b200_tune_set", k.encode(), v)
 
 
@@ -107,7 +108,6 @@ def test_copy_implementations_bit_exact(orc, impl, knobs):
         KA.copyto_(be, A, B)
         KA.synchronize(be)
         assert np.array_equal(KA.Array(A), src)
-    tune(copy__bulk_stage_kb=32, copy__bulk_stages=4)
 
 
 def test_copy_c1_size_property(orc):

@@ -1,0 +1,25 @@
+#!/bin/bash
+# One gpurun call: clocks + library reference point for SGEMM, one `ncu --set full` capture per hot kernel (each only
+# after the identical plain command exited 0), and the launch list of bench.py.  Outputs land in gpurun_out/.
+mkdir -p gpurun_out
+P=python
+run_ncu() { # name kernel-regex run_one-args...
+  name=$1; k=$2; shift 2
+  $P tools/run_one.py "$@" > gpurun_out/plain_$name.log 2>&1 && \
+  ncu --set full --clock-control none --import-source on -k regex:$k -s 1 -c 1 -f -o gpurun_out/prof_$name \
+      $P tools/run_one.py "$@" > gpurun_out/ncu_$name.log 2>&1
+  echo "ncu $name rc=$?"; cat gpurun_out/plain_$name.log
+}
+$P tools/run_one.py sgemm 8192 0 20
+$P tools/run_one.py sgemm 8192 1 20
+$P tools/run_one.py cublas_sgemm 8192 0 20
+$P tools/run_one.py tcgemm 8192 0 50
+run_ncu sgemm sgemm128 sgemm 4096 0 3
+run_ncu transpose transpose64 transpose 16384 0 3
+run_ncu hist hist_atomic hist 1073741824 0 3
+run_ncu copy copy_bulk copy 67108864 0 3
+run_ncu tcgemm gemm_bf16 tcgemm 8192 0 3
+$P bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_plain.log 2>&1 && \
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
+    $P bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_ncu.log 2>&1
+echo "launch list rc=$?"; tail -c 600 gpurun_out/bench_plain.log

@@ -1,0 +1,122 @@
+#!/usr/bin/env python
+"""Run ONE kernel configuration a few times (the short command line handed to ncu; see profiles/README.md).
+
+usage: run_one.py {copy|transpose|hist|sgemm|tcgemm|cublas_sgemm} [size] [mode] [iters]
+Prints the CUDA-event time of the launches and the SM clock / power sampled through NVML while they run."""
+import ctypes as C
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "kernelabstractions.jl_b200"))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import b200ka as KA  # noqa: E402
+import ka_oracle as orc  # noqa: E402
+from b200ka import _lib  # noqa: E402
+
+kind = sys.argv[1]
+size = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+mode = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+iters = int(sys.argv[4]) if len(sys.argv) > 4 else 3
+be = KA.B200Backend()
+
+
+def ev():
+    e = C.c_void_p()
+    _lib.call("b200_event_create", C.byref(e))
+    return e
+
+
+class Clocks:
+    def __init__(self):
+        self.s, self.p, self.stop = [], [], threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(0)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        while not self.stop.is_set():
+            try:
+                self.s.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                self.p.append(self.nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+
+def run(fn, work, unit):
+    fn()
+    KA.synchronize(be)
+    clk = Clocks()
+    th = None
+    if clk.nv:
+        th = threading.Thread(target=clk.run, daemon=True)
+        th.start()
+    a, b = ev(), ev()
+    _lib.call("b200_event_record", a)
+    for _ in range(iters):
+        fn()
+    _lib.call("b200_event_record", b)
+    KA.synchronize(be)
+    if th:
+        clk.stop.set()
+        th.join()
+    ms = C.c_float()
+    _lib.call("b200_event_elapsed_ms", a, b, C.byref(ms))
+    per = ms.value / iters
+    scale = 1e9 if unit == "GB/s" else 1e12
+    print(f"{kind} size={size} mode={mode}: {per:.4f} ms/launch, {work / (per * 1e-3) / scale:.1f} {unit}; "
+          f"sm_mhz median {np.median(clk.s) if clk.s else None} min {min(clk.s) if clk.s else None} "
+          f"power_w max {max(clk.p) if clk.p else None} samples {len(clk.s)}", flush=True)
+
+
+if kind == "copy":
+    n = size or (1 << 26)
+    s, d = KA.to_device(orc.gen_uniform_f32((n,), 1)), KA.zeros(be, np.float32, n)
+    run(lambda: _lib.call("b200_copy", C.c_void_p(d.ptr), C.c_void_p(s.ptr), 4 * n), 8.0 * n, "GB/s")
+elif kind == "transpose":
+    n = size or 16384
+    b_, a_ = KA.to_device(orc.gen_uniform_f32((n, n), 1235)), KA.zeros(be, np.float32, n, n)
+    run(lambda: _lib.call("b200_transpose", C.c_void_p(a_.ptr), C.c_void_p(b_.ptr), n, n, n, n, 4), 8.0 * n * n, "GB/s")
+elif kind == "hist":
+    n = size or (1 << 30)
+    d_in = KA.to_device(orc.gen_bins_i32(n, 1236, 256) if mode == 0 else np.full(n, 2, dtype=np.int32))
+    bins = KA.zeros(be, np.int32, 256)
+    run(lambda: _lib.call("b200_histogram_i32", C.c_void_p(bins.ptr), 256, C.c_void_p(d_in.ptr), n), 4.0 * n, "GB/s")
+elif kind in ("sgemm", "tcgemm"):
+    n = size or 8192
+    A, B = KA.to_device(orc.gen_uniform_f32((n, n), 1237)), KA.to_device(orc.gen_uniform_f32((n, n), 1238))
+    Cd = KA.zeros(be, np.float32, n, n)
+    if kind == "sgemm":
+        run(lambda: _lib.call("b200_matmul_f32", C.c_void_p(Cd.ptr), C.c_void_p(A.ptr), C.c_void_p(B.ptr), n, n, n, n, n, n, mode),
+            2.0 * n ** 3, "TFLOP/s")
+    else:
+        ws = KA.allocate(be, np.uint16, 2 * n * n)
+        _lib.call("b200_convert_f32_bf16", C.c_void_p(ws.ptr), C.c_void_p(A.ptr), n, n, n, 1)
+        _lib.call("b200_convert_f32_bf16", C.c_void_p(ws.ptr + 2 * n * n), C.c_void_p(B.ptr), n, n, n, 0)
+        run(lambda: _lib.call("b200_matmul_bf16", C.c_void_p(Cd.ptr), C.c_void_p(ws.ptr), C.c_void_p(ws.ptr + 2 * n * n), n, n, n, n),
+            2.0 * n ** 3, "TFLOP/s")
+elif kind == "cublas_sgemm":
+    # library reference point only (never on the product path): cuBLAS FP32 SIMT GEMM through torch
+    import torch
+    n = size or 8192
+    torch.backends.cuda.matmul.allow_tf32 = False
+    a = torch.rand(n, n, device="cuda")
+    b = torch.rand(n, n, device="cuda")
+    torch.matmul(a, b)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        torch.matmul(a, b)
+    e1.record()
+    torch.cuda.synchronize()
+    per = e0.elapsed_time(e1) / iters
+    print(f"cublas_sgemm n={n}: {per:.4f} ms, {2.0 * n ** 3 / (per * 1e-3) / 1e12:.1f} TFLOP/s")
