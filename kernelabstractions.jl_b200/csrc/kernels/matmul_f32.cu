@@ -18,8 +18,8 @@ namespace b200 {
 
 constexpr int BM = 128, BN = 128, BK = 16;
 
-template <bool TILE16, bool ALIGNED>
-__global__ void __launch_bounds__(256, TILE16 ? 1 : 2)
+template <bool TILE16, bool ALIGNED, int V>
+__global__ void __launch_bounds__(256, 1)
     sgemm128_kernel(float *__restrict__ C, const float *__restrict__ A, const float *__restrict__ B, int M, int K,
                     int N, int64_t lda, int64_t ldb, int64_t ldc, int tiles_m, int tiles_n, int group_m) {
     __shared__ __align__(16) float As[2][BK][BM];
@@ -37,21 +37,28 @@ __global__ void __launch_bounds__(256, TILE16 ? 1 : 2)
 
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int wm = warp & 1, wn = warp >> 1;        // 2 x 4 warps -> warp tile 64 x 32
-    const int lx = lane & 7, ly = lane >> 3;        // 8 x 4 lanes
+    // Lane -> fragment mapping chosen from tools/micro/lds_patterns.cu (profiles/r02_lds_wavefront_patterns.csv): an
+    // LDS.128 costs 2 wavefronts when its address ignores lane bit 0 or lane bit 1, 4 otherwise.  A rows use lane
+    // bits 1-3, B columns use lane bits 0 and 4, so all four fragment loads of a k step take the 2-wavefront path.
+    const int lx = (V & 2) ? ((lane >> 1) & 7) : (lane & 7);
+    const int ly = (V & 2) ? ((lane & 1) | ((lane >> 4) << 1)) : (lane >> 3);   // 8 x 4 lanes
     const int mrow = wm * 64 + 4 * lx;              // + {0, 32}
     const int ncol = wn * 32 + 4 * ly;              // + {0, 16}
 
-    float acc[8][8];
-    float tot[TILE16 ? 8 : 1][TILE16 ? 8 : 1];
+    // Accumulators are float2 pairs along m so that the inner product issues packed FFMA2 (a pair from one LDS.128,
+    // b as the scalar-broadcast operand): tools/micro/fma_peak.cu measures 65 TFLOP/s for FFMA2 against 46 for
+    // scalar 3-register FFMA on this part.  Each lane of an FFMA2 is an IEEE fused multiply-add -> same bits.
+    float2 acc[4][8];
+    float2 tot[TILE16 ? 4 : 1][TILE16 ? 8 : 1];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
+        for (int j = 0; j < 8; ++j) acc[i][j] = make_float2(0.0f, 0.0f);
     if (TILE16) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) tot[TILE16 ? i : 0][TILE16 ? j : 0] = -0.0f;
+            for (int j = 0; j < 8; ++j) tot[TILE16 ? i : 0][TILE16 ? j : 0] = make_float2(-0.0f, -0.0f);
     }
 
     // global -> register staging of one k tile
@@ -109,30 +116,36 @@ __global__ void __launch_bounds__(256, TILE16 ? 1 : 2)
         if (kt + 1 < ntiles) load_global((kt + 1) * BK);
 #pragma unroll
         for (int kk = 0; kk < BK; ++kk) {
-            float a[8], b[8];
+            float b[8];
             const float4 a0 = *reinterpret_cast<const float4 *>(&As[buf][kk][mrow]);
             const float4 a1 = *reinterpret_cast<const float4 *>(&As[buf][kk][mrow + 32]);
             const float4 b0 = *reinterpret_cast<const float4 *>(&Bs[buf][kk][ncol]);
             const float4 b1 = *reinterpret_cast<const float4 *>(&Bs[buf][kk][ncol + 16]);
-            a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w;
-            a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+            const float2 a[4] = {make_float2(a0.x, a0.y), make_float2(a0.z, a0.w), make_float2(a1.x, a1.y),
+                                 make_float2(a1.z, a1.w)};
             b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w;
             b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
+            for (int i = 0; i < 4; ++i)
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    if (TILE16 && kk == 0)
-                        acc[i][j] = fmaf(a[i], b[j], 0.0f);   // out = zero(T); out += a*b
+                    const float2 bb = make_float2(b[j], b[j]);
+                    const float2 c = (TILE16 && kk == 0) ? make_float2(0.0f, 0.0f) : acc[i][j];  // out = zero(T)
+                    if (V & 1)
+                        acc[i][j] = __ffma2_rn(a[i], bb, c);                                      // out += a*b
                     else
-                        acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+                        acc[i][j] = make_float2(fmaf(a[i].x, b[j], c.x), fmaf(a[i].y, b[j], c.y));
                 }
         }
         if (TILE16) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
+            for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < 8; ++j) tot[TILE16 ? i : 0][TILE16 ? j : 0] += acc[i][j];  // outval += out
+                for (int j = 0; j < 8; ++j)
+                {
+                    float2 &tt = tot[TILE16 ? i : 0][TILE16 ? j : 0];                // outval += out
+                    tt = (V & 1) ? __fadd2_rn(tt, acc[i][j]) : make_float2(tt.x + acc[i][j].x, tt.y + acc[i][j].y);
+                }
         }
         if (kt + 1 < ntiles) store_shared(buf ^ 1);
         __syncthreads();
@@ -145,9 +158,9 @@ __global__ void __launch_bounds__(256, TILE16 ? 1 : 2)
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int m = m0 + mrow + 32 * h;
-            float v[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) v[e] = TILE16 ? tot[TILE16 ? 4 * h + e : 0][TILE16 ? j : 0] : acc[4 * h + e][j];
+            const float2 lo = TILE16 ? tot[TILE16 ? 2 * h : 0][TILE16 ? j : 0] : acc[2 * h][j];
+            const float2 hi = TILE16 ? tot[TILE16 ? 2 * h + 1 : 0][TILE16 ? j : 0] : acc[2 * h + 1][j];
+            const float v[4] = {lo.x, lo.y, hi.x, hi.y};
             if (ALIGNED) {
                 *reinterpret_cast<float4 *>(C + m + (int64_t)n * ldc) = make_float4(v[0], v[1], v[2], v[3]);
             } else if (n < N) {
@@ -159,34 +172,45 @@ __global__ void __launch_bounds__(256, TILE16 ? 1 : 2)
     }
 }
 
+int sgemm_tma_applicable(const float *A, const float *B, int64_t M, int64_t K, int64_t N, int64_t lda, int64_t ldb);
+int sgemm_tma_launch(float *C, const float *A, const float *B, int64_t M, int64_t K, int64_t N, int64_t lda, int64_t ldb,
+                     int64_t ldc, int mode, cudaStream_t st);
+
 int sgemm_launch(float *C, const float *A, const float *B, int64_t M, int64_t K, int64_t N, int64_t lda, int64_t ldb,
                  int64_t ldc, int mode, cudaStream_t st) {
     if (M == 0 || N == 0) return B200_OK;
     if (M > INT32_MAX || N > INT32_MAX || K > INT32_MAX)
         return set_error(B200_ERR_UNSUPPORTED, "matmul: dimension exceeds 2^31-1");
+    if (mode != B200_MATMUL_TILE16 && mode != B200_MATMUL_RUNNING)
+        return set_error(B200_ERR_INVALID_VALUE, "matmul: unknown mode %d", mode);
+    // engine 1 (default): TMA-fed warp-specialised kernel (matmul_f32_tma.cu); engine 0 or operands TMA cannot address
+    // (leading dimension / base not 16-byte aligned, K == 0): the register-staged kernel below.  Same bits either way.
+    if (tune_get("sgemm.engine", 1) == 1 && sgemm_tma_applicable(A, B, M, K, N, lda, ldb))
+        return sgemm_tma_launch(C, A, B, M, K, N, lda, ldb, ldc, mode, st);
     int tiles_m = (int)cdiv(M, BM), tiles_n = (int)cdiv(N, BN);
     if ((int64_t)tiles_m * tiles_n > INT32_MAX) return set_error(B200_ERR_UNSUPPORTED, "matmul: too many tiles");
     unsigned grid = (unsigned)(tiles_m * tiles_n);
     int group_m = tune_get("sgemm.group_m", 8);
     bool aligned = (M % BM == 0) && (N % BN == 0) && (K % BK == 0) && K > 0 && (lda % 4 == 0) && (ldb % 4 == 0) &&
                    (ldc % 4 == 0) && ((((uintptr_t)A | (uintptr_t)B | (uintptr_t)C) & 15) == 0);
-    if (mode == B200_MATMUL_TILE16) {
-        if (aligned)
-            sgemm128_kernel<true, true><<<grid, 256, 0, st>>>(C, A, B, (int)M, (int)K, (int)N, lda, ldb, ldc, tiles_m,
-                                                              tiles_n, group_m);
-        else
-            sgemm128_kernel<true, false><<<grid, 256, 0, st>>>(C, A, B, (int)M, (int)K, (int)N, lda, ldb, ldc, tiles_m,
-                                                               tiles_n, group_m);
-    } else if (mode == B200_MATMUL_RUNNING) {
-        if (aligned)
-            sgemm128_kernel<false, true><<<grid, 256, 0, st>>>(C, A, B, (int)M, (int)K, (int)N, lda, ldb, ldc, tiles_m,
-                                                               tiles_n, group_m);
-        else
-            sgemm128_kernel<false, false><<<grid, 256, 0, st>>>(C, A, B, (int)M, (int)K, (int)N, lda, ldb, ldc,
-                                                                tiles_m, tiles_n, group_m);
-    } else {
-        return set_error(B200_ERR_INVALID_VALUE, "matmul: unknown mode %d", mode);
+    const int variant = tune_get("sgemm.variant", 2) & 3;
+#define B200_SGEMM_LAUNCH(T16, AL, VV)                                                                              \
+    sgemm128_kernel<T16, AL, VV><<<grid, 256, 0, st>>>(C, A, B, (int)M, (int)K, (int)N, lda, ldb, ldc, tiles_m,      \
+                                                       tiles_n, group_m)
+#define B200_SGEMM_VARIANT(T16, AL)                                                                                 \
+    switch (variant) {                                                                                              \
+        case 0: B200_SGEMM_LAUNCH(T16, AL, 0); break;                                                               \
+        case 1: B200_SGEMM_LAUNCH(T16, AL, 1); break;                                                               \
+        case 2: B200_SGEMM_LAUNCH(T16, AL, 2); break;                                                               \
+        default: B200_SGEMM_LAUNCH(T16, AL, 3); break;                                                              \
     }
+    if (mode == B200_MATMUL_TILE16) {
+        if (aligned) { B200_SGEMM_VARIANT(true, true) } else { B200_SGEMM_VARIANT(true, false) }
+    } else {
+        if (aligned) { B200_SGEMM_VARIANT(false, true) } else { B200_SGEMM_VARIANT(false, false) }
+    }
+#undef B200_SGEMM_VARIANT
+#undef B200_SGEMM_LAUNCH
     B200_CHECK_LAUNCH("sgemm128_kernel");
     return B200_OK;
 }

@@ -1,0 +1,202 @@
+// matmul_f32_tma.cu -- FP32 SIMT GEMM fed by TMA: the default engine behind b200_matmul_f32.
+//
+// Reference: coalesced_matmul_kernel! (examples/performant_matmul.jl:15-77).  Arithmetic per output element (kept
+// bit for bit in mode B200_MATMUL_TILE16, see matmul_f32.cu and oracle/ka_oracle.c):
+//     outval = -0.0;  per 16-wide k tile: out = 0; for k ascending: out = fma(a, b, out);  outval += out
+// with ragged edge tiles zero-padded (:40-49) -- which is what TMA's out-of-bounds zero fill produces for free.
+//
+// Why a second engine (measured in profiles/r02_*): the register-staged kernel of matmul_f32.cu spends issue slots and
+// ~16 registers on LDG -> STS staging, transposes B through 4-byte shared stores, and leaves the position of the
+// global loads to ptxas (which sank them next to the stores when the FMAs became FFMA2, exposing DRAM latency).  Here
+//   * thread 0 is the producer: it issues two cp.async.bulk.tensor.2d per 16-k stage (A box 128 m x 16 k,
+//     B box 16 k x 128 n) into a STAGES-deep ring, completion on `full` mbarriers, slot release on `empty` mbarriers.
+//     It refills the slot every warp finished TWO k tiles ago, so its wait on `empty` practically never blocks and no
+//     ninth warp (which would cost a 4-warp register allocation unit) is needed;
+//   * all 8 warps are consumers: 2 x 4 warps, warp tile 64 x 32, thread tile 8 x 8 held as float2 pairs along m, inner
+//     product issued as packed FFMA2 (a pair = half of one LDS.128, b = scalar-broadcast operand).  FFMA2 peaks at
+//     65 TFLOP/s on this part against 46 for 3-register scalar FFMA (tools/micro/fma_peak.cu);
+//   * B stays k-contiguous in shared memory exactly as it is in HBM (no transpose): a thread reads two consecutive k of
+//     one column with one LDS.64 and walks its 8 columns;
+//   * lane -> (row, column) mapping takes the cheap shared-memory path measured by tools/micro/lds_patterns.cu: a
+//     wavefront serves a whole request only if its address ignores lane bit 0 or lane bit 1, so A rows use lane bits
+//     1-3 and B columns lane bits 0 and 4: 8 wavefronts per k step per warp instead of 13.
+// Bound: FP32 FMA pipe, 2*M*N*K flop.
+#include "../common.cuh"
+#include "../tma_pipe.cuh"
+#include "../tune.h"
+
+namespace b200 {
+namespace sg {
+
+constexpr int BM = 128, BN = 128, BK = 16;
+constexpr int STAGES = 8;
+constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4, STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int CONSUMER_WARPS = 8, NUM_THREADS = CONSUMER_WARPS * 32;
+constexpr int LAG = 2;                       // a slot is refilled LAG k tiles after it was consumed
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * STAGES * 8;
+
+template <bool TILE16>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+    sgemm_tma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                     float *__restrict__ C, int M, int N, int64_t ldc, int ntiles, int tiles_m, int tiles_n, int group_m,
+                     int vec_ok) {
+    using namespace pipe;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    uint64_t *full = (uint64_t *)(smem + STAGES * STAGE_BYTES);
+    uint64_t *empty = full + STAGES;
+
+    // grouped rasterisation: consecutive CTAs share A row-panels / B column-panels in L2
+    const int pid = blockIdx.x;
+    const int width = group_m * tiles_n;
+    const int group = pid / width;
+    const int first_m = group * group_m;
+    const int gsz = min(tiles_m - first_m, group_m);
+    const int tm = first_m + (pid % width) % gsz;
+    const int tn = (pid % width) / gsz;
+    const int m0 = tm * BM, n0 = tn * BN;
+
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    if (t == 0) {
+        tma_prefetch_desc(&tmap_a);
+        tma_prefetch_desc(&tmap_b);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], CONSUMER_WARPS);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    auto produce = [&](int kt) {   // thread 0 only
+        const int s = kt % STAGES;
+        if (kt >= STAGES) mbar_wait(&empty[s], ((kt / STAGES) - 1) & 1);
+        mbar_expect_tx(&full[s], STAGE_BYTES);
+        unsigned char *stage = smem + s * STAGE_BYTES;
+        tma_load_2d(stage, &tmap_a, m0, kt * BK, &full[s]);            // As[k][m]: 16 rows of 512 B
+        tma_load_2d(stage + A_BYTES, &tmap_b, kt * BK, n0, &full[s]);  // Bs[n][k]: 128 rows of 64 B
+    };
+    if (t == 0)
+        for (int kt = 0; kt < STAGES - LAG && kt < ntiles; ++kt) produce(kt);
+
+    // ---------------------------------------------------------------------- consumers
+    const int wm = warp & 1, wn = warp >> 1;                        // 2 x 4 warps -> warp tile 64 x 32
+    const int lx = (lane >> 1) & 7;                                 // lane bits 1-3 -> rows 4 lx .. 4 lx + 3 (+32)
+    const int ly = (lane & 1) | ((lane >> 4) << 1);                 // lane bits 0,4 -> columns ly + 4 j
+    const int mrow = wm * 64 + 4 * lx;
+    const int ncol = wn * 32 + ly;
+
+    float2 acc[4][8];
+    float2 tot[TILE16 ? 4 : 1][TILE16 ? 8 : 1];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = make_float2(0.0f, 0.0f);
+    if (TILE16) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) tot[TILE16 ? i : 0][TILE16 ? j : 0] = make_float2(-0.0f, -0.0f);
+    }
+
+    for (int kt = 0; kt < ntiles; ++kt) {
+        const int s = kt % STAGES;
+        if (t == 0 && kt + STAGES - LAG < ntiles) produce(kt + STAGES - LAG);
+        mbar_wait(&full[s], (kt / STAGES) & 1);
+        const float *As = reinterpret_cast<const float *>(smem + s * STAGE_BYTES) + mrow;
+        const float *Bs = reinterpret_cast<const float *>(smem + s * STAGE_BYTES + A_BYTES) + ncol * BK;
+#pragma unroll
+        for (int k2 = 0; k2 < BK; k2 += 2) {
+            float2 b[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) b[j] = *reinterpret_cast<const float2 *>(Bs + (4 * j) * BK + k2);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int kk = k2 + h;
+                const float4 a0 = *reinterpret_cast<const float4 *>(As + kk * BM);
+                const float4 a1 = *reinterpret_cast<const float4 *>(As + kk * BM + 32);
+                const float2 a[4] = {make_float2(a0.x, a0.y), make_float2(a0.z, a0.w), make_float2(a1.x, a1.y),
+                                     make_float2(a1.z, a1.w)};
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float bj = h ? b[j].y : b[j].x;
+                        const float2 c = (TILE16 && kk == 0) ? make_float2(0.0f, 0.0f) : acc[i][j];  // out = zero(T)
+                        acc[i][j] = __ffma2_rn(a[i], make_float2(bj, bj), c);                         // out += a*b
+                    }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);   // this warp no longer reads stage s
+        if (TILE16) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float2 &tt = tot[TILE16 ? i : 0][TILE16 ? j : 0];
+                    tt = __fadd2_rn(tt, acc[i][j]);                                                  // outval += out
+                }
+        }
+    }
+
+    // epilogue: rows {mrow..+3, mrow+32..+35} of columns ncol + 4 j
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int n = n0 + ncol + 4 * j;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int m = m0 + mrow + 32 * h;
+            const float2 lo = TILE16 ? tot[TILE16 ? 2 * h : 0][TILE16 ? j : 0] : acc[2 * h][j];
+            const float2 hi = TILE16 ? tot[TILE16 ? 2 * h + 1 : 0][TILE16 ? j : 0] : acc[2 * h + 1][j];
+            if (n < N) {
+                float *dst = C + m + (int64_t)n * ldc;
+                if (vec_ok && m + 3 < M) {
+                    *reinterpret_cast<float4 *>(dst) = make_float4(lo.x, lo.y, hi.x, hi.y);
+                } else {
+                    const float v[4] = {lo.x, lo.y, hi.x, hi.y};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if (m + e < M) dst[e] = v[e];
+                }
+            }
+        }
+    }
+}
+
+}  // namespace sg
+
+// Returns B200_OK after launching, B200_ERR_UNSUPPORTED (without touching the error string's meaning for the caller)
+// when the operands do not satisfy TMA's alignment rules -- the caller then uses the register-staged engine.
+int sgemm_tma_applicable(const float *A, const float *B, int64_t M, int64_t K, int64_t N, int64_t lda, int64_t ldb) {
+    return M > 0 && N > 0 && K > 0 && (lda % 4 == 0) && (ldb % 4 == 0) && ((((uintptr_t)A | (uintptr_t)B) & 15) == 0) &&
+           M < (1LL << 31) && N < (1LL << 31) && K < (1LL << 31);
+}
+
+int sgemm_tma_launch(float *C, const float *A, const float *B, int64_t M, int64_t K, int64_t N, int64_t lda,
+                     int64_t ldb, int64_t ldc, int mode, cudaStream_t st) {
+    using namespace sg;
+    CUtensorMap ta, tb;
+    B200_TRY(pipe::make_tmap_2d(&ta, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, A, M, K, lda, BM, BK, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B));
+    B200_TRY(pipe::make_tmap_2d(&tb, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, B, K, N, ldb, BK, BN, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_128B));
+    const int tiles_m = (int)cdiv(M, BM), tiles_n = (int)cdiv(N, BN);
+    if ((int64_t)tiles_m * tiles_n > INT32_MAX) return set_error(B200_ERR_UNSUPPORTED, "matmul: too many tiles");
+    const unsigned grid = (unsigned)(tiles_m * tiles_n);
+    const int ntiles = (int)cdiv(K, BK);
+    const int group_m = tune_get("sgemm.group_m", 8);
+    const int vec_ok = (ldc % 4 == 0) && (((uintptr_t)C & 15) == 0);
+    if (mode == B200_MATMUL_TILE16) {
+        B200_CUDA(cudaFuncSetAttribute(sgemm_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        sgemm_tma_kernel<true><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ta, tb, C, (int)M, (int)N, ldc, ntiles, tiles_m,
+                                                                       tiles_n, group_m, vec_ok);
+    } else {
+        B200_CUDA(cudaFuncSetAttribute(sgemm_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        sgemm_tma_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ta, tb, C, (int)M, (int)N, ldc, ntiles, tiles_m,
+                                                                        tiles_n, group_m, vec_ok);
+    }
+    B200_CHECK_LAUNCH("sgemm_tma_kernel");
+    return B200_OK;
+}
+
+}  // namespace b200

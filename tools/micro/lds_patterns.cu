@@ -46,6 +46,18 @@ int main() {
         {"l     (32 distinct)", [](int l) { return l; }},
         {"(l%8)*2 (8 distinct, stride 2 chunks)", [](int l) { return (l % 8) * 2; }},
         {"(l/8)*8 (4 distinct, 128B apart in units)", [](int l) { return (l / 8) * 8; }},
+        // which lane bits may differ inside one wavefront?  (partner l^1 vs l^2 merging)
+        {"(l>>1)&7 (8 distinct, bits 1-3)", [](int l) { return (l >> 1) & 7; }},
+        {"bits 0,4 (4 distinct)", [](int l) { return (l & 1) | ((l >> 4) << 1); }},
+        {"bits 0,3,4 (8 distinct)", [](int l) { return (l & 1) | ((l >> 3) << 1); }},
+        {"bits 0,2,3,4 (16 distinct)", [](int l) { return (l & 1) | (((l >> 2) & 7) << 1); }},
+        {"bits 2,4 (4 distinct)", [](int l) { return ((l >> 2) & 1) | ((l >> 4) << 1); }},
+        {"bits 0,2 (4 distinct)", [](int l) { return (l & 1) | (((l >> 2) & 1) << 1); }},
+        {"bits 1,2,3,4 (16 distinct) = l/2", [](int l) { return l >> 1; }},
+        {"bits 2,3,4 (8 distinct) = l/4", [](int l) { return l >> 2; }},
+        {"bits 0,1 + rows 64B apart: (l&3)*4", [](int l) { return (l & 3) * 4; }},
+        {"bits 3,4 rows 64B apart: (l>>3)*4", [](int l) { return (l >> 3) * 4; }},
+        {"bits 3,4 rows 64B apart swz64: ", [](int l) { int n = l >> 3; return n * 4 + ((n >> 1) & 3); }},
     };
     for (auto &p : pats) {
         int h[32];

@@ -95,6 +95,10 @@ elif kind in ("sgemm", "tcgemm"):
     A, B = KA.to_device(orc.gen_uniform_f32((n, n), 1237)), KA.to_device(orc.gen_uniform_f32((n, n), 1238))
     Cd = KA.zeros(be, np.float32, n, n)
     if kind == "sgemm":
+        if os.environ.get("SGEMM_VARIANT"):
+            _lib.call("b200_tune_set", b"sgemm.variant", int(os.environ["SGEMM_VARIANT"]))
+        if os.environ.get("SGEMM_ENGINE"):
+            _lib.call("b200_tune_set", b"sgemm.engine", int(os.environ["SGEMM_ENGINE"]))
         run(lambda: _lib.call("b200_matmul_f32", C.c_void_p(Cd.ptr), C.c_void_p(A.ptr), C.c_void_p(B.ptr), n, n, n, n, n, n, mode),
             2.0 * n ** 3, "TFLOP/s")
     else:

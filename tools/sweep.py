@@ -163,12 +163,13 @@ if want("sgemm"):
     Cd = KA.zeros(be, np.float32, n, n)
     work = 2.0 * n ** 3
     for mode in (0, 1):
-        for gm in (4, 8, 16):
-            tune(sgemm__group_m=gm)
-            med, mn = time_ms(lambda: _lib.call("b200_matmul_f32", C.c_void_p(Cd.ptr), C.c_void_p(A.ptr), C.c_void_p(B.ptr), n, n, n, n, n, n, mode),
-                              iters=4, warm=1)
-            record("sgemm", dict(n=n, mode=["tile16", "running"][mode], group_m=gm), med, mn, work, "TFLOP/s")
-    tune(sgemm__group_m=8)
+        for variant in (2, 4):       # 0-3: register-staged engine variants (bit0 FFMA2, bit1 lane map); 4: TMA engine
+            for gm in (8,) if variant != 4 else (4, 8, 16, 32):
+                tune(sgemm__group_m=gm, sgemm__variant=variant & 3, sgemm__engine=1 if variant == 4 else 0)
+                med, mn = time_ms(lambda: _lib.call("b200_matmul_f32", C.c_void_p(Cd.ptr), C.c_void_p(A.ptr), C.c_void_p(B.ptr), n, n, n, n, n, n, mode),
+                                  iters=4, warm=1)
+                record("sgemm", dict(n=n, mode=["tile16", "running"][mode], group_m=gm, variant=variant), med, mn, work, "TFLOP/s")
+    tune(sgemm__group_m=8, sgemm__variant=2, sgemm__engine=1)
     # ------------------------------------------------------------------------------------------ tcgen05
     if want("tc"):
         r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "gpu_tc_check.py")], capture_output=True, text=True, timeout=300)
