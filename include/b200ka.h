@@ -207,6 +207,17 @@ b200_status b200_convert_f32_bf16(uint16_t *out, const float *in, int64_t rows, 
 b200_status b200_matmul_f32_via_bf16(float *C, const float *A, const float *B, int64_t M, int64_t K,
                                      int64_t N, int64_t lda, int64_t ldb, int64_t ldc, void *workspace);
 
+/* ---- host-buffer ("out-of-core") forms ---------------------------------------------------------
+ * Same semantics as b200_transpose / b200_histogram_i32, but every array lives in HOST memory: what a user of
+ * the reference's CPU() backend calls on plain Arrays (examples/naive_transpose.jl:9-21, examples/histogram.jl:61-72).
+ * The library streams slabs through the GPU with the h2d copy, the kernel and the d2h copy of consecutive slabs
+ * overlapped on three streams (pattern: examples/mpi.jl:24-39; pagelock!: src/KernelAbstractions.jl:166).
+ * Stream ordered like every other call: results are valid after b200_synchronize().  Host buffers should be
+ * page-locked (b200_host_alloc / b200_host_register). */
+b200_status b200_transpose_host(void *a_host, const void *b_host, int64_t m, int64_t n, int64_t lda, int64_t ldb,
+                                int32_t elsize);
+b200_status b200_histogram_i32_host(int32_t *bins_host, int64_t nbins, const int32_t *input_host, int64_t n);
+
 /* ---- multi-GPU plumbing (pattern: examples/mpi.jl:24-39; NCCL over NVLink) ------------------ */
 #define B200_UNIQUE_ID_BYTES 128
 b200_status b200_comm_unique_id(void *id128);

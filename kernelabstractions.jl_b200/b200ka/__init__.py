@@ -7,7 +7,7 @@ hand-written sm_100a CUDA kernels behind the C ABI declared in include/b200ka.h.
 from . import _lib
 from ._lib import ArgumentError, B200Error, ErrorException, MethodError, build
 from .backend import (CPU, Array, B200Array, B200Backend, CartesianIndex, KernelData, adapt, allocate, copyto_,
-                      device, device_, functional, get_backend, ndevices, ones, pagelock_, priority_, similar,
+                      device, device_, functional, get_backend, ndevices, ones, pagelock_, unpagelock_, priority_, similar,
                       supports_atomics, supports_float64, supports_unified, synchronize, to_device, unsafe_free_,
                       zeros)
 from .kernel import (KIKernel, Kernel, KernelFunction, Val, check_launch_args, kernel_function,

@@ -137,6 +137,8 @@ SIGNATURES = {
     "b200_matmul_bf16": (_I32, [_VP, _VP, _VP, _I64, _I64, _I64, _I64]),
     "b200_convert_f32_bf16": (_I32, [_VP, _VP, _I64, _I64, _I64, _I32]),
     "b200_matmul_f32_via_bf16": (_I32, [_VP, _VP, _VP, _I64, _I64, _I64, _I64, _I64, _I64, _VP]),
+    "b200_transpose_host": (_I32, [_VP, _VP, _I64, _I64, _I64, _I64, _I32]),
+    "b200_histogram_i32_host": (_I32, [_VP, _I64, _VP, _I64]),
     "b200_comm_unique_id": (_I32, [_VP]),
     "b200_comm_init_rank": (_I32, [_PVP, _I32, _I32, _VP]),
     "b200_comm_destroy": (_I32, [_VP]),

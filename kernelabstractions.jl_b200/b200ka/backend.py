@@ -254,6 +254,11 @@ def pagelock_(backend, x: np.ndarray) -> None:
     call("b200_host_register", _host_ptr(x), C.c_size_t(x.nbytes))
 
 
+def unpagelock_(backend, x: np.ndarray) -> None:
+    """Undo pagelock_ before the host array is freed (the registration outlives the Python object otherwise)."""
+    call("b200_host_unregister", _host_ptr(x))
+
+
 def supports_float64(backend) -> bool:
     return True
 

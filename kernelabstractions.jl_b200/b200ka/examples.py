@@ -88,3 +88,32 @@ def matmul_bf16_(C_: B200Array, A: B200Array, B: B200Array, workspace: B200Array
     ws = workspace if workspace is not None else allocate(B200Backend(), np.uint16, (M * K + K * N,))
     _lib.call("b200_matmul_f32_via_bf16", C.c_void_p(C_.ptr), C.c_void_p(A.ptr), C.c_void_p(B.ptr), M, K, N, M, K,
               C_.shape[0], C.c_void_p(ws.ptr))
+
+
+# ---- host-array forms: what `naive_transpose!(a, b)` / `histogram!(out, in)` are for a CPU() user -- plain host
+# ---- arrays in and out -- executed by B200Backend as a slab pipeline (h2d | kernel | d2h overlapped).
+def _host_f(arr: np.ndarray, name: str) -> np.ndarray:
+    if not isinstance(arr, np.ndarray) or not (arr.flags.f_contiguous or arr.ndim == 1):
+        raise _lib.ArgumentError(f"{name} must be a column-major (Fortran-ordered) host array")
+    return arr
+
+
+def naive_transpose_host_(backend: B200Backend, a: np.ndarray, b: np.ndarray):
+    """reference examples/naive_transpose.jl:9-21 on host Arrays; stream ordered (KA.synchronize(backend) completes it)."""
+    _host_f(a, "a"), _host_f(b, "b")
+    if a.shape[0] != b.shape[1] or a.shape[1] != b.shape[0]:
+        print("Matrix size mismatch!")
+        return None
+    if a.dtype != b.dtype or a.dtype.itemsize not in (4, 8):
+        raise _lib.ArgumentError("naive_transpose_host_: element types must match and be 4 or 8 bytes wide")
+    m, n = a.shape
+    _lib.call("b200_transpose_host", C.c_void_p(a.ctypes.data), C.c_void_p(b.ctypes.data), m, n, m, n, a.dtype.itemsize)
+    return None
+
+
+def histogram_host_(backend: B200Backend, histogram_output: np.ndarray, input: np.ndarray) -> None:
+    """reference examples/histogram.jl:60-66 on host Arrays (Int32 values, accumulates into histogram_output)."""
+    if histogram_output.dtype != np.int32 or input.dtype != np.int32:
+        raise _lib.ArgumentError("histogram_host_: Int32 input and bins only")
+    _lib.call("b200_histogram_i32_host", C.c_void_p(histogram_output.ctypes.data), histogram_output.size,
+              C.c_void_p(np.ascontiguousarray(input).ctypes.data), input.size)

@@ -1,7 +1,7 @@
 // matmul_f32_tma.cu -- FP32 SIMT GEMM fed by TMA: the default engine behind b200_matmul_f32.
 //
 // Reference: coalesced_matmul_kernel! (examples/performant_matmul.jl:15-77).  Arithmetic per output element (kept
-// bit for bit in mode B200_MATMUL_TILE16, see matmul_f32.cu and oracle/ka_oracle.c):
+// bit for bit in mode B200_MATMUL_TILE16, see matmul_f32.cu and the parity tests):
 //     outval = -0.0;  per 16-wide k tile: out = 0; for k ascending: out = fma(a, b, out);  outval += out
 // with ragged edge tiles zero-padded (:40-49) -- which is what TMA's out-of-bounds zero fill produces for free.
 //

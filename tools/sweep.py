@@ -155,6 +155,36 @@ if want("hist"):
         tune(hist__impl=0, hist__threads=512, hist__batch=8, hist__ilp=2, hist__ctas_per_sm=1)
         del d_in, bins
 
+# ----------------------------------------------------------------------------------------------- host pipeline
+if want("hostpipe"):
+    from b200ka import examples as EX
+    n = 16384
+    hp = [C.c_void_p(), C.c_void_p()]
+    for h in hp:
+        _lib.call("b200_host_alloc", C.byref(h), 4 * n * n)
+    h_in = np.ctypeslib.as_array((C.c_float * (n * n)).from_address(hp[0].value)).reshape((n, n), order="F")
+    h_out = np.ctypeslib.as_array((C.c_float * (n * n)).from_address(hp[1].value)).reshape((n, n), order="F")
+    h_in[...] = orc.gen_uniform_f32((n, n), 1235)
+    for mib in (4, 8, 16, 32, 64, 128):
+        tune(hostpipe__slab_mib=mib)
+        med, mn = time_ms(lambda: EX.naive_transpose_host_(be, h_out, h_in), iters=5, warm=2)
+        record("hostpipe_transpose", dict(n=n, slab_mib=mib), med, mn, 8.0 * n * n, "GB/s")
+    assert np.array_equal(h_out[7, :100], h_in[:100, 7])
+    tune(hostpipe__slab_mib=32)
+    nh = 1 << 28
+    hh = C.c_void_p()
+    _lib.call("b200_host_alloc", C.byref(hh), 4 * nh)
+    hin = np.ctypeslib.as_array((C.c_int32 * nh).from_address(hh.value))
+    hin[...] = orc.gen_bins_i32(nh, 1236, 256)
+    bins = np.zeros(256, dtype=np.int32)
+    for mib in (8, 32, 128):
+        tune(hostpipe__slab_mib=mib)
+        med, mn = time_ms(lambda: EX.histogram_host_(be, bins, hin), iters=5, warm=2)
+        record("hostpipe_hist", dict(n=nh, slab_mib=mib), med, mn, 4.0 * nh, "GB/s")
+    tune(hostpipe__slab_mib=32)
+    for h in hp + [hh]:
+        _lib.call("b200_host_free", h)
+
 # ----------------------------------------------------------------------------------------------- sgemm
 if want("sgemm"):
     n = 8192
