@@ -81,6 +81,26 @@ def move(backend, input: np.ndarray) -> B200Array:
     return out
 
 
+def performance_variants(backend, N: int = 2048, T=np.float32, TILE_DIM: int = 32, BLOCK_ROWS: int = 8):
+    """reference examples/performance.jl:140-205: yields (label, launch) for the script's 14 launch shapes.
+    `launch(output, input)` enqueues one kernel exactly as the script does (same block_dims / Val(bank) / ndrange)."""
+    for block_dims in ((TILE_DIM, TILE_DIM), (TILE_DIM * TILE_DIM, 1), (1, TILE_DIM * TILE_DIM)):
+        for name, ctor in (("copy", kernels.simple_copy_kernel_), ("transpose", kernels.simple_transpose_kernel_)):
+            k = ctor(backend, block_dims)
+            yield f"Simple {name} {block_dims}", (lambda o, i, k=k: k(o, i, ndrange=o.shape))
+    for name, ctor in (("copy", kernels.lmem_copy_kernel_), ("transpose", kernels.lmem_transpose_kernel_)):
+        k = ctor(backend, (TILE_DIM, TILE_DIM))
+        for bank in (True, False):
+            yield (f"Localmem {name} ({TILE_DIM}, {TILE_DIM}) bank={bank}",
+                   (lambda o, i, k=k, bank=bank: k(o, i, Val(int(bank)), ndrange=o.shape)))
+    for name, ctor in (("copy", kernels.coalesced_copy_kernel_), ("transpose", kernels.coalesced_transpose_kernel_)):
+        k = ctor(backend, (TILE_DIM, BLOCK_ROWS))
+        for bank in (True, False):
+            block_factor = TILE_DIM // BLOCK_ROWS
+            yield (f"Localmem + multiple elements {name} ({TILE_DIM}, {BLOCK_ROWS}) bank={bank}",
+                   (lambda o, i, k=k, bank=bank, bf=block_factor: k(o, i, Val(int(bank)), ndrange=(o.shape[0], o.shape[1] // bf))))
+
+
 def matmul_bf16_(C_: B200Array, A: B200Array, B: B200Array, workspace: B200Array = None) -> None:
     """Opt-in tensor-core path (no reference twin): FP32 in/out, BF16 tcgen05 arithmetic."""
     M, K = A.shape

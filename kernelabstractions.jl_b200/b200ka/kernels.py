@@ -11,6 +11,13 @@ copy_kernel_ = KernelFunction("copy_kernel!")                    # examples/memc
 naive_transpose_kernel_ = KernelFunction("naive_transpose_kernel!")  # examples/naive_transpose.jl:4-7
 matmul_kernel_ = KernelFunction("matmul_kernel!")                # examples/matmul.jl:5-15
 saxpy_kernel_ = KernelFunction("saxpy_kernel!")                  # benchmark/benchmarks.jl:29-32
+# examples/performance.jl:17-138
+simple_copy_kernel_ = KernelFunction("simple_copy_kernel!")
+simple_transpose_kernel_ = KernelFunction("simple_transpose_kernel!")
+lmem_copy_kernel_ = KernelFunction("lmem_copy_kernel!")
+lmem_transpose_kernel_ = KernelFunction("lmem_transpose_kernel!")
+coalesced_copy_kernel_ = KernelFunction("coalesced_copy_kernel!")
+coalesced_transpose_kernel_ = KernelFunction("coalesced_transpose_kernel!")
 # test/localmem.jl
 localmem = KernelFunction("localmem")
 localmem2 = KernelFunction("localmem2")

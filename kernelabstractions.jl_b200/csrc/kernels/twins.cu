@@ -367,6 +367,87 @@ int twin_saxpy(const KaCtx &c, void *Z, double a, const void *X, const void *Y, 
     return B200_OK;
 }
 
+// ---- examples/performance.jl:17-138: simple / local-memory / multi-element copy and transpose ----
+// WHICH: 0 simple_copy, 1 simple_transpose (bounds-checked lanes); 2 lmem_copy, 3 lmem_transpose, 4 coalesced_copy,
+// 5 coalesced_transpose (`unsafe_indices = true`: no lane guard, plain barrier -- src/macros.jl:72-76).
+// tile = @localmem eltype(output) (N + BANK, M)  resp.  (TILE_DIM + BANK, TILE_DIM), column-major.
+template <typename T, int WHICH>
+__global__ void performance_twin_kernel(KaCtx c, T *__restrict__ output, const T *__restrict__ input,
+                                        long long rows_out, long long rows_in, long long bank) {
+    extern __shared__ __align__(16) unsigned char perf_tile_raw[];
+    T *tile = reinterpret_cast<T *>(perf_tile_raw);
+    if (WHICH <= 1) {
+        if (ka_valid(c)) {
+            long long I[KA_MAX_NDIM];
+            ka_expand(c, I);
+            if (WHICH == 0)
+                output[(I[0] - 1) + (I[1] - 1) * rows_out] = input[(I[0] - 1) + (I[1] - 1) * rows_in];
+            else
+                output[(I[1] - 1) + (I[0] - 1) * rows_out] = input[(I[0] - 1) + (I[1] - 1) * rows_in];
+        }
+        return;
+    }
+    long long g[KA_MAX_NDIM], l[KA_MAX_NDIM];
+    ka_group_cartesian(c, g);
+    ka_local_cartesian(c, l);
+    const long long gi = g[0], gj = g[1], i = l[0], j = l[1];
+    const long long N = c.wgs[0], M = c.wgs[1];   // @uniform @groupsize()[1], [2]
+    const long long trows = N + bank;
+    if (WHICH == 2 || WHICH == 3) {
+        long long I = (gi - 1) * N + i, J = (gj - 1) * M + j;
+        tile[(i - 1) + (j - 1) * trows] = input[(I - 1) + (J - 1) * rows_in];
+        __syncthreads();
+        if (WHICH == 2) {
+            output[(I - 1) + (J - 1) * rows_out] = tile[(i - 1) + (j - 1) * trows];
+        } else {
+            I = (gj - 1) * M + i;   // pivot the group index
+            J = (gi - 1) * N + j;
+            output[(I - 1) + (J - 1) * rows_out] = tile[(j - 1) + (i - 1) * trows];
+        }
+    } else {
+        const long long TILE = N, ROWS = M;       // TILE_DIM, BLOCK_ROWS
+        long long I = (gi - 1) * TILE + i, J = (gj - 1) * TILE + j;
+        for (long long k = 0; k <= TILE - 1; k += ROWS)
+            tile[(i - 1) + (j + k - 1) * trows] = input[(I - 1) + (J + k - 1) * rows_in];
+        __syncthreads();
+        if (WHICH == 4) {
+            for (long long k = 0; k <= TILE - 1; k += ROWS)
+                output[(I - 1) + (J + k - 1) * rows_out] = tile[(i - 1) + (j + k - 1) * trows];
+        } else {
+            I = (gj - 1) * TILE + i;   // transpose block offsets
+            J = (gi - 1) * TILE + j;
+            for (long long k = 0; k <= TILE - 1; k += ROWS)
+                output[(I - 1) + (J + k - 1) * rows_out] = tile[(j + k - 1) + (i - 1) * trows];
+        }
+    }
+}
+template <typename T>
+static int launch_performance(const KaCtx &c, int which, T *out, const T *in, long long rows_out, long long rows_in,
+                              long long bank, long long groups, long long items, cudaStream_t st) {
+    size_t smem = 0;
+    if (which >= 2) smem = (size_t)(c.wgs[0] + bank) * (size_t)(which >= 4 ? c.wgs[0] : c.wgs[1]) * sizeof(T);
+    if (smem > 48 * 1024) return set_error(B200_ERR_LAUNCH_DIMS, "performance kernel: %zu bytes of @localmem", smem);
+#define B200_PERF_CASE(W)                                                                                          \
+    case W: performance_twin_kernel<T, W><<<(unsigned)groups, (unsigned)items, smem, st>>>(c, out, in, rows_out,    \
+                                                                                           rows_in, bank); break;
+    switch (which) {
+        B200_PERF_CASE(0) B200_PERF_CASE(1) B200_PERF_CASE(2) B200_PERF_CASE(3) B200_PERF_CASE(4) B200_PERF_CASE(5)
+        default: return set_error(B200_ERR_INVALID_VALUE, "performance kernel: variant %d", which);
+    }
+#undef B200_PERF_CASE
+    B200_CHECK_LAUNCH("performance_twin_kernel");
+    return B200_OK;
+}
+int twin_performance(const KaCtx &c, int which, void *out, const void *in, long long rows_out, long long rows_in,
+                     long long bank, int elsize, cudaStream_t st) {
+    KA_LAUNCH_1D(c, groups, items);
+    if (elsize == 4)
+        return launch_performance<uint32_t>(c, which, (uint32_t *)out, (const uint32_t *)in, rows_out, rows_in, bank, groups, items, st);
+    if (elsize == 8)
+        return launch_performance<uint64_t>(c, which, (uint64_t *)out, (const uint64_t *)in, rows_out, rows_in, bank, groups, items, st);
+    return set_error(B200_ERR_UNSUPPORTED, "performance kernel: element size %d", elsize);
+}
+
 // ==================================================================================================
 // KI twins: true <=3-D launches, no implicit bounds check (src/intrinsics.jl:300-373, pocl/backend.jl:156-205)
 // ==================================================================================================

@@ -36,6 +36,8 @@ int twin_index_cartesian(const KaCtx &c, int which, long long *A, int ndimA, con
 int twin_kernel_val(const KaCtx &c, long long *a, long long m, cudaStream_t st);
 int twin_kernel_empty(const KaCtx &c, cudaStream_t st);
 int twin_saxpy(const KaCtx &c, void *Z, double a, const void *X, const void *Y, int is_f64, cudaStream_t st);
+int twin_performance(const KaCtx &c, int which, void *out, const void *in, long long rows_out, long long rows_in,
+                     long long bank, int elsize, cudaStream_t st);
 // literal twins (KI launches)
 int twin_histogram(int32_t *out, long long N, const int32_t *input, long long len, long long gs, long long groups,
                    cudaStream_t st);

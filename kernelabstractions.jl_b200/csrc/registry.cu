@@ -238,6 +238,56 @@ static int h_saxpy(const Launch &L) {
     return twin_saxpy(L.ctx, Z.ptr, L.args[1].fscalar, X.ptr, Y.ptr, Z.eltype == B200_T_F64, L.st);
 }
 
+// examples/performance.jl:17-138.  The launch describes a rectangle of `output`/`input`; when the arrays are dense
+// over that rectangle the tuned copy / transpose kernels do the work, otherwise (and with registry.force_twins) the
+// literal twin with the script's own @localmem tile runs.
+template <int WHICH>
+static int h_performance(const Launch &L) {
+    REQUIRE((L.nargs == 2 || L.nargs == 3) && is_array(L.args[0]) && is_array(L.args[1]) &&
+                (L.nargs == 2 || is_value(L.args[2])),
+            "performance.jl kernel(output, input[, Val(BANK)])");
+    const b200_arg &o = L.args[0], &in = L.args[1];
+    REQUIRE(L.ctx.ndim == 2, "performance.jl kernels need a 2-d ndrange (got %d-d)", L.ctx.ndim);
+    REQUIRE(o.elsize == in.elsize && (o.elsize == 4 || o.elsize == 8), "performance.jl kernels: 4- or 8-byte elements of one type");
+    const long long bank = (WHICH >= 2 && L.nargs == 3) ? L.args[2].scalar : 1;   // ::Val{BANK} = Val(1)
+    REQUIRE(bank >= 0 && bank <= 32, "performance.jl kernels: Val(BANK) = %lld", bank);
+    const bool transposing = (WHICH & 1) != 0;
+    const long long N = L.ctx.wgs[0], M = L.ctx.wgs[1];
+    long long r0, r1;   // rectangle of `input` the launch touches: rows 1..r0, columns 1..r1
+    if (WHICH <= 1) {
+        r0 = L.ctx.ndrange[0];
+        r1 = L.ctx.ndrange[1];
+    } else if (WHICH <= 3) {   // unsafe_indices: whole groups run
+        r0 = L.ctx.blocks[0] * N;
+        r1 = L.ctx.blocks[1] * M;
+        if (WHICH == 3) REQUIRE(N <= M && M <= N + bank, "lmem_transpose_kernel!: tile[j, i] needs groupsize (%lld,%lld) square", N, M);
+    } else {                   // (TILE_DIM, BLOCK_ROWS) groups cover TILE_DIM x TILE_DIM tiles
+        REQUIRE(M >= 1 && M <= N, "coalesced kernels: groupsize (TILE_DIM, BLOCK_ROWS) with BLOCK_ROWS <= TILE_DIM");
+        REQUIRE(N % M == 0, "coalesced kernels: TILE_DIM %% BLOCK_ROWS != 0 would index the tile out of bounds");
+        r0 = L.ctx.blocks[0] * N;
+        r1 = L.ctx.blocks[1] * N;
+    }
+    if (r0 == 0 || r1 == 0) return B200_OK;
+    REQUIRE(r0 <= dim(in, 0) && r1 <= dim(in, 1), "performance.jl kernel: launch reaches (%lld,%lld) beyond size(input)=(%lld,%lld)",
+            r0, r1, dim(in, 0), dim(in, 1));
+    if (transposing)
+        REQUIRE(r1 <= dim(o, 0) && r0 <= dim(o, 1), "performance.jl kernel: launch reaches (%lld,%lld) beyond size(output)=(%lld,%lld)",
+                r1, r0, dim(o, 0), dim(o, 1));
+    else
+        REQUIRE(r0 <= dim(o, 0) && r1 <= dim(o, 1), "performance.jl kernel: launch reaches (%lld,%lld) beyond size(output)=(%lld,%lld)",
+                r0, r1, dim(o, 0), dim(o, 1));
+    if (!force_twins()) {
+        if (transposing)   // output[J, I] = input[I, J]:  a = output (r1 x r0), b = input (r0 x r1)
+            return transpose_launch(o.ptr, in.ptr, r1, r0, dim(o, 0), dim(in, 0), o.elsize, L.st);
+        if (r0 == dim(o, 0) && r0 == dim(in, 0)) {   // whole columns: one contiguous run
+            const size_t bytes = (size_t)r0 * (size_t)r1 * (size_t)o.elsize;
+            const char *d = (const char *)o.ptr, *s = (const char *)in.ptr;
+            if (!(d < s + bytes && s < d + bytes)) return copy_bytes(o.ptr, in.ptr, bytes, L.st);
+        }
+    }
+    return twin_performance(L.ctx, WHICH, o.ptr, in.ptr, dim(o, 0), dim(in, 0), bank, o.elsize, L.st);
+}
+
 // ---- KI kernels ----------------------------------------------------------------------------------
 static int h_histogram(const Launch &L) {
     REQUIRE(L.nargs == 3 && is_array(L.args[0]) && is_array(L.args[1]) && is_value(L.args[2]),
@@ -328,6 +378,12 @@ static const Entry kTable[] = {
     {"gpu_kernel_empty", B200_LAUNCH_KA, h_kernel_empty},           // test/test.jl:226-228
     {"gpu_saxpy_kernel!", B200_LAUNCH_KA, h_saxpy},                 // benchmark/benchmarks.jl:29-32
     {"gpu_saxpy_kernel", B200_LAUNCH_KA, h_saxpy},                  // examples/numa_aware.jl:10-13
+    {"gpu_simple_copy_kernel!", B200_LAUNCH_KA, h_performance<0>},            // examples/performance.jl:17-20
+    {"gpu_simple_transpose_kernel!", B200_LAUNCH_KA, h_performance<1>},       // examples/performance.jl:22-25
+    {"gpu_lmem_copy_kernel!", B200_LAUNCH_KA, h_performance<2>},              // examples/performance.jl:29-46
+    {"gpu_lmem_transpose_kernel!", B200_LAUNCH_KA, h_performance<3>},         // examples/performance.jl:48-76
+    {"gpu_coalesced_copy_kernel!", B200_LAUNCH_KA, h_performance<4>},         // examples/performance.jl:80-106
+    {"gpu_coalesced_transpose_kernel!", B200_LAUNCH_KA, h_performance<5>},    // examples/performance.jl:108-138
     // KI.@kernel launches: name = function name
     {"histogram_kernel!", B200_LAUNCH_KI, h_histogram},             // examples/histogram.jl:18-58
     {"coalesced_matmul_kernel!", B200_LAUNCH_KI, h_coalesced_matmul}, // examples/performant_matmul.jl:15-77

@@ -240,6 +240,93 @@ void orc_matmul_naive_f64(const ka_ctx *c, double *out, const double *a, const d
         }
 }
 
+/* ---- examples/performance.jl:17-138: six copy/transpose variants ----------------------------------------
+ * which: 0 simple_copy (:17-20)        output[I,J] = input[I,J]               (bounds-checked lanes)
+ *        1 simple_transpose (:22-25)   output[J,I] = input[I,J]
+ *        2 lmem_copy (:29-46)          unsafe_indices: tile[i,j] = input[I,J]; @synchronize; output[I,J] = tile[i,j]
+ *        3 lmem_transpose (:48-76)     tile[i,j] = input[I,J]; @synchronize; pivot group; output[I',J'] = tile[j,i]
+ *        4 coalesced_copy (:80-106)    groupsize (TILE_DIM, BLOCK_ROWS), TILE_DIM/BLOCK_ROWS elements per lane
+ *        5 coalesced_transpose (:108-138)
+ * tile is (N + BANK, M) resp. (TILE_DIM + BANK, TILE_DIM), column-major.  4-byte elements (const T = Float32, :9).
+ * rows_out = size(output,1), rows_in = size(input,1).  The unsafe_indices kernels have no lane guard (macros.jl:72-76):
+ * the caller guarantees the launch stays inside the arrays, as the script does (N = 2048 divisible by the tiles). */
+void orc_performance_kernel(const ka_ctx *c, int which, uint32_t *output, const uint32_t *input, Int rows_out,
+                            Int rows_in, Int bank) {
+    Int G = ka_num_groups(c), L = ka_group_items(c);
+    const Int N = c->wgs[0], M = c->wgs[1];
+    if (which <= 1) {
+#pragma omp parallel for schedule(static)
+        for (Int g = 1; g <= G; ++g)
+            for (Int l = 1; l <= L; ++l) {
+                if (!ka_validindex(c, g, l)) continue;
+                Int I[KA_MAX_NDIM];
+                ka_expand(c, g, l, I);
+                if (which == 0)
+                    output[(I[0] - 1) + (I[1] - 1) * rows_out] = input[(I[0] - 1) + (I[1] - 1) * rows_in];
+                else
+                    output[(I[1] - 1) + (I[0] - 1) * rows_out] = input[(I[0] - 1) + (I[1] - 1) * rows_in];
+            }
+        return;
+    }
+    const Int trows = N + bank;                          /* tile leading dimension */
+    const Int tcols = (which >= 4) ? N : M;              /* coalesced: (TILE_DIM + BANK, TILE_DIM) */
+#pragma omp parallel for schedule(static)
+    for (Int g = 1; g <= G; ++g) {
+        uint32_t *tile = (uint32_t *)calloc((size_t)(trows * tcols), sizeof(uint32_t));
+        Int gI[KA_MAX_NDIM];
+        ka_group_cartesian(c, g, gI);
+        const Int gi = gI[0], gj = gI[1];
+        if (which == 2 || which == 3) {
+            for (Int l = 1; l <= L; ++l) {
+                Int lI[KA_MAX_NDIM];
+                ka_local_cartesian(c, l, lI);
+                const Int i = lI[0], j = lI[1];
+                const Int I = (gi - 1) * N + i, J = (gj - 1) * M + j;
+                tile[(i - 1) + (j - 1) * trows] = input[(I - 1) + (J - 1) * rows_in];
+            }
+            /* @synchronize */
+            for (Int l = 1; l <= L; ++l) {
+                Int lI[KA_MAX_NDIM];
+                ka_local_cartesian(c, l, lI);
+                const Int i = lI[0], j = lI[1];
+                if (which == 2) {
+                    const Int I = (gi - 1) * N + i, J = (gj - 1) * M + j;
+                    output[(I - 1) + (J - 1) * rows_out] = tile[(i - 1) + (j - 1) * trows];
+                } else {
+                    const Int I = (gj - 1) * M + i, J = (gi - 1) * N + j;   /* pivoted group index */
+                    output[(I - 1) + (J - 1) * rows_out] = tile[(j - 1) + (i - 1) * trows];
+                }
+            }
+        } else {
+            const Int TILE = N, ROWS = M;
+            for (Int l = 1; l <= L; ++l) {
+                Int lI[KA_MAX_NDIM];
+                ka_local_cartesian(c, l, lI);
+                const Int i = lI[0], j = lI[1];
+                const Int I = (gi - 1) * TILE + i, J = (gj - 1) * TILE + j;
+                for (Int k = 0; k <= TILE - 1; k += ROWS)
+                    tile[(i - 1) + (j + k - 1) * trows] = input[(I - 1) + (J + k - 1) * rows_in];
+            }
+            /* @synchronize */
+            for (Int l = 1; l <= L; ++l) {
+                Int lI[KA_MAX_NDIM];
+                ka_local_cartesian(c, l, lI);
+                const Int i = lI[0], j = lI[1];
+                if (which == 4) {
+                    const Int I = (gi - 1) * TILE + i, J = (gj - 1) * TILE + j;
+                    for (Int k = 0; k <= TILE - 1; k += ROWS)
+                        output[(I - 1) + (J + k - 1) * rows_out] = tile[(i - 1) + (j + k - 1) * trows];
+                } else {
+                    const Int I = (gj - 1) * TILE + i, J = (gi - 1) * TILE + j;   /* transposed block offsets */
+                    for (Int k = 0; k <= TILE - 1; k += ROWS)
+                        output[(I - 1) + (J + k - 1) * rows_out] = tile[(j + k - 1) + (i - 1) * trows];
+                }
+            }
+        }
+        free(tile);
+    }
+}
+
 /* ---- test/localmem.jl:4-65 (lowering: SURVEY.md Appendix A) -------------------------------- */
 /* variant 0 localmem, 1 localmem2, 2 localmem_unsafe_indices, 3 many_localmem; A::Int64[lenA] */
 void orc_localmem(const ka_ctx *c, int variant, Int *A, Int lenA) {

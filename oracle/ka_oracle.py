@@ -191,6 +191,19 @@ def matmul_naive(out: np.ndarray, a: np.ndarray, b: np.ndarray, workgroupsize=No
     f(C.byref(ctx), _p(_F(out)), _p(_F(a)), _p(_F(b)), C.c_int64(a.shape[0]), C.c_int64(a.shape[1]))
 
 
+PERF_KERNELS = ("simple_copy", "simple_transpose", "lmem_copy", "lmem_transpose", "coalesced_copy", "coalesced_transpose")
+
+
+def performance_kernel(which, output: np.ndarray, input: np.ndarray, ndrange, workgroupsize, bank: int = 1) -> None:
+    """reference examples/performance.jl:17-138; `which` is an index into PERF_KERNELS or one of its names.
+    4-byte elements; kernels 2-5 are unsafe_indices kernels (launch must stay inside the arrays)."""
+    which = PERF_KERNELS.index(which) if isinstance(which, str) else int(which)
+    assert output.dtype.itemsize == 4 and input.dtype.itemsize == 4
+    ctx = make_ctx(ndrange, workgroupsize)
+    lib().orc_performance_kernel(C.byref(ctx), C.c_int(which), _p(_F(output)), _p(_F(input)), C.c_int64(output.shape[0]),
+                                 C.c_int64(input.shape[0]), C.c_int64(bank))
+
+
 def localmem(variant: int, A: np.ndarray, ndrange, workgroupsize) -> None:
     """reference test/localmem.jl:4-65; variant 0 localmem, 1 localmem2, 2 unsafe_indices, 3 many_localmem"""
     ctx = make_ctx(ndrange, workgroupsize)

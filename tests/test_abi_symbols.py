@@ -61,7 +61,9 @@ def test_registry_lists_the_catalogue():
               "gpu_matmul_kernel!", "histogram_kernel!", "coalesced_matmul_kernel!", "gpu_localmem", "gpu_localmem2",
               "gpu_localmem_unsafe_indices", "gpu_many_localmem", "gpu_stmt_form", "gpu_typetest", "gpu_private",
               "gpu_forloop", "gpu_reduce_private", "gpu_kernel_unroll!", "gpu_kernel_unroll2!",
-              "test_intrinsics_kernel", "launch_kernel1d", "launch_kernel2d", "launch_kernel3d"]:
+              "test_intrinsics_kernel", "launch_kernel1d", "launch_kernel2d", "launch_kernel3d",
+              "gpu_simple_copy_kernel!", "gpu_simple_transpose_kernel!", "gpu_lmem_copy_kernel!",
+              "gpu_lmem_transpose_kernel!", "gpu_coalesced_copy_kernel!", "gpu_coalesced_transpose_kernel!"]:
         assert k in names
 
 

@@ -441,3 +441,74 @@ def test_histogram_host_pipeline_matches_oracle(orc, n, slab_mib):
         assert np.array_equal(bins, want)
     finally:
         tune(hostpipe__slab_mib=32)
+
+
+# =====================================================================================================
+# examples/performance.jl: six copy/transpose variants x the script's launch shapes, tuned route and literal twins
+# =====================================================================================================
+@pytest.mark.parametrize("force_twins", [0, 1])
+@pytest.mark.parametrize("N", [256, 2048])
+def test_performance_jl_variants_match_oracle(orc, force_twins, N):
+    if N == 2048 and force_twins:
+        N = 512   # the literal twins are slow by construction; the script's own size is covered by the tuned route
+    tune(registry__force_twins=force_twins)
+    inp = np.asfortranarray(orc.gen_uniform_f32((N, N), 77))
+    d_in = KA.to_device(inp)
+    labels = []
+    shapes = {"Simple": None}
+    for label, launch in EX.performance_variants(be, N=N):
+        out = KA.allocate(be, np.float32, N, N).fill_(-1.0)
+        launch(out, d_in)
+        KA.synchronize(be)
+        which = ("simple_" if label.startswith("Simple") else "lmem_" if "multiple" not in label else "coalesced_") + \
+                ("transpose" if "transpose" in label else "copy")
+        if label.startswith("Simple"):
+            wg = eval(label.split(" ", 2)[2])
+            nd, bank = (N, N), 1
+        elif "multiple" in label:
+            wg, nd, bank = (32, 8), (N, N // 4), int("bank=True" in label)
+        else:
+            wg, nd, bank = (32, 32), (N, N), int("bank=True" in label)
+        ref = np.full((N, N), -1.0, dtype=np.float32, order="F")
+        orc.performance_kernel(which, ref, inp, nd, wg, bank)
+        assert np.array_equal(KA.Array(out), ref), label
+        assert np.array_equal(ref, inp.T if "transpose" in label else inp), label
+        labels.append(label)
+    assert len(labels) == 14
+
+
+@pytest.mark.parametrize("force_twins", [0, 1])
+def test_performance_jl_partial_and_rectangular(orc, force_twins):
+    """ndrange smaller than the arrays / non-square input: only the launched rectangle may be written."""
+    tune(registry__force_twins=force_twins)
+    inp = np.asfortranarray(orc.gen_uniform_f32((160, 96), 5))
+    d_in = KA.to_device(inp)
+    # bounds-checked kernels with a ragged ndrange
+    for name, ctor, oshape in (("simple_copy", K.simple_copy_kernel_, (160, 96)), ("simple_transpose", K.simple_transpose_kernel_, (96, 160))):
+        out = KA.allocate(be, np.float32, *oshape).fill_(-2.0)
+        ctor(be, (32, 8))(out, d_in, ndrange=(100, 50))
+        KA.synchronize(be)
+        ref = np.full(oshape, -2.0, dtype=np.float32, order="F")
+        orc.performance_kernel(name, ref, inp, (100, 50), (32, 8), 1)
+        assert np.array_equal(KA.Array(out), ref), name
+    # unsafe_indices kernels on a sub-rectangle of whole groups
+    for name, ctor, wg, nd, oshape in (("lmem_copy", K.lmem_copy_kernel_, (32, 32), (64, 96), (160, 96)),
+                                       ("lmem_transpose", K.lmem_transpose_kernel_, (16, 16), (160, 48), (96, 160)),
+                                       ("coalesced_copy", K.coalesced_copy_kernel_, (32, 8), (128, 16), (160, 96)),
+                                       ("coalesced_transpose", K.coalesced_transpose_kernel_, (32, 4), (160, 12), (96, 160))):
+        for bank in (0, 1):
+            out = KA.allocate(be, np.float32, *oshape).fill_(-3.0)
+            ctor(be, wg)(out, d_in, Val(bank), ndrange=nd)
+            KA.synchronize(be)
+            ref = np.full(oshape, -3.0, dtype=np.float32, order="F")
+            orc.performance_kernel(name, ref, inp, nd, wg, bank)
+            assert np.array_equal(KA.Array(out), ref), (name, bank)
+
+
+def test_performance_jl_out_of_bounds_launch_is_rejected():
+    d_in = KA.zeros(be, np.float32, 64, 64)
+    out = KA.zeros(be, np.float32, 64, 64)
+    with pytest.raises(_lib.B200Error):
+        K.lmem_copy_kernel_(be, (32, 32))(out, d_in, ndrange=(96, 64))     # third group row would read past the array
+    with pytest.raises(_lib.B200Error):
+        K.lmem_transpose_kernel_(be, (32, 8))(out, d_in, Val(1), ndrange=(64, 64))   # tile[j, i] needs a square group

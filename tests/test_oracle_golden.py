@@ -192,6 +192,29 @@ def test_naive_transpose_rect_and_ragged(orc):
 
 
 # ---- examples/histogram.jl:74-100 -----------------------------------------------------------------------------
+@pytest.mark.parametrize("which,wg,div", [("simple_copy", (32, 32), 1), ("simple_transpose", (32, 32), 1), ("simple_copy", (1024, 1), 1),
+                                          ("simple_transpose", (1, 1024), 1), ("lmem_copy", (32, 32), 1), ("lmem_transpose", (32, 32), 1),
+                                          ("coalesced_copy", (32, 8), 4), ("coalesced_transpose", (32, 8), 4)])
+@pytest.mark.parametrize("bank", [0, 1])
+def test_performance_jl_kernels(orc, which, wg, div, bank):
+    """examples/performance.jl:17-205: every variant, at the script's launch shapes, is a copy resp. a transpose."""
+    N = 256
+    inp = np.asfortranarray(orc.gen_uniform_f32((N, N), 3))
+    out = np.full((N, N), -1.0, dtype=np.float32, order="F")
+    orc.performance_kernel(which, out, inp, (N, N // div), wg, bank)
+    assert np.array_equal(out, inp.T if "transpose" in which else inp)
+
+
+def test_performance_jl_ragged_simple(orc):
+    """The bounds-checked variants honour a ragged ndrange (lanes outside it are masked by __validindex)."""
+    inp = np.asfortranarray(orc.gen_uniform_f32((70, 50), 4))
+    out = np.full((50, 70), -1.0, dtype=np.float32, order="F")
+    orc.performance_kernel("simple_transpose", out, inp, (33, 21), (32, 8), 1)
+    want = np.full((50, 70), -1.0, dtype=np.float32, order="F")
+    want[:21, :33] = inp[:33, :21].T
+    assert np.array_equal(out, want)
+
+
 def test_histogram_examples(orc):
     rng = np.random.default_rng(1236)
     rand_input = rng.integers(1, 129, size=1000).astype(np.int32)

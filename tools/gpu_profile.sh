@@ -14,7 +14,7 @@ $P tools/run_one.py sgemm 8192 0 20
 $P tools/run_one.py sgemm 8192 1 20
 $P tools/run_one.py cublas_sgemm 8192 0 20
 $P tools/run_one.py tcgemm 8192 0 50
-run_ncu sgemm sgemm128 sgemm 4096 0 3
+run_ncu sgemm sgemm_tma sgemm 4096 0 3
 run_ncu transpose transpose64 transpose 16384 0 3
 run_ncu hist hist_atomic hist 1073741824 0 3
 run_ncu copy copy_bulk copy 67108864 0 3
