@@ -366,6 +366,30 @@ def run_suite(KA, _lib, EX, mg, orc, be, rank, world, dist, timed, peaks, steps,
     except Exception as ex:
         out["copy_2^26_f32"] = {"error": str(ex)[:300]}
 
+    # ---- SAXPY 2^26 F32 (benchmark/benchmarks.jl:29-70 kernel at a size beyond L2): 12 bytes per element ----
+    try:
+        n = N_COPY
+        from b200ka import kernels as Kc
+        X = [KA.to_device(orc.gen_uniform_f32((n,), 1300 + i)) for i in range(2)]
+        Y = [KA.to_device(orc.gen_uniform_f32((n,), 1310 + i)) for i in range(2)]
+        Z = [KA.zeros(be, np.float32, n) for _ in range(2)]
+        kern = Kc.saxpy_kernel_(be, 1024)
+        state = {"i": 0}
+
+        def step_saxpy():
+            i = state["i"] & 1
+            kern(Z[i], np.float32(2.0), X[i], Y[i], ndrange=Z[i].shape)
+            state["i"] += 1
+
+        ms, launches = timed(step_saxpy, steps, warmup)
+        gbs = 3 * 4 * n / (ms * 1e-3) / 1e9
+        out["saxpy_2^26_f32"] = {"value": world * gbs, "unit": "GB/s", "ms_per_step": ms, "gpu_launches": launches,
+                                 "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm"], "frac": gbs / peaks["hbm"],
+                                              "traffic": None}, "scaling": "weak"}
+        del X, Y, Z
+    except Exception as ex:
+        out["saxpy_2^26_f32"] = {"error": str(ex)[:300]}
+
     # ---- histogram 2^30 Int32 -> 256 bins, input slab per rank, one all-reduce of the bins (strong scaling) ----
     try:
         n = N_HIST

@@ -182,6 +182,11 @@ b200_status b200_transpose(void *a, const void *b, int64_t m, int64_t n, int64_t
  * (examples/histogram.jl:18-58).  Accumulates into `bins` like the reference's atomic +=. */
 b200_status b200_histogram_i32(int32_t *bins, int64_t nbins, const int32_t *input, int64_t n);
 
+/* saxpy_kernel! / saxpy_kernel: Z[I] = a * X[I] + Y[I], product and sum rounded separately like the reference's
+ * unfused Julia expression (benchmark/benchmarks.jl:29-32; examples/numa_aware.jl:10-13 is the in-place form Z == Y).
+ * n elements of Float32 (is_f64 == 0) or Float64; Z may alias Y but not X (-> B200_ERR_ALIAS). */
+b200_status b200_saxpy(void *Z, double a, const void *X, const void *Y, size_t n, int32_t is_f64);
+
 /* matmul_kernel! / coalesced_matmul_kernel!: C(MxN) = A(MxK) * B(KxN), column-major
  * (examples/matmul.jl:5-15, examples/performant_matmul.jl:15-77).
  * mode 0: FP32 SIMT, summation order of the reference tiled kernel (16-wide k partials, k ascending,

@@ -101,6 +101,29 @@ def performance_variants(backend, N: int = 2048, T=np.float32, TILE_DIM: int = 3
                    (lambda o, i, k=k, bank=bank, bf=block_factor: k(o, i, Val(int(bank)), ndrange=(o.shape[0], o.shape[1] // bf))))
 
 
+def measure_membw(backend, N: int = 1024 * 500_000, dtype=np.float32, evals: int = 2, samples: int = 10, X=None, Y=None):
+    """reference examples/numa_aware.jl:21-56: time the in-place SAXPY `Y = a*X + Y`, return (GB/s, GFLOP/s)."""
+    import time
+    from .backend import synchronize, to_device
+    nbytes = 3 * np.dtype(dtype).itemsize * N
+    flops = 2 * N
+    a = np.dtype(dtype).type(3.1415)
+    if X is None:
+        rng = np.random.default_rng(0)
+        X = to_device(rng.random(N, dtype=dtype))
+        Y = to_device(rng.random(N, dtype=dtype))
+    best = float("inf")
+    for _ in range(samples):
+        synchronize(backend)
+        t0 = time.perf_counter()
+        for _ in range(evals):
+            kernel = kernels.saxpy_kernel(backend, 1024, Y.shape)
+            kernel(a, X, Y, ndrange=Y.shape)
+            synchronize(backend)
+        best = min(best, (time.perf_counter() - t0) / evals)
+    return nbytes * 1.0e-9 / best, flops * 1.0e-9 / best
+
+
 def matmul_bf16_(C_: B200Array, A: B200Array, B: B200Array, workspace: B200Array = None) -> None:
     """Opt-in tensor-core path (no reference twin): FP32 in/out, BF16 tcgen05 arithmetic."""
     M, K = A.shape

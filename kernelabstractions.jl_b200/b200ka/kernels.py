@@ -11,6 +11,7 @@ copy_kernel_ = KernelFunction("copy_kernel!")                    # examples/memc
 naive_transpose_kernel_ = KernelFunction("naive_transpose_kernel!")  # examples/naive_transpose.jl:4-7
 matmul_kernel_ = KernelFunction("matmul_kernel!")                # examples/matmul.jl:5-15
 saxpy_kernel_ = KernelFunction("saxpy_kernel!")                  # benchmark/benchmarks.jl:29-32
+saxpy_kernel = KernelFunction("saxpy_kernel")                    # examples/numa_aware.jl:10-13 (a, X, Y) in place
 # examples/performance.jl:17-138
 simple_copy_kernel_ = KernelFunction("simple_copy_kernel!")
 simple_transpose_kernel_ = KernelFunction("simple_transpose_kernel!")
@@ -42,3 +43,7 @@ index_cartesian_group = KernelFunction("index_cartesian_group")
 constarg = KernelFunction("constarg")
 kernel_val_ = KernelFunction("kernel_val!")
 kernel_empty = KernelFunction("kernel_empty")
+context_kernel = KernelFunction("context_kernel")                        # test/test.jl:275-282
+gpu_return_kernel_ = KernelFunction("gpu_return_kernel!")                # test/test.jl:307-313
+unaliased_accumulate_ = KernelFunction("unaliased_accumulate!")          # test/test.jl:339-345
+unaliased_accumulate_local_ = KernelFunction("unaliased_accumulate_local!")  # test/test.jl:347-356

@@ -349,6 +349,60 @@ int twin_kernel_empty(const KaCtx &c, cudaStream_t st) {
     return B200_OK;
 }
 
+// ---- test/test.jl:275-321 context_kernel / gpu_return_kernel!, :339-385 unaliased_accumulate(_local)! ----
+// which 0: context_kernel      f(@context, a): a[@index(Global, Linear)] = 1
+//       1: gpu_return_kernel!  if i <= length(x) / 2 { x[i] = 1; return }
+__global__ void misc_i64_twin_kernel(KaCtx c, int which, long long *__restrict__ a, long long len) {
+    if (ka_valid(c)) {
+        const long long I = ka_global_linear();
+        if (which == 0) {
+            a[I - 1] = 1;
+        } else if (I <= len / 2) {
+            a[I - 1] = 1;
+            return;
+        }
+    }
+}
+int twin_misc_i64(const KaCtx &c, int which, long long *a, long long len, cudaStream_t st) {
+    KA_LAUNCH_1D(c, groups, items);
+    misc_i64_twin_kernel<<<(unsigned)groups, (unsigned)items, 0, st>>>(c, which, a, len);
+    B200_CHECK_LAUNCH("misc_i64_twin_kernel");
+    return B200_OK;
+}
+// LOCAL == false: output[i, j] += input[i, k] for k in j:n (read-modify-write of global memory every step);
+// LOCAL == true : sum_val = zero(T); sum_val += input[i, k]; output[i, j] = sum_val.  Plain adds, k ascending.
+template <typename T, bool LOCAL>
+__global__ void unaliased_accumulate_twin_kernel(KaCtx c, T *output, const T *input, long long n, long long rows_out,
+                                                 long long rows_in) {
+    if (ka_valid(c)) {
+        long long I[KA_MAX_NDIM];
+        ka_expand(c, I);
+        const long long i = I[0], j = I[1];
+        if (LOCAL) {
+            T sum_val = (T)0;
+            for (long long k = j; k <= n; ++k) sum_val = add_rn(sum_val, input[(i - 1) + (k - 1) * rows_in]);
+            output[(i - 1) + (j - 1) * rows_out] = sum_val;
+        } else {
+            volatile T *o = output + (i - 1) + (j - 1) * rows_out;
+            for (long long k = j; k <= n; ++k) *o = add_rn(*o, input[(i - 1) + (k - 1) * rows_in]);
+        }
+    }
+}
+int twin_unaliased_accumulate(const KaCtx &c, int local, void *output, const void *input, long long n,
+                              long long rows_out, long long rows_in, int is_f64, cudaStream_t st) {
+    KA_LAUNCH_1D(c, groups, items);
+    const unsigned g = (unsigned)groups, t = (unsigned)items;
+    if (is_f64) {
+        if (local) unaliased_accumulate_twin_kernel<double, true><<<g, t, 0, st>>>(c, (double *)output, (const double *)input, n, rows_out, rows_in);
+        else unaliased_accumulate_twin_kernel<double, false><<<g, t, 0, st>>>(c, (double *)output, (const double *)input, n, rows_out, rows_in);
+    } else {
+        if (local) unaliased_accumulate_twin_kernel<float, true><<<g, t, 0, st>>>(c, (float *)output, (const float *)input, n, rows_out, rows_in);
+        else unaliased_accumulate_twin_kernel<float, false><<<g, t, 0, st>>>(c, (float *)output, (const float *)input, n, rows_out, rows_in);
+    }
+    B200_CHECK_LAUNCH("unaliased_accumulate_twin_kernel");
+    return B200_OK;
+}
+
 // ---- saxpy_kernel!  (benchmark/benchmarks.jl:29-32, examples/numa_aware.jl:10-13): Z = a*X + Y, unfused ----
 template <typename T>
 __global__ void saxpy_twin_kernel(KaCtx c, T *__restrict__ Z, T a, const T *__restrict__ X, const T *__restrict__ Y) {

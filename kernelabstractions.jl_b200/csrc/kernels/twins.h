@@ -15,6 +15,7 @@ int transpose_launch(void *a, const void *b, int64_t m, int64_t n, int64_t lda, 
 int histogram_launch(int32_t *bins, int64_t nbins, const int32_t *input, int64_t n, cudaStream_t st);
 int sgemm_launch(float *C, const float *A, const float *B, int64_t M, int64_t K, int64_t N, int64_t lda, int64_t ldb,
                  int64_t ldc, int mode, cudaStream_t st);
+int saxpy_launch(void *Z, double a, const void *X, const void *Y, size_t n, int is_f64, cudaStream_t st);
 // literal twins (KA launches)
 int twin_copy(const KaCtx &c, void *A, const void *B, int elsize, cudaStream_t st);
 int twin_init(const KaCtx &c, void *arr, const void *value, int elsize, cudaStream_t st);
@@ -36,6 +37,9 @@ int twin_index_cartesian(const KaCtx &c, int which, long long *A, int ndimA, con
 int twin_kernel_val(const KaCtx &c, long long *a, long long m, cudaStream_t st);
 int twin_kernel_empty(const KaCtx &c, cudaStream_t st);
 int twin_saxpy(const KaCtx &c, void *Z, double a, const void *X, const void *Y, int is_f64, cudaStream_t st);
+int twin_misc_i64(const KaCtx &c, int which, long long *a, long long len, cudaStream_t st);
+int twin_unaliased_accumulate(const KaCtx &c, int local, void *output, const void *input, long long n,
+                              long long rows_out, long long rows_in, int is_f64, cudaStream_t st);
 int twin_performance(const KaCtx &c, int which, void *out, const void *in, long long rows_out, long long rows_in,
                      long long bank, int elsize, cudaStream_t st);
 // literal twins (KI launches)

@@ -228,14 +228,45 @@ static int h_kernel_val(const Launch &L) {
 }
 static int h_kernel_empty(const Launch &L) { return twin_kernel_empty(L.ctx, L.st); }
 static int h_saxpy(const Launch &L) {
-    REQUIRE(L.nargs == 4 && is_array(L.args[0]) && is_value(L.args[1]) && is_array(L.args[2]) && is_array(L.args[3]),
-            "saxpy_kernel!(Z, a, X, Y)");
-    const b200_arg &Z = L.args[0], &X = L.args[2], &Y = L.args[3];
+    // saxpy_kernel!(Z, a, X, Y) (benchmark/benchmarks.jl:29-32) or saxpy_kernel(a, X, Y) with Y updated in place
+    // (examples/numa_aware.jl:10-13)
+    const bool inplace = L.nargs == 3;
+    REQUIRE((L.nargs == 4 && is_array(L.args[0]) && is_value(L.args[1]) && is_array(L.args[2]) && is_array(L.args[3])) ||
+                (inplace && is_value(L.args[0]) && is_array(L.args[1]) && is_array(L.args[2])),
+            "saxpy_kernel!(Z, a, X, Y) or saxpy_kernel(a, X, Y)");
+    const b200_arg &Z = inplace ? L.args[2] : L.args[0], &A = inplace ? L.args[0] : L.args[1];
+    const b200_arg &X = inplace ? L.args[1] : L.args[2], &Y = inplace ? L.args[2] : L.args[3];
     REQUIRE((Z.eltype == B200_T_F32 || Z.eltype == B200_T_F64) && X.eltype == Z.eltype && Y.eltype == Z.eltype,
             "saxpy_kernel!: Float32/Float64 arrays of one type");
     long long maxI = ka_max_global_linear(L.ctx);
     REQUIRE(maxI <= numel(Z) && maxI <= numel(X) && maxI <= numel(Y), "saxpy_kernel!: ndrange exceeds arrays");
-    return twin_saxpy(L.ctx, Z.ptr, L.args[1].fscalar, X.ptr, Y.ptr, Z.eltype == B200_T_F64, L.st);
+    if (maxI == 0) return B200_OK;
+    if (!force_twins() && ka_covers_linear_prefix(L.ctx)) {
+        const size_t n = (size_t)ka_ndrange_prod(L.ctx), bytes = n * Z.elsize;
+        const char *z = (const char *)Z.ptr, *x = (const char *)X.ptr;
+        if (!(z < x + bytes && x < z + bytes))
+            return saxpy_launch(Z.ptr, A.fscalar, X.ptr, Y.ptr, n, Z.eltype == B200_T_F64, L.st);
+    }
+    return twin_saxpy(L.ctx, Z.ptr, A.fscalar, X.ptr, Y.ptr, Z.eltype == B200_T_F64, L.st);
+}
+
+template <int WHICH>
+static int h_misc_i64(const Launch &L) {
+    REQUIRE(L.nargs == 1 && is_array(L.args[0]) && L.args[0].elsize == 8, "kernel(a::Array{Int64})");
+    REQUIRE(ka_max_global_linear(L.ctx) <= numel(L.args[0]), "kernel: ndrange exceeds length(a)");
+    return twin_misc_i64(L.ctx, WHICH, (long long *)L.args[0].ptr, numel(L.args[0]), L.st);
+}
+template <int LOCAL>
+static int h_unaliased_accumulate(const Launch &L) {
+    REQUIRE(L.nargs == 3 && is_array(L.args[0]) && is_array(L.args[1]) && is_value(L.args[2]),
+            "unaliased_accumulate!(output, input, n)");
+    const b200_arg &o = L.args[0], &in = L.args[1];
+    REQUIRE((o.eltype == B200_T_F32 || o.eltype == B200_T_F64) && in.eltype == o.eltype, "unaliased_accumulate!: Float32/Float64");
+    REQUIRE(L.ctx.ndim == 2, "unaliased_accumulate!: 2-d ndrange");
+    const long long n = L.args[2].scalar;
+    REQUIRE(L.ctx.ndrange[0] <= dim(o, 0) && L.ctx.ndrange[1] <= dim(o, 1) && L.ctx.ndrange[0] <= dim(in, 0) && n <= dim(in, 1),
+            "unaliased_accumulate!: ndrange / n exceed the arrays");
+    return twin_unaliased_accumulate(L.ctx, LOCAL, o.ptr, in.ptr, n, dim(o, 0), dim(in, 0), o.eltype == B200_T_F64, L.st);
 }
 
 // examples/performance.jl:17-138.  The launch describes a rectangle of `output`/`input`; when the arrays are dense
@@ -378,6 +409,10 @@ static const Entry kTable[] = {
     {"gpu_kernel_empty", B200_LAUNCH_KA, h_kernel_empty},           // test/test.jl:226-228
     {"gpu_saxpy_kernel!", B200_LAUNCH_KA, h_saxpy},                 // benchmark/benchmarks.jl:29-32
     {"gpu_saxpy_kernel", B200_LAUNCH_KA, h_saxpy},                  // examples/numa_aware.jl:10-13
+    {"gpu_context_kernel", B200_LAUNCH_KA, h_misc_i64<0>},                    // test/test.jl:275-290
+    {"gpu_gpu_return_kernel!", B200_LAUNCH_KA, h_misc_i64<1>},                // test/test.jl:307-321
+    {"gpu_unaliased_accumulate!", B200_LAUNCH_KA, h_unaliased_accumulate<0>}, // test/test.jl:339-345
+    {"gpu_unaliased_accumulate_local!", B200_LAUNCH_KA, h_unaliased_accumulate<1>}, // test/test.jl:347-356
     {"gpu_simple_copy_kernel!", B200_LAUNCH_KA, h_performance<0>},            // examples/performance.jl:17-20
     {"gpu_simple_transpose_kernel!", B200_LAUNCH_KA, h_performance<1>},       // examples/performance.jl:22-25
     {"gpu_lmem_copy_kernel!", B200_LAUNCH_KA, h_performance<2>},              // examples/performance.jl:29-46

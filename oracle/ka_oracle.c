@@ -506,6 +506,36 @@ void orc_kernel_val(const ka_ctx *c, Int *a, Int m) {
             if (ka_validindex(c, g, l)) a[global_linear(c, g, l) - 1] = m;
 }
 
+/* context_kernel (test/test.jl:275-282): a[I] = 1;  gpu_return_kernel! (:307-313): if i <= length(x) / 2: x[i] = 1 */
+void orc_misc_i64(const ka_ctx *c, int which, Int *a, Int len) {
+    Int G = ka_num_groups(c), W = ka_group_items(c);
+#pragma omp parallel for schedule(static)
+    for (Int g = 1; g <= G; ++g)
+        for (Int l = 1; l <= W; ++l) {
+            if (!ka_validindex(c, g, l)) continue;
+            Int I = global_linear(c, g, l);
+            if (which == 0 || I <= len / 2) a[I - 1] = 1;
+        }
+}
+
+/* unaliased_accumulate! / unaliased_accumulate_local! (test/test.jl:339-356): plain adds, k ascending from j to n.
+ * Both forms produce the same bits when output starts at zero(T) (0 + x == x exactly). */
+void orc_unaliased_accumulate_f32(const ka_ctx *c, int local, float *output, const float *input, Int n, Int rows_out,
+                                  Int rows_in) {
+    Int G = ka_num_groups(c), W = ka_group_items(c);
+#pragma omp parallel for schedule(static)
+    for (Int g = 1; g <= G; ++g)
+        for (Int l = 1; l <= W; ++l) {
+            if (!ka_validindex(c, g, l)) continue;
+            Int I[KA_MAX_NDIM];
+            ka_expand(c, g, l, I);
+            const Int i = I[0], j = I[1];
+            float acc = local ? 0.0f : output[(i - 1) + (j - 1) * rows_out];
+            for (Int k = j; k <= n; ++k) acc = acc + input[(i - 1) + (k - 1) * rows_in];
+            output[(i - 1) + (j - 1) * rows_out] = acc;
+        }
+}
+
 /* ==========================================================================================
  * KI.@kernel twins: raw <=3-D launches, ids 1-based, no implicit bounds check
  * (reference src/intrinsics.jl:19-103,300-373; src/pocl/backend.jl:156-205).
@@ -674,6 +704,18 @@ void orc_saxpy_f32(const ka_ctx *c, float *Z, float a, const float *X, const flo
             if (!ka_validindex(c, g, l)) continue;
             Int I = global_linear(c, g, l);
             float p = a * X[I - 1];
+            Z[I - 1] = p + Y[I - 1];
+        }
+}
+
+void orc_saxpy_f64(const ka_ctx *c, double *Z, double a, const double *X, const double *Y) {
+    Int G = ka_num_groups(c), W = ka_group_items(c);
+#pragma omp parallel for schedule(static)
+    for (Int g = 1; g <= G; ++g)
+        for (Int l = 1; l <= W; ++l) {
+            if (!ka_validindex(c, g, l)) continue;
+            Int I = global_linear(c, g, l);
+            double p = a * X[I - 1];
             Z[I - 1] = p + Y[I - 1];
         }
 }

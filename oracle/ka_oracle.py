@@ -258,10 +258,27 @@ def kernel_val(a: np.ndarray, m: int, ndrange, workgroupsize) -> None:
     lib().orc_kernel_val(C.byref(ctx), _p(a), C.c_int64(m))
 
 
+def misc_i64(which: int, a: np.ndarray, ndrange, workgroupsize) -> None:
+    """which 0: context_kernel (reference test/test.jl:275-282); 1: gpu_return_kernel! (:307-313)"""
+    ctx = make_ctx(ndrange, workgroupsize)
+    lib().orc_misc_i64(C.byref(ctx), C.c_int(which), _p(a), C.c_int64(a.size))
+
+
+def unaliased_accumulate(local: bool, output: np.ndarray, input: np.ndarray, n: int, ndrange, workgroupsize) -> None:
+    """reference test/test.jl:339-356 (Float32)"""
+    assert output.dtype == np.float32 and input.dtype == np.float32
+    ctx = make_ctx(ndrange, workgroupsize)
+    lib().orc_unaliased_accumulate_f32(C.byref(ctx), C.c_int(int(local)), _p(_F(output)), _p(_F(input)), C.c_int64(n),
+                                       C.c_int64(output.shape[0]), C.c_int64(input.shape[0]))
+
+
 def saxpy(Z, a, X, Y, ndrange, workgroupsize) -> None:
     """reference benchmark/benchmarks.jl:29-32"""
     ctx = make_ctx(ndrange, workgroupsize)
-    lib().orc_saxpy_f32(C.byref(ctx), _p(Z), C.c_float(a), _p(X), _p(Y))
+    if Z.dtype == np.float64:
+        lib().orc_saxpy_f64(C.byref(ctx), _p(Z), C.c_double(a), _p(X), _p(Y))
+    else:
+        lib().orc_saxpy_f32(C.byref(ctx), _p(Z), C.c_float(a), _p(X), _p(Y))
 
 
 # --------------------------------------------------------------------------------------------

@@ -512,3 +512,45 @@ def test_performance_jl_out_of_bounds_launch_is_rejected():
         K.lmem_copy_kernel_(be, (32, 32))(out, d_in, ndrange=(96, 64))     # third group row would read past the array
     with pytest.raises(_lib.B200Error):
         K.lmem_transpose_kernel_(be, (32, 8))(out, d_in, Val(1), ndrange=(64, 64))   # tile[j, i] needs a square group
+
+
+# =====================================================================================================
+# SAXPY (benchmark/benchmarks.jl:29-70, examples/numa_aware.jl:10-56): unfused a*x + y, bit-exact
+# =====================================================================================================
+@pytest.mark.parametrize("force_twins", [0, 1])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_saxpy_benchmark_sizes_match_oracle(orc, dtype, force_twins):
+    tune(registry__force_twins=force_twins)
+    rng = np.random.default_rng(11)
+    for N in (64, 256, 512, 1024, 2048, 4096, 16384, 32768, 65536, 262144, 1048576, 1000003):
+        X, Y = rng.random(N).astype(dtype), rng.random(N).astype(dtype)
+        dX, dY = KA.to_device(X), KA.to_device(Y)
+        for static in (True, False):
+            Z = KA.zeros(be, dtype, N)
+            kernel = K.saxpy_kernel_(be, 1024) if static else K.saxpy_kernel_(be)
+            kernel(Z, dtype(2.0), dX, dY, ndrange=Z.shape)
+            KA.synchronize(be)
+            ref = np.zeros(N, dtype=dtype)
+            orc.saxpy(ref, 2.0, X, Y, (N,), (1024,))
+            assert np.array_equal(KA.Array(Z), ref), (N, static)
+
+
+def test_saxpy_inplace_numa_aware_form(orc):
+    rng = np.random.default_rng(12)
+    N = 3 * 1024 * 1024 + 7
+    X, Y = rng.random(N, dtype=np.float32), rng.random(N, dtype=np.float32)
+    dX, dY = KA.to_device(X), KA.to_device(Y)
+    a = np.float32(3.1415)
+    K.saxpy_kernel(be, 1024, dY.shape)(a, dX, dY, ndrange=dY.shape)
+    KA.synchronize(be)
+    ref = np.zeros(N, dtype=np.float32)
+    orc.saxpy(ref, float(a), X, Y, (N,), (1024,))
+    assert np.array_equal(KA.Array(dY), ref)
+    # partial ndrange: the tail of Y stays untouched
+    dY2 = KA.to_device(Y)
+    K.saxpy_kernel(be, 256)(a, dX, dY2, ndrange=1000)
+    KA.synchronize(be)
+    got = KA.Array(dY2)
+    assert np.array_equal(got[:1000], ref[:1000]) and np.array_equal(got[1000:], Y[1000:])
+    bw, fl = EX.measure_membw(be, N=1 << 22, samples=2)
+    assert bw > 0 and fl > 0

@@ -245,6 +245,52 @@ def test_zero_size_allocations():
         KA.allocate(be, object(), (4,))
 
 
+# ---- test/test.jl:275-321, 339-385 -----------------------------------------------------------------------------------------
+def test_context_kernel_and_gpu_return():
+    be = backend()
+    A = KA.zeros(be, np.int64, 1024)
+    K.context_kernel(be)(A, ndrange=A.shape)          # "No CPU kernel" (test/test.jl:284-289)
+    KA.synchronize(be)
+    assert np.all(KA.Array(A) == 1)
+
+    A = KA.zeros(be, np.int64, 1024)
+    K.gpu_return_kernel_(be)(A, ndrange=A.size)       # "GPU kernel return statement" (test/test.jl:314-321)
+    KA.synchronize(be)
+    Ah = KA.Array(A)
+    assert np.all(Ah[:512] == 1) and np.all(Ah[512:] == 0)
+
+
+def test_unaliased_accumulate(orc):
+    # test/test.jl:358-385: N = 8, M = 5, input[i,k] = i + k
+    be = backend()
+    N, M = 8, 5
+    inp = np.asfortranarray(np.array([[i + k for k in range(1, N + 1)] for i in range(1, M + 1)], dtype=np.float32))
+    reference = np.zeros((M, N), dtype=np.float32, order="F")
+    for i in range(M):
+        for j in range(N):
+            for k in range(j, N):
+                reference[i, j] = np.float32(reference[i, j] + inp[i, k])
+    d_in = KA.adapt(be, inp)
+    out = KA.zeros(be, np.float32, M, N)
+    K.unaliased_accumulate_(be)(out, d_in, N, ndrange=out.shape)
+    KA.synchronize(be)
+    assert np.array_equal(KA.Array(out), reference)
+    out.fill_(0)
+    K.unaliased_accumulate_local_(be)(out, d_in, N, ndrange=out.shape)
+    KA.synchronize(be)
+    assert np.array_equal(KA.Array(out), reference)
+    # random data, ragged ndrange, against the oracle (bit-exact: plain adds, k ascending)
+    inp = np.asfortranarray(orc.gen_uniform_f32((37, 50), 9))
+    d_in = KA.adapt(be, inp)
+    for local, ctor in ((False, K.unaliased_accumulate_), (True, K.unaliased_accumulate_local_)):
+        out = KA.zeros(be, np.float32, 37, 50)
+        ctor(be, (8, 4))(out, d_in, 50, ndrange=(33, 47))
+        KA.synchronize(be)
+        ref = np.zeros((37, 50), dtype=np.float32, order="F")
+        orc.unaliased_accumulate(local, ref, inp, 50, (33, 47), (8, 4))
+        assert np.array_equal(KA.Array(out), ref)
+
+
 # ---- test/intrinsics.jl:27-124 ---------------------------------------------------------------------------------------------
 def test_ki_launch_parameters():
     be = backend()

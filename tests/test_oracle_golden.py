@@ -215,6 +215,27 @@ def test_performance_jl_ragged_simple(orc):
     assert np.array_equal(out, want)
 
 
+def test_context_return_and_unaliased_accumulate(orc):
+    """test/test.jl:284-289 (all ones), :314-321 (first half ones), :358-385 (triangular row sums)."""
+    a = np.zeros(1024, dtype=np.int64)
+    orc.misc_i64(0, a, 1024, 256)
+    assert np.all(a == 1)
+    a = np.zeros(1024, dtype=np.int64)
+    orc.misc_i64(1, a, 1024, 256)
+    assert np.all(a[:512] == 1) and np.all(a[512:] == 0)
+    N, M = 8, 5
+    inp = np.asfortranarray(np.array([[i + k for k in range(1, N + 1)] for i in range(1, M + 1)], dtype=np.float32))
+    reference = np.zeros((M, N), dtype=np.float32)
+    for i in range(M):
+        for j in range(N):
+            for k in range(j, N):
+                reference[i, j] += inp[i, k]
+    for local in (False, True):
+        out = np.zeros((M, N), dtype=np.float32, order="F")
+        orc.unaliased_accumulate(local, out, inp, N, (M, N), (M, N))
+        assert np.array_equal(out, reference)
+
+
 def test_histogram_examples(orc):
     rng = np.random.default_rng(1236)
     rand_input = rng.integers(1, 129, size=1000).astype(np.int32)

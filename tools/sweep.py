@@ -155,6 +155,17 @@ if want("hist"):
         tune(hist__impl=0, hist__threads=512, hist__batch=8, hist__ilp=2, hist__ctas_per_sm=1)
         del d_in, bins
 
+# ----------------------------------------------------------------------------------------------- saxpy
+if want("saxpy"):
+    for n in (1 << 26, 1 << 28):
+        X, Y, Z = (KA.to_device(orc.gen_uniform_f32((n,), 5 + i)) for i in range(3))
+        for cps in (2, 4, 8, 16, 32):
+            tune(saxpy__ctas_per_sm=cps)
+            med, mn = time_ms(lambda: _lib.call("b200_saxpy", C.c_void_p(Z.ptr), C.c_double(2.0), C.c_void_p(X.ptr), C.c_void_p(Y.ptr), n, 0))
+            record("saxpy", dict(n=n, ctas_per_sm=cps), med, mn, 12.0 * n, "GB/s")
+        del X, Y, Z
+    tune(saxpy__ctas_per_sm=32)
+
 # ----------------------------------------------------------------------------------------------- host pipeline
 if want("hostpipe"):
     from b200ka import examples as EX
