@@ -230,6 +230,28 @@ b200_status b200_comm_init_rank(void **comm, int32_t nranks, int32_t rank, const
 b200_status b200_comm_destroy(void *comm);
 b200_status b200_allreduce_sum_i32(void *comm, int32_t *buf, int64_t count);
 b200_status b200_broadcast(void *comm, void *buf, size_t bytes, int32_t root);
+/* exchange! (examples/mpi.jl:24-39): send to dst_rank, receive from src_rank, device buffers, stream ordered. */
+b200_status b200_sendrecv(void *comm, const void *sendbuf, int32_t dst_rank, void *recvbuf, int32_t src_rank,
+                          size_t bytes);
+
+
+/* ---- fused compute + collective over NVLink peer memory ------------------------------------------------------
+ * One rank (process) per GPU of one NVLink/NVSwitch domain.  Each rank allocates a small symmetric buffer, the
+ * launcher exchanges the 64-byte IPC handles (all-gather), every rank maps its peers' buffers, and from then on
+ *   b200_histogram_i32_allreduce == b200_histogram_i32 on the rank's input slab + all-reduce(sum) of the bins
+ * in ONE kernel: the last CTA stores the rank's partial bins as {count, tag} words straight into every peer's slot
+ * array over NVLink and sums the slots the peers stored into its own (csrc/kernels/histogram.cu).  bins[b] += total count over ALL ranks, on
+ * every rank -- bit-identical to b200_histogram_i32 + b200_allreduce_sum_i32 (integer adds).  Collective: every
+ * rank must call it the same number of times.  nbins <= 14336, input 16-byte aligned, at most 8 ranks. */
+#define B200_IPC_HANDLE_BYTES 64
+b200_status b200_p2p_alloc(void **handle);
+b200_status b200_p2p_export(void *handle, void *ipc64);
+b200_status b200_p2p_connect(void *handle, int32_t world, int32_t rank, const void *all_handles /* world x 64 bytes */);
+b200_status b200_p2p_free(void *handle);
+/* diagnostic: four %globaltimer stamps (ns) of the last fused launch (slowest CTA left the counting loop, local counts
+ * merged, slots sent, all ranks' slots summed) */
+b200_status b200_p2p_debug(void *handle, uint64_t *stamps4);
+b200_status b200_histogram_i32_allreduce(void *handle, int32_t *bins, int64_t nbins, const int32_t *input, int64_t n);
 
 #ifdef __cplusplus
 }

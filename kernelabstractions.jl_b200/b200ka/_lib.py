@@ -39,6 +39,7 @@ B200_ARG_ARRAY, B200_ARG_SCALAR, B200_ARG_VAL = 0, 1, 2
  B200_T_F16, B200_T_BF16, B200_T_F32, B200_T_F64, B200_T_BOOL) = range(14)
 B200_MATMUL_TILE16, B200_MATMUL_RUNNING = 0, 1
 B200_UNIQUE_ID_BYTES = 128
+B200_IPC_HANDLE_BYTES = 64
 
 
 class ErrorException(RuntimeError):
@@ -145,6 +146,13 @@ SIGNATURES = {
     "b200_comm_destroy": (_I32, [_VP]),
     "b200_allreduce_sum_i32": (_I32, [_VP, _VP, _I64]),
     "b200_broadcast": (_I32, [_VP, _VP, _SZ, _I32]),
+    "b200_sendrecv": (_I32, [_VP, _VP, _I32, _VP, _I32, _SZ]),
+    "b200_p2p_alloc": (_I32, [_PVP]),
+    "b200_p2p_export": (_I32, [_VP, _VP]),
+    "b200_p2p_connect": (_I32, [_VP, _I32, _I32, _VP]),
+    "b200_p2p_free": (_I32, [_VP]),
+    "b200_p2p_debug": (_I32, [_VP, _VP]),
+    "b200_histogram_i32_allreduce": (_I32, [_VP, _VP, _I64, _VP, _I64]),
 }
 
 _lib = None

@@ -75,7 +75,58 @@ class Comm:
     def broadcast(self, ptr: int, nbytes: int, root: int = 0) -> None:
         _lib.call("b200_broadcast", self.handle, C.c_void_p(ptr), nbytes, root)
 
+    def sendrecv(self, send_ptr: int, dst_rank: int, recv_ptr: int, src_rank: int, nbytes: int) -> None:
+        _lib.call("b200_sendrecv", self.handle, C.c_void_p(send_ptr), dst_rank, C.c_void_p(recv_ptr), src_rank, nbytes)
+
     def destroy(self) -> None:
         if self.handle:
             _lib.call("b200_comm_destroy", self.handle)
             self.handle = C.c_void_p()
+
+
+class PeerGroup:
+    """Symmetric NVLink peer buffers for the fused compute+collective kernels (b200_p2p_*): every rank allocates its
+    buffer, the 64-byte IPC handles are all-gathered by the launcher (`gather` = a callable bytes -> list of bytes, e.g.
+    built on torch.distributed.all_gather_object or MPI.Allgather), and every rank maps its peers."""
+
+    def __init__(self, world_size: int, rank: int, gather):
+        self.handle = C.c_void_p()
+        _lib.call("b200_p2p_alloc", C.byref(self.handle))
+        buf = C.create_string_buffer(_lib.B200_IPC_HANDLE_BYTES)
+        _lib.call("b200_p2p_export", self.handle, buf)
+        handles = gather(buf.raw)
+        assert len(handles) == world_size and all(len(h) == _lib.B200_IPC_HANDLE_BYTES for h in handles)
+        allh = C.create_string_buffer(b"".join(handles), world_size * _lib.B200_IPC_HANDLE_BYTES)
+        _lib.call("b200_p2p_connect", self.handle, world_size, rank, allh)
+        self.world_size, self.rank = world_size, rank
+
+    def histogram_allreduce(self, bins, input) -> None:
+        """bins += histogram of every rank's `input`, on every rank, in one fused kernel per rank."""
+        _lib.call("b200_histogram_i32_allreduce", self.handle, C.c_void_p(bins.ptr), bins.size, C.c_void_p(input.ptr), input.size)
+
+    def debug_stamps(self):
+        """ns timeline of the last fused launch after its slowest CTA left the counting loop: [counts_merged, slots_sent, all_summed]."""
+        buf = (C.c_uint64 * 4)()
+        _lib.call("b200_p2p_debug", self.handle, buf)
+        return [int(buf[i]) - int(buf[0]) for i in (1, 2, 3)]
+
+    def free(self) -> None:
+        if self.handle:
+            _lib.call("b200_p2p_free", self.handle)
+            self.handle = C.c_void_p()
+
+
+def torch_gather(dist):
+    """`gather` callable for PeerGroup on top of torch.distributed (any backend)."""
+    def gather(blob: bytes):
+        out = [None] * dist.get_world_size()
+        dist.all_gather_object(out, blob)
+        return out
+    return gather
+
+
+def exchange_(comm: "Comm", backend, d_send_buf, d_recv_buf, src_rank: int, dst_rank: int) -> None:
+    """exchange! of reference examples/mpi.jl:24-39 on device buffers: the ring neighbour's payload lands in
+    d_recv_buf, stream ordered behind whatever produced d_send_buf; KA.synchronize(backend) completes it."""
+    assert d_send_buf.nbytes == d_recv_buf.nbytes
+    comm.sendrecv(d_send_buf.ptr, dst_rank, d_recv_buf.ptr, src_rank, d_send_buf.nbytes)

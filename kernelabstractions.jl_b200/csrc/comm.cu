@@ -27,6 +27,10 @@ struct NcclApi {
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Broadcast)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
     bool ok = false;
 };
@@ -48,9 +52,14 @@ static void load_nccl() {
     B200_SYM(AllReduce, "ncclAllReduce");
     B200_SYM(Broadcast, "ncclBroadcast");
     B200_SYM(GetErrorString, "ncclGetErrorString");
+    B200_SYM(Send, "ncclSend");
+    B200_SYM(Recv, "ncclRecv");
+    B200_SYM(GroupStart, "ncclGroupStart");
+    B200_SYM(GroupEnd, "ncclGroupEnd");
 #undef B200_SYM
     g_nccl.ok = g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.CommDestroy && g_nccl.AllReduce &&
-                g_nccl.Broadcast && g_nccl.GetErrorString;
+                g_nccl.Broadcast && g_nccl.GetErrorString && g_nccl.Send && g_nccl.Recv && g_nccl.GroupStart &&
+                g_nccl.GroupEnd;
 }
 
 static int need_nccl() {
@@ -116,5 +125,23 @@ extern "C" b200_status b200_broadcast(void *comm, void *buf, size_t bytes, int32
     cudaStream_t st;
     B200_TRY(current_stream(&st));
     B200_NCCL(g_nccl.Broadcast(buf, buf, bytes, ncclUint8, root, (ncclComm_t)comm, st));
+    return B200_OK;
+}
+
+// exchange! of examples/mpi.jl:24-39 without the host staging: send `bytes` to dst_rank and receive `bytes` from
+// src_rank, device buffers, stream ordered (the MPI.Isend/Irecv pair becomes one NCCL group over NVLink).
+extern "C" b200_status b200_sendrecv(void *comm, const void *sendbuf, int32_t dst_rank, void *recvbuf, int32_t src_rank,
+                                     size_t bytes) {
+    if (!comm || (bytes > 0 && (!sendbuf || !recvbuf))) return set_error(B200_ERR_INVALID_VALUE, "NULL argument");
+    if (bytes == 0) return B200_OK;
+    B200_TRY(need_nccl());
+    cudaStream_t st;
+    B200_TRY(current_stream(&st));
+    B200_NCCL(g_nccl.GroupStart());
+    ncclResult_t r1 = g_nccl.Send(sendbuf, bytes, ncclUint8, dst_rank, (ncclComm_t)comm, st);
+    ncclResult_t r2 = g_nccl.Recv(recvbuf, bytes, ncclUint8, src_rank, (ncclComm_t)comm, st);
+    B200_NCCL(g_nccl.GroupEnd());
+    if (r1 != 0) return set_error(B200_ERR_NCCL, "ncclSend failed: %s", g_nccl.GetErrorString(r1));
+    if (r2 != 0) return set_error(B200_ERR_NCCL, "ncclRecv failed: %s", g_nccl.GetErrorString(r2));
     return B200_OK;
 }

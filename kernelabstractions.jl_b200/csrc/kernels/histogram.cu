@@ -16,6 +16,8 @@
 //       (also the path for 256 < nbins <= 14336).
 //   larger nbins: one red.global.add per in-range element.
 // Values outside 1..nbins are ignored, exactly like the reference's range test (:45-46).
+#include <cstring>
+
 #include "../common.cuh"
 #include "../tune.h"
 
@@ -139,12 +141,14 @@ __global__ void __launch_bounds__(T, 1) hist256_bytes_kernel(int32_t *__restrict
 // ---------------------------------------------------------------------------------------------
 // impl 1: shared-memory atomics on `copies` private 32-bit histograms per CTA
 // ---------------------------------------------------------------------------------------------
+//
+// The counting phase is one NOT-inlined device function shared by the plain kernel and by the fused
+// histogram + all-reduce kernel, so both run exactly the same SASS for the hot loop: inlined into the larger fused
+// kernel, ptxas scheduled the four in-flight LDG.128 differently and the loop lost 13 % (745 us instead of 650 us for
+// 2^30 elements; profiles/r02_hist_fused_notes.md).
 template <int T, int P>
-__global__ void __launch_bounds__(T) hist_atomic_kernel(int32_t *__restrict__ bins, uint32_t nbins,
-                                                        const int4 *__restrict__ in4, int64_t n4,
-                                                        const int32_t *__restrict__ tail, int ntail, int copies) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint32_t *sh = reinterpret_cast<uint32_t *>(smem_raw);
+__device__ __noinline__ void hist_count_phase(uint32_t *sh, uint32_t nbins, const int4 *__restrict__ in4, int64_t n4,
+                                              const int32_t *__restrict__ tail, int ntail, int copies) {
     const int t = threadIdx.x, warp = t >> 5;
     for (uint32_t i = t; i < nbins * (uint32_t)copies; i += T) sh[i] = 0;
     __syncthreads();
@@ -179,11 +183,121 @@ __global__ void __launch_bounds__(T) hist_atomic_kernel(int32_t *__restrict__ bi
     }
     if (blockIdx.x == 0 && t < ntail) bump(tail[t]);
     __syncthreads();
-    for (uint32_t b = t; b < nbins; b += T) {
+}
+
+template <int T, int P>
+__global__ void __launch_bounds__(T) hist_atomic_kernel(int32_t *__restrict__ bins, uint32_t nbins,
+                                                        const int4 *__restrict__ in4, int64_t n4,
+                                                        const int32_t *__restrict__ tail, int ntail, int copies) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t *sh = reinterpret_cast<uint32_t *>(smem_raw);
+    hist_count_phase<T, P>(sh, nbins, in4, n4, tail, ntail, copies);
+    for (uint32_t b = threadIdx.x; b < nbins; b += T) {
         uint32_t s = 0;
         for (int c = 0; c < copies; ++c) s += sh[(uint32_t)c * nbins + b];
         if (s) atomicAdd(reinterpret_cast<unsigned int *>(bins) + b, s);
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// fused histogram + all-reduce over NVLink peer memory (b200_histogram_i32_allreduce)
+// ---------------------------------------------------------------------------------------------
+// The CTAs merge their counts into a device-local partial; the LAST CTA to finish (ticket counter) then stores that
+// partial into a slot of EVERY rank's symmetric buffer through NVLink peer memory (cudaIpc mappings) and sums the slots
+// the other ranks stored into its own buffer.  Each slot word is an 8-byte {count, tag} pair written with ONE store, so
+// data and "it has arrived" travel together and no fence, flag or atomic crosses NVLink (the LL idea of NCCL): a
+// system-scope fence alone costs ~7 us on this box (b200_p2p_debug timeline), more than a whole NCCL all-reduce of 1 KiB.
+// tag = step + 1; slots are double-buffered by step parity, which is race-free because a rank can start step e+2 only
+// after every rank has finished step e+1, hence has long read its step-e slots.  Sums are taken in rank order: integer
+// adds, bit-identical to b200_histogram_i32 + b200_allreduce_sum_i32.  One launch per step, no NCCL kernel.
+struct HistPeer {
+    int world;
+    int rank;
+    uint32_t epoch;                   // step counter, identical on all ranks
+    uint32_t nbins_max;               // slot stride
+    uint32_t *counter;                // local ticket counter (zero between launches)
+    uint32_t *partial;                // local per-bin partial (zero between launches)
+    unsigned long long *stamps;       // %globaltimer stamps of the last launch (b200_p2p_debug)
+    unsigned long long *slots[8];     // rank r's slot array: [2 halves][8 source ranks][nbins_max] x {count, tag}
+};
+
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long v;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v));
+    return v;
+}
+__device__ __forceinline__ void st_slot(unsigned long long *p, uint32_t count, uint32_t tag) {
+    asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(count), "r"(tag) : "memory");
+}
+__device__ __forceinline__ void ld_slot(const unsigned long long *p, uint32_t &count, uint32_t &tag) {
+    asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(count), "=r"(tag) : "l"(p) : "memory");
+}
+
+template <int T>
+__device__ __noinline__ void fused_exchange(uint32_t *sh, uint32_t nbins, int copies, int32_t *__restrict__ bins,
+                                            const HistPeer &peer) {
+    const int t = threadIdx.x, warp = t >> 5;
+    if (t == 0) atomicMax(peer.stamps + 0, globaltimer_ns());                          // slowest CTA leaves the counting loop
+    // Fold the private copies into copy 0, then let ONE warp publish the CTA's counts, fence and take the ticket (a
+    // device-scope fence waits for the warp's outstanding atomics; one fencing warp per CTA is enough).
+    for (uint32_t b = t; b < nbins; b += T) {
+        uint32_t s = 0;
+        for (int c = 0; c < copies; ++c) s += sh[(uint32_t)c * nbins + b];
+        sh[b] = s;   // only thread (b mod T) touches column b
+    }
+    uint32_t &ticket = sh[nbins * (uint32_t)copies];   // one spare word behind the private copies (dynamic smem)
+    __syncthreads();
+    if (warp == 0) {
+        for (uint32_t b = t; b < nbins; b += 32) {
+            const uint32_t s = sh[b];
+            if (s) atomicAdd(peer.partial + b, s);
+        }
+        __threadfence();
+        __syncwarp();
+        if (t == 0) {
+            ticket = atomicAdd(peer.counter, 1u);
+            __threadfence();
+        }
+    }
+    __syncthreads();
+    if (ticket != gridDim.x - 1) return;   // only the last CTA of this GPU goes on
+    if (t == 0) {
+        peer.stamps[1] = globaltimer_ns();                                               // local counting done
+        *peer.counter = 0;                                                               // ready for the next launch
+    }
+    const uint32_t tag = peer.epoch + 1u;
+    const size_t half = (size_t)(peer.epoch & 1u) * 8u * peer.nbins_max;
+    for (uint32_t b = t; b < nbins; b += T) {
+        const uint32_t v = __ldcg(peer.partial + b);
+        peer.partial[b] = 0;
+        for (int r = 0; r < peer.world; ++r) st_slot(peer.slots[r] + half + (size_t)peer.rank * peer.nbins_max + b, v, tag);
+    }
+    if (t == 0) peer.stamps[2] = globaltimer_ns();                                       // slots sent
+    const unsigned long long *mine = peer.slots[peer.rank] + half;
+    for (uint32_t b = t; b < nbins; b += T) {
+        uint32_t sum = 0;
+        for (int src = 0; src < peer.world; ++src) {
+            uint32_t v, g;
+            do {
+                ld_slot(mine + (size_t)src * peer.nbins_max + b, v, g);
+            } while (g != tag);
+            sum += v;
+        }
+        bins[b] += (int32_t)sum;                                                         // accumulate like the reference's +=
+    }
+    __syncthreads();
+    if (t == 0) peer.stamps[3] = globaltimer_ns();                                       // every rank's slots summed
+}
+
+template <int T, int P>
+__global__ void __launch_bounds__(T) hist_allreduce_kernel(int32_t *__restrict__ bins, uint32_t nbins,
+                                                           const int4 *__restrict__ in4, int64_t n4,
+                                                           const int32_t *__restrict__ tail, int ntail, int copies,
+                                                           const __grid_constant__ HistPeer peer) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t *sh = reinterpret_cast<uint32_t *>(smem_raw);
+    hist_count_phase<T, P>(sh, nbins, in4, n4, tail, ntail, copies);
+    fused_exchange<T>(sh, nbins, copies, bins, peer);
 }
 
 // nbins too large for shared memory: one global reduction per in-range element.
@@ -293,9 +407,137 @@ int histogram_launch(int32_t *bins, int64_t nbins, const int32_t *input, int64_t
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// symmetric peer buffers (cudaIpc) for the fused histogram + all-reduce
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t kP2PMaxBins = 14336;
+constexpr size_t kP2PCounterOff = 0, kP2PStampsOff = 8, kP2PPartialOff = 128;
+constexpr size_t kP2PSlotsOff = (kP2PPartialOff + (size_t)kP2PMaxBins * 4 + 255) / 256 * 256;
+constexpr size_t kP2PBytes = kP2PSlotsOff + 2 * 8 * (size_t)kP2PMaxBins * 8;
+
+struct P2P {
+    void *local = nullptr;
+    int world = 0, rank = -1;
+    void *peer[8] = {};
+    uint32_t epoch = 0;
+};
+
+int histogram_allreduce_launch(P2P *h, int32_t *bins, int64_t nbins, const int32_t *input, int64_t n, cudaStream_t st) {
+    if (h->world < 1) return set_error(B200_ERR_INVALID_VALUE, "b200_histogram_i32_allreduce: b200_p2p_connect has not been called");
+    if (nbins > kP2PMaxBins || nbins < 1)
+        return set_error(B200_ERR_UNSUPPORTED, "b200_histogram_i32_allreduce: nbins must be 1..%u", kP2PMaxBins);
+    if (((uintptr_t)input & 15) != 0)
+        return set_error(B200_ERR_UNSUPPORTED, "b200_histogram_i32_allreduce: input must be 16-byte aligned");
+    HistPeer peer;
+    peer.world = h->world;
+    peer.rank = h->rank;
+    peer.epoch = h->epoch++;
+    peer.nbins_max = kP2PMaxBins;
+    peer.counter = (uint32_t *)((char *)h->local + kP2PCounterOff);
+    peer.stamps = (unsigned long long *)((char *)h->local + kP2PStampsOff);
+    peer.partial = (uint32_t *)((char *)h->local + kP2PPartialOff);
+    for (int r = 0; r < 8; ++r)
+        peer.slots[r] = r < h->world ? (unsigned long long *)((char *)h->peer[r] + kP2PSlotsOff) : nullptr;
+    const int64_t n4 = n / 4;
+    const int tail_n = (int)(n - n4 * 4);
+    constexpr int T = 1024, P = 4;
+    int copies = (int)((48 * 1024 - 16) / (nbins * 4));
+    if (copies > T / 32) copies = T / 32;
+    if (copies < 1) copies = 1;
+    int grid = sm_count();
+    if ((int64_t)grid > (n4 + T - 1) / T) grid = (int)((n4 + T - 1) / T);
+    if (grid < 1) grid = 1;   // n == 0 still takes part in the exchange
+    const size_t smem = (size_t)nbins * copies * 4 + 16;   // + the ticket word of fused_exchange
+    if (smem > 48 * 1024)
+        B200_CUDA(cudaFuncSetAttribute(hist_allreduce_kernel<T, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    hist_allreduce_kernel<T, P><<<grid, T, smem, st>>>(bins, (uint32_t)nbins, reinterpret_cast<const int4 *>(input), n4,
+                                                      input + n4 * 4, tail_n, copies, peer);
+    B200_CHECK_LAUNCH("hist_allreduce_kernel");
+    return B200_OK;
+}
+
 }  // namespace b200
 
 using namespace b200;
+
+extern "C" b200_status b200_p2p_alloc(void **handle) {
+    if (!handle) return set_error(B200_ERR_INVALID_VALUE, "handle is NULL");
+    B200_TRY(ensure_device());
+    P2P *h = new P2P();
+    cudaError_t e = cudaMalloc(&h->local, kP2PBytes);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        delete h;
+        return set_error(B200_ERR_OOM, "b200_p2p_alloc: cudaMalloc failed: %s", cudaGetErrorString(e));
+    }
+    B200_CUDA(cudaMemset(h->local, 0, kP2PBytes));
+    *handle = h;
+    return B200_OK;
+}
+
+extern "C" b200_status b200_p2p_export(void *handle, void *ipc64) {
+    if (!handle || !ipc64) return set_error(B200_ERR_INVALID_VALUE, "NULL argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == B200_IPC_HANDLE_BYTES, "ipc handle size");
+    cudaIpcMemHandle_t ipc;
+    B200_CUDA(cudaIpcGetMemHandle(&ipc, ((P2P *)handle)->local));
+    memcpy(ipc64, &ipc, sizeof(ipc));
+    return B200_OK;
+}
+
+extern "C" b200_status b200_p2p_connect(void *handle, int32_t world, int32_t rank, const void *all_handles) {
+    if (!handle || !all_handles) return set_error(B200_ERR_INVALID_VALUE, "NULL argument");
+    if (world < 1 || world > 8 || rank < 0 || rank >= world)
+        return set_error(B200_ERR_INVALID_VALUE, "b200_p2p_connect: bad rank %d / world %d (1..8 ranks of one NVLink domain)", rank, world);
+    B200_TRY(ensure_device());
+    P2P *h = (P2P *)handle;
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) {
+            h->peer[r] = h->local;
+            continue;
+        }
+        cudaIpcMemHandle_t ipc;
+        memcpy(&ipc, (const char *)all_handles + (size_t)r * B200_IPC_HANDLE_BYTES, sizeof(ipc));
+        B200_CUDA(cudaIpcOpenMemHandle(&h->peer[r], ipc, cudaIpcMemLazyEnablePeerAccess));
+    }
+    h->world = world;
+    h->rank = rank;
+    h->epoch = 0;
+    return B200_OK;
+}
+
+// Diagnostic: four %globaltimer stamps (ns) of the last fused launch: slowest CTA left the counting loop, local counting
+// merged (ticket), slots sent to all ranks, all ranks' slots summed.  Synchronises the calling thread's stream.
+extern "C" b200_status b200_p2p_debug(void *handle, uint64_t *stamps4) {
+    uint64_t *stamps6 = stamps4;
+    if (!handle || !stamps6) return set_error(B200_ERR_INVALID_VALUE, "NULL argument");
+    cudaStream_t st;
+    B200_TRY(current_stream(&st));
+    B200_CUDA(cudaStreamSynchronize(st));
+    B200_CUDA(cudaMemcpy(stamps6, (char *)((P2P *)handle)->local + kP2PStampsOff, 32, cudaMemcpyDeviceToHost));
+    B200_CUDA(cudaMemset((char *)((P2P *)handle)->local + kP2PStampsOff, 0, 8));   // stamp 0 is an atomicMax
+    return B200_OK;
+}
+
+extern "C" b200_status b200_p2p_free(void *handle) {
+    if (!handle) return B200_OK;
+    P2P *h = (P2P *)handle;
+    B200_CUDA(cudaDeviceSynchronize());
+    for (int r = 0; r < h->world; ++r)
+        if (r != h->rank && h->peer[r]) (void)cudaIpcCloseMemHandle(h->peer[r]);
+    if (h->local) (void)cudaFree(h->local);
+    delete h;
+    return B200_OK;
+}
+
+extern "C" b200_status b200_histogram_i32_allreduce(void *handle, int32_t *bins, int64_t nbins, const int32_t *input,
+                                                    int64_t n) {
+    if (!handle) return set_error(B200_ERR_INVALID_VALUE, "b200_histogram_i32_allreduce: handle is NULL");
+    if (nbins < 0 || n < 0) return set_error(B200_ERR_INVALID_VALUE, "b200_histogram_i32_allreduce: negative size");
+    if (!bins || (n > 0 && !input)) return set_error(B200_ERR_INVALID_VALUE, "b200_histogram_i32_allreduce: NULL pointer");
+    cudaStream_t st;
+    B200_TRY(current_stream(&st));
+    return histogram_allreduce_launch((P2P *)handle, bins, nbins, input, n, st);
+}
 
 extern "C" b200_status b200_histogram_i32(int32_t *bins, int64_t nbins, const int32_t *input, int64_t n) {
     if (nbins < 0 || n < 0) return set_error(B200_ERR_INVALID_VALUE, "b200_histogram_i32: negative size");

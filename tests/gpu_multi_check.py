@@ -1,0 +1,157 @@
+#!/usr/bin/env python
+"""Multi-GPU parity + timing check, one rank per GPU:
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29517 \
+        tests/gpu_multi_check.py [--time]
+
+Checks (every rank asserts; rank 0 prints one JSON line):
+  * sharded histogram, NCCL route  (b200_histogram_i32 + b200_allreduce_sum_i32)          == oracle of the whole input
+  * sharded histogram, fused route (b200_histogram_i32_allreduce: one kernel, NVLink peer reductions) == the same bits,
+    over several consecutive steps with different sizes (step parity / flag epochs), ragged and empty slabs
+  * ring exchange (examples/mpi.jl:24-39) through b200_sendrecv
+  * row-panel matmul: each rank's C panel is bit-identical to the same rows of the 1-GPU result
+With --time: per-step device time (max over ranks) of both histogram routes at 2^30 elements total.
+"""
+import ctypes as C
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "kernelabstractions.jl_b200"))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+import b200ka as KA  # noqa: E402
+import ka_oracle as orc  # noqa: E402
+from b200ka import _lib, examples as EX, multigpu as mg  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    _lib.call("b200_set_device", local)
+    be = KA.B200Backend()
+    out = {"world": world}
+
+    uid = torch.zeros(_lib.B200_UNIQUE_ID_BYTES, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        uid = torch.frombuffer(bytearray(mg.Comm.unique_id()), dtype=torch.uint8).cuda()
+    dist.broadcast(uid, 0)
+    comm = mg.Comm(world, rank, bytes(uid.cpu().numpy().tobytes()))
+    peers = mg.PeerGroup(world, rank, mg.torch_gather(dist))
+
+    # ---- histogram: both routes against the oracle, several steps back to back ----
+    sizes = [100003, 4 * 1000 * world, 17, 0, 5 * (1 << 20) + 4 * world, 999999]
+    nbins_list = [256, 256, 256, 256, 1000, 64]
+    for step, (n, nbins) in enumerate(zip(sizes, nbins_list)):
+        s0, s1 = mg.histogram_shard(n, world, rank)
+        whole = orc.gen_bins_i32(max(n, 1), 4000 + step, nbins)[:n]
+        mine = np.ascontiguousarray(whole[s0:s1])
+        d_in = EX.move(be, mine) if mine.size else KA.allocate(be, np.int32, 0)
+        want = np.zeros(nbins, dtype=np.int32)
+        if n:
+            orc.histogram(want, whole, 256)
+        # NCCL route
+        bins = KA.zeros(be, np.int32, nbins)
+        if mine.size:
+            EX.histogram_(bins, d_in)
+        comm.allreduce_sum_i32(bins.ptr, nbins)
+        KA.synchronize(be)
+        assert np.array_equal(KA.Array(bins), want), f"NCCL route mismatch at step {step} on rank {rank}"
+        # fused route (accumulates into existing counts)
+        bins2 = KA.to_device(np.arange(nbins, dtype=np.int32))
+        peers.histogram_allreduce(bins2, d_in)
+        KA.synchronize(be)
+        assert np.array_equal(KA.Array(bins2), want + np.arange(nbins, dtype=np.int32)), f"fused route mismatch at step {step} on rank {rank}"
+    out["histogram_routes_match_oracle"] = True
+
+    # ---- ring exchange (examples/mpi.jl:41-75): M = 10 Int64, payload = sender's rank ----
+    dst_rank, src_rank = (rank + 1) % world, (rank - 1) % world
+    d_recv = KA.allocate(be, np.int64, 10).fill_(-1)
+    d_send = KA.to_device(np.full(10, rank, dtype=np.int64))
+    mg.exchange_(comm, be, d_send, d_recv, src_rank, dst_rank)
+    KA.synchronize(be)
+    assert np.all(KA.Array(d_recv) == src_rank)
+    out["ring_exchange"] = True
+
+    # ---- matmul row panels: bit-identical to the same rows of the full product ----
+    n = 512
+    A, B = orc.gen_uniform_f32((n, n), 1237), orc.gen_uniform_f32((n, n), 1238)
+    m0, m1 = mg.matmul_shard(n, world, rank)
+    dB = KA.allocate(be, np.float32, n, n)
+    if rank == 0:
+        KA.copyto_(be, dB, B)
+        KA.synchronize(be)
+    comm.broadcast(dB.ptr, dB.nbytes, 0)           # B replicated with one broadcast
+    Cp = KA.zeros(be, np.float32, m1 - m0, n)
+    EX.performant_matmul_(Cp, KA.to_device(np.asfortranarray(A[m0:m1, :])), dB)
+    KA.synchronize(be)
+    Cref = np.zeros((n, n), dtype=np.float32, order="F")
+    orc.coalesced_matmul(Cref, A, B)
+    assert np.array_equal(KA.Array(Cp), Cref[m0:m1, :])
+    out["matmul_row_panels_bit_exact"] = True
+
+    # ---- timing: NCCL route vs fused route at the C3 size ----
+    if "--time" in sys.argv:
+        n = 1 << 30
+        s0, s1 = mg.histogram_shard(n, world, rank)
+        d_in = EX.move(be, orc.gen_bins_i32(s1 - s0, 1236 + rank, 256))
+        bins = KA.zeros(be, np.int32, 256)
+        e0, e1 = C.c_void_p(), C.c_void_p()
+        _lib.call("b200_event_create", C.byref(e0))
+        _lib.call("b200_event_create", C.byref(e1))
+
+        def timed(fn, steps=50, warm=5):
+            for _ in range(warm):
+                fn()
+            KA.synchronize(be)
+            dist.barrier()
+            _lib.call("b200_event_record", e0)
+            for _ in range(steps):
+                fn()
+            _lib.call("b200_event_record", e1)
+            KA.synchronize(be)
+            ms = C.c_float()
+            _lib.call("b200_event_elapsed_ms", e0, e1, C.byref(ms))
+            t = torch.tensor([ms.value / steps], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+
+        def step_nccl():
+            EX.histogram_(bins, d_in)
+            comm.allreduce_sum_i32(bins.ptr, 256)
+
+        def step_fused():
+            peers.histogram_allreduce(bins, d_in)
+
+        def step_local():
+            EX.histogram_(bins, d_in)
+
+        for name, fn in (("local_only", step_local), ("nccl", step_nccl), ("fused", step_fused)):
+            ms = timed(fn)
+            out[f"hist_{name}_ms"] = ms
+            out[f"hist_{name}_GBps"] = 4.0 * n / (ms * 1e-3) / 1e9
+            if name == "fused":
+                stamps = peers.debug_stamps()
+                gathered = [None] * world
+                dist.all_gather_object(gathered, stamps)
+                out["fused_timeline_ns_per_rank"] = gathered
+
+    KA.synchronize(be)
+    dist.barrier()
+    peers.free()
+    comm.destroy()
+    if rank == 0:
+        print(json.dumps(out))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

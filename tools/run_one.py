@@ -90,6 +90,15 @@ elif kind == "hist":
     d_in = KA.to_device(orc.gen_bins_i32(n, 1236, 256) if mode == 0 else np.full(n, 2, dtype=np.int32))
     bins = KA.zeros(be, np.int32, 256)
     run(lambda: _lib.call("b200_histogram_i32", C.c_void_p(bins.ptr), 256, C.c_void_p(d_in.ptr), n), 4.0 * n, "GB/s")
+elif kind == "hist_fused":
+    # the fused histogram + peer all-reduce kernel with a world of one rank (the exchange degenerates to local reductions)
+    from b200ka import multigpu as mg
+    n = size or (1 << 30)
+    d_in = KA.to_device(orc.gen_bins_i32(n, 1236, 256))
+    bins = KA.zeros(be, np.int32, 256)
+    peers = mg.PeerGroup(1, 0, lambda blob: [blob])
+    run(lambda: peers.histogram_allreduce(bins, d_in), 4.0 * n, "GB/s")
+    print("timeline ns after the counting loop [counts_merged, slots_sent, all_summed]:", peers.debug_stamps())
 elif kind in ("sgemm", "tcgemm"):
     n = size or 8192
     A, B = KA.to_device(orc.gen_uniform_f32((n, n), 1237)), KA.to_device(orc.gen_uniform_f32((n, n), 1238))
