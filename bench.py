@@ -398,7 +398,7 @@ def run_suite(KA, _lib, EX, mg, orc, be, rank, world, dist, timed, peaks, steps,
         d_in = EX.move(be, inp)
         KA.synchronize(be)
         bins = KA.zeros(be, np.int32, 256)
-        comm = None
+        comm, peers = None, None
         if world > 1:
             import torch
             uid = torch.zeros(_lib.B200_UNIQUE_ID_BYTES, dtype=torch.uint8, device="cuda")
@@ -406,11 +406,17 @@ def run_suite(KA, _lib, EX, mg, orc, be, rank, world, dist, timed, peaks, steps,
                 uid = torch.frombuffer(bytearray(mg.Comm.unique_id()), dtype=torch.uint8).cuda()
             dist.broadcast(uid, 0)
             comm = mg.Comm(world, rank, bytes(uid.cpu().numpy().tobytes()))
+            peers = mg.PeerGroup(world, rank, mg.torch_gather(dist))
 
         def step_hist():
+            if peers is not None:
+                peers.histogram_allreduce(bins, d_in)      # one kernel: counting + all-reduce over NVLink peer memory
+            else:
+                EX.histogram_(bins, d_in)
+
+        def step_hist_nccl():
             EX.histogram_(bins, d_in)
-            if comm is not None:
-                comm.allreduce_sum_i32(bins.ptr, 256)
+            comm.allreduce_sum_i32(bins.ptr, 256)
 
         bins.fill_(0)
         step_hist()
@@ -423,7 +429,19 @@ def run_suite(KA, _lib, EX, mg, orc, be, rank, world, dist, timed, peaks, steps,
                                              "sum_conserved": check, "scaling": "strong",
                                              "roofline": {"bound": "hbm", "achieved": gbs / world, "peak": peaks["hbm"],
                                                           "frac": gbs / world / peaks["hbm"], "traffic": None},
-                                             "collective": "NCCL all-reduce of 256 x Int32 per step" if world > 1 else None}
+                                             "collective": ("fused in the counting kernel: {count,tag} slot stores over NVLink peer memory "
+                                                            "(b200_histogram_i32_allreduce), no NCCL launch") if world > 1 else None}
+        if comm is not None:
+            bins.fill_(0)
+            step_hist_nccl()
+            KA.synchronize(be)
+            check2 = bool(np.array_equal(KA.Array(bins), got))
+            ms2, _ = timed(step_hist_nccl, steps, warmup)
+            out["histogram_2^30_i32_256bins"]["nccl_route"] = {"value": 4.0 * n / (ms2 * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": ms2,
+                                                                "same_bits_as_fused": check2,
+                                                                "collective": "b200_histogram_i32 + NCCL all-reduce of 256 x Int32 (2 launches)"}
+        if peers is not None:
+            peers.free()
         if comm is not None:
             comm.destroy()
         del d_in, bins

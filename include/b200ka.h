@@ -202,6 +202,11 @@ b200_status b200_matmul_f32(float *C, const float *A, const float *B, int64_t M,
  * (i.e. the column-major K x N matrix B as stored); C: M x N float32 column-major, ldc >= M. */
 b200_status b200_matmul_bf16(float *C, const uint16_t *Abf, const uint16_t *Bbf, int64_t M, int64_t K,
                              int64_t N, int64_t ldc);
+/* TF32 tensor-core path: C = A*B straight from the FP32 column-major matrices (no conversion pass, no workspace);
+ * the tensor core uses the top 19 bits of every operand word, FP32 accumulate.  lda, ldb multiples of 4, A and B
+ * 16-byte aligned; any M, N, K > 0 (edge tiles are zero-filled by TMA and stores are predicated). */
+b200_status b200_matmul_tf32(float *C, const float *A, const float *B, int64_t M, int64_t K, int64_t N,
+                             int64_t lda, int64_t ldb, int64_t ldc);
 /* float32 column-major (rows x cols, ld) -> bf16; transpose!=0 writes the cols x rows... see DESIGN.md:
  * out is K-contiguous storage for the GEMM above: for A (M x K col-major) use transpose=1,
  * for B (K x N col-major) use transpose=0. Round-to-nearest-even. */

@@ -137,6 +137,7 @@ SIGNATURES = {
     "b200_saxpy": (_I32, [_VP, C.c_double, _VP, _VP, _SZ, _I32]),
     "b200_matmul_f32": (_I32, [_VP, _VP, _VP, _I64, _I64, _I64, _I64, _I64, _I64, _I32]),
     "b200_matmul_bf16": (_I32, [_VP, _VP, _VP, _I64, _I64, _I64, _I64]),
+    "b200_matmul_tf32": (_I32, [_VP, _VP, _VP, _I64, _I64, _I64, _I64, _I64, _I64]),
     "b200_convert_f32_bf16": (_I32, [_VP, _VP, _I64, _I64, _I64, _I32]),
     "b200_matmul_f32_via_bf16": (_I32, [_VP, _VP, _VP, _I64, _I64, _I64, _I64, _I64, _I64, _VP]),
     "b200_transpose_host": (_I32, [_VP, _VP, _I64, _I64, _I64, _I64, _I32]),

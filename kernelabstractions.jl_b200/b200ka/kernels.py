@@ -47,3 +47,7 @@ context_kernel = KernelFunction("context_kernel")                        # test/
 gpu_return_kernel_ = KernelFunction("gpu_return_kernel!")                # test/test.jl:307-313
 unaliased_accumulate_ = KernelFunction("unaliased_accumulate!")          # test/test.jl:339-345
 unaliased_accumulate_local_ = KernelFunction("unaliased_accumulate_local!")  # test/test.jl:347-356
+convert_kernel_ = KernelFunction("convert_kernel!")                      # test/convert.jl:5-44
+gamma_knl = KernelFunction("gamma_knl")                                  # test/specialfunctions.jl:5-18
+erf_knl = KernelFunction("erf_knl")
+erfc_knl = KernelFunction("erfc_knl")

@@ -10,6 +10,17 @@
 // so both are "K-major" for UMMA and one SWIZZLE_128B TMA box per operand per stage lands them in shared
 // memory in exactly the canonical layout the UMMA shared-memory descriptor expects.
 //
+// TF32 variant (b200_matmul_tf32, template parameter TF32): the SAME pipeline fed with the FP32 matrices exactly as they
+// lie in HBM -- no conversion pass at all.  B (K x N column-major) is K-major as before (box 32 k x 256 n, 128-byte rows);
+// A (M x K column-major) is M-contiguous, i.e. "MN-major" for UMMA: four TMA boxes of 32 m x 32 k per stage land as four
+// 4 KiB slabs [k][32 m].  For 32-bit MN-major operands the tensor core accepts ONE shared-memory layout only, the 128-byte
+// swizzle with a 32-byte atom (TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B <-> descriptor layout type 1): 32-byte chunk c of
+// k-row r is stored at chunk c ^ (r & 3); canonical form ((8,n),(4,k)):((1,LBO),(8,SBO)) in 16-byte units with
+// LBO = 4096 B (next 32 rows of M) and SBO = 512 B (next 4 k).  With the ordinary SWIZZLE_128B image the MMA silently
+// produces zeros (tools/micro/tf32_probe.cu tries the variants).  The instruction descriptor sets a_major = MN and
+// formats = TF32; each tcgen05.mma.kind::tf32 consumes K = 8 (two 4-k atoms, +1024 B per step).  The tensor core reads the FP32 words and
+// uses their top 19 bits.  Edge tiles: TMA zero-fills out-of-range rows/columns/k, the epilogue predicates its stores.
+//
 // CTA (192 threads, 1 per SM, persistent over 128x256 output tiles):
 //   warp 0   : TMA producer   -- cp.async.bulk.tensor.2d A(128x64) + B(256x64) per stage, 4 stages (192 KiB)
 //   warp 1   : TMEM allocator + MMA issuer -- one elected lane issues 4 x tcgen05.mma 128x256x16 per stage,
@@ -20,13 +31,16 @@
 #include <cuda_bf16.h>
 
 #include "../common.cuh"
+#include "../tma_pipe.cuh"
 #include "../tune.h"
 
 namespace b200 {
 
 namespace tc {
-constexpr int BM = 128, BN = 256, BK = 64, UMMA_K = 16, STAGES = 4;
+constexpr int BM = 128, BN = 256, BK = 64, UMMA_K = 16, STAGES = 4;   // BF16: 64 k per stage, 16 per MMA
+constexpr int BK_TF32 = 32, UMMA_K_TF32 = 8;                          // TF32: 32 k per stage, 8 per MMA (same bytes)
 constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+static_assert(BM * BK_TF32 * 4 == A_BYTES && BN * BK_TF32 * 4 == B_BYTES, "both variants use 128-byte operand rows");
 constexpr int NUM_THREADS = 192;
 constexpr int TMEM_COLS = 512;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
@@ -78,6 +92,23 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// MN-major, SWIZZLE_128B_BASE32B (layout type 1) canonical layout of a 128 (M) x 32 (k) FP32 operand staged as four
+// [k][32 m] slabs: LBO = 4096 B between 32-row groups of M, SBO = 512 B between groups of 4 k, version 1 (sm_100)
+__device__ __forceinline__ uint64_t make_desc_mn128(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(4096 >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)1 << 61);
+}
 // K-major, SWIZZLE_128B canonical layout: rows 128 B apart, 8-row atoms 1024 B apart (SBO), version 1 (sm_100)
 __device__ __forceinline__ uint64_t make_desc_k128(uint32_t saddr) {
     return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
@@ -85,6 +116,9 @@ __device__ __forceinline__ uint64_t make_desc_k128(uint32_t saddr) {
 }
 // kind::f16 instruction descriptor: D=F32, A=B=BF16, both K-major, N=BN, M=BM
 constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+// kind::tf32 instruction descriptor: D=F32, A=B=TF32, A MN-major (bit 15), B K-major, N=BN, M=BM
+constexpr uint32_t kIdescTf32 =
+    (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
@@ -99,9 +133,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+template <bool TF32>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-    gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                             float *__restrict__ C, int64_t ldc, int tiles_m, int tiles_n, int num_kb, int group_m) {
+    gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                        float *__restrict__ C, int64_t ldc, int M, int N, int tiles_m, int tiles_n, int num_kb,
+                        int group_m) {
+    constexpr int KB = TF32 ? BK_TF32 : BK;   // k elements per stage
     extern __shared__ unsigned char smem_raw[];
     // SWIZZLE_128B operands need 1024-byte aligned stage bases
     unsigned char *smem = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -160,8 +197,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
                     unsigned char *sa = smem + stage * STAGE_BYTES;
                     unsigned char *sb = sa + A_BYTES;
                     mbar_expect_tx(&full[stage], STAGE_BYTES);
-                    tma_load_2d(sa, &tmap_a, kb * BK, tm * BM, &full[stage]);
-                    tma_load_2d(sb, &tmap_b, kb * BK, tn * BN, &full[stage]);
+                    if (TF32) {
+#pragma unroll
+                        for (int g = 0; g < BM / 32; ++g)   // A slabs [k][32 m]: coordinates (m, k) of column-major A
+                            tma_load_2d(sa + g * 4096, &tmap_a, tm * BM + 32 * g, kb * KB, &full[stage]);
+                    } else {
+                        tma_load_2d(sa, &tmap_a, kb * KB, tm * BM, &full[stage]);
+                    }
+                    tma_load_2d(sb, &tmap_b, kb * KB, tn * BN, &full[stage]);
                     if (++stage == STAGES) {
                         stage = 0;
                         phase ^= 1;
@@ -185,11 +228,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-                    const uint64_t da = make_desc_k128(sa), db = make_desc_k128(sa + A_BYTES);
+                    const uint64_t db = make_desc_k128(sa + A_BYTES);
+                    if (TF32) {
+                        const uint64_t da = make_desc_mn128(sa);
 #pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; ++k) {
-                        // advance along K inside the 128-byte swizzle row: UMMA_K * 2 bytes = 32 B = 2 (16-byte units)
-                        umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), kIdesc, (kb | k) != 0);
+                        for (int k = 0; k < BK_TF32 / UMMA_K_TF32; ++k) {
+                            // A: next group of 8 k = +1024 B = 64 units; B: +32 B inside the 128-byte swizzle row = 2 units
+                            umma_tf32(tmem_d, da + (uint64_t)(64 * k), db + (uint64_t)(2 * k), kIdescTf32, (kb | k) != 0);
+                        }
+                    } else {
+                        const uint64_t da = make_desc_k128(sa);
+#pragma unroll
+                        for (int k = 0; k < BK / UMMA_K; ++k) {
+                            // advance along K inside the 128-byte swizzle row: UMMA_K * 2 bytes = 32 B = 2 (16-byte units)
+                            umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), kIdesc, (kb | k) != 0);
+                        }
                     }
                     umma_commit(&empty[stage]);  // stage reusable once these MMAs have read it
                     if (++stage == STAGES) {
@@ -212,14 +265,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
             const int64_t m = (int64_t)tm * BM + lane_grp * 32 + lane;
-            float *crow = C + m + (int64_t)tn * BN * ldc;
+            const int n0 = tn * BN;
+            float *crow = C + m + (int64_t)n0 * ldc;
             const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(acc * BN);
+            const bool full_tile = (tm + 1) * BM <= M && n0 + BN <= N;
 #pragma unroll 1
             for (int c = 0; c < BN; c += 32) {
                 uint32_t r[32];
-                tmem_ld32(taddr + (uint32_t)c, r);
+                tmem_ld32(taddr + (uint32_t)c, r);   // warp-collective: every lane takes part, stores are predicated
+                if (full_tile) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) crow[(int64_t)(c + j) * ldc] = __uint_as_float(r[j]);
+                    for (int j = 0; j < 32; ++j) crow[(int64_t)(c + j) * ldc] = __uint_as_float(r[j]);
+                } else if (m < M) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (n0 + c + j < N) crow[(int64_t)(c + j) * ldc] = __uint_as_float(r[j]);
+                }
             }
             tc_fence_before();
             mbar_arrive(&tmem_empty[acc]);
@@ -267,58 +328,55 @@ __global__ void __launch_bounds__(256) convert_bf16_transpose_kernel(__nv_bfloat
     }
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static int get_encode_fn(EncodeTiledFn *fn) {
-    static EncodeTiledFn cached = nullptr;
-    if (!cached) {
-        void *p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        B200_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
-        if (!p || q != cudaDriverEntryPointSuccess)
-            return set_error(B200_ERR_CUDA, "cuTensorMapEncodeTiled not available from the driver");
-        cached = (EncodeTiledFn)p;
-    }
-    *fn = cached;
-    return B200_OK;
-}
-
-// [rows x K] bf16, K contiguous; box = box_rows x 64 elements (128 bytes) with 128B swizzle
+// [rows x K] bf16, K contiguous; box = 64 elements (128 bytes) x box_rows with 128B swizzle
 static int make_tmap_bf16_kmajor(CUtensorMap *tm, const void *ptr, int64_t rows, int64_t K, int box_rows) {
-    EncodeTiledFn enc = nullptr;
-    B200_TRY(get_encode_fn(&enc));
-    cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
-    cuuint64_t gstride[1] = {(cuuint64_t)K * 2};
-    cuuint32_t box[2] = {(cuuint32_t)tc::BK, (cuuint32_t)box_rows};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(ptr), gdim, gstride, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return set_error(B200_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
-    return B200_OK;
+    return pipe::make_tmap_2d(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ptr, K, rows, K, tc::BK, box_rows,
+                              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
 }
 
 int gemm_bf16_launch(float *C, const uint16_t *A, const uint16_t *B, int64_t M, int64_t K, int64_t N, int64_t ldc,
                      cudaStream_t st) {
     using namespace tc;
-    if (M % BM || N % BN || K % BK || K <= 0)
+    if (M <= 0 || N <= 0 || K <= 0 || K % 8 != 0 || M > INT32_MAX || N > INT32_MAX || K > INT32_MAX)
         return set_error(B200_ERR_UNSUPPORTED,
-                         "b200_matmul_bf16: M, N, K must be positive multiples of %d, %d, %d (got %lld, %lld, %lld)", BM,
-                         BN, BK, (long long)M, (long long)N, (long long)K);
+                         "b200_matmul_bf16: M, N, K must be positive and K a multiple of 8 (TMA row pitch) (got %lld, %lld, %lld)",
+                         (long long)M, (long long)N, (long long)K);
     if ((((uintptr_t)A | (uintptr_t)B) & 15) != 0)
         return set_error(B200_ERR_INVALID_VALUE, "b200_matmul_bf16: operands must be 16-byte aligned");
     CUtensorMap ta, tb;
     B200_TRY(make_tmap_bf16_kmajor(&ta, A, M, K, BM));
     B200_TRY(make_tmap_bf16_kmajor(&tb, B, N, K, BN));
-    int tiles_m = (int)(M / BM), tiles_n = (int)(N / BN);
+    int tiles_m = (int)cdiv(M, BM), tiles_n = (int)cdiv(N, BN);
     int grid = sm_count();
     if (grid > tiles_m * tiles_n) grid = tiles_m * tiles_n;
-    B200_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    gemm_bf16_tcgen05_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ta, tb, C, ldc, tiles_m, tiles_n, (int)(K / BK),
-                                                                    tune_get("tcgemm.group_m", 16));
-    B200_CHECK_LAUNCH("gemm_bf16_tcgen05_kernel");
+    B200_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    gemm_tcgen05_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ta, tb, C, ldc, (int)M, (int)N, tiles_m, tiles_n,
+                                                                      (int)cdiv(K, BK), tune_get("tcgemm.group_m", 16));
+    B200_CHECK_LAUNCH("gemm_tcgen05_kernel<bf16>");
+    return B200_OK;
+}
+
+// FP32 operands straight from HBM: A (M x K, lda) column-major -> boxes of 32 m x 32 k; B (K x N, ldb) -> 32 k x 256 n
+int gemm_tf32_launch(float *C, const float *A, const float *B, int64_t M, int64_t K, int64_t N, int64_t lda, int64_t ldb,
+                     int64_t ldc, cudaStream_t st) {
+    using namespace tc;
+    if (M <= 0 || N <= 0 || K <= 0 || M > INT32_MAX || N > INT32_MAX || K > INT32_MAX)
+        return set_error(B200_ERR_UNSUPPORTED, "b200_matmul_tf32: M, N, K must be positive (got %lld, %lld, %lld)",
+                         (long long)M, (long long)N, (long long)K);
+    if ((lda % 4) || (ldb % 4) || ((((uintptr_t)A | (uintptr_t)B) & 15) != 0))
+        return set_error(B200_ERR_UNSUPPORTED, "b200_matmul_tf32: TMA needs 16-byte aligned operands and leading dimensions that are multiples of 4");
+    CUtensorMap ta, tb;
+    B200_TRY(pipe::make_tmap_2d(&ta, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, A, M, K, lda, 32, BK_TF32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B));
+    B200_TRY(pipe::make_tmap_2d(&tb, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, B, K, N, ldb, BK_TF32, BN, CU_TENSOR_MAP_SWIZZLE_128B,
+                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B));
+    int tiles_m = (int)cdiv(M, BM), tiles_n = (int)cdiv(N, BN);
+    int grid = sm_count();
+    if (grid > tiles_m * tiles_n) grid = tiles_m * tiles_n;
+    B200_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    gemm_tcgen05_kernel<true><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ta, tb, C, ldc, (int)M, (int)N, tiles_m, tiles_n,
+                                                                     (int)cdiv(K, BK_TF32), tune_get("tcgemm.group_m", 16));
+    B200_CHECK_LAUNCH("gemm_tcgen05_kernel<tf32>");
     return B200_OK;
 }
 
@@ -350,6 +408,17 @@ extern "C" b200_status b200_matmul_bf16(float *C, const uint16_t *Abf, const uin
     cudaStream_t st;
     B200_TRY(current_stream(&st));
     return gemm_bf16_launch(C, Abf, Bbf, M, K, N, ldc, st);
+}
+
+extern "C" b200_status b200_matmul_tf32(float *C, const float *A, const float *B, int64_t M, int64_t K, int64_t N,
+                                        int64_t lda, int64_t ldb, int64_t ldc) {
+    if (M < 0 || N < 0 || K < 0 || lda < M || ldb < K || ldc < M)
+        return set_error(B200_ERR_INVALID_VALUE, "b200_matmul_tf32: bad shape");
+    if (M == 0 || N == 0) return B200_OK;
+    if (!C || !A || !B) return set_error(B200_ERR_INVALID_VALUE, "b200_matmul_tf32: NULL pointer");
+    cudaStream_t st;
+    B200_TRY(current_stream(&st));
+    return gemm_tf32_launch(C, A, B, M, K, N, lda, ldb, ldc, st);
 }
 
 extern "C" b200_status b200_convert_f32_bf16(uint16_t *out, const float *in, int64_t rows, int64_t cols, int64_t ld,

@@ -403,6 +403,56 @@ int twin_unaliased_accumulate(const KaCtx &c, int local, void *output, const voi
     return B200_OK;
 }
 
+// ---- test/convert.jl:5-44 convert_kernel!: ceil / floor / round(ties to even) of A[tid] through ten integer types ----
+// Columns 5, 10, 15, 20, 25, 30 (Int128 / UInt128) are left untouched like the commented-out lines of the reference.
+template <typename T, typename I>
+__device__ __forceinline__ T through_int(T x) { return (T)(I)x; }
+template <typename T>
+__global__ void convert_twin_kernel(KaCtx c, const T *__restrict__ A, T *__restrict__ B, long long rowsB) {
+    if (ka_valid(c)) {
+        long long tid = ka_global_linear();
+        tid = (long long)(int)tid;   // Int64(Int32(tid))
+        const T a = A[tid - 1];
+        const T v[3] = {(T)ceil((double)a), (T)floor((double)a), (T)rint((double)a)};
+#pragma unroll
+        for (int op = 0; op < 3; ++op) {
+            T *col = B + (tid - 1) + (long long)(10 * op) * rowsB;
+            col[0 * rowsB] = through_int<T, signed char>(v[op]);
+            col[1 * rowsB] = through_int<T, short>(v[op]);
+            col[2 * rowsB] = through_int<T, int>(v[op]);
+            col[3 * rowsB] = through_int<T, long long>(v[op]);
+            col[5 * rowsB] = through_int<T, unsigned char>(v[op]);
+            col[6 * rowsB] = through_int<T, unsigned short>(v[op]);
+            col[7 * rowsB] = through_int<T, unsigned int>(v[op]);
+            col[8 * rowsB] = through_int<T, unsigned long long>(v[op]);
+        }
+    }
+}
+int twin_convert(const KaCtx &c, const void *A, void *B, long long rowsB, int is_f64, cudaStream_t st) {
+    KA_LAUNCH_1D(c, groups, items);
+    if (is_f64)
+        convert_twin_kernel<double><<<(unsigned)groups, (unsigned)items, 0, st>>>(c, (const double *)A, (double *)B, rowsB);
+    else
+        convert_twin_kernel<float><<<(unsigned)groups, (unsigned)items, 0, st>>>(c, (const float *)A, (float *)B, rowsB);
+    B200_CHECK_LAUNCH("convert_twin_kernel");
+    return B200_OK;
+}
+
+// ---- test/specialfunctions.jl:5-18 gamma_knl / erf_knl / erfc_knl (Float32; compared with isapprox upstream) ----
+__global__ void specialfn_twin_kernel(KaCtx c, int which, float *__restrict__ A, const float *__restrict__ B) {
+    if (ka_valid(c)) {
+        const long long I = ka_global_linear();
+        const float x = B[I - 1];
+        A[I - 1] = which == 0 ? tgammaf(x) : (which == 1 ? erff(x) : erfcf(x));
+    }
+}
+int twin_specialfn(const KaCtx &c, int which, float *A, const float *B, cudaStream_t st) {
+    KA_LAUNCH_1D(c, groups, items);
+    specialfn_twin_kernel<<<(unsigned)groups, (unsigned)items, 0, st>>>(c, which, A, B);
+    B200_CHECK_LAUNCH("specialfn_twin_kernel");
+    return B200_OK;
+}
+
 // ---- saxpy_kernel!  (benchmark/benchmarks.jl:29-32, examples/numa_aware.jl:10-13): Z = a*X + Y, unfused ----
 template <typename T>
 __global__ void saxpy_twin_kernel(KaCtx c, T *__restrict__ Z, T a, const T *__restrict__ X, const T *__restrict__ Y) {

@@ -40,6 +40,8 @@ int twin_saxpy(const KaCtx &c, void *Z, double a, const void *X, const void *Y, 
 int twin_misc_i64(const KaCtx &c, int which, long long *a, long long len, cudaStream_t st);
 int twin_unaliased_accumulate(const KaCtx &c, int local, void *output, const void *input, long long n,
                               long long rows_out, long long rows_in, int is_f64, cudaStream_t st);
+int twin_convert(const KaCtx &c, const void *A, void *B, long long rowsB, int is_f64, cudaStream_t st);
+int twin_specialfn(const KaCtx &c, int which, float *A, const float *B, cudaStream_t st);
 int twin_performance(const KaCtx &c, int which, void *out, const void *in, long long rows_out, long long rows_in,
                      long long bank, int elsize, cudaStream_t st);
 // literal twins (KI launches)

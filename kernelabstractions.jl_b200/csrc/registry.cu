@@ -269,6 +269,24 @@ static int h_unaliased_accumulate(const Launch &L) {
     return twin_unaliased_accumulate(L.ctx, LOCAL, o.ptr, in.ptr, n, dim(o, 0), dim(in, 0), o.eltype == B200_T_F64, L.st);
 }
 
+static int h_convert(const Launch &L) {
+    REQUIRE(L.nargs == 2 && is_array(L.args[0]) && is_array(L.args[1]), "convert_kernel!(A, B)");
+    const b200_arg &A = L.args[0], &B = L.args[1];
+    REQUIRE((A.eltype == B200_T_F32 || A.eltype == B200_T_F64) && B.eltype == A.eltype, "convert_kernel!: Float32/Float64 arrays of one type");
+    REQUIRE(B.ndim == 2 && dim(B, 1) >= 30, "convert_kernel!: B must have 30 columns");
+    const long long maxI = ka_max_global_linear(L.ctx);
+    REQUIRE(maxI <= numel(A) && maxI <= dim(B, 0) && maxI <= 2147483647LL, "convert_kernel!: ndrange exceeds the arrays");
+    return twin_convert(L.ctx, A.ptr, B.ptr, dim(B, 0), A.eltype == B200_T_F64, L.st);
+}
+template <int WHICH>
+static int h_specialfn(const Launch &L) {
+    REQUIRE(L.nargs == 2 && is_array(L.args[0]) && is_array(L.args[1]) && L.args[0].eltype == B200_T_F32 &&
+                L.args[1].eltype == B200_T_F32, "gamma_knl/erf_knl/erfc_knl(A::Array{Float32}, B::Array{Float32})");
+    const long long maxI = ka_max_global_linear(L.ctx);
+    REQUIRE(maxI <= numel(L.args[0]) && maxI <= numel(L.args[1]), "special function kernel: ndrange exceeds the arrays");
+    return twin_specialfn(L.ctx, WHICH, (float *)L.args[0].ptr, (const float *)L.args[1].ptr, L.st);
+}
+
 // examples/performance.jl:17-138.  The launch describes a rectangle of `output`/`input`; when the arrays are dense
 // over that rectangle the tuned copy / transpose kernels do the work, otherwise (and with registry.force_twins) the
 // literal twin with the script's own @localmem tile runs.
@@ -413,6 +431,10 @@ static const Entry kTable[] = {
     {"gpu_gpu_return_kernel!", B200_LAUNCH_KA, h_misc_i64<1>},                // test/test.jl:307-321
     {"gpu_unaliased_accumulate!", B200_LAUNCH_KA, h_unaliased_accumulate<0>}, // test/test.jl:339-345
     {"gpu_unaliased_accumulate_local!", B200_LAUNCH_KA, h_unaliased_accumulate<1>}, // test/test.jl:347-356
+    {"gpu_convert_kernel!", B200_LAUNCH_KA, h_convert},                       // test/convert.jl:5-44
+    {"gpu_gamma_knl", B200_LAUNCH_KA, h_specialfn<0>},                        // test/specialfunctions.jl:5-8
+    {"gpu_erf_knl", B200_LAUNCH_KA, h_specialfn<1>},                          // test/specialfunctions.jl:10-13
+    {"gpu_erfc_knl", B200_LAUNCH_KA, h_specialfn<2>},                         // test/specialfunctions.jl:15-18
     {"gpu_simple_copy_kernel!", B200_LAUNCH_KA, h_performance<0>},            // examples/performance.jl:17-20
     {"gpu_simple_transpose_kernel!", B200_LAUNCH_KA, h_performance<1>},       // examples/performance.jl:22-25
     {"gpu_lmem_copy_kernel!", B200_LAUNCH_KA, h_performance<2>},              // examples/performance.jl:29-46

@@ -47,4 +47,57 @@ for (M, K, N) in [(128, 64, 256), (128, 256, 256), (256, 512, 512), (1024, 2048,
     print(f"bf16 gemm {M}x{K}x{N}: convert_bit_exact={conv_ok} max_rel_err_vs_oracle={err_oracle:.3e} "
           f"vs_fp64_truth={err_truth:.3e} allclose_rtol1e-2={close}", flush=True)
     ok = ok and conv_ok and close and err_truth < 1e-4
+
+
+def tf32_trunc(x):
+    return (x.view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
+
+
+def tf32_rn(x):
+    u = x.view(np.uint32).astype(np.uint64)
+    u = (u + 0x0FFF + ((u >> 13) & 1)) & 0xFFFFE000
+    return u.astype(np.uint32).view(np.float32)
+
+
+# ---- TF32 path: FP32 operands straight from HBM (A is MN-major for the tensor core), incl. ragged edge tiles ----
+for (M, K, N) in [(128, 32, 256), (128, 256, 256), (256, 512, 512), (1024, 2048, 1024), (384, 4096, 768), (200, 100, 300), (129, 40, 257)]:
+    A = orc.gen_uniform_f32((M, K), 1237) - 0.5
+    B = orc.gen_uniform_f32((K, N), 1238) - 0.5
+    lda, ldb = (M + 3) // 4 * 4, (K + 3) // 4 * 4           # TMA needs leading dimensions that are multiples of 4
+    Ap = np.zeros((lda, K), dtype=np.float32, order="F")
+    Ap[:M] = A
+    Bp = np.zeros((ldb, N), dtype=np.float32, order="F")
+    Bp[:K] = B
+    dA, dB = KA.to_device(Ap), KA.to_device(Bp)
+    dC = KA.allocate(be, np.float32, M, N).fill_(-7.0)
+    _lib.call("b200_matmul_tf32", C.c_void_p(dC.ptr), C.c_void_p(dA.ptr), C.c_void_p(dB.ptr), M, K, N, lda, ldb, M)
+    KA.synchronize(be)
+    got = KA.Array(dC)
+    errs = {}
+    for name, f in (("trunc", tf32_trunc), ("rn", tf32_rn)):
+        truth = orc.matmul_f64_truth(np.asfortranarray(f(A)), np.asfortranarray(f(B)))
+        errs[name] = np.abs(got - truth).max() / np.abs(truth).max()
+    Ar, Br = np.asfortranarray(tf32_rn(A)), np.asfortranarray(tf32_rn(B))
+    ref = np.zeros((M, N), dtype=np.float32, order="F")
+    orc.coalesced_matmul(ref, Ar, Br)
+    scale = np.abs(ref).max()
+    close = np.allclose(got, ref, rtol=1e-2, atol=1e-2 * scale)
+    print(f"tf32 gemm {M}x{K}x{N}: max_rel_err vs fp64 truth on truncated inputs={errs['trunc']:.3e}, on RN-rounded inputs={errs['rn']:.3e} "
+          f"allclose_rtol1e-2_vs_fp32_oracle_on_tf32_inputs={close}", flush=True)
+    ok = ok and close and min(errs.values()) < 2e-3
+
+# ---- BF16 path on ragged shapes (edge tiles: TMA zero fill + predicated stores) ----
+for (M, K, N) in [(200, 104, 300), (129, 72, 257)]:
+    A = orc.gen_uniform_f32((M, K), 1237) - 0.5
+    B = orc.gen_uniform_f32((K, N), 1238) - 0.5
+    dA, dB = KA.to_device(A), KA.to_device(B)
+    dC = KA.allocate(be, np.float32, M, N).fill_(-7.0)
+    ws = KA.allocate(be, np.uint16, M * K + K * N)
+    _lib.call("b200_matmul_f32_via_bf16", C.c_void_p(dC.ptr), C.c_void_p(dA.ptr), C.c_void_p(dB.ptr), M, K, N, M, K, M, C.c_void_p(ws.ptr))
+    KA.synchronize(be)
+    got = KA.Array(dC)
+    truth = orc.matmul_f64_truth(np.asfortranarray(orc.round_bf16(A)), np.asfortranarray(orc.round_bf16(B)))
+    err = np.abs(got - truth).max() / np.abs(truth).max()
+    print(f"bf16 gemm ragged {M}x{K}x{N}: max_rel_err_vs_fp64_truth={err:.3e}", flush=True)
+    ok = ok and err < 1e-4
 sys.exit(0 if ok else 1)

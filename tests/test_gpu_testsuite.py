@@ -291,6 +291,46 @@ def test_unaliased_accumulate(orc):
         assert np.array_equal(KA.Array(out), ref)
 
 
+# ---- test/convert.jl:46-73, test/specialfunctions.jl:20-59 -----------------------------------------------------------------
+@pytest.mark.parametrize("ET", [np.float64, np.float32])
+def test_convert_testsuite(ET):
+    be = backend()
+    N = 32
+    rng = np.random.default_rng(3)
+    A = (rng.random(N) * 3).astype(ET)
+    A[:4] = [0.5, 1.5, 2.5, 2.0]          # ties: round() is round-half-to-even in Julia
+    d_A = KA.to_device(A)
+    d_B = KA.zeros(be, ET, N, 30)
+    K.convert_kernel_(be, 4)(d_A, d_B, ndrange=N)
+    KA.synchronize(be)
+    B = KA.Array(d_B)
+    for i in range(1, 11):
+        if i in (5, 10):
+            assert np.all(B[:, i - 1] == 0) and np.all(B[:, i + 9] == 0) and np.all(B[:, i + 19] == 0)   # Int128 lines are commented out
+            continue
+        assert np.array_equal(B[:, i - 1], np.ceil(A))
+        assert np.array_equal(B[:, i + 9], np.floor(A))
+        assert np.array_equal(B[:, i + 19], np.rint(A))
+
+
+def test_specialfunctions_testsuite():
+    import math
+    be = backend()
+    rtol = float(np.sqrt(np.finfo(np.float32).eps))     # Julia's isapprox default for Float32
+    cases = [(K.gamma_knl, math.gamma, [1.0, 2.0, 3.0, 5.5]),
+             (K.erf_knl, math.erf, [-1.0, -0.5, 0.0, 1.0e-3, 1.0, 2.0, 5.5]),
+             (K.erfc_knl, math.erfc, [-1.0, -0.5, 0.0, 1.0e-3, 1.0, 2.0, 5.5])]
+    for kern, f, xs in cases:
+        x = np.array(xs, dtype=np.float32)
+        cx = KA.allocate(be, np.float32, len(x))
+        KA.copyto_(be, cx, x)
+        cy = KA.similar(cx)
+        kern(be)(cy, cx, ndrange=len(x))
+        KA.synchronize(be)
+        want = np.array([f(float(v)) for v in x], dtype=np.float64)
+        assert np.allclose(KA.Array(cy).astype(np.float64), want, rtol=rtol, atol=0.0), kern.fname
+
+
 # ---- test/intrinsics.jl:27-124 ---------------------------------------------------------------------------------------------
 def test_ki_launch_parameters():
     be = backend()

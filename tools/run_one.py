@@ -99,6 +99,12 @@ elif kind == "hist_fused":
     peers = mg.PeerGroup(1, 0, lambda blob: [blob])
     run(lambda: peers.histogram_allreduce(bins, d_in), 4.0 * n, "GB/s")
     print("timeline ns after the counting loop [counts_merged, slots_sent, all_summed]:", peers.debug_stamps())
+elif kind == "tf32gemm":
+    n = size or 8192
+    A, B = KA.to_device(orc.gen_uniform_f32((n, n), 1237)), KA.to_device(orc.gen_uniform_f32((n, n), 1238))
+    Cd = KA.zeros(be, np.float32, n, n)
+    run(lambda: _lib.call("b200_matmul_tf32", C.c_void_p(Cd.ptr), C.c_void_p(A.ptr), C.c_void_p(B.ptr), n, n, n, n, n, n),
+        2.0 * n ** 3, "TFLOP/s")
 elif kind in ("sgemm", "tcgemm"):
     n = size or 8192
     A, B = KA.to_device(orc.gen_uniform_f32((n, n), 1237)), KA.to_device(orc.gen_uniform_f32((n, n), 1238))
