@@ -133,6 +133,16 @@ def matmul_bf16_(C_: B200Array, A: B200Array, B: B200Array, workspace: B200Array
               C_.shape[0], C.c_void_p(ws.ptr))
 
 
+def matmul_tf32_(C_: B200Array, A: B200Array, B: B200Array) -> None:
+    """Opt-in tensor-core path (no reference twin): tcgen05 kind::tf32 straight from the FP32 column-major operands --
+    no conversion pass, no workspace; the tensor core uses the top 19 bits of every operand, FP32 accumulate."""
+    M, K = A.shape
+    N = B.shape[1]
+    if B.shape[0] != K or C_.shape != (M, N):
+        raise _lib.ArgumentError("matmul_tf32_: shapes do not conform")
+    _lib.call("b200_matmul_tf32", C.c_void_p(C_.ptr), C.c_void_p(A.ptr), C.c_void_p(B.ptr), M, K, N, M, K, M)
+
+
 # ---- host-array forms: what `naive_transpose!(a, b)` / `histogram!(out, in)` are for a CPU() user -- plain host
 # ---- arrays in and out -- executed by B200Backend as a slab pipeline (h2d | kernel | d2h overlapped).
 def _host_f(arr: np.ndarray, name: str) -> np.ndarray:

@@ -300,6 +300,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 // ---- FP32 -> BF16 operand preparation (round to nearest even) ----------------------------------------
 // transpose == 0: out[r + c*rows] = bf16(in[r + c*ld])        (B: K x N column-major is already K-contiguous)
 // transpose != 0: out[c + r*cols] = bf16(in[r + c*ld])        (A: M x K column-major -> M rows of K)
+__device__ __forceinline__ float4 ld_nc_v4(const float4 *p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t *>(&v);
+}
+// generic form: any rows / ld / alignment
 __global__ void convert_bf16_kernel(__nv_bfloat16 *__restrict__ out, const float *__restrict__ in, int64_t rows,
                                     int64_t cols, int64_t ld) {
     const int64_t total = rows * cols;
@@ -308,6 +318,30 @@ __global__ void convert_bf16_kernel(__nv_bfloat16 *__restrict__ out, const float
         out[i] = __float2bfloat16_rn(in[r + c * ld]);
     }
 }
+// contiguous form (ld == rows, 16-byte aligned, total % 8 == 0): two 128-bit loads -> one 128-bit store per item,
+// four items in flight per thread
+__global__ void __launch_bounds__(256) convert_bf16_vec_kernel(uint4 *__restrict__ out, const float4 *__restrict__ in,
+                                                               int64_t n8) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < n8; i += 4 * stride) {
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            v[2 * u] = ld_nc_v4(in + 2 * (i + u * stride));
+            v[2 * u + 1] = ld_nc_v4(in + 2 * (i + u * stride) + 1);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            out[i + u * stride] = make_uint4(pack_bf16x2(v[2 * u].x, v[2 * u].y), pack_bf16x2(v[2 * u].z, v[2 * u].w),
+                                             pack_bf16x2(v[2 * u + 1].x, v[2 * u + 1].y), pack_bf16x2(v[2 * u + 1].z, v[2 * u + 1].w));
+    }
+    for (; i < n8; i += stride) {
+        const float4 a = ld_nc_v4(in + 2 * i), b = ld_nc_v4(in + 2 * i + 1);
+        out[i] = make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(b.x, b.y), pack_bf16x2(b.z, b.w));
+    }
+}
+// generic transposing form: 32 x 32 tiles, scalar accesses
 __global__ void __launch_bounds__(256) convert_bf16_transpose_kernel(__nv_bfloat16 *__restrict__ out,
                                                                      const float *__restrict__ in, int64_t rows,
                                                                      int64_t cols, int64_t ld, int64_t tiles_r) {
@@ -326,6 +360,32 @@ __global__ void __launch_bounds__(256) convert_bf16_transpose_kernel(__nv_bfloat
         int64_t c = c0 + tx, r = r0 + ty + q;
         if (r < rows && c < cols) out[c + r * cols] = __float2bfloat16_rn(tile[tx][ty + q]);
     }
+}
+// aligned transposing form (rows % 64 == 0, cols % 64 == 0, ld % 4 == 0, 16-byte aligned): 64 x 64 tiles; 128-bit
+// coalesced loads along r into tile[c][r] (row pitch 68 words: 16-byte aligned rows, conflict-free column reads), then
+// every thread converts 16 consecutive c of one r and writes one full 32-byte sector.
+__global__ void __launch_bounds__(256) convert_bf16_transpose64_kernel(__nv_bfloat16 *__restrict__ out,
+                                                                       const float *__restrict__ in, int64_t rows,
+                                                                       int64_t cols, int64_t ld, int64_t tiles_r) {
+    __shared__ __align__(16) float tile[64][68];
+    const int64_t r0 = (blockIdx.x % tiles_r) * 64, c0 = (blockIdx.x / tiles_r) * 64;
+    const int t = threadIdx.x;
+    {
+        const int rq = (t & 15) * 4, cl = t >> 4;   // 16 lanes x float4 = 64 r of one column; 16 columns per pass
+        float4 v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[q] = ld_nc_v4(reinterpret_cast<const float4 *>(in + (r0 + rq) + (c0 + cl + 16 * q) * ld));
+#pragma unroll
+        for (int q = 0; q < 4; ++q) *reinterpret_cast<float4 *>(&tile[cl + 16 * q][rq]) = v[q];
+    }
+    __syncthreads();
+    const int r = t & 63, cg = (t >> 6) * 16;
+    uint32_t w[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) w[j] = pack_bf16x2(tile[cg + 2 * j][r], tile[cg + 2 * j + 1][r]);
+    uint4 *dst = reinterpret_cast<uint4 *>(out + (c0 + cg) + (r0 + r) * cols);
+    dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
 }
 
 // [rows x K] bf16, K contiguous; box = 64 elements (128 bytes) x box_rows with 128B swizzle
@@ -383,10 +443,23 @@ int gemm_tf32_launch(float *C, const float *A, const float *B, int64_t M, int64_
 int convert_bf16_launch(uint16_t *out, const float *in, int64_t rows, int64_t cols, int64_t ld, int transpose,
                         cudaStream_t st) {
     if (rows == 0 || cols == 0) return B200_OK;
+    const bool al16 = ((((uintptr_t)out | (uintptr_t)in) & 15) == 0);
     if (!transpose) {
-        int grid = sm_count() * 8;
-        convert_bf16_kernel<<<grid, 256, 0, st>>>((__nv_bfloat16 *)out, in, rows, cols, ld);
-        B200_CHECK_LAUNCH("convert_bf16_kernel");
+        const int64_t total = rows * cols;
+        if (ld == rows && al16 && total % 8 == 0) {
+            int64_t blocks = cdiv(total / 8, 256 * 4);
+            int grid = (int)(blocks < (int64_t)sm_count() * 8 ? blocks : (int64_t)sm_count() * 8);
+            convert_bf16_vec_kernel<<<grid, 256, 0, st>>>((uint4 *)out, (const float4 *)in, total / 8);
+            B200_CHECK_LAUNCH("convert_bf16_vec_kernel");
+        } else {
+            int grid = sm_count() * 8;
+            convert_bf16_kernel<<<grid, 256, 0, st>>>((__nv_bfloat16 *)out, in, rows, cols, ld);
+            B200_CHECK_LAUNCH("convert_bf16_kernel");
+        }
+    } else if (al16 && rows % 64 == 0 && cols % 64 == 0 && ld % 4 == 0 && (rows / 64) * (cols / 64) <= 2147483647LL) {
+        convert_bf16_transpose64_kernel<<<(unsigned)((rows / 64) * (cols / 64)), 256, 0, st>>>((__nv_bfloat16 *)out, in, rows,
+                                                                                             cols, ld, rows / 64);
+        B200_CHECK_LAUNCH("convert_bf16_transpose64_kernel");
     } else {
         int64_t tiles_r = cdiv(rows, 32), tiles_c = cdiv(cols, 32);
         if (tiles_r * tiles_c > 2147483647LL) return set_error(B200_ERR_UNSUPPORTED, "convert: matrix too large");
