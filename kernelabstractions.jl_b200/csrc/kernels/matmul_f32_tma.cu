@@ -35,7 +35,9 @@ constexpr int CONSUMER_WARPS = 8, NUM_THREADS = CONSUMER_WARPS * 32;
 constexpr int LAG = 2;                       // a slot is refilled LAG k tiles after it was consumed
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * STAGES * 8;
 
-template <bool TILE16>
+// NJ = columns per thread (8, 7 or 6): the CTA tile is 128 x 16 NJ.  The narrower tiles exist only to fill whole waves of
+// the 148-SM grid (pick_nj below); the arithmetic per output element -- and therefore every bit of C -- does not change.
+template <bool TILE16, int NJ>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
     sgemm_tma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                      float *__restrict__ C, int M, int N, int64_t ldc, int ntiles, int tiles_m, int tiles_n, int group_m,
@@ -53,7 +55,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     const int gsz = min(tiles_m - first_m, group_m);
     const int tm = first_m + (pid % width) % gsz;
     const int tn = (pid % width) / gsz;
-    const int m0 = tm * BM, n0 = tn * BN;
+    constexpr int BN_ = 16 * NJ;
+    const int m0 = tm * BM, n0 = tn * BN_;
 
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     if (t == 0) {
@@ -70,32 +73,32 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     auto produce = [&](int kt) {   // thread 0 only
         const int s = kt % STAGES;
         if (kt >= STAGES) mbar_wait(&empty[s], ((kt / STAGES) - 1) & 1);
-        mbar_expect_tx(&full[s], STAGE_BYTES);
+        mbar_expect_tx(&full[s], A_BYTES + BN_ * BK * 4);
         unsigned char *stage = smem + s * STAGE_BYTES;
         tma_load_2d(stage, &tmap_a, m0, kt * BK, &full[s]);            // As[k][m]: 16 rows of 512 B
-        tma_load_2d(stage + A_BYTES, &tmap_b, kt * BK, n0, &full[s]);  // Bs[n][k]: 128 rows of 64 B
+        tma_load_2d(stage + A_BYTES, &tmap_b, kt * BK, n0, &full[s]);  // Bs[n][k]: 16 NJ rows of 64 B
     };
     if (t == 0)
         for (int kt = 0; kt < STAGES - LAG && kt < ntiles; ++kt) produce(kt);
 
     // ---------------------------------------------------------------------- consumers
-    const int wm = warp & 1, wn = warp >> 1;                        // 2 x 4 warps -> warp tile 64 x 32
+    const int wm = warp & 1, wn = warp >> 1;                        // 2 x 4 warps -> warp tile 64 x 4 NJ
     const int lx = (lane >> 1) & 7;                                 // lane bits 1-3 -> rows 4 lx .. 4 lx + 3 (+32)
     const int ly = (lane & 1) | ((lane >> 4) << 1);                 // lane bits 0,4 -> columns ly + 4 j
     const int mrow = wm * 64 + 4 * lx;
-    const int ncol = wn * 32 + ly;
+    const int ncol = wn * (4 * NJ) + ly;
 
-    float2 acc[4][8];
-    float2 tot[TILE16 ? 4 : 1][TILE16 ? 8 : 1];
+    float2 acc[4][NJ];
+    float2 tot[TILE16 ? 4 : 1][TILE16 ? NJ : 1];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = make_float2(0.0f, 0.0f);
+        for (int j = 0; j < NJ; ++j) acc[i][j] = make_float2(0.0f, 0.0f);
     if (TILE16) {
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) tot[TILE16 ? i : 0][TILE16 ? j : 0] = make_float2(-0.0f, -0.0f);
+            for (int j = 0; j < NJ; ++j) tot[TILE16 ? i : 0][TILE16 ? j : 0] = make_float2(-0.0f, -0.0f);
     }
 
     for (int kt = 0; kt < ntiles; ++kt) {
@@ -106,9 +109,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
         const float *Bs = reinterpret_cast<const float *>(smem + s * STAGE_BYTES + A_BYTES) + ncol * BK;
 #pragma unroll
         for (int k2 = 0; k2 < BK; k2 += 2) {
-            float2 b[8];
+            float2 b[NJ];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) b[j] = *reinterpret_cast<const float2 *>(Bs + (4 * j) * BK + k2);
+            for (int j = 0; j < NJ; ++j) b[j] = *reinterpret_cast<const float2 *>(Bs + (4 * j) * BK + k2);
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int kk = k2 + h;
@@ -119,7 +122,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
+                    for (int j = 0; j < NJ; ++j) {
                         const float bj = h ? b[j].y : b[j].x;
                         const float2 c = (TILE16 && kk == 0) ? make_float2(0.0f, 0.0f) : acc[i][j];  // out = zero(T)
                         acc[i][j] = __ffma2_rn(a[i], make_float2(bj, bj), c);                         // out += a*b
@@ -132,7 +135,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
+                for (int j = 0; j < NJ; ++j) {
                     float2 &tt = tot[TILE16 ? i : 0][TILE16 ? j : 0];
                     tt = __fadd2_rn(tt, acc[i][j]);                                                  // outval += out
                 }
@@ -141,7 +144,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 
     // epilogue: rows {mrow..+3, mrow+32..+35} of columns ncol + 4 j
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < NJ; ++j) {
         const int n = n0 + ncol + 4 * j;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -172,31 +175,58 @@ int sgemm_tma_applicable(const float *A, const float *B, int64_t M, int64_t K, i
            M < (1LL << 31) && N < (1LL << 31) && K < (1LL << 31);
 }
 
-int sgemm_tma_launch(float *C, const float *A, const float *B, int64_t M, int64_t K, int64_t N, int64_t lda,
-                     int64_t ldb, int64_t ldc, int mode, cudaStream_t st) {
+template <bool TILE16, int NJ>
+static int sgemm_tma_launch_nj(float *C, const float *A, const float *B, int64_t M, int64_t K, int64_t N, int64_t lda,
+                               int64_t ldb, int64_t ldc, cudaStream_t st) {
     using namespace sg;
+    constexpr int BN_ = 16 * NJ;
     CUtensorMap ta, tb;
     B200_TRY(pipe::make_tmap_2d(&ta, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, A, M, K, lda, BM, BK, CU_TENSOR_MAP_SWIZZLE_NONE,
                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B));
-    B200_TRY(pipe::make_tmap_2d(&tb, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, B, K, N, ldb, BK, BN, CU_TENSOR_MAP_SWIZZLE_NONE,
+    B200_TRY(pipe::make_tmap_2d(&tb, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, B, K, N, ldb, BK, BN_, CU_TENSOR_MAP_SWIZZLE_NONE,
                                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B));
-    const int tiles_m = (int)cdiv(M, BM), tiles_n = (int)cdiv(N, BN);
+    const int tiles_m = (int)cdiv(M, BM), tiles_n = (int)cdiv(N, BN_);
     if ((int64_t)tiles_m * tiles_n > INT32_MAX) return set_error(B200_ERR_UNSUPPORTED, "matmul: too many tiles");
     const unsigned grid = (unsigned)(tiles_m * tiles_n);
     const int ntiles = (int)cdiv(K, BK);
     const int group_m = tune_get("sgemm.group_m", 8);
     const int vec_ok = (ldc % 4 == 0) && (((uintptr_t)C & 15) == 0);
-    if (mode == B200_MATMUL_TILE16) {
-        B200_CUDA(cudaFuncSetAttribute(sgemm_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        sgemm_tma_kernel<true><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ta, tb, C, (int)M, (int)N, ldc, ntiles, tiles_m,
-                                                                       tiles_n, group_m, vec_ok);
-    } else {
-        B200_CUDA(cudaFuncSetAttribute(sgemm_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        sgemm_tma_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ta, tb, C, (int)M, (int)N, ldc, ntiles, tiles_m,
-                                                                        tiles_n, group_m, vec_ok);
-    }
+    B200_CUDA(cudaFuncSetAttribute(sgemm_tma_kernel<TILE16, NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    sgemm_tma_kernel<TILE16, NJ><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ta, tb, C, (int)M, (int)N, ldc, ntiles, tiles_m,
+                                                                         tiles_n, group_m, vec_ok);
     B200_CHECK_LAUNCH("sgemm_tma_kernel");
     return B200_OK;
+}
+
+// Columns per thread: CTAs run one per SM in rounds of `sms`, a round lasts ~NJ units, so minimise rounds * NJ (ties keep
+// the widest tile).  A 1024 x 8192 row panel (the 8-GPU shard of 8192^3) is 512 tiles of 128 x 128 = 3.46 rounds -> 4,
+// but 592 tiles of 128 x 112 = exactly 4 rounds of 7/8 the length.  `sgemm.nj` pins a value.
+static int pick_nj(int64_t M, int64_t N, int sms) {
+    const int forced = tune_get("sgemm.nj", 0);
+    if (forced >= 6 && forced <= 8) return forced;
+    int best = 8;
+    int64_t best_cost = INT64_MAX;
+    for (int nj = 8; nj >= 6; --nj) {
+        const int64_t cost = cdiv(cdiv(M, sg::BM) * cdiv(N, 16 * nj), sms) * nj;
+        if (cost < best_cost) {
+            best_cost = cost;
+            best = nj;
+        }
+    }
+    return best;
+}
+
+int sgemm_tma_launch(float *C, const float *A, const float *B, int64_t M, int64_t K, int64_t N, int64_t lda,
+                     int64_t ldb, int64_t ldc, int mode, cudaStream_t st) {
+    const int nj = pick_nj(M, N, sm_count());
+    if (mode == B200_MATMUL_TILE16) {
+        if (nj == 8) return sgemm_tma_launch_nj<true, 8>(C, A, B, M, K, N, lda, ldb, ldc, st);
+        if (nj == 7) return sgemm_tma_launch_nj<true, 7>(C, A, B, M, K, N, lda, ldb, ldc, st);
+        return sgemm_tma_launch_nj<true, 6>(C, A, B, M, K, N, lda, ldb, ldc, st);
+    }
+    if (nj == 8) return sgemm_tma_launch_nj<false, 8>(C, A, B, M, K, N, lda, ldb, ldc, st);
+    if (nj == 7) return sgemm_tma_launch_nj<false, 7>(C, A, B, M, K, N, lda, ldb, ldc, st);
+    return sgemm_tma_launch_nj<false, 6>(C, A, B, M, K, N, lda, ldb, ldc, st);
 }
 
 }  // namespace b200

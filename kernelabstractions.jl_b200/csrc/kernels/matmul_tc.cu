@@ -115,10 +115,10 @@ __device__ __forceinline__ uint64_t make_desc_k128(uint32_t saddr) {
            ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
 // kind::f16 instruction descriptor: D=F32, A=B=BF16, both K-major, N=BN, M=BM
-constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BM >> 4) << 24);   // | (bn >> 3) << 17 at run time
 // kind::tf32 instruction descriptor: D=F32, A=B=TF32, A MN-major (bit 15), B K-major, N=BN, M=BM
 constexpr uint32_t kIdescTf32 =
-    (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+    (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | ((uint32_t)(BM >> 4) << 24);
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
@@ -137,7 +137,9 @@ template <bool TF32>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
     gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                         float *__restrict__ C, int64_t ldc, int M, int N, int tiles_m, int tiles_n, int num_kb,
-                        int group_m) {
+                        int group_m, int bn) {
+    // bn = columns per output tile (multiple of 16, <= BN): chosen by the host so that the tile count fills whole
+    // waves of the persistent grid (pick_bn); shared-memory stages and TMEM accumulators stay sized for BN.
     constexpr int KB = TF32 ? BK_TF32 : BK;   // k elements per stage
     extern __shared__ unsigned char smem_raw[];
     // SWIZZLE_128B operands need 1024-byte aligned stage bases
@@ -196,7 +198,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
                     mbar_wait(&empty[stage], phase ^ 1);
                     unsigned char *sa = smem + stage * STAGE_BYTES;
                     unsigned char *sb = sa + A_BYTES;
-                    mbar_expect_tx(&full[stage], STAGE_BYTES);
+                    mbar_expect_tx(&full[stage], A_BYTES + bn * 128);
                     if (TF32) {
 #pragma unroll
                         for (int g = 0; g < BM / 32; ++g)   // A slabs [k][32 m]: coordinates (m, k) of column-major A
@@ -204,7 +206,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
                     } else {
                         tma_load_2d(sa, &tmap_a, kb * KB, tm * BM, &full[stage]);
                     }
-                    tma_load_2d(sb, &tmap_b, kb * KB, tn * BN, &full[stage]);
+                    tma_load_2d(sb, &tmap_b, kb * KB, tn * bn, &full[stage]);
                     if (++stage == STAGES) {
                         stage = 0;
                         phase ^= 1;
@@ -215,6 +217,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     } else if (warp == 1) {
         // ===== MMA issuer =====
         if (lane == 0) {
+            const uint32_t idesc = (TF32 ? kIdescTf32 : kIdesc) | ((uint32_t)(bn >> 3) << 17);
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
@@ -234,14 +237,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 #pragma unroll
                         for (int k = 0; k < BK_TF32 / UMMA_K_TF32; ++k) {
                             // A: next group of 8 k = +1024 B = 64 units; B: +32 B inside the 128-byte swizzle row = 2 units
-                            umma_tf32(tmem_d, da + (uint64_t)(64 * k), db + (uint64_t)(2 * k), kIdescTf32, (kb | k) != 0);
+                            umma_tf32(tmem_d, da + (uint64_t)(64 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
                         }
                     } else {
                         const uint64_t da = make_desc_k128(sa);
 #pragma unroll
                         for (int k = 0; k < BK / UMMA_K; ++k) {
                             // advance along K inside the 128-byte swizzle row: UMMA_K * 2 bytes = 32 B = 2 (16-byte units)
-                            umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), kIdesc, (kb | k) != 0);
+                            umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
                         }
                     }
                     umma_commit(&empty[stage]);  // stage reusable once these MMAs have read it
@@ -265,12 +268,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
             const int64_t m = (int64_t)tm * BM + lane_grp * 32 + lane;
-            const int n0 = tn * BN;
+            const int n0 = tn * bn;
             float *crow = C + m + (int64_t)n0 * ldc;
             const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(acc * BN);
-            const bool full_tile = (tm + 1) * BM <= M && n0 + BN <= N;
+            const bool full_tile = (tm + 1) * BM <= M && n0 + bn <= N && (bn & 31) == 0;
 #pragma unroll 1
-            for (int c = 0; c < BN; c += 32) {
+            for (int c = 0; c < bn; c += 32) {
                 uint32_t r[32];
                 tmem_ld32(taddr + (uint32_t)c, r);   // warp-collective: every lane takes part, stores are predicated
                 if (full_tile) {
@@ -279,7 +282,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
                 } else if (m < M) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
-                        if (n0 + c + j < N) crow[(int64_t)(c + j) * ldc] = __uint_as_float(r[j]);
+                        if (c + j < bn && n0 + c + j < N) crow[(int64_t)(c + j) * ldc] = __uint_as_float(r[j]);
                 }
             }
             tc_fence_before();
@@ -388,6 +391,27 @@ __global__ void __launch_bounds__(256) convert_bf16_transpose64_kernel(__nv_bflo
     dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
 }
 
+// Columns per output tile: the persistent grid works through ceil(tiles / SMs) rounds of tiles whose duration is
+// proportional to bn, so choose the bn (multiple of 16) that minimises rounds * bn -- e.g. a 1024 x 8192 row panel on
+// 148 SMs takes 2 rounds either way, 296 tiles of 128 x 224 instead of 256 tiles of 128 x 256 (-12.5 %).  Ties keep the
+// widest tile (fewest B re-reads); `tcgemm.bn` pins a value.
+static int pick_bn(int64_t M, int64_t N, int sms) {
+    const int forced = tune_get("tcgemm.bn", 0);
+    if (forced >= 16 && forced <= tc::BN && forced % 16 == 0) return forced;
+    const int64_t tiles_m = cdiv(M, tc::BM);
+    int best = tc::BN;
+    int64_t best_cost = INT64_MAX;
+    for (int bn = tc::BN; bn >= 128; bn -= 16) {
+        const int64_t tiles = tiles_m * cdiv(N, bn);
+        const int64_t cost = cdiv(tiles, sms) * (bn + 8);   // + 8: per-tile fixed cost (pipeline refill, epilogue hand-over)
+        if (cost < best_cost) {
+            best_cost = cost;
+            best = bn;
+        }
+    }
+    return best;
+}
+
 // [rows x K] bf16, K contiguous; box = 64 elements (128 bytes) x box_rows with 128B swizzle
 static int make_tmap_bf16_kmajor(CUtensorMap *tm, const void *ptr, int64_t rows, int64_t K, int box_rows) {
     return pipe::make_tmap_2d(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ptr, K, rows, K, tc::BK, box_rows,
@@ -404,14 +428,15 @@ int gemm_bf16_launch(float *C, const uint16_t *A, const uint16_t *B, int64_t M, 
     if ((((uintptr_t)A | (uintptr_t)B) & 15) != 0)
         return set_error(B200_ERR_INVALID_VALUE, "b200_matmul_bf16: operands must be 16-byte aligned");
     CUtensorMap ta, tb;
+    const int bn = pick_bn(M, N, sm_count());
     B200_TRY(make_tmap_bf16_kmajor(&ta, A, M, K, BM));
-    B200_TRY(make_tmap_bf16_kmajor(&tb, B, N, K, BN));
-    int tiles_m = (int)cdiv(M, BM), tiles_n = (int)cdiv(N, BN);
+    B200_TRY(make_tmap_bf16_kmajor(&tb, B, N, K, bn));
+    int tiles_m = (int)cdiv(M, BM), tiles_n = (int)cdiv(N, bn);
     int grid = sm_count();
     if (grid > tiles_m * tiles_n) grid = tiles_m * tiles_n;
     B200_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     gemm_tcgen05_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ta, tb, C, ldc, (int)M, (int)N, tiles_m, tiles_n,
-                                                                      (int)cdiv(K, BK), tune_get("tcgemm.group_m", 16));
+                                                                      (int)cdiv(K, BK), tune_get("tcgemm.group_m", 16), bn);
     B200_CHECK_LAUNCH("gemm_tcgen05_kernel<bf16>");
     return B200_OK;
 }
@@ -426,16 +451,17 @@ int gemm_tf32_launch(float *C, const float *A, const float *B, int64_t M, int64_
     if ((lda % 4) || (ldb % 4) || ((((uintptr_t)A | (uintptr_t)B) & 15) != 0))
         return set_error(B200_ERR_UNSUPPORTED, "b200_matmul_tf32: TMA needs 16-byte aligned operands and leading dimensions that are multiples of 4");
     CUtensorMap ta, tb;
+    const int bn = pick_bn(M, N, sm_count());
     B200_TRY(pipe::make_tmap_2d(&ta, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, A, M, K, lda, 32, BK_TF32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B));
-    B200_TRY(pipe::make_tmap_2d(&tb, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, B, K, N, ldb, BK_TF32, BN, CU_TENSOR_MAP_SWIZZLE_128B,
+    B200_TRY(pipe::make_tmap_2d(&tb, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, B, K, N, ldb, BK_TF32, bn, CU_TENSOR_MAP_SWIZZLE_128B,
                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B));
-    int tiles_m = (int)cdiv(M, BM), tiles_n = (int)cdiv(N, BN);
+    int tiles_m = (int)cdiv(M, BM), tiles_n = (int)cdiv(N, bn);
     int grid = sm_count();
     if (grid > tiles_m * tiles_n) grid = tiles_m * tiles_n;
     B200_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     gemm_tcgen05_kernel<true><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ta, tb, C, ldc, (int)M, (int)N, tiles_m, tiles_n,
-                                                                     (int)cdiv(K, BK_TF32), tune_get("tcgemm.group_m", 16));
+                                                                     (int)cdiv(K, BK_TF32), tune_get("tcgemm.group_m", 16), bn);
     B200_CHECK_LAUNCH("gemm_tcgen05_kernel<tf32>");
     return B200_OK;
 }

@@ -100,4 +100,27 @@ for (M, K, N) in [(200, 104, 300), (129, 72, 257)]:
     err = np.abs(got - truth).max() / np.abs(truth).max()
     print(f"bf16 gemm ragged {M}x{K}x{N}: max_rel_err_vs_fp64_truth={err:.3e}", flush=True)
     ok = ok and err < 1e-4
+
+# ---- every tile width the wave-filling heuristic may choose (tcgemm.bn pinned), both kinds, ragged N ----
+M, K, N = 256, 256, 1000
+A = orc.gen_uniform_f32((M, K), 1237) - 0.5
+B = orc.gen_uniform_f32((K, N), 1238) - 0.5
+dA, dB = KA.to_device(A), KA.to_device(B)
+ws = KA.allocate(be, np.uint16, M * K + K * N)
+truth_bf = orc.matmul_f64_truth(np.asfortranarray(orc.round_bf16(A)), np.asfortranarray(orc.round_bf16(B)))
+truth_tf = orc.matmul_f64_truth(np.asfortranarray(tf32_trunc(A)), np.asfortranarray(tf32_trunc(B)))
+worst = {"bf16": 0.0, "tf32": 0.0}
+for bn in range(128, 257, 16):
+    _lib.call("b200_tune_set", b"tcgemm.bn", bn)
+    dC = KA.allocate(be, np.float32, M, N).fill_(-7.0)
+    _lib.call("b200_matmul_f32_via_bf16", C.c_void_p(dC.ptr), C.c_void_p(dA.ptr), C.c_void_p(dB.ptr), M, K, N, M, K, M, C.c_void_p(ws.ptr))
+    KA.synchronize(be)
+    worst["bf16"] = max(worst["bf16"], np.abs(KA.Array(dC) - truth_bf).max() / np.abs(truth_bf).max())
+    dC.fill_(-7.0)
+    _lib.call("b200_matmul_tf32", C.c_void_p(dC.ptr), C.c_void_p(dA.ptr), C.c_void_p(dB.ptr), M, K, N, M, K, M)
+    KA.synchronize(be)
+    worst["tf32"] = max(worst["tf32"], np.abs(KA.Array(dC) - truth_tf).max() / np.abs(truth_tf).max())
+_lib.call("b200_tune_set", b"tcgemm.bn", 0)
+print(f"tile widths 128..256 step 16 on {M}x{K}x{N}: worst max_rel_err bf16={worst['bf16']:.3e} tf32={worst['tf32']:.3e}", flush=True)
+ok = ok and worst["bf16"] < 1e-4 and worst["tf32"] < 1e-4
 sys.exit(0 if ok else 1)

@@ -358,6 +358,26 @@ def test_matmul_signed_and_running_mode(orc):
         assert np.array_equal(KA.Array(dC2).view(np.uint32), ref2.view(np.uint32))
 
 
+@pytest.mark.parametrize("nj", [6, 7, 8])
+@pytest.mark.parametrize("shape", [(256, 200, 1000), (130, 17, 129), (384, 64, 112)])
+def test_matmul_tile_width_variants_bit_exact(orc, nj, shape):
+    # the wave-filling tile widths (128 x 16 nj, csrc/kernels/matmul_f32_tma.cu pick_nj) must not change a single bit
+    M, Kd, N = shape
+    A = orc.gen_uniform_f32((M, Kd), 1237) - 0.5
+    B = orc.gen_uniform_f32((Kd, N), 1238) - 0.5
+    dA, dB = KA.to_device(A), KA.to_device(B)
+    tune(sgemm__nj=nj)
+    try:
+        for mode, ref_fn in ((_lib.B200_MATMUL_TILE16, orc.coalesced_matmul), (_lib.B200_MATMUL_RUNNING, orc.matmul_running)):
+            dC = KA.allocate(be, np.float32, M, N).fill_(-7.0)
+            _lib.call("b200_matmul_f32", C.c_void_p(dC.ptr), C.c_void_p(dA.ptr), C.c_void_p(dB.ptr), M, Kd, N, M, Kd, M, mode)
+            ref = F((M, N), np.float32)
+            ref_fn(ref, A, B)
+            assert np.array_equal(KA.Array(dC).view(np.uint32), ref.view(np.uint32))
+    finally:
+        tune(sgemm__nj=0)
+
+
 def test_matmul_c4_size_sampled_blocks(orc):
     # BASELINE config: 8192^3 FP32.  The oracle cannot run 1.1 TFLOP in seconds, so bit-exactness is checked on
     # three 128x128 output blocks (each needs only a row panel of A and a column panel of B) and rtol 1e-5 vs FP64.

@@ -101,27 +101,32 @@ elif kind == "hist_fused":
     print("timeline ns after the counting loop [counts_merged, slots_sent, all_summed]:", peers.debug_stamps())
 elif kind == "tf32gemm":
     n = size or 8192
-    A, B = KA.to_device(orc.gen_uniform_f32((n, n), 1237)), KA.to_device(orc.gen_uniform_f32((n, n), 1238))
-    Cd = KA.zeros(be, np.float32, n, n)
-    run(lambda: _lib.call("b200_matmul_tf32", C.c_void_p(Cd.ptr), C.c_void_p(A.ptr), C.c_void_p(B.ptr), n, n, n, n, n, n),
-        2.0 * n ** 3, "TFLOP/s")
+    m = int(os.environ.get("RUN_M", n))      # rows of A / C (a row panel of the sharded problem)
+    A, B = KA.to_device(orc.gen_uniform_f32((m, n), 1237)), KA.to_device(orc.gen_uniform_f32((n, n), 1238))
+    Cd = KA.zeros(be, np.float32, m, n)
+    run(lambda: _lib.call("b200_matmul_tf32", C.c_void_p(Cd.ptr), C.c_void_p(A.ptr), C.c_void_p(B.ptr), m, n, n, m, n, m),
+        2.0 * m * n * n, "TFLOP/s")
 elif kind in ("sgemm", "tcgemm"):
     n = size or 8192
-    A, B = KA.to_device(orc.gen_uniform_f32((n, n), 1237)), KA.to_device(orc.gen_uniform_f32((n, n), 1238))
-    Cd = KA.zeros(be, np.float32, n, n)
+    m = int(os.environ.get("RUN_M", n))      # rows of A / C (a row panel of the sharded problem)
+    A, B = KA.to_device(orc.gen_uniform_f32((m, n), 1237)), KA.to_device(orc.gen_uniform_f32((n, n), 1238))
+    Cd = KA.zeros(be, np.float32, m, n)
+    for knob in ("sgemm.nj", "tcgemm.bn"):
+        if os.environ.get(knob.upper().replace(".", "_")):
+            _lib.call("b200_tune_set", knob.encode(), int(os.environ[knob.upper().replace(".", "_")]))
     if kind == "sgemm":
         if os.environ.get("SGEMM_VARIANT"):
             _lib.call("b200_tune_set", b"sgemm.variant", int(os.environ["SGEMM_VARIANT"]))
         if os.environ.get("SGEMM_ENGINE"):
             _lib.call("b200_tune_set", b"sgemm.engine", int(os.environ["SGEMM_ENGINE"]))
-        run(lambda: _lib.call("b200_matmul_f32", C.c_void_p(Cd.ptr), C.c_void_p(A.ptr), C.c_void_p(B.ptr), n, n, n, n, n, n, mode),
-            2.0 * n ** 3, "TFLOP/s")
+        run(lambda: _lib.call("b200_matmul_f32", C.c_void_p(Cd.ptr), C.c_void_p(A.ptr), C.c_void_p(B.ptr), m, n, n, m, n, m, mode),
+            2.0 * m * n * n, "TFLOP/s")
     else:
-        ws = KA.allocate(be, np.uint16, 2 * n * n)
-        _lib.call("b200_convert_f32_bf16", C.c_void_p(ws.ptr), C.c_void_p(A.ptr), n, n, n, 1)
-        _lib.call("b200_convert_f32_bf16", C.c_void_p(ws.ptr + 2 * n * n), C.c_void_p(B.ptr), n, n, n, 0)
-        run(lambda: _lib.call("b200_matmul_bf16", C.c_void_p(Cd.ptr), C.c_void_p(ws.ptr), C.c_void_p(ws.ptr + 2 * n * n), n, n, n, n),
-            2.0 * n ** 3, "TFLOP/s")
+        ws = KA.allocate(be, np.uint16, m * n + n * n)
+        _lib.call("b200_convert_f32_bf16", C.c_void_p(ws.ptr), C.c_void_p(A.ptr), m, n, m, 1)
+        _lib.call("b200_convert_f32_bf16", C.c_void_p(ws.ptr + 2 * m * n), C.c_void_p(B.ptr), n, n, n, 0)
+        run(lambda: _lib.call("b200_matmul_bf16", C.c_void_p(Cd.ptr), C.c_void_p(ws.ptr), C.c_void_p(ws.ptr + 2 * m * n), m, n, n, m),
+            2.0 * m * n * n, "TFLOP/s")
 elif kind == "cublas_sgemm":
     # library reference point only (never on the product path): cuBLAS FP32 SIMT GEMM through torch
     import torch
