@@ -37,13 +37,12 @@
 namespace b200 {
 
 namespace tc {
-constexpr int BM = 128, BN = 256, BK = 64, UMMA_K = 16, STAGES = 4;   // BF16: 64 k per stage, 16 per MMA
-constexpr int BK_TF32 = 32, UMMA_K_TF32 = 8;                          // TF32: 32 k per stage, 8 per MMA (same bytes)
-constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int BM = 128, BN = 256, BK = 64;   // BF16: 64 k per stage, 16 per MMA (4 MMAs per stage)
+constexpr int BK_TF32 = 32;                  // TF32: 32 k per stage,  8 per MMA (same bytes, 4 MMAs per stage)
+constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
 static_assert(BM * BK_TF32 * 4 == A_BYTES && BN * BK_TF32 * 4 == B_BYTES, "both variants use 128-byte operand rows");
 constexpr int NUM_THREADS = 192;
 constexpr int TMEM_COLS = 512;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
@@ -115,10 +114,10 @@ __device__ __forceinline__ uint64_t make_desc_k128(uint32_t saddr) {
            ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
 // kind::f16 instruction descriptor: D=F32, A=B=BF16, both K-major, N=BN, M=BM
-constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BM >> 4) << 24);   // | (bn >> 3) << 17 at run time
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10);   // | (bn >> 3) << 17 | (M >> 4) << 24 at run time
 // kind::tf32 instruction descriptor: D=F32, A=B=TF32, A MN-major (bit 15), B K-major, N=BN, M=BM
 constexpr uint32_t kIdescTf32 =
-    (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | ((uint32_t)(BM >> 4) << 24);
+    (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15);
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
@@ -133,16 +132,75 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// ---- CTA-pair (cta_group::2) plumbing -------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same variable in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load into THIS CTA's shared memory whose completion bytes are credited to the mbarrier at `bar_cluster_addr`
+// (the leader CTA's `full` barrier): the cta_group::2 form allows the barrier to live in the peer CTA.
+__device__ __forceinline__ void tma_load_2d_pair(void *smem_dst, const CUtensorMap *tmap, int c0, int c1,
+                                                 uint32_t bar_cluster_addr) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::
+            "r"(smem_u32(smem_dst)),
+        "l"(tmap), "r"(c0), "r"(c1), "r"(bar_cluster_addr)
+        : "memory");
+}
+// tcgen05.commit of a CTA pair: arrives on the barrier at the same offset in BOTH CTAs
+__device__ __forceinline__ void umma_commit_pair(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
 template <bool TF32>
+__device__ __forceinline__ void umma_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    if (TF32)
+        asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+                     "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+                     : "memory");
+    else
+        asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+                     "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+                     : "memory");
+}
+
+// NCTA = 1: one CTA per 128 x bn tile.  NCTA = 2: a CTA pair (cluster of 2, one TPC) per 256 x bn tile -- each CTA stages
+// its own 128 rows of A and HALF of the tile's B columns; the leader's tcgen05.mma.cta_group::2 (M = 256) reads both
+// halves, so every SM pulls 16 + 16 KiB per k block through L2 instead of 16 + 32, and six stages fit instead of four.
+template <int NCTA>
+struct PipeCfg {
+    static constexpr int STAGES = NCTA == 2 ? 6 : 4;
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES / NCTA;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <bool TF32, int NCTA>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
     gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                         float *__restrict__ C, int64_t ldc, int M, int N, int tiles_m, int tiles_n, int num_kb,
                         int group_m, int bn) {
-    // bn = columns per output tile (multiple of 16, <= BN): chosen by the host so that the tile count fills whole
-    // waves of the persistent grid (pick_bn); shared-memory stages and TMEM accumulators stay sized for BN.
+    // bn = columns per output tile (multiple of 16 NCTA, <= BN): chosen by the host so that the tile count fills whole
+    // rounds of the persistent grid (pick_bn); shared-memory stages and TMEM accumulators stay sized for BN.
     constexpr int KB = TF32 ? BK_TF32 : BK;   // k elements per stage
+    constexpr int STAGES = PipeCfg<NCTA>::STAGES, STAGE_BYTES = PipeCfg<NCTA>::STAGE_BYTES;
     extern __shared__ unsigned char smem_raw[];
-    // SWIZZLE_128B operands need 1024-byte aligned stage bases
+    // SWIZZLE_128B operands need 1024-byte aligned stage bases (the dynamic window starts at the same offset in both
+    // CTAs of a pair, so the aligned bases coincide as the pair MMA requires)
     unsigned char *smem = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t *full = (uint64_t *)(smem + STAGES * STAGE_BYTES);
     uint64_t *empty = full + STAGES;
@@ -152,28 +210,38 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_tiles = tiles_m * tiles_n;
+    const uint32_t rank = NCTA == 2 ? cluster_ctarank() : 0u;     // 0 = leader (issues the MMAs)
+    const int unit = blockIdx.x / NCTA, num_units = gridDim.x / NCTA;
+    const int bnh = bn / NCTA;                                      // B rows staged by this CTA
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(&full[s], 1);
-            mbar_init(&empty[s], 1);
+            mbar_init(&full[s], 1);    // leader's expect_tx arrive; bytes from both CTAs' TMA loads
+            mbar_init(&empty[s], 1);   // one tcgen05.commit (multicast to both CTAs of a pair)
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tmem_full[a], 1);
-            mbar_init(&tmem_empty[a], 128);
+            mbar_init(&tmem_empty[a], 4 * NCTA);   // one arrive per epilogue warp of every CTA of the pair
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                     "r"((uint32_t)TMEM_COLS)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (NCTA == 2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                         "r"((uint32_t)TMEM_COLS)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                         "r"((uint32_t)TMEM_COLS)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
-    __syncthreads();
+    if (NCTA == 2) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -187,26 +255,40 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     };
 
     if (warp == 0) {
-        // ===== TMA producer =====
+        // ===== TMA producer (every CTA: own A rows, own share of the B columns) =====
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int tile = unit; tile < num_tiles; tile += num_units) {
                 int tm, tn;
                 tile_coords(tile, tm, tn);
+                const int m_base = (tm * NCTA + (int)rank) * BM, n_base = tn * bn + (int)rank * bnh;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1);
                     unsigned char *sa = smem + stage * STAGE_BYTES;
                     unsigned char *sb = sa + A_BYTES;
-                    mbar_expect_tx(&full[stage], A_BYTES + bn * 128);
-                    if (TF32) {
+                    if (NCTA == 2) {
+                        const uint32_t lead_full = mapa_u32(smem_u32(&full[stage]), 0);
+                        if (rank == 0) mbar_expect_tx(&full[stage], 2 * (A_BYTES + bnh * 128));
+                        if (TF32) {
 #pragma unroll
-                        for (int g = 0; g < BM / 32; ++g)   // A slabs [k][32 m]: coordinates (m, k) of column-major A
-                            tma_load_2d(sa + g * 4096, &tmap_a, tm * BM + 32 * g, kb * KB, &full[stage]);
+                            for (int g = 0; g < BM / 32; ++g)
+                                tma_load_2d_pair(sa + g * 4096, &tmap_a, m_base + 32 * g, kb * KB, lead_full);
+                        } else {
+                            tma_load_2d_pair(sa, &tmap_a, kb * KB, m_base, lead_full);
+                        }
+                        tma_load_2d_pair(sb, &tmap_b, kb * KB, n_base, lead_full);
                     } else {
-                        tma_load_2d(sa, &tmap_a, kb * KB, tm * BM, &full[stage]);
+                        mbar_expect_tx(&full[stage], A_BYTES + bn * 128);
+                        if (TF32) {
+#pragma unroll
+                            for (int g = 0; g < BM / 32; ++g)   // A slabs [k][32 m]: coordinates (m, k) of column-major A
+                                tma_load_2d(sa + g * 4096, &tmap_a, m_base + 32 * g, kb * KB, &full[stage]);
+                        } else {
+                            tma_load_2d(sa, &tmap_a, kb * KB, m_base, &full[stage]);
+                        }
+                        tma_load_2d(sb, &tmap_b, kb * KB, n_base, &full[stage]);
                     }
-                    tma_load_2d(sb, &tmap_b, kb * KB, tn * bn, &full[stage]);
                     if (++stage == STAGES) {
                         stage = 0;
                         phase ^= 1;
@@ -215,13 +297,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0) {
-            const uint32_t idesc = (TF32 ? kIdescTf32 : kIdesc) | ((uint32_t)(bn >> 3) << 17);
+        // ===== MMA issuer (leader CTA only) =====
+        if (lane == 0 && rank == 0) {
+            const uint32_t idesc = (TF32 ? kIdescTf32 : kIdesc) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)((BM * NCTA) >> 4) << 24);
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+            for (int tile = unit; tile < num_tiles; tile += num_units, ++it) {
                 const int acc = it & 1;
                 const uint32_t acc_phase = (uint32_t)(it >> 1) & 1;
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
@@ -232,46 +314,46 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
                     const uint64_t db = make_desc_k128(sa + A_BYTES);
-                    if (TF32) {
-                        const uint64_t da = make_desc_mn128(sa);
+                    const uint64_t da = TF32 ? make_desc_mn128(sa) : make_desc_k128(sa);
+                    // TF32: A's next group of 8 k = +1024 B = 64 units; K-major operands: +32 B inside the 128-byte
+                    // swizzle row = 2 units per MMA (UMMA_K * 2 bytes for BF16, UMMA_K_TF32 * 4 bytes for TF32)
+                    constexpr int a_step = TF32 ? 64 : 2;
 #pragma unroll
-                        for (int k = 0; k < BK_TF32 / UMMA_K_TF32; ++k) {
-                            // A: next group of 8 k = +1024 B = 64 units; B: +32 B inside the 128-byte swizzle row = 2 units
-                            umma_tf32(tmem_d, da + (uint64_t)(64 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
-                        }
-                    } else {
-                        const uint64_t da = make_desc_k128(sa);
-#pragma unroll
-                        for (int k = 0; k < BK / UMMA_K; ++k) {
-                            // advance along K inside the 128-byte swizzle row: UMMA_K * 2 bytes = 32 B = 2 (16-byte units)
-                            umma_bf16(tmem_d, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                    for (int k = 0; k < 4; ++k) {
+                        if (NCTA == 2) {
+                            umma_pair<TF32>(tmem_d, da + (uint64_t)(a_step * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                        } else if (TF32) {
+                            umma_tf32(tmem_d, da + (uint64_t)(a_step * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                        } else {
+                            umma_bf16(tmem_d, da + (uint64_t)(a_step * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
                         }
                     }
-                    umma_commit(&empty[stage]);  // stage reusable once these MMAs have read it
+                    if (NCTA == 2) umma_commit_pair(&empty[stage]); else umma_commit(&empty[stage]);  // stage reusable once read
                     if (++stage == STAGES) {
                         stage = 0;
                         phase ^= 1;
                     }
                 }
-                umma_commit(&tmem_full[acc]);  // accumulator complete
+                if (NCTA == 2) umma_commit_pair(&tmem_full[acc]); else umma_commit(&tmem_full[acc]);  // accumulator complete
             }
         }
     } else {
-        // ===== epilogue: warps 2..5 own TMEM lanes 32*(warp%4) .. +31 =====
+        // ===== epilogue warps 2..5: TMEM lane group = warp % 4 (own 128 rows of the tile) =====
         const int lane_grp = warp & 3;
+        const uint32_t lead_empty0 = NCTA == 2 ? mapa_u32(smem_u32(&tmem_empty[0]), 0) : 0u;
         int it = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        for (int tile = unit; tile < num_tiles; tile += num_units, ++it) {
             int tm, tn;
             tile_coords(tile, tm, tn);
             const int acc = it & 1;
             const uint32_t acc_phase = (uint32_t)(it >> 1) & 1;
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
-            const int64_t m = (int64_t)tm * BM + lane_grp * 32 + lane;
+            const int64_t m = (int64_t)(tm * NCTA + (int)rank) * BM + lane_grp * 32 + lane;
             const int n0 = tn * bn;
             float *crow = C + m + (int64_t)n0 * ldc;
             const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(acc * BN);
-            const bool full_tile = (tm + 1) * BM <= M && n0 + bn <= N && (bn & 31) == 0;
+            const bool full_tile = (int64_t)(tm * NCTA + (int)rank + 1) * BM <= M && n0 + bn <= N && (bn & 31) == 0;
 #pragma unroll 1
             for (int c = 0; c < bn; c += 32) {
                 uint32_t r[32];
@@ -286,16 +368,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
                 }
             }
             tc_fence_before();
-            mbar_arrive(&tmem_empty[acc]);
+            __syncwarp();
+            if (lane == 0) {   // this warp has drained its quarter of the accumulator
+                if (NCTA == 2) mbar_arrive_cluster(lead_empty0 + (uint32_t)(acc * 8)); else mbar_arrive(&tmem_empty[acc]);
+            }
         }
     }
+    __syncwarp();   // role branches diverged inside the warp; the cluster barrier is warp-aligned
     tc_fence_before();
-    __syncthreads();
+    if (NCTA == 2) cluster_sync_all(); else __syncthreads();
     if (warp == 1) {
         __syncwarp();
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS)
-                     : "memory");
+        if (NCTA == 2)
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
     }
 }
 }  // namespace tc
@@ -391,19 +479,20 @@ __global__ void __launch_bounds__(256) convert_bf16_transpose64_kernel(__nv_bflo
     dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
 }
 
-// Columns per output tile: the persistent grid works through ceil(tiles / SMs) rounds of tiles whose duration is
-// proportional to bn, so choose the bn (multiple of 16) that minimises rounds * bn -- e.g. a 1024 x 8192 row panel on
-// 148 SMs takes 2 rounds either way, 296 tiles of 128 x 224 instead of 256 tiles of 128 x 256 (-12.5 %).  Ties keep the
-// widest tile (fewest B re-reads); `tcgemm.bn` pins a value.
-static int pick_bn(int64_t M, int64_t N, int sms) {
+// Columns per output tile: the persistent grid works through ceil(tiles / units) rounds of tiles whose duration is
+// proportional to bn, so choose the bn that minimises rounds * bn -- e.g. a 1024 x 8192 row panel on 74 CTA pairs takes
+// 2 rounds either way, 148 tiles of 256 x 224 instead of 128 tiles of 256 x 256.  Ties keep the widest tile (fewest
+// re-reads of A); `tcgemm.bn` pins a value.  bn is a multiple of 16 per CTA of the unit.
+static int pick_bn(int64_t M, int64_t N, int units, int ncta) {
+    const int step = 16 * ncta;
     const int forced = tune_get("tcgemm.bn", 0);
-    if (forced >= 16 && forced <= tc::BN && forced % 16 == 0) return forced;
-    const int64_t tiles_m = cdiv(M, tc::BM);
+    if (forced >= step && forced <= tc::BN && forced % step == 0) return forced;
+    const int64_t tiles_m = cdiv(M, tc::BM * ncta);
     int best = tc::BN;
     int64_t best_cost = INT64_MAX;
-    for (int bn = tc::BN; bn >= 128; bn -= 16) {
+    for (int bn = tc::BN; bn >= 128; bn -= step) {
         const int64_t tiles = tiles_m * cdiv(N, bn);
-        const int64_t cost = cdiv(tiles, sms) * (bn + 8);   // + 8: per-tile fixed cost (pipeline refill, epilogue hand-over)
+        const int64_t cost = cdiv(tiles, units) * (bn + 8);   // + 8: per-tile fixed cost (pipeline refill, epilogue hand-over)
         if (cost < best_cost) {
             best_cost = cost;
             best = bn;
@@ -411,6 +500,36 @@ static int pick_bn(int64_t M, int64_t N, int sms) {
     }
     return best;
 }
+
+// One persistent CTA per SM; NCTA = 2 launches clusters of two (a CTA pair shares a TPC) -- chosen when the matrix has
+// more than one 128-row tile (`tcgemm.cta2` = 0 forces single CTAs).
+template <bool TF32, int NCTA>
+static int launch_tcgen05(const CUtensorMap &ta, const CUtensorMap &tb, float *C, int64_t ldc, int64_t M, int64_t N, int num_kb,
+                          int bn, cudaStream_t st) {
+    using namespace tc;
+    const int tiles_m = (int)cdiv(M, BM * NCTA), tiles_n = (int)cdiv(N, bn);
+    int grid = sm_count() / NCTA * NCTA;
+    if ((int64_t)grid > (int64_t)tiles_m * tiles_n * NCTA) grid = tiles_m * tiles_n * NCTA;
+    auto kfn = gemm_tcgen05_kernel<TF32, NCTA>;
+    B200_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, PipeCfg<NCTA>::SMEM_BYTES));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = PipeCfg<NCTA>::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = NCTA;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    B200_CUDA(cudaLaunchKernelEx(&cfg, kfn, ta, tb, C, ldc, (int)M, (int)N, tiles_m, tiles_n, num_kb,
+                                 tune_get("tcgemm.group_m", NCTA == 2 ? 8 : 16), bn));
+    B200_CHECK_LAUNCH(TF32 ? "gemm_tcgen05_kernel<tf32>" : "gemm_tcgen05_kernel<bf16>");
+    return B200_OK;
+}
+static int use_cta_pairs(int64_t M) { return tune_get("tcgemm.cta2", 1) != 0 && M > tc::BM; }
 
 // [rows x K] bf16, K contiguous; box = 64 elements (128 bytes) x box_rows with 128B swizzle
 static int make_tmap_bf16_kmajor(CUtensorMap *tm, const void *ptr, int64_t rows, int64_t K, int box_rows) {
@@ -428,17 +547,12 @@ int gemm_bf16_launch(float *C, const uint16_t *A, const uint16_t *B, int64_t M, 
     if ((((uintptr_t)A | (uintptr_t)B) & 15) != 0)
         return set_error(B200_ERR_INVALID_VALUE, "b200_matmul_bf16: operands must be 16-byte aligned");
     CUtensorMap ta, tb;
-    const int bn = pick_bn(M, N, sm_count());
+    const int ncta = use_cta_pairs(M) ? 2 : 1;
+    const int bn = pick_bn(M, N, sm_count() / ncta, ncta);
     B200_TRY(make_tmap_bf16_kmajor(&ta, A, M, K, BM));
-    B200_TRY(make_tmap_bf16_kmajor(&tb, B, N, K, bn));
-    int tiles_m = (int)cdiv(M, BM), tiles_n = (int)cdiv(N, bn);
-    int grid = sm_count();
-    if (grid > tiles_m * tiles_n) grid = tiles_m * tiles_n;
-    B200_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    gemm_tcgen05_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ta, tb, C, ldc, (int)M, (int)N, tiles_m, tiles_n,
-                                                                      (int)cdiv(K, BK), tune_get("tcgemm.group_m", 16), bn);
-    B200_CHECK_LAUNCH("gemm_tcgen05_kernel<bf16>");
-    return B200_OK;
+    B200_TRY(make_tmap_bf16_kmajor(&tb, B, N, K, bn / ncta));
+    if (ncta == 2) return launch_tcgen05<false, 2>(ta, tb, C, ldc, M, N, (int)cdiv(K, BK), bn, st);
+    return launch_tcgen05<false, 1>(ta, tb, C, ldc, M, N, (int)cdiv(K, BK), bn, st);
 }
 
 // FP32 operands straight from HBM: A (M x K, lda) column-major -> boxes of 32 m x 32 k; B (K x N, ldb) -> 32 k x 256 n
@@ -451,19 +565,14 @@ int gemm_tf32_launch(float *C, const float *A, const float *B, int64_t M, int64_
     if ((lda % 4) || (ldb % 4) || ((((uintptr_t)A | (uintptr_t)B) & 15) != 0))
         return set_error(B200_ERR_UNSUPPORTED, "b200_matmul_tf32: TMA needs 16-byte aligned operands and leading dimensions that are multiples of 4");
     CUtensorMap ta, tb;
-    const int bn = pick_bn(M, N, sm_count());
+    const int ncta = use_cta_pairs(M) ? 2 : 1;
+    const int bn = pick_bn(M, N, sm_count() / ncta, ncta);
     B200_TRY(pipe::make_tmap_2d(&ta, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, A, M, K, lda, 32, BK_TF32, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B));
-    B200_TRY(pipe::make_tmap_2d(&tb, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, B, K, N, ldb, BK_TF32, bn, CU_TENSOR_MAP_SWIZZLE_128B,
+    B200_TRY(pipe::make_tmap_2d(&tb, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, B, K, N, ldb, BK_TF32, bn / ncta, CU_TENSOR_MAP_SWIZZLE_128B,
                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B));
-    int tiles_m = (int)cdiv(M, BM), tiles_n = (int)cdiv(N, bn);
-    int grid = sm_count();
-    if (grid > tiles_m * tiles_n) grid = tiles_m * tiles_n;
-    B200_CUDA(cudaFuncSetAttribute(gemm_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    gemm_tcgen05_kernel<true><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ta, tb, C, ldc, (int)M, (int)N, tiles_m, tiles_n,
-                                                                     (int)cdiv(K, BK_TF32), tune_get("tcgemm.group_m", 16), bn);
-    B200_CHECK_LAUNCH("gemm_tcgen05_kernel<tf32>");
-    return B200_OK;
+    if (ncta == 2) return launch_tcgen05<true, 2>(ta, tb, C, ldc, M, N, (int)cdiv(K, BK_TF32), bn, st);
+    return launch_tcgen05<true, 1>(ta, tb, C, ldc, M, N, (int)cdiv(K, BK_TF32), bn, st);
 }
 
 int convert_bf16_launch(uint16_t *out, const float *in, int64_t rows, int64_t cols, int64_t ld, int transpose,
