@@ -23,6 +23,9 @@ size = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 mode = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 iters = int(sys.argv[4]) if len(sys.argv) > 4 else 3
 be = KA.B200Backend()
+for kv in filter(None, os.environ.get("B200_TUNE", "").split(",")):     # e.g. B200_TUNE=tcgemm.group_m=4,tcgemm.cta2=0
+    k, v = kv.rsplit("=", 1)
+    _lib.call("b200_tune_set", k.encode(), int(v))
 
 
 def ev():
@@ -85,6 +88,12 @@ elif kind == "transpose":
     n = size or 16384
     b_, a_ = KA.to_device(orc.gen_uniform_f32((n, n), 1235)), KA.zeros(be, np.float32, n, n)
     run(lambda: _lib.call("b200_transpose", C.c_void_p(a_.ptr), C.c_void_p(b_.ptr), n, n, n, n, 4), 8.0 * n * n, "GB/s")
+elif kind == "saxpy":
+    n = size or (1 << 26)
+    x, y = KA.to_device(orc.gen_uniform_f32((n,), 2)), KA.to_device(orc.gen_uniform_f32((n,), 3))
+    z = KA.zeros(be, np.float32, n)
+    run(lambda: _lib.call("b200_saxpy", C.c_void_p(z.ptr), C.c_double(3.1415), C.c_void_p(x.ptr), C.c_void_p(y.ptr), C.c_size_t(n), 4),
+        12.0 * n, "GB/s")
 elif kind == "hist":
     n = size or (1 << 30)
     d_in = KA.to_device(orc.gen_bins_i32(n, 1236, 256) if mode == 0 else np.full(n, 2, dtype=np.int32))
