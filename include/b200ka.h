@@ -217,6 +217,25 @@ b200_status b200_convert_f32_bf16(uint16_t *out, const float *in, int64_t rows, 
 b200_status b200_matmul_f32_via_bf16(float *C, const float *A, const float *B, int64_t M, int64_t K,
                                      int64_t N, int64_t lda, int64_t ldb, int64_t ldc, void *workspace);
 
+/* ---- device-array conveniences: what Base / LinearAlgebra give a CPU() user for free on plain Arrays ----------------
+ * (SURVEY.md 8(f)-4).  These return a VALUE, so they wait for the calling thread's stream.  Arrays 16-byte aligned.
+ *
+ * maximum / minimum / sum over n elements (examples/histogram.jl:10,88-90 sizes the histogram with `maximum(input)`).
+ * op: 0 = sum, 1 = maximum, 2 = minimum.  eltype: B200_T_I32/U32/I64/U64/F32/F64.  *result_host receives a value of the
+ * element type for maximum/minimum (NaN propagates, max(-0.0, 0.0) == 0.0 as in Julia) and an 8-byte Int64 / UInt64 /
+ * Float64 for sum.  n == 0: sum is 0, maximum/minimum are B200_ERR_INVALID_VALUE (Julia throws ArgumentError). */
+b200_status b200_reduce(int32_t op, int32_t eltype, const void *x, size_t n, void *result_host);
+/* `A == B` (examples/memcopy.jl:23, naive_transpose.jl:32, test/copyto.jl:17-19): number of positions with !(a == b);
+ * F32/F64 compare numerically (NaN != NaN, -0.0 == 0.0), every other eltype compares elsize bytes per element. */
+b200_status b200_count_mismatch(const void *a, const void *b, size_t n, int32_t eltype, int32_t elsize, int64_t *count_host);
+/* isapprox(A, B) (examples/matmul.jl:36, performant_matmul.jl:92): out3_host = { sum (x-y)^2, sum x^2, sum y^2 } in Float64;
+ * the host layer applies  sqrt(out[0]) <= max(atol, rtol * max(sqrt(out[1]), sqrt(out[2]))). */
+b200_status b200_norms(const void *x, const void *y, size_t n, int32_t is_f64, double *out3_host);
+/* Deterministic input streams of SURVEY.md 8(d) generated on the device, bit-identical to the oracle's generators:
+ * uniform Float32 in [0,1) with 24 random bits, and Int32 values uniform in 1..nbins (examples/histogram.jl:76). */
+b200_status b200_rand_uniform_f32(float *out, size_t n, uint64_t seed);
+b200_status b200_rand_bins_i32(int32_t *out, size_t n, uint64_t seed, int32_t nbins);
+
 /* ---- host-buffer ("out-of-core") forms ---------------------------------------------------------
  * Same semantics as b200_transpose / b200_histogram_i32, but every array lives in HOST memory: what a user of
  * the reference's CPU() backend calls on plain Arrays (examples/naive_transpose.jl:9-21, examples/histogram.jl:61-72).

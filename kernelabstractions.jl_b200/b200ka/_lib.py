@@ -140,6 +140,11 @@ SIGNATURES = {
     "b200_matmul_tf32": (_I32, [_VP, _VP, _VP, _I64, _I64, _I64, _I64, _I64, _I64]),
     "b200_convert_f32_bf16": (_I32, [_VP, _VP, _I64, _I64, _I64, _I32]),
     "b200_matmul_f32_via_bf16": (_I32, [_VP, _VP, _VP, _I64, _I64, _I64, _I64, _I64, _I64, _VP]),
+    "b200_reduce": (_I32, [_I32, _I32, _VP, _SZ, _VP]),
+    "b200_count_mismatch": (_I32, [_VP, _VP, _SZ, _I32, _I32, _VP]),
+    "b200_norms": (_I32, [_VP, _VP, _SZ, _I32, _VP]),
+    "b200_rand_uniform_f32": (_I32, [_VP, _SZ, C.c_uint64]),
+    "b200_rand_bins_i32": (_I32, [_VP, _SZ, C.c_uint64, _I32]),
     "b200_transpose_host": (_I32, [_VP, _VP, _I64, _I64, _I64, _I64, _I32]),
     "b200_histogram_i32_host": (_I32, [_VP, _I64, _VP, _I64]),
     "b200_comm_unique_id": (_I32, [_VP]),

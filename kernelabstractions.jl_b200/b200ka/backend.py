@@ -329,3 +329,97 @@ def adapt(backend, x):
     if isinstance(backend, B200Backend):
         return x if isinstance(x, B200Array) else to_device(x)
     raise MethodError("adapt: unknown backend")
+
+
+# ---- device-array conveniences: what Base / LinearAlgebra give a CPU() user on plain Arrays -----------
+_RESULT_KIND = {"i": np.int64, "u": np.uint64, "f": np.float64}
+
+
+def _reduce(A: B200Array, op: int):
+    code = eltype_code(A.dtype)
+    out = np.zeros(1, dtype=(_RESULT_KIND[A.dtype.kind] if op == 0 else A.dtype))
+    call("b200_reduce", C.c_int32(op), C.c_int32(code), C.c_void_p(A.ptr), C.c_size_t(A.size), out.ctypes.data_as(C.c_void_p))
+    return out[0]
+
+
+def sum(A: B200Array):  # noqa: A001 -- Base.sum
+    """sum(A): integers are carried in Int64/UInt64 like Julia's widening, floats in Float64."""
+    return _reduce(A, 0)
+
+
+def maximum(A: B200Array):
+    """maximum(A) on the device (reference examples/histogram.jl:10,88-90); empty -> ArgumentError like Julia."""
+    if A.size == 0:
+        raise ArgumentError("reducing over an empty collection is not allowed")
+    return _reduce(A, 1)
+
+
+def minimum(A: B200Array):
+    if A.size == 0:
+        raise ArgumentError("reducing over an empty collection is not allowed")
+    return _reduce(A, 2)
+
+
+def isequal(A: B200Array, B: B200Array) -> bool:
+    """`A == B` for device arrays (reference examples/memcopy.jl:23, test/copyto.jl:17-19): same shape and every
+    element equal (floats numerically: NaN != NaN, -0.0 == 0.0)."""
+    if tuple(A.shape) != tuple(B.shape):
+        return False
+    if A.dtype != B.dtype:
+        raise MethodError("isequal: element types differ")
+    bad = np.zeros(1, dtype=np.int64)
+    call("b200_count_mismatch", C.c_void_p(A.ptr), C.c_void_p(B.ptr), C.c_size_t(A.size), C.c_int32(eltype_code(A.dtype)),
+         C.c_int32(A.dtype.itemsize), bad.ctypes.data_as(C.c_void_p))
+    return int(bad[0]) == 0
+
+
+def isapprox(A: B200Array, B: B200Array, rtol=None, atol: float = 0.0) -> bool:
+    """isapprox(A, B) for Float32/Float64 device arrays (reference examples/matmul.jl:36): norm(A - B) <=
+    max(atol, rtol * max(norm(A), norm(B))) with Julia's default rtol = sqrt(eps(T)) when atol == 0."""
+    if tuple(A.shape) != tuple(B.shape) or A.dtype != B.dtype or A.dtype.kind != "f" or A.dtype.itemsize not in (4, 8):
+        raise MethodError("isapprox: two Float32 or two Float64 arrays of the same shape")
+    if rtol is None:
+        rtol = float(np.sqrt(np.finfo(A.dtype).eps)) if atol == 0.0 else 0.0
+    out = np.zeros(3, dtype=np.float64)
+    call("b200_norms", C.c_void_p(A.ptr), C.c_void_p(B.ptr), C.c_size_t(A.size), C.c_int32(A.dtype.itemsize == 8),
+         out.ctypes.data_as(C.c_void_p))
+    nd, nx, ny = np.sqrt(out)
+    return bool(nd <= max(atol, rtol * max(nx, ny)))
+
+
+def rand_uniform_(A: B200Array, seed: int) -> B200Array:
+    """Fill a Float32 device array with the deterministic uniform [0,1) stream of SURVEY.md 8(d) (same bits as the
+    oracle's generator) -- the device-side stand-in for `rand(Float32, dims)` + copyto!."""
+    if A.dtype != np.float32:
+        raise MethodError("rand_uniform_: Float32 arrays only")
+    call("b200_rand_uniform_f32", C.c_void_p(A.ptr), C.c_size_t(A.size), C.c_uint64(seed))
+    return A
+
+
+def rand_bins_(A: B200Array, seed: int, nbins: int) -> B200Array:
+    """Fill an Int32 device array with values uniform in 1..nbins (reference examples/histogram.jl:76)."""
+    if A.dtype != np.int32:
+        raise MethodError("rand_bins_: Int32 arrays only")
+    call("b200_rand_bins_i32", C.c_void_p(A.ptr), C.c_size_t(A.size), C.c_uint64(seed), C.c_int32(nbins))
+    return A
+
+
+def mul_(C_: B200Array, A: B200Array, B: B200Array) -> B200Array:
+    """LinearAlgebra.mul!(C, A, B) for Float32 device matrices -> the FP32 SIMT GEMM (k ascending, fused multiply-add)."""
+    if A.ndim != 2 or B.ndim != 2 or A.shape[1] != B.shape[0] or tuple(C_.shape) != (A.shape[0], B.shape[1]):
+        raise _lib.ErrorException("DimensionMismatch: mul_")
+    if not (A.dtype == B.dtype == C_.dtype == np.float32):
+        raise MethodError("mul_: Float32 matrices only")
+    M, K = A.shape
+    N = B.shape[1]
+    if M and N:
+        if K == 0:
+            C_.fill_(0)
+        else:
+            call("b200_matmul_f32", C.c_void_p(C_.ptr), C.c_void_p(A.ptr), C.c_void_p(B.ptr), M, K, N, M, K, M, _lib.B200_MATMUL_TILE16)
+    return C_
+
+
+def matmul(A: B200Array, B: B200Array) -> B200Array:
+    """`A * B` (reference examples/matmul.jl:36 compares the kernel's output with it)."""
+    return mul_(B200Array(A.dtype, (A.shape[0], B.shape[1])), A, B)

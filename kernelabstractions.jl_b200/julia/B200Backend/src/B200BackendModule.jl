@@ -131,13 +131,77 @@ function Base.fill!(A::B200Array{T}, x) where {T}                 # also `A .= x
 end
 Base.Broadcast.materialize!(A::B200Array, bc::Base.Broadcast.Broadcasted{<:Any, <:Any, typeof(identity), <:Tuple{Number}}) =
     fill!(A, bc.args[1])
-# verification-only operations of the examples/tests: host round trip (documented in DESIGN.md)
+# ---------------------------------------------------------------------------------------------------------
+# Device-array conveniences (SURVEY.md 8(f)-4): what Base / LinearAlgebra give a CPU() user on plain Arrays, computed on the
+# device (csrc/kernels/arrayops.cu) so the examples run without host round trips.  Mixed host/device operands fall back
+# to a host copy.
+# ---------------------------------------------------------------------------------------------------------
+eltype_code(::Type{Int32}) = Int32(5);  eltype_code(::Type{UInt32}) = Int32(6)
+eltype_code(::Type{Int64}) = Int32(7);  eltype_code(::Type{UInt64}) = Int32(8)
+eltype_code(::Type{Float32}) = Int32(11); eltype_code(::Type{Float64}) = Int32(12)
+eltype_code(::Type{Bool}) = Int32(13);  eltype_code(::Type) = Int32(0)
+const Reducible = Union{Int32, UInt32, Int64, UInt64, Float32, Float64}
+sumtype(::Type{T}) where {T <: Signed} = Int64
+sumtype(::Type{T}) where {T <: Unsigned} = UInt64
+sumtype(::Type{T}) where {T <: AbstractFloat} = Float64
+
+function reduce_device(op::Integer, A::B200Array{T}, ::Type{R}) where {T <: Reducible, R}
+    out = Ref{R}(zero(R))
+    GC.@preserve out @b200 b200_reduce (Int32, Int32, Ptr{Cvoid}, Csize_t, Ptr{Cvoid}) Int32(op) eltype_code(T) A.ptr length(A) Base.unsafe_convert(Ptr{Cvoid}, out)
+    return out[]
+end
+Base.sum(A::B200Array{T}) where {T <: Reducible} = reduce_device(0, A, sumtype(T))
+function Base.maximum(A::B200Array{T}) where {T <: Reducible}       # reference examples/histogram.jl:10,88-90
+    isempty(A) && throw(ArgumentError("reducing over an empty collection is not allowed"))
+    return reduce_device(1, A, T)
+end
+function Base.minimum(A::B200Array{T}) where {T <: Reducible}
+    isempty(A) && throw(ArgumentError("reducing over an empty collection is not allowed"))
+    return reduce_device(2, A, T)
+end
+
+function Base.:(==)(A::B200Array{T}, B::B200Array{T}) where {T}     # reference examples/memcopy.jl:23, test/copyto.jl:17-19
+    size(A) == size(B) || return false
+    isbitstype(T) || return Array(A) == Array(B)
+    bad = Ref{Int64}(0)
+    @b200 b200_count_mismatch (Ptr{Cvoid}, Ptr{Cvoid}, Csize_t, Int32, Int32, Ptr{Int64}) A.ptr B.ptr length(A) eltype_code(T) Int32(sizeof(T)) bad
+    return bad[] == 0
+end
 Base.:(==)(A::B200Array, B::AbstractArray) = Array(A) == (B isa B200Array ? Array(B) : collect(B))
 Base.:(==)(A::AbstractArray, B::B200Array) = B == A
+
+function Base.isapprox(A::B200Array{T}, B::B200Array{T}; atol::Real = 0, rtol::Real = atol > 0 ? 0 : sqrt(eps(T))) where {T <: Union{Float32, Float64}}
+    size(A) == size(B) || throw(DimensionMismatch("isapprox"))
+    out = zeros(Float64, 3)                                         # sum (x-y)^2, sum x^2, sum y^2   (examples/matmul.jl:36)
+    GC.@preserve out @b200 b200_norms (Ptr{Cvoid}, Ptr{Cvoid}, Csize_t, Int32, Ptr{Float64}) A.ptr B.ptr length(A) Int32(T === Float64) pointer(out)
+    return sqrt(out[1]) <= max(atol, rtol * max(sqrt(out[2]), sqrt(out[3])))
+end
 Base.isapprox(A::B200Array, B::AbstractArray; kw...) = isapprox(Array(A), B isa B200Array ? Array(B) : collect(B); kw...)
 Base.isapprox(A::AbstractArray, B::B200Array; kw...) = isapprox(B, A; kw...)
-Base.maximum(A::B200Array) = maximum(Array(A))
-Base.:*(A::B200Array{Float32, 2}, B::B200Array{Float32, 2}) = Array(A) * Array(B)
+
+# LinearAlgebra.mul!(C, A, B) / A * B -> the FP32 SIMT GEMM in the reference kernel's summation order (mode 0)
+function mul!(C::B200Array{Float32, 2}, A::B200Array{Float32, 2}, B::B200Array{Float32, 2})
+    (size(A, 2) == size(B, 1) && size(C) == (size(A, 1), size(B, 2))) || throw(DimensionMismatch("mul!"))
+    M, K, N = size(A, 1), size(A, 2), size(B, 2)
+    (M == 0 || N == 0) && return C
+    K == 0 && return fill!(C, 0.0f0)
+    @b200 b200_matmul_f32 (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Int64, Int64, Int64, Int64, Int32) C.ptr A.ptr B.ptr M K N M K M Int32(0)
+    return C
+end
+Base.:*(A::B200Array{Float32, 2}, B::B200Array{Float32, 2}) = mul!(B200Array{Float32, 2}(undef, (size(A, 1), size(B, 2))), A, B)
+
+# opt-in tensor-core products (no reference twin): C = A * B with TF32 / BF16 tcgen05 arithmetic, FP32 storage
+function matmul_tf32!(C::B200Array{Float32, 2}, A::B200Array{Float32, 2}, B::B200Array{Float32, 2})
+    M, K, N = size(A, 1), size(A, 2), size(B, 2)
+    @b200 b200_matmul_tf32 (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Int64, Int64, Int64, Int64) C.ptr A.ptr B.ptr M K N M K M
+    return C
+end
+function matmul_bf16!(C::B200Array{Float32, 2}, A::B200Array{Float32, 2}, B::B200Array{Float32, 2};
+                      workspace::B200Array{UInt16, 1} = B200Array{UInt16, 1}(undef, (length(A) + length(B),)))
+    M, K, N = size(A, 1), size(A, 2), size(B, 2)
+    @b200 b200_matmul_f32_via_bf16 (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Int64, Int64, Int64, Int64, Ptr{Cvoid}) C.ptr A.ptr B.ptr M K N M K M workspace.ptr
+    return C
+end
 Base.view(A::B200Array{T}, r::UnitRange{Int}) where {T} =
     B200Array{T, 1}(A.ptr + (first(r) - 1) * sizeof(T), (length(r),), A.unified, A)
 
