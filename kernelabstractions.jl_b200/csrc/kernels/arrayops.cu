@@ -7,9 +7,9 @@
 //
 // All of them stream their operands once: HBM-bound, n * elsize bytes per operand.  One persistent grid (8 CTAs of 256
 // threads per SM), 16-byte ld.global.nc loads with four in flight per thread, warp-shuffle + shared-memory block
-// reduction, per-block partials in a per-thread scratch buffer, a one-block second kernel folds them, and the result
-// (<= 24 bytes) is copied to the caller's host variable on the calling thread's stream -- these calls return a VALUE,
-// so they are the one place where the library waits for the stream.
+// reduction, per-block partials in a per-thread scratch buffer; the block that takes the last ticket folds the partials
+// and stores the result (<= 24 bytes) straight into a pinned host landing pad (zero-copy), so a call is ONE launch plus
+// one stream wait -- these calls return a VALUE, so they are the one place where the library waits for the stream.
 #include <cmath>
 #include <cstring>
 #include <type_traits>
@@ -37,9 +37,10 @@ __device__ __forceinline__ T jl_max(T a, T b) { return a > b ? a : b; }
 template <typename T>
 __device__ __forceinline__ T jl_min(T a, T b) { return a < b ? a : b; }
 template <>
-__device__ __forceinline__ float jl_max<float>(float a, float b) {
-    if (isnan(a) || isnan(b)) return a + b;
-    return a == b ? (signbit(a) ? b : a) : (a > b ? a : b);
+__device__ __forceinline__ float jl_max<float>(float a, float b) {   // one instruction: NaN-propagating, -0.0 < +0.0
+    float r;
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
 }
 template <>
 __device__ __forceinline__ double jl_max<double>(double a, double b) {
@@ -48,8 +49,9 @@ __device__ __forceinline__ double jl_max<double>(double a, double b) {
 }
 template <>
 __device__ __forceinline__ float jl_min<float>(float a, float b) {
-    if (isnan(a) || isnan(b)) return a + b;
-    return a == b ? (signbit(a) ? a : b) : (a < b ? a : b);
+    float r;
+    asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
 }
 template <>
 __device__ __forceinline__ double jl_min<double>(double a, double b) {
@@ -110,10 +112,50 @@ __device__ __forceinline__ Acc block_reduce(Acc v, F comb, Acc *sh) {
     return v;
 }
 
+
+// Grid-wide finish: every block publishes Q partial values, the block that draws the last ticket folds all of them and
+// writes the Q results to `result` (a device-visible pinned host buffer), then re-arms the ticket for the next call.
+template <typename Acc, int Q, typename F>
+__device__ __forceinline__ void finish(const Acc (&v)[Q], Acc *partials, unsigned int *ticket, Acc *result, F comb, bool seed_from_first) {
+    __shared__ bool last;
+    __shared__ Acc fold[Q][THREADS];
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int q = 0; q < Q; ++q) partials[Q * blockIdx.x + q] = v[q];
+        __threadfence();
+        last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    Acc acc[Q];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) acc[q] = seed_from_first ? __ldcg(partials + q) : (Acc)0;
+    for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x)
+#pragma unroll
+        for (int q = 0; q < Q; ++q) acc[q] = comb(acc[q], __ldcg(partials + Q * i + q));
+#pragma unroll
+    for (int q = 0; q < Q; ++q) fold[q][threadIdx.x] = acc[q];
+    __syncthreads();
+    for (int s = THREADS / 2; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s)
+#pragma unroll
+            for (int q = 0; q < Q; ++q) fold[q][threadIdx.x] = comb(fold[q][threadIdx.x], fold[q][threadIdx.x + s]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int q = 0; q < Q; ++q) result[q] = fold[q][0];
+        __threadfence_system();
+        *ticket = 0;
+    }
+}
+
 // every thread starts from the first element it owns (so max/min need no identity); threads without an element
 // contribute `first` of the array (x[0]) for max/min and 0 for sum
 template <typename T, int OP>
-__global__ void __launch_bounds__(THREADS) reduce_kernel(const T *__restrict__ x, size_t n, typename Red<T, OP>::Acc *partials) {
+__global__ void __launch_bounds__(THREADS) reduce_kernel(const T *__restrict__ x, size_t n, typename Red<T, OP>::Acc *partials, unsigned int *ticket,
+                                                         typename Red<T, OP>::Acc *result) {
     using R = Red<T, OP>;
     using Acc = typename R::Acc;
     constexpr int VEC = 16 / sizeof(T);
@@ -138,8 +180,8 @@ __global__ void __launch_bounds__(THREADS) reduce_kernel(const T *__restrict__ x
     }
     for (size_t j = nvec * VEC + tid; j < n; j += stride) acc = R::comb(acc, R::lift(x[j]));
     __shared__ Acc sh[32];
-    // for sum, lanes beyond the warp count must add 0 in the second stage
-    if (OP == OP_SUM) {
+    Acc blk[1];
+    if (OP == OP_SUM) {   // lanes beyond the warp count must not contribute twice: plain two-level sum
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -148,35 +190,20 @@ __global__ void __launch_bounds__(THREADS) reduce_kernel(const T *__restrict__ x
         }
         if (lane == 0) sh[warp] = acc;
         __syncthreads();
-        if (threadIdx.x == 0) {
-            Acc s = 0;
-            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s = s + sh[w];
-            partials[blockIdx.x] = s;
-        }
+        Acc sum = 0;
+        if (threadIdx.x == 0)
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) sum = sum + sh[w];
+        blk[0] = sum;
     } else {
-        acc = block_reduce<Acc>(acc, [](Acc a, Acc b) { return R::comb(a, b); }, sh);
-        if (threadIdx.x == 0) partials[blockIdx.x] = acc;
+        blk[0] = block_reduce<Acc>(acc, [](Acc a, Acc b) { return R::comb(a, b); }, sh);
     }
+    finish<Acc, 1>(blk, partials, ticket, result, [](Acc a, Acc b) { return R::comb(a, b); }, OP != OP_SUM);
 }
-template <typename Acc, int OP, typename T>
-__global__ void __launch_bounds__(THREADS) fold_kernel(Acc *partials, int nparts) {
-    using R = Red<T, OP>;
-    __shared__ Acc sh[THREADS];
-    Acc acc = OP == OP_SUM ? (Acc)0 : partials[0];
-    for (int i = threadIdx.x; i < nparts; i += blockDim.x) acc = R::comb(acc, partials[i]);
-    sh[threadIdx.x] = acc;
-    __syncthreads();
-    for (int s = THREADS / 2; s > 0; s >>= 1) {
-        if ((int)threadIdx.x < s) sh[threadIdx.x] = R::comb(sh[threadIdx.x], sh[threadIdx.x + s]);
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) partials[0] = sh[0];
-}
-
 // ---- A == B: number of positions where !(a == b) (so NaN never equals, -0.0 == 0.0), bit patterns for opaque types ----
 template <typename T>
 __global__ void __launch_bounds__(THREADS) mismatch_kernel(const T *__restrict__ a, const T *__restrict__ b, size_t n,
-                                                           unsigned long long *partials) {
+                                                           unsigned long long *partials, unsigned int *ticket,
+                                                           unsigned long long *result) {
     constexpr int VEC = 16 / sizeof(T);
     struct alignas(16) V { T e[VEC]; };
     const size_t nvec = n / VEC, tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
@@ -199,16 +226,16 @@ __global__ void __launch_bounds__(THREADS) mismatch_kernel(const T *__restrict__
     for (int o = 16; o > 0; o >>= 1) bad += __shfl_xor_sync(0xffffffffu, bad, o);
     if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = bad;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned long long s = 0;
-        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += sh[w];
-        partials[blockIdx.x] = s;
-    }
+    unsigned long long blk[1] = {0};
+    if (threadIdx.x == 0)
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) blk[0] += sh[w];
+    finish<unsigned long long, 1>(blk, partials, ticket, result, [](unsigned long long x, unsigned long long y) { return x + y; }, false);
 }
 
 // ---- isapprox: sum (x-y)^2, sum x^2, sum y^2 in Float64 ----
 template <typename T>
-__global__ void __launch_bounds__(THREADS) norms_kernel(const T *__restrict__ a, const T *__restrict__ b, size_t n, double *partials) {
+__global__ void __launch_bounds__(THREADS) norms_kernel(const T *__restrict__ a, const T *__restrict__ b, size_t n, double *partials,
+                                                        unsigned int *ticket, double *result) {
     constexpr int VEC = 16 / sizeof(T);
     struct alignas(16) V { T e[VEC]; };
     const size_t nvec = n / VEC, tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
@@ -243,42 +270,13 @@ __global__ void __launch_bounds__(THREADS) norms_kernel(const T *__restrict__ a,
         if ((threadIdx.x & 31) == 0) sh[q][threadIdx.x >> 5] = v[q];
     }
     __syncthreads();
-    if (threadIdx.x < 3) {
-        double s = 0;
-        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += sh[threadIdx.x][w];
-        partials[3 * blockIdx.x + threadIdx.x] = s;
-    }
-}
-__global__ void __launch_bounds__(THREADS) fold3_kernel(double *partials, int nparts) {
-    __shared__ double sh[3][THREADS];
-    double v[3] = {0, 0, 0};
-    for (int i = threadIdx.x; i < nparts; i += blockDim.x)
+    double blk[3] = {0, 0, 0};
+    if (threadIdx.x == 0)
 #pragma unroll
-        for (int q = 0; q < 3; ++q) v[q] += partials[3 * i + q];
-#pragma unroll
-    for (int q = 0; q < 3; ++q) sh[q][threadIdx.x] = v[q];
-    __syncthreads();
-    for (int s = THREADS / 2; s > 0; s >>= 1) {
-        if ((int)threadIdx.x < s)
-#pragma unroll
-            for (int q = 0; q < 3; ++q) sh[q][threadIdx.x] += sh[q][threadIdx.x + s];
-        __syncthreads();
-    }
-    if (threadIdx.x < 3) partials[threadIdx.x] = sh[threadIdx.x][0];
+        for (int q = 0; q < 3; ++q)
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) blk[q] += sh[q][w];
+    finish<double, 3>(blk, partials, ticket, result, [](double x, double y) { return x + y; }, false);
 }
-__global__ void __launch_bounds__(THREADS) fold_u64_kernel(unsigned long long *partials, int nparts) {
-    __shared__ unsigned long long sh[THREADS];
-    unsigned long long v = 0;
-    for (int i = threadIdx.x; i < nparts; i += blockDim.x) v += partials[i];
-    sh[threadIdx.x] = v;
-    __syncthreads();
-    for (int s = THREADS / 2; s > 0; s >>= 1) {
-        if ((int)threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) partials[0] = sh[0];
-}
-
 // ---- deterministic input streams: a splitmix-style counter hash (mix32), four elements per 16-byte store ----
 __device__ __forceinline__ uint32_t mix32(unsigned long long x) {
     x += 0x9E3779B97F4A7C15ull;
@@ -288,11 +286,17 @@ __device__ __forceinline__ uint32_t mix32(unsigned long long x) {
     return (uint32_t)(x >> 32);
 }
 template <bool BINS>
-__global__ void __launch_bounds__(THREADS) gen_kernel(uint32_t *__restrict__ out, size_t n, unsigned long long base, uint32_t nbins) {
+__global__ void __launch_bounds__(THREADS) gen_kernel(uint32_t *__restrict__ out, size_t n, unsigned long long base, uint32_t nbins, uint32_t recip) {
     const size_t nvec = n / 4, tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
     auto one = [&](size_t i) -> uint32_t {
         const uint32_t h = mix32(base + (unsigned long long)i);
-        if (BINS) return h % nbins + 1u;
+        if (BINS && nbins == 1u) return 1u;
+        if (BINS) {   // h % nbins without a divide: recip = floor(2^32 / nbins) underestimates the quotient by at most 2
+            uint32_t r = h - __umulhi(h, recip) * nbins;
+            r -= r >= nbins ? nbins : 0u;
+            r -= r >= nbins ? nbins : 0u;
+            return r + 1u;
+        }
         return __float_as_uint((float)(h >> 8) * (1.0f / 16777216.0f));
     };
     for (size_t v = tid; v < nvec; v += stride)
@@ -300,9 +304,11 @@ __global__ void __launch_bounds__(THREADS) gen_kernel(uint32_t *__restrict__ out
     for (size_t j = nvec * 4 + tid; j < n; j += stride) out[j] = one(j);
 }
 
-// ---- per-thread, per-device scratch: MAX_BLOCKS * 24 bytes of partials + a pinned 32-byte landing pad ----
+// ---- per-thread, per-device scratch: MAX_BLOCKS * 24 bytes of partials, a ticket, and a pinned 32-byte landing pad that
+// ---- the device writes directly (UVA: the pinned host pointer is valid on the device) ----
 struct Scratch {
-    void *dev = nullptr;
+    void *dev = nullptr;             // partials
+    unsigned int *ticket = nullptr;  // zero between calls (re-armed by the finishing block)
     void *pinned = nullptr;
 };
 static thread_local Scratch g_scratch[kMaxDevices];
@@ -311,8 +317,10 @@ static int scratch(Scratch **out) {
     B200_TRY(ensure_device());
     Scratch &s = g_scratch[tls().device];
     if (!s.dev) {
-        B200_CUDA(cudaMalloc(&s.dev, (size_t)MAX_BLOCKS * 24));
-        B200_CUDA(cudaHostAlloc(&s.pinned, 32, cudaHostAllocDefault));
+        B200_CUDA(cudaMalloc(&s.dev, (size_t)MAX_BLOCKS * 24 + 16));
+        s.ticket = (unsigned int *)((char *)s.dev + (size_t)MAX_BLOCKS * 24);
+        B200_CUDA(cudaMemset(s.ticket, 0, 16));
+        B200_CUDA(cudaHostAlloc(&s.pinned, 32, cudaHostAllocMapped | cudaHostAllocPortable));
     }
     *out = &s;
     return B200_OK;
@@ -324,8 +332,11 @@ static int grid_for(size_t nvec) {
     return (int)(blocks < cap ? (blocks < 1 ? 1 : blocks) : cap);
 }
 static int fetch(Scratch *s, void *out_host, size_t bytes, cudaStream_t st) {
-    B200_CUDA(cudaMemcpyAsync(s->pinned, s->dev, bytes, cudaMemcpyDeviceToHost, st));
-    B200_CUDA(cudaStreamSynchronize(st));
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) {
+        cudaMemset(s->ticket, 0, 16);   // a failed launch must not leave a half-drawn ticket behind
+        return set_error(B200_ERR_CUDA, "array reduction failed: %s", cudaGetErrorString(e));
+    }
     memcpy(out_host, s->pinned, bytes);
     return B200_OK;
 }
@@ -336,10 +347,8 @@ static int reduce_typed(const void *x, size_t n, void *out_host, cudaStream_t st
     Scratch *s;
     B200_TRY(scratch(&s));
     const int grid = grid_for(n / (16 / sizeof(T)));
-    reduce_kernel<T, OP><<<grid, THREADS, 0, st>>>((const T *)x, n, (Acc *)s->dev);
+    reduce_kernel<T, OP><<<grid, THREADS, 0, st>>>((const T *)x, n, (Acc *)s->dev, s->ticket, (Acc *)s->pinned);
     B200_CHECK_LAUNCH("reduce_kernel");
-    fold_kernel<Acc, OP, T><<<1, THREADS, 0, st>>>((Acc *)s->dev, grid);
-    B200_CHECK_LAUNCH("fold_kernel");
     return fetch(s, out_host, sizeof(Acc), st);
 }
 template <typename T>
@@ -394,27 +403,26 @@ extern "C" b200_status b200_count_mismatch(const void *a, const void *b, size_t 
     int grid;
     if (eltype == B200_T_F32) {
         grid = ao::grid_for(n / 4);
-        ao::mismatch_kernel<float><<<grid, ao::THREADS, 0, st>>>((const float *)a, (const float *)b, n, part);
+        ao::mismatch_kernel<float><<<grid, ao::THREADS, 0, st>>>((const float *)a, (const float *)b, n, part, s->ticket, (unsigned long long *)s->pinned);
     } else if (eltype == B200_T_F64) {
         grid = ao::grid_for(n / 2);
-        ao::mismatch_kernel<double><<<grid, ao::THREADS, 0, st>>>((const double *)a, (const double *)b, n, part);
+        ao::mismatch_kernel<double><<<grid, ao::THREADS, 0, st>>>((const double *)a, (const double *)b, n, part, s->ticket, (unsigned long long *)s->pinned);
     } else {   // integers, Bool, opaque isbits: equality of the bit patterns, compared in the widest unit that divides elsize
         if (elsize <= 0) return set_error(B200_ERR_INVALID_VALUE, "b200_count_mismatch: bad element size");
         const size_t bytes = n * (size_t)elsize;
         if (elsize % 8 == 0) {
             grid = ao::grid_for(bytes / 16);
-            ao::mismatch_kernel<unsigned long long><<<grid, ao::THREADS, 0, st>>>((const unsigned long long *)a, (const unsigned long long *)b, bytes / 8, part);
+            ao::mismatch_kernel<unsigned long long><<<grid, ao::THREADS, 0, st>>>((const unsigned long long *)a, (const unsigned long long *)b, bytes / 8, part, s->ticket, (unsigned long long *)s->pinned);
         } else if (elsize % 4 == 0) {
             grid = ao::grid_for(bytes / 16);
-            ao::mismatch_kernel<unsigned int><<<grid, ao::THREADS, 0, st>>>((const unsigned int *)a, (const unsigned int *)b, bytes / 4, part);
+            ao::mismatch_kernel<unsigned int><<<grid, ao::THREADS, 0, st>>>((const unsigned int *)a, (const unsigned int *)b, bytes / 4, part, s->ticket, (unsigned long long *)s->pinned);
         } else {
             grid = ao::grid_for(bytes / 16);
-            ao::mismatch_kernel<unsigned char><<<grid, ao::THREADS, 0, st>>>((const unsigned char *)a, (const unsigned char *)b, bytes, part);
+            ao::mismatch_kernel<unsigned char><<<grid, ao::THREADS, 0, st>>>((const unsigned char *)a, (const unsigned char *)b, bytes, part, s->ticket, (unsigned long long *)s->pinned);
         }
     }
     B200_CHECK_LAUNCH("mismatch_kernel");
-    ao::fold_u64_kernel<<<1, ao::THREADS, 0, st>>>(part, grid);
-    B200_CHECK_LAUNCH("fold_u64_kernel");
+    (void)grid;
     return ao::fetch(s, count_host, 8, st);
 }
 
@@ -430,12 +438,10 @@ extern "C" b200_status b200_norms(const void *x, const void *y, size_t n, int32_
     B200_TRY(ao::scratch(&s));
     const int grid = ao::grid_for(n / (is_f64 ? 2 : 4));
     if (is_f64)
-        ao::norms_kernel<double><<<grid, ao::THREADS, 0, st>>>((const double *)x, (const double *)y, n, (double *)s->dev);
+        ao::norms_kernel<double><<<grid, ao::THREADS, 0, st>>>((const double *)x, (const double *)y, n, (double *)s->dev, s->ticket, (double *)s->pinned);
     else
-        ao::norms_kernel<float><<<grid, ao::THREADS, 0, st>>>((const float *)x, (const float *)y, n, (double *)s->dev);
+        ao::norms_kernel<float><<<grid, ao::THREADS, 0, st>>>((const float *)x, (const float *)y, n, (double *)s->dev, s->ticket, (double *)s->pinned);
     B200_CHECK_LAUNCH("norms_kernel");
-    ao::fold3_kernel<<<1, ao::THREADS, 0, st>>>((double *)s->dev, grid);
-    B200_CHECK_LAUNCH("fold3_kernel");
     return ao::fetch(s, out3_host, 24, st);
 }
 
@@ -445,7 +451,7 @@ extern "C" b200_status b200_rand_uniform_f32(float *out, size_t n, uint64_t seed
     if (((uintptr_t)out & 15) != 0) return set_error(B200_ERR_UNSUPPORTED, "b200_rand_uniform_f32: array must be 16-byte aligned");
     cudaStream_t st;
     B200_TRY(current_stream(&st));
-    ao::gen_kernel<false><<<ao::grid_for(n / 4), ao::THREADS, 0, st>>>((uint32_t *)out, n, seed * 0x100000001B3ull, 1u);
+    ao::gen_kernel<false><<<ao::grid_for(n / 4), ao::THREADS, 0, st>>>((uint32_t *)out, n, seed * 0x100000001B3ull, 1u, 0u);
     B200_CHECK_LAUNCH("gen_kernel<uniform>");
     return B200_OK;
 }
@@ -457,7 +463,8 @@ extern "C" b200_status b200_rand_bins_i32(int32_t *out, size_t n, uint64_t seed,
     if (((uintptr_t)out & 15) != 0) return set_error(B200_ERR_UNSUPPORTED, "b200_rand_bins_i32: array must be 16-byte aligned");
     cudaStream_t st;
     B200_TRY(current_stream(&st));
-    ao::gen_kernel<true><<<ao::grid_for(n / 4), ao::THREADS, 0, st>>>((uint32_t *)out, n, seed * 0x100000001B3ull, (uint32_t)nbins);
+    ao::gen_kernel<true><<<ao::grid_for(n / 4), ao::THREADS, 0, st>>>((uint32_t *)out, n, seed * 0x100000001B3ull, (uint32_t)nbins,
+                                                                 (uint32_t)(0x100000000ull / (uint32_t)nbins));
     B200_CHECK_LAUNCH("gen_kernel<bins>");
     return B200_OK;
 }

@@ -94,6 +94,24 @@ elif kind == "saxpy":
     z = KA.zeros(be, np.float32, n)
     run(lambda: _lib.call("b200_saxpy", C.c_void_p(z.ptr), C.c_double(3.1415), C.c_void_p(x.ptr), C.c_void_p(y.ptr), C.c_size_t(n), 4),
         12.0 * n, "GB/s")
+elif kind in ("reduce_max", "reduce_sum", "mismatch", "norms", "gen_uniform", "gen_bins"):
+    n = size or (1 << 28)
+    if kind.startswith("reduce"):
+        d = KA.rand_bins_(KA.allocate(be, np.int32, n), 1236, 256) if mode == 0 else KA.rand_uniform_(KA.allocate(be, np.float32, n), 7)
+        f = KA.maximum if kind == "reduce_max" else KA.sum
+        run(lambda: f(d), 4.0 * n, "GB/s")
+    elif kind == "mismatch":
+        a, b = KA.rand_uniform_(KA.allocate(be, np.float32, n), 7), KA.rand_uniform_(KA.allocate(be, np.float32, n), 7)
+        run(lambda: KA.isequal(a, b), 8.0 * n, "GB/s")
+    elif kind == "norms":
+        a, b = KA.rand_uniform_(KA.allocate(be, np.float32, n), 7), KA.rand_uniform_(KA.allocate(be, np.float32, n), 8)
+        run(lambda: KA.isapprox(a, b), 8.0 * n, "GB/s")
+    elif kind == "gen_uniform":
+        a = KA.allocate(be, np.float32, n)
+        run(lambda: KA.rand_uniform_(a, 7), 4.0 * n, "GB/s")
+    else:
+        a = KA.allocate(be, np.int32, n)
+        run(lambda: KA.rand_bins_(a, 7, 256), 4.0 * n, "GB/s")
 elif kind == "hist":
     n = size or (1 << 30)
     d_in = KA.to_device(orc.gen_bins_i32(n, 1236, 256) if mode == 0 else np.full(n, 2, dtype=np.int32))
