@@ -31,18 +31,20 @@ namespace sg {
 constexpr int BM = 128, BN = 128, BK = 16;
 constexpr int STAGES = 8;
 constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4, STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int CONSUMER_WARPS = 8, NUM_THREADS = CONSUMER_WARPS * 32;
+// MI = float4 row groups per thread: 2 -> 8 warps (2 x 4), thread tile 8 x nj; 1 -> 16 warps (4 x 4), thread tile 4 x nj
+constexpr int consumer_warps(int MI) { return 16 / MI; }
 constexpr int LAG = 2;                       // a slot is refilled LAG k tiles after it was consumed
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * STAGES * 8;
 
 // NJ = columns per thread (8, 7 or 6): the CTA tile is 128 x 16 NJ.  The narrower tiles exist only to fill whole waves of
 // the 148-SM grid (pick_nj below); the arithmetic per output element -- and therefore every bit of C -- does not change.
-template <bool TILE16, int NJ>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+template <bool TILE16, int NJ, int MI>
+__global__ void __launch_bounds__(consumer_warps(MI) * 32, 1)
     sgemm_tma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                      float *__restrict__ C, int M, int N, int64_t ldc, int ntiles, int tiles_m, int tiles_n, int group_m,
                      int vec_ok) {
     using namespace pipe;
+    constexpr int CONSUMER_WARPS = consumer_warps(MI);
     extern __shared__ __align__(1024) unsigned char smem[];
     uint64_t *full = (uint64_t *)(smem + STAGES * STAGE_BYTES);
     uint64_t *empty = full + STAGES;
@@ -82,21 +84,22 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
         for (int kt = 0; kt < STAGES - LAG && kt < ntiles; ++kt) produce(kt);
 
     // ---------------------------------------------------------------------- consumers
-    const int wm = warp & 1, wn = warp >> 1;                        // 2 x 4 warps -> warp tile 64 x 4 NJ
+    constexpr int WARPS_M = 4 / MI;                                 // (4 / MI) x 4 warps -> warp tile 32 MI x 4 NJ
+    const int wm = warp % WARPS_M, wn = warp / WARPS_M;
     const int lx = (lane >> 1) & 7;                                 // lane bits 1-3 -> rows 4 lx .. 4 lx + 3 (+32)
     const int ly = (lane & 1) | ((lane >> 4) << 1);                 // lane bits 0,4 -> columns ly + 4 j
-    const int mrow = wm * 64 + 4 * lx;
+    const int mrow = wm * (32 * MI) + 4 * lx;
     const int ncol = wn * (4 * NJ) + ly;
 
-    float2 acc[4][NJ];
-    float2 tot[TILE16 ? 4 : 1][TILE16 ? NJ : 1];
+    float2 acc[2 * MI][NJ];
+    float2 tot[TILE16 ? 2 * MI : 1][TILE16 ? NJ : 1];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 2 * MI; ++i)
 #pragma unroll
         for (int j = 0; j < NJ; ++j) acc[i][j] = make_float2(0.0f, 0.0f);
     if (TILE16) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < 2 * MI; ++i)
 #pragma unroll
             for (int j = 0; j < NJ; ++j) tot[TILE16 ? i : 0][TILE16 ? j : 0] = make_float2(-0.0f, -0.0f);
     }
@@ -115,12 +118,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int kk = k2 + h;
-                const float4 a0 = *reinterpret_cast<const float4 *>(As + kk * BM);
-                const float4 a1 = *reinterpret_cast<const float4 *>(As + kk * BM + 32);
-                const float2 a[4] = {make_float2(a0.x, a0.y), make_float2(a0.z, a0.w), make_float2(a1.x, a1.y),
-                                     make_float2(a1.z, a1.w)};
+                float2 a[2 * MI];
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
+                for (int g = 0; g < MI; ++g) {
+                    const float4 av = *reinterpret_cast<const float4 *>(As + kk * BM + 32 * g);
+                    a[2 * g] = make_float2(av.x, av.y);
+                    a[2 * g + 1] = make_float2(av.z, av.w);
+                }
+#pragma unroll
+                for (int i = 0; i < 2 * MI; ++i)
 #pragma unroll
                     for (int j = 0; j < NJ; ++j) {
                         const float bj = h ? b[j].y : b[j].x;
@@ -133,7 +139,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
         if (lane == 0) mbar_arrive(&empty[s]);   // this warp no longer reads stage s
         if (TILE16) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < 2 * MI; ++i)
 #pragma unroll
                 for (int j = 0; j < NJ; ++j) {
                     float2 &tt = tot[TILE16 ? i : 0][TILE16 ? j : 0];
@@ -142,12 +148,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
         }
     }
 
-    // epilogue: rows {mrow..+3, mrow+32..+35} of columns ncol + 4 j
+    // epilogue: rows mrow + 32 h .. + 3 (h < MI) of columns ncol + 4 j
 #pragma unroll
     for (int j = 0; j < NJ; ++j) {
         const int n = n0 + ncol + 4 * j;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < MI; ++h) {
             const int m = m0 + mrow + 32 * h;
             const float2 lo = TILE16 ? tot[TILE16 ? 2 * h : 0][TILE16 ? j : 0] : acc[2 * h][j];
             const float2 hi = TILE16 ? tot[TILE16 ? 2 * h + 1 : 0][TILE16 ? j : 0] : acc[2 * h + 1][j];
@@ -175,7 +181,7 @@ int sgemm_tma_applicable(const float *A, const float *B, int64_t M, int64_t K, i
            M < (1LL << 31) && N < (1LL << 31) && K < (1LL << 31);
 }
 
-template <bool TILE16, int NJ>
+template <bool TILE16, int NJ, int MI>
 static int sgemm_tma_launch_nj(float *C, const float *A, const float *B, int64_t M, int64_t K, int64_t N, int64_t lda,
                                int64_t ldb, int64_t ldc, cudaStream_t st) {
     using namespace sg;
@@ -191,8 +197,8 @@ static int sgemm_tma_launch_nj(float *C, const float *A, const float *B, int64_t
     const int ntiles = (int)cdiv(K, BK);
     const int group_m = tune_get("sgemm.group_m", 8);
     const int vec_ok = (ldc % 4 == 0) && (((uintptr_t)C & 15) == 0);
-    B200_CUDA(cudaFuncSetAttribute(sgemm_tma_kernel<TILE16, NJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    sgemm_tma_kernel<TILE16, NJ><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ta, tb, C, (int)M, (int)N, ldc, ntiles, tiles_m,
+    B200_CUDA(cudaFuncSetAttribute(sgemm_tma_kernel<TILE16, NJ, MI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    sgemm_tma_kernel<TILE16, NJ, MI><<<grid, consumer_warps(MI) * 32, SMEM_BYTES, st>>>(ta, tb, C, (int)M, (int)N, ldc, ntiles, tiles_m,
                                                                          tiles_n, group_m, vec_ok);
     B200_CHECK_LAUNCH("sgemm_tma_kernel");
     return B200_OK;
@@ -219,14 +225,16 @@ static int pick_nj(int64_t M, int64_t N, int sms) {
 int sgemm_tma_launch(float *C, const float *A, const float *B, int64_t M, int64_t K, int64_t N, int64_t lda,
                      int64_t ldb, int64_t ldc, int mode, cudaStream_t st) {
     const int nj = pick_nj(M, N, sm_count());
-    if (mode == B200_MATMUL_TILE16) {
-        if (nj == 8) return sgemm_tma_launch_nj<true, 8>(C, A, B, M, K, N, lda, ldb, ldc, st);
-        if (nj == 7) return sgemm_tma_launch_nj<true, 7>(C, A, B, M, K, N, lda, ldb, ldc, st);
-        return sgemm_tma_launch_nj<true, 6>(C, A, B, M, K, N, lda, ldb, ldc, st);
-    }
-    if (nj == 8) return sgemm_tma_launch_nj<false, 8>(C, A, B, M, K, N, lda, ldb, ldc, st);
-    if (nj == 7) return sgemm_tma_launch_nj<false, 7>(C, A, B, M, K, N, lda, ldb, ldc, st);
-    return sgemm_tma_launch_nj<false, 6>(C, A, B, M, K, N, lda, ldb, ldc, st);
+    const int mi = tune_get("sgemm.mi", 2) == 1 ? 1 : 2;
+#define B200_SGEMM_CASE(T16, NJ_, MI_) \
+    if ((mode == B200_MATMUL_TILE16) == T16 && nj == NJ_ && mi == MI_) \
+        return sgemm_tma_launch_nj<T16, NJ_, MI_>(C, A, B, M, K, N, lda, ldb, ldc, st);
+    B200_SGEMM_CASE(true, 8, 2) B200_SGEMM_CASE(true, 7, 2) B200_SGEMM_CASE(true, 6, 2)
+    B200_SGEMM_CASE(false, 8, 2) B200_SGEMM_CASE(false, 7, 2) B200_SGEMM_CASE(false, 6, 2)
+    B200_SGEMM_CASE(true, 8, 1) B200_SGEMM_CASE(true, 7, 1) B200_SGEMM_CASE(true, 6, 1)
+    B200_SGEMM_CASE(false, 8, 1) B200_SGEMM_CASE(false, 7, 1) B200_SGEMM_CASE(false, 6, 1)
+#undef B200_SGEMM_CASE
+    return set_error(B200_ERR_UNSUPPORTED, "sgemm: no kernel for nj=%d mi=%d", nj, mi);
 }
 
 }  // namespace b200
