@@ -8,11 +8,16 @@
 // Why a second engine (measured in profiles/r02_*): the register-staged kernel of matmul_f32.cu spends issue slots and
 // ~16 registers on LDG -> STS staging, transposes B through 4-byte shared stores, and leaves the position of the
 // global loads to ptxas (which sank them next to the stores when the FMAs became FFMA2, exposing DRAM latency).  Here
-//   * thread 0 is the producer: it issues two cp.async.bulk.tensor.2d per 16-k stage (A box 128 m x 16 k,
-//     B box 16 k x 128 n) into a STAGES-deep ring, completion on `full` mbarriers, slot release on `empty` mbarriers.
-//     It refills the slot every warp finished TWO k tiles ago, so its wait on `empty` practically never blocks and no
-//     ninth warp (which would cost a 4-warp register allocation unit) is needed;
-//   * all 8 warps are consumers: 2 x 4 warps, warp tile 64 x 32, thread tile 8 x 8 held as float2 pairs along m, inner
+//   * a dedicated producer warp group (warps 8-11, one active lane) issues two cp.async.bulk.tensor.2d per 16-k stage (A box
+//     128 m x 16 k, B box 16 k x 16 nj n) into a STAGES-deep ring, completion on `full` mbarriers, slot release on `empty`
+//     mbarriers.  Registers are handed to warps in groups of four, so the group gives its registers back with `setmaxnreg.dec`
+//     and the consumers take them with `setmaxnreg.inc` (TILE16 needs 206).  Against thread 0 of a consumer warp producing
+//     (PW = 0, kept for comparison): 58.6 -> 61.2 TFLOP/s in the running-sum mode;
+//   * the consumers software-pipeline the whole k stream: operands of the next k step are in flight while the current
+//     step's FFMA2s issue, across tile boundaries too (the next `full` barrier is polled before the last step of a tile).
+//     tools/micro/sgemm_inner.cu isolates the inner loop: 64.1 TFLOP/s with both operand streams from shared memory,
+//     68.4 without loads -- the pipeline around it now costs 4.5 %;
+//   * 8 consumer warps: 2 x 4 warps, warp tile 64 x 4 nj, thread tile 8 x nj held as float2 pairs along m, inner
 //     product issued as packed FFMA2 (a pair = half of one LDS.128, b = scalar-broadcast operand).  FFMA2 peaks at
 //     65 TFLOP/s on this part against 46 for 3-register scalar FFMA (tools/micro/fma_peak.cu);
 //   * B stays k-contiguous in shared memory exactly as it is in HBM (no transpose): a thread reads two consecutive k of
@@ -38,8 +43,13 @@ constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * STAGES * 8;
 
 // NJ = columns per thread (8, 7 or 6): the CTA tile is 128 x 16 NJ.  The narrower tiles exist only to fill whole waves of
 // the 148-SM grid (pick_nj below); the arithmetic per output element -- and therefore every bit of C -- does not change.
-template <bool TILE16, int NJ, int MI>
-__global__ void __launch_bounds__(consumer_warps(MI) * 32, 1)
+// PW = 1: a dedicated producer warp group (warps CONSUMER_WARPS .. +3; registers are allocated to warps in groups of four, so a
+// single extra warp would cost as much) issues the TMA loads, so no consumer warp ever diverges into producer code or blocks
+// on an `empty` barrier.  The kernel is compiled for 384 threads (168 registers each); the producer group gives its
+// registers back (`setmaxnreg.dec 40`) and the consumer groups take them (`setmaxnreg.inc 232`): 8*32*232 + 4*32*40 = 64512.
+// PW = 0: thread 0 of consumer warp 0 produces with a lag of LAG tiles.
+template <bool TILE16, int NJ, int MI, int PW>
+__global__ void __launch_bounds__((consumer_warps(MI) + 4 * PW) * 32, 1)
     sgemm_tma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                      float *__restrict__ C, int M, int N, int64_t ldc, int ntiles, int tiles_m, int tiles_n, int group_m,
                      int vec_ok) {
@@ -72,16 +82,38 @@ __global__ void __launch_bounds__(consumer_warps(MI) * 32, 1)
     }
     __syncthreads();
 
+    // 32-bit shared-window addresses, computed once (every smem_u32() inside the loop would re-read SR_CgaCtaId)
+    uint32_t smem_a = smem_u32(smem), full_a = smem_u32(full), empty_a = smem_u32(empty);
+    asm volatile("" : "+r"(smem_a), "+r"(full_a), "+r"(empty_a));
+    auto wait_a = [](uint32_t bar, uint32_t parity) {
+        asm volatile(
+            "{\n.reg .pred p;\nW_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra D_%=;\nbra W_%=;\nD_%=:\n}\n" ::"r"(bar),
+            "r"(parity)
+            : "memory");
+    };
     auto produce = [&](int kt) {   // thread 0 only
         const int s = kt % STAGES;
-        if (kt >= STAGES) mbar_wait(&empty[s], ((kt / STAGES) - 1) & 1);
-        mbar_expect_tx(&full[s], A_BYTES + BN_ * BK * 4);
-        unsigned char *stage = smem + s * STAGE_BYTES;
-        tma_load_2d(stage, &tmap_a, m0, kt * BK, &full[s]);            // As[k][m]: 16 rows of 512 B
-        tma_load_2d(stage + A_BYTES, &tmap_b, kt * BK, n0, &full[s]);  // Bs[n][k]: 16 NJ rows of 64 B
+        if (kt >= STAGES) wait_a(empty_a + 8 * s, ((kt / STAGES) - 1) & 1);
+        const uint32_t bar = full_a + 8 * s, stage = smem_a + s * STAGE_BYTES;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(A_BYTES + BN_ * BK * 4) : "memory");
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(stage),
+                     "l"(&tmap_a), "r"(m0), "r"(kt * BK), "r"(bar)
+                     : "memory");                                               // As[k][m]: 16 rows of 512 B
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(stage + A_BYTES),
+                     "l"(&tmap_b), "r"(kt * BK), "r"(n0), "r"(bar)
+                     : "memory");                                               // Bs[n][k]: 16 NJ rows of 64 B
     };
-    if (t == 0)
+    if (PW) {
+        if (warp >= CONSUMER_WARPS) {          // producer warp group: one lane runs ahead as far as the ring allows
+            asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+            if (t == CONSUMER_WARPS * 32)
+                for (int kt = 0; kt < ntiles; ++kt) produce(kt);
+            return;
+        }
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    } else if (t == 0) {
         for (int kt = 0; kt < STAGES - LAG && kt < ntiles; ++kt) produce(kt);
+    }
 
     // ---------------------------------------------------------------------- consumers
     constexpr int WARPS_M = 4 / MI;                                 // (4 / MI) x 4 warps -> warp tile 32 MI x 4 NJ
@@ -104,39 +136,62 @@ __global__ void __launch_bounds__(consumer_warps(MI) * 32, 1)
             for (int j = 0; j < NJ; ++j) tot[TILE16 ? i : 0][TILE16 ? j : 0] = make_float2(-0.0f, -0.0f);
     }
 
+    // Software pipeline over the whole k stream: while the FFMA2s of k step (kt, k2) issue, the operands of the NEXT step are
+    // already in flight -- including across the tile boundary, where the next step is (kt+1, 0) and its `full` barrier is
+    // polled before the last step of tile kt is computed.  tools/micro/sgemm_inner.cu: the inner loop alone sustains
+    // 64 TFLOP/s; what the kernel lost against it was the exposed barrier poll + shared-memory latency at every tile start.
+    float2 b[2][NJ];
+    float4 av[2][2][MI];
+    auto load_frags = [&](int buf, int stage, int k2) {
+        const float *As = reinterpret_cast<const float *>(smem + stage * STAGE_BYTES) + mrow;
+        const float *Bs = reinterpret_cast<const float *>(smem + stage * STAGE_BYTES + A_BYTES) + ncol * BK;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) b[buf][j] = *reinterpret_cast<const float2 *>(Bs + (4 * j) * BK + k2);
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int g = 0; g < MI; ++g) av[buf][h][g] = *reinterpret_cast<const float4 *>(As + (k2 + h) * BM + 32 * g);
+    };
+    int s = 0;
+    uint32_t phase = 0;
+    wait_a(full_a, 0);
+    load_frags(0, 0, 0);
     for (int kt = 0; kt < ntiles; ++kt) {
-        const int s = kt % STAGES;
-        if (t == 0 && kt + STAGES - LAG < ntiles) produce(kt + STAGES - LAG);
-        mbar_wait(&full[s], (kt / STAGES) & 1);
-        const float *As = reinterpret_cast<const float *>(smem + s * STAGE_BYTES) + mrow;
-        const float *Bs = reinterpret_cast<const float *>(smem + s * STAGE_BYTES + A_BYTES) + ncol * BK;
+        if (!PW && t == 0 && kt + STAGES - LAG < ntiles) produce(kt + STAGES - LAG);
+        const int s_next = s + 1 == STAGES ? 0 : s + 1;
+        const uint32_t phase_next = s + 1 == STAGES ? phase ^ 1 : phase;
 #pragma unroll
         for (int k2 = 0; k2 < BK; k2 += 2) {
-            float2 b[NJ];
-#pragma unroll
-            for (int j = 0; j < NJ; ++j) b[j] = *reinterpret_cast<const float2 *>(Bs + (4 * j) * BK + k2);
+            const int cur = (k2 >> 1) & 1;
+            if (k2 + 2 < BK) {
+                load_frags(cur ^ 1, s, k2 + 2);
+            } else if (kt + 1 < ntiles) {
+                wait_a(full_a + 8 * s_next, phase_next);
+                load_frags(cur ^ 1, s_next, 0);
+            }
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int kk = k2 + h;
                 float2 a[2 * MI];
 #pragma unroll
                 for (int g = 0; g < MI; ++g) {
-                    const float4 av = *reinterpret_cast<const float4 *>(As + kk * BM + 32 * g);
-                    a[2 * g] = make_float2(av.x, av.y);
-                    a[2 * g + 1] = make_float2(av.z, av.w);
+                    a[2 * g] = make_float2(av[cur][h][g].x, av[cur][h][g].y);
+                    a[2 * g + 1] = make_float2(av[cur][h][g].z, av[cur][h][g].w);
                 }
 #pragma unroll
                 for (int i = 0; i < 2 * MI; ++i)
 #pragma unroll
                     for (int j = 0; j < NJ; ++j) {
-                        const float bj = h ? b[j].y : b[j].x;
+                        const float bj = h ? b[cur][j].y : b[cur][j].x;
                         const float2 c = (TILE16 && kk == 0) ? make_float2(0.0f, 0.0f) : acc[i][j];  // out = zero(T)
                         acc[i][j] = __ffma2_rn(a[i], make_float2(bj, bj), c);                         // out += a*b
                     }
             }
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[s]);   // this warp no longer reads stage s
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(empty_a + 8 * s) : "memory");   // stage s released
+        s = s_next;
+        phase = phase_next;
         if (TILE16) {
 #pragma unroll
             for (int i = 0; i < 2 * MI; ++i)
@@ -181,7 +236,7 @@ int sgemm_tma_applicable(const float *A, const float *B, int64_t M, int64_t K, i
            M < (1LL << 31) && N < (1LL << 31) && K < (1LL << 31);
 }
 
-template <bool TILE16, int NJ, int MI>
+template <bool TILE16, int NJ, int MI, int PW>
 static int sgemm_tma_launch_nj(float *C, const float *A, const float *B, int64_t M, int64_t K, int64_t N, int64_t lda,
                                int64_t ldb, int64_t ldc, cudaStream_t st) {
     using namespace sg;
@@ -197,8 +252,8 @@ static int sgemm_tma_launch_nj(float *C, const float *A, const float *B, int64_t
     const int ntiles = (int)cdiv(K, BK);
     const int group_m = tune_get("sgemm.group_m", 8);
     const int vec_ok = (ldc % 4 == 0) && (((uintptr_t)C & 15) == 0);
-    B200_CUDA(cudaFuncSetAttribute(sgemm_tma_kernel<TILE16, NJ, MI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    sgemm_tma_kernel<TILE16, NJ, MI><<<grid, consumer_warps(MI) * 32, SMEM_BYTES, st>>>(ta, tb, C, (int)M, (int)N, ldc, ntiles, tiles_m,
+    B200_CUDA(cudaFuncSetAttribute(sgemm_tma_kernel<TILE16, NJ, MI, PW>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    sgemm_tma_kernel<TILE16, NJ, MI, PW><<<grid, (consumer_warps(MI) + 4 * PW) * 32, SMEM_BYTES, st>>>(ta, tb, C, (int)M, (int)N, ldc, ntiles, tiles_m,
                                                                          tiles_n, group_m, vec_ok);
     B200_CHECK_LAUNCH("sgemm_tma_kernel");
     return B200_OK;
@@ -225,16 +280,17 @@ static int pick_nj(int64_t M, int64_t N, int sms) {
 int sgemm_tma_launch(float *C, const float *A, const float *B, int64_t M, int64_t K, int64_t N, int64_t lda,
                      int64_t ldb, int64_t ldc, int mode, cudaStream_t st) {
     const int nj = pick_nj(M, N, sm_count());
-    const int mi = tune_get("sgemm.mi", 2) == 1 ? 1 : 2;
-#define B200_SGEMM_CASE(T16, NJ_, MI_) \
-    if ((mode == B200_MATMUL_TILE16) == T16 && nj == NJ_ && mi == MI_) \
-        return sgemm_tma_launch_nj<T16, NJ_, MI_>(C, A, B, M, K, N, lda, ldb, ldc, st);
-    B200_SGEMM_CASE(true, 8, 2) B200_SGEMM_CASE(true, 7, 2) B200_SGEMM_CASE(true, 6, 2)
-    B200_SGEMM_CASE(false, 8, 2) B200_SGEMM_CASE(false, 7, 2) B200_SGEMM_CASE(false, 6, 2)
-    B200_SGEMM_CASE(true, 8, 1) B200_SGEMM_CASE(true, 7, 1) B200_SGEMM_CASE(true, 6, 1)
-    B200_SGEMM_CASE(false, 8, 1) B200_SGEMM_CASE(false, 7, 1) B200_SGEMM_CASE(false, 6, 1)
+    const int mi = 2;   // MI = 1 (16 warps, thread tile 4 x nj) measured no faster (54.3 vs 54.5 TFLOP/s) and is not instantiated
+    const int pw = tune_get("sgemm.producer_warp", 1) != 0;
+#define B200_SGEMM_CASE(T16, NJ_, MI_, PW_) \
+    if ((mode == B200_MATMUL_TILE16) == T16 && nj == NJ_ && mi == MI_ && pw == PW_) \
+        return sgemm_tma_launch_nj<T16, NJ_, MI_, PW_>(C, A, B, M, K, N, lda, ldb, ldc, st);
+    B200_SGEMM_CASE(true, 8, 2, 1) B200_SGEMM_CASE(true, 7, 2, 1) B200_SGEMM_CASE(true, 6, 2, 1)
+    B200_SGEMM_CASE(false, 8, 2, 1) B200_SGEMM_CASE(false, 7, 2, 1) B200_SGEMM_CASE(false, 6, 2, 1)
+    B200_SGEMM_CASE(true, 8, 2, 0) B200_SGEMM_CASE(true, 7, 2, 0) B200_SGEMM_CASE(true, 6, 2, 0)
+    B200_SGEMM_CASE(false, 8, 2, 0) B200_SGEMM_CASE(false, 7, 2, 0) B200_SGEMM_CASE(false, 6, 2, 0)
 #undef B200_SGEMM_CASE
-    return set_error(B200_ERR_UNSUPPORTED, "sgemm: no kernel for nj=%d mi=%d", nj, mi);
+    return set_error(B200_ERR_UNSUPPORTED, "sgemm: no kernel for nj=%d mi=%d pw=%d", nj, mi, pw);
 }
 
 }  // namespace b200

@@ -358,16 +358,17 @@ def test_matmul_signed_and_running_mode(orc):
         assert np.array_equal(KA.Array(dC2).view(np.uint32), ref2.view(np.uint32))
 
 
-@pytest.mark.parametrize("mi", [2, 1])
+@pytest.mark.parametrize("pw", [1, 0])
 @pytest.mark.parametrize("nj", [6, 7, 8])
 @pytest.mark.parametrize("shape", [(256, 200, 1000), (130, 17, 129), (384, 64, 112)])
-def test_matmul_tile_width_variants_bit_exact(orc, nj, shape, mi):
-    # the wave-filling tile widths (128 x 16 nj, csrc/kernels/matmul_f32_tma.cu pick_nj) must not change a single bit
+def test_matmul_tile_width_variants_bit_exact(orc, nj, shape, pw):
+    # the wave-filling tile widths (128 x 16 nj, csrc/kernels/matmul_f32_tma.cu pick_nj) and the producer placement
+    # (dedicated warp group vs thread 0) must not change a single bit
     M, Kd, N = shape
     A = orc.gen_uniform_f32((M, Kd), 1237) - 0.5
     B = orc.gen_uniform_f32((Kd, N), 1238) - 0.5
     dA, dB = KA.to_device(A), KA.to_device(B)
-    tune(sgemm__nj=nj, sgemm__mi=mi)
+    tune(sgemm__nj=nj, sgemm__producer_warp=pw)
     try:
         for mode, ref_fn in ((_lib.B200_MATMUL_TILE16, orc.coalesced_matmul), (_lib.B200_MATMUL_RUNNING, orc.matmul_running)):
             dC = KA.allocate(be, np.float32, M, N).fill_(-7.0)
@@ -376,7 +377,7 @@ def test_matmul_tile_width_variants_bit_exact(orc, nj, shape, mi):
             ref_fn(ref, A, B)
             assert np.array_equal(KA.Array(dC).view(np.uint32), ref.view(np.uint32))
     finally:
-        tune(sgemm__nj=0, sgemm__mi=2)
+        tune(sgemm__nj=0, sgemm__producer_warp=1)
 
 
 def test_matmul_c4_size_sampled_blocks(orc):
