@@ -164,6 +164,25 @@ def test_transpose_matches_oracle(orc, shape, order):
     assert np.array_equal(KA.Array(dA).view(np.uint32), a_ref.view(np.uint32))
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64, np.int64])
+@pytest.mark.parametrize("shape", [(132, 68), (68, 132), (1000, 1004), (4, 4), (2, 6), (64, 64), (192, 320), (100, 36), (2050, 130)])
+def test_transpose_any_shape_vector_path(shape, dtype):
+    # leading dimensions that are multiples of 16 bytes take transpose64_any_kernel (interior + predicated edge tiles)
+    m, n = shape
+    rng = np.random.default_rng(m * 131 + n)
+    b = np.asfortranarray((rng.standard_normal((n, m)) * 1e3).astype(dtype))
+    dA = KA.allocate(be, dtype, m, n).fill_(7)
+    dB = KA.to_device(b)
+    EX.naive_transpose_(dA, dB)
+    assert np.array_equal(KA.Array(dA), b.T)
+    pad = 4 if np.dtype(dtype).itemsize == 4 else 2             # keeps lda a multiple of 16 bytes whenever m is
+    guard = KA.allocate(be, dtype, m + pad, n).fill_(7)         # a with lda = m + pad: the extra rows must stay untouched
+    _lib.call("b200_transpose", C.c_void_p(guard.ptr), C.c_void_p(dB.ptr), m, n, m + pad, n, np.dtype(dtype).itemsize)
+    KA.synchronize(be)
+    g = KA.Array(guard)
+    assert np.array_equal(g[:m, :], b.T) and np.all(g[m:, :] == 7)
+
+
 def test_transpose_variants(orc):
     b = orc.gen_uniform_f32((256, 192), 5)
     a_ref = F((192, 256), np.float32)
