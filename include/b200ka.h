@@ -181,6 +181,8 @@ b200_status b200_transpose(void *a, const void *b, int64_t m, int64_t n, int64_t
 /* histogram_kernel!: bins[v-1] += #{t : input[t] == v}, v in 1..nbins (values outside are ignored)
  * (examples/histogram.jl:18-58).  Accumulates into `bins` like the reference's atomic +=. */
 b200_status b200_histogram_i32(int32_t *bins, int64_t nbins, const int32_t *input, int64_t n);
+/* the same for Int64 values and bins (Julia's default integer; the reference kernel is generic in the element type) */
+b200_status b200_histogram_i64(int64_t *bins, int64_t nbins, const int64_t *input, int64_t n);
 
 /* saxpy_kernel! / saxpy_kernel: Z[I] = a * X[I] + Y[I], product and sum rounded separately like the reference's
  * unfused Julia expression (benchmark/benchmarks.jl:29-32; examples/numa_aware.jl:10-13 is the in-place form Z == Y).

@@ -134,6 +134,7 @@ SIGNATURES = {
     "b200_fill": (_I32, [_VP, _SZ, _I32, _VP]),
     "b200_transpose": (_I32, [_VP, _VP, _I64, _I64, _I64, _I64, _I32]),
     "b200_histogram_i32": (_I32, [_VP, _I64, _VP, _I64]),
+    "b200_histogram_i64": (_I32, [_VP, _I64, _VP, _I64]),
     "b200_saxpy": (_I32, [_VP, C.c_double, _VP, _VP, _SZ, _I32]),
     "b200_matmul_f32": (_I32, [_VP, _VP, _VP, _I64, _I64, _I64, _I64, _I64, _I64, _I32]),
     "b200_matmul_bf16": (_I32, [_VP, _VP, _VP, _I64, _I64, _I64, _I64]),

@@ -408,6 +408,95 @@ int histogram_launch(int32_t *bins, int64_t nbins, const int32_t *input, int64_t
 }
 
 // ---------------------------------------------------------------------------------------------
+// Int64 values and bins (Julia's default integer; histogram_kernel! is generic in T, examples/histogram.jl:18): the same
+// design -- per-warp private 32-bit shared counters (a CTA sees < 2^32 elements), two values per 128-bit load, one
+// 64-bit red.global.add per non-empty bin per CTA.  8 bytes/element read: HBM-bound at half the atomics per byte.
+// ---------------------------------------------------------------------------------------------
+template <int T, int P>
+__global__ void __launch_bounds__(T) hist64_atomic_kernel(long long *__restrict__ bins, uint32_t nbins,
+                                                          const int4 *__restrict__ in4, int64_t n4,
+                                                          const long long *__restrict__ tail, int ntail, int copies) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t *sh = reinterpret_cast<uint32_t *>(smem_raw);
+    const int t = threadIdx.x, warp = t >> 5;
+    for (uint32_t i = t; i < nbins * (uint32_t)copies; i += T) sh[i] = 0;
+    __syncthreads();
+    uint32_t *mine = sh + (uint32_t)(warp % copies) * nbins;
+    auto bump = [&](int lo, int hi) {   // value = hi:lo, 1-based bin
+        const unsigned long long b = (((unsigned long long)(uint32_t)hi << 32) | (uint32_t)lo) - 1ull;
+        if (b < (unsigned long long)nbins) atomicAdd(mine + (uint32_t)b, 1u);
+    };
+    const int64_t u0 = n4 * (int64_t)blockIdx.x / gridDim.x;
+    const int64_t u1 = n4 * (int64_t)(blockIdx.x + 1) / gridDim.x;
+    const int64_t nbatch = (u1 - u0 + (int64_t)P * T - 1) / ((int64_t)P * T);
+    int4 cur[P], nxt[P];
+    auto load_batch = [&](int64_t k, int4 *buf) {
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            int64_t u = u0 + (k * P + p) * (int64_t)T + t;
+            buf[p] = u < u1 ? ldg_stream_i4(in4 + u) : make_int4(0, 0, 0, 0);   // 0 is outside 1..nbins
+        }
+    };
+    if (nbatch > 0) load_batch(0, cur);
+    for (int64_t k = 0; k < nbatch; ++k) {
+        if (k + 1 < nbatch) load_batch(k + 1, nxt);
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            bump(cur[p].x, cur[p].y);
+            bump(cur[p].z, cur[p].w);
+        }
+#pragma unroll
+        for (int p = 0; p < P; ++p) cur[p] = nxt[p];
+    }
+    if (blockIdx.x == 0 && t < ntail) bump((int)(uint32_t)tail[t], (int)(uint32_t)((unsigned long long)tail[t] >> 32));
+    __syncthreads();
+    for (uint32_t b = t; b < nbins; b += T) {
+        uint32_t sum = 0;
+        for (int c = 0; c < copies; ++c) sum += sh[(uint32_t)c * nbins + b];
+        if (sum) atomicAdd(reinterpret_cast<unsigned long long *>(bins) + b, (unsigned long long)sum);
+    }
+}
+__global__ void hist64_global_kernel(long long *__restrict__ bins, uint64_t nbins, const long long *__restrict__ in, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t b = (uint64_t)in[i] - 1ull;
+        if (b < nbins) atomicAdd(reinterpret_cast<unsigned long long *>(bins) + b, 1ull);
+    }
+}
+
+int histogram64_launch(long long *bins, int64_t nbins, const long long *input, int64_t n, cudaStream_t st) {
+    if (n == 0 || nbins == 0) return B200_OK;
+    const int sms = sm_count();
+    if (nbins > 14336) {
+        hist64_global_kernel<<<sms * 8, 256, 0, st>>>(bins, (uint64_t)nbins, input, n);
+        B200_CHECK_LAUNCH("hist64_global_kernel");
+        return B200_OK;
+    }
+    // [8-byte aligned but not 16-byte aligned head element | int4 body of value pairs | odd tail element]
+    int64_t head = ((uintptr_t)input & 15) ? 1 : 0;
+    if (head > n) head = n;
+    if (head) {
+        hist64_global_kernel<<<1, 32, 0, st>>>(bins, (uint64_t)nbins, input, head);
+        B200_CHECK_LAUNCH("hist64_global_kernel");
+    }
+    const long long *body = input + head;
+    const int64_t n4 = (n - head) / 2, tail_n = (n - head) - 2 * n4;
+    constexpr int T = 1024, P = 4;
+    int copies = (int)((48 * 1024) / (nbins * 4));
+    if (copies > T / 32) copies = T / 32;
+    if (copies < 1) copies = 1;
+    int grid = sms;
+    if ((int64_t)grid > (n4 + T - 1) / T) grid = (int)((n4 + T - 1) / T);
+    if (grid < 1) grid = 1;
+    const size_t smem = (size_t)nbins * copies * 4;
+    if (smem > 48 * 1024)
+        B200_CUDA(cudaFuncSetAttribute(hist64_atomic_kernel<T, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    hist64_atomic_kernel<T, P><<<grid, T, smem, st>>>(bins, (uint32_t)nbins, reinterpret_cast<const int4 *>(body), n4, body + 2 * n4,
+                                                      (int)tail_n, copies);
+    B200_CHECK_LAUNCH("hist64_atomic_kernel");
+    return B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // symmetric peer buffers (cudaIpc) for the fused histogram + all-reduce
 // ---------------------------------------------------------------------------------------------
 constexpr uint32_t kP2PMaxBins = 14336;
@@ -546,4 +635,14 @@ extern "C" b200_status b200_histogram_i32(int32_t *bins, int64_t nbins, const in
     cudaStream_t st;
     B200_TRY(current_stream(&st));
     return histogram_launch(bins, nbins, input, n, st);
+}
+
+extern "C" b200_status b200_histogram_i64(int64_t *bins, int64_t nbins, const int64_t *input, int64_t n) {
+    if (nbins < 0 || n < 0) return set_error(B200_ERR_INVALID_VALUE, "b200_histogram_i64: negative size");
+    if (n == 0 || nbins == 0) return B200_OK;
+    if (!bins || !input) return set_error(B200_ERR_INVALID_VALUE, "b200_histogram_i64: NULL pointer");
+    if (((uintptr_t)input & 7) != 0) return set_error(B200_ERR_UNSUPPORTED, "b200_histogram_i64: input must be 8-byte aligned");
+    cudaStream_t st;
+    B200_TRY(current_stream(&st));
+    return histogram64_launch((long long *)bins, nbins, (const long long *)input, n, st);
 }

@@ -13,6 +13,7 @@ int fill_elems(void *dst, size_t count, int elsize, const void *value, cudaStrea
 int transpose_launch(void *a, const void *b, int64_t m, int64_t n, int64_t lda, int64_t ldb, int elsize,
                      cudaStream_t st);
 int histogram_launch(int32_t *bins, int64_t nbins, const int32_t *input, int64_t n, cudaStream_t st);
+int histogram64_launch(long long *bins, int64_t nbins, const long long *input, int64_t n, cudaStream_t st);
 int sgemm_launch(float *C, const float *A, const float *B, int64_t M, int64_t K, int64_t N, int64_t lda, int64_t ldb,
                  int64_t ldc, int mode, cudaStream_t st);
 int saxpy_launch(void *Z, double a, const void *X, const void *Y, size_t n, int is_f64, cudaStream_t st);

@@ -342,13 +342,17 @@ static int h_histogram(const Launch &L) {
     REQUIRE(L.nargs == 3 && is_array(L.args[0]) && is_array(L.args[1]) && is_value(L.args[2]),
             "histogram_kernel!(histogram_output, input, Val(gs))");
     const b200_arg &out = L.args[0], &in = L.args[1];
-    REQUIRE(out.eltype == B200_T_I32 && in.eltype == B200_T_I32,
-            "histogram_kernel!: only Int32 bins/inputs are precompiled (examples/histogram.jl:75)");
+    REQUIRE((out.eltype == B200_T_I32 && in.eltype == B200_T_I32) || (out.eltype == B200_T_I64 && in.eltype == B200_T_I64),
+            "histogram_kernel!: Int32 or Int64 bins/inputs of the same type are precompiled (examples/histogram.jl:75)");
     const long long gs = L.args[2].scalar;
     REQUIRE(L.wgs[1] == 1 && L.wgs[2] == 1 && L.groups[1] == 1 && L.groups[2] == 1, "histogram_kernel!: 1-d launch");
     REQUIRE(L.wgs[0] == gs, "histogram_kernel!: workgroupsize %lld must equal Val(gs)=%lld", L.wgs[0], gs);
     const long long N = numel(out), len = numel(in);
     if (L.groups[0] == 0 || N == 0) return B200_OK;
+    if (in.eltype == B200_T_I64) {   // no literal Int64 twin: the regrouped kernel is the only Int64 path
+        long long covered = L.groups[0] * gs;
+        return histogram64_launch((long long *)out.ptr, N, (const long long *)in.ptr, covered < len ? covered : len, L.st);
+    }
     if (!force_twins()) {
         long long covered = L.groups[0] * gs;
         return histogram_launch((int32_t *)out.ptr, N, (const int32_t *)in.ptr, covered < len ? covered : len, L.st);

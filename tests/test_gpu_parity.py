@@ -428,6 +428,31 @@ def test_matmul_bf16_tensor_core():
     assert r.returncode == 0, "tensor-core GEMM check failed:\n" + r.stdout[-2000:] + r.stderr[-2000:]
 
 
+@pytest.mark.parametrize("n,nbins", [(1000, 128), (1, 1), (2, 7), (100003, 256), (1 << 20, 1000), (50000, 14336), (50000, 20000), ((1 << 22) + 1, 256)])
+def test_histogram_int64_matches_int32_oracle(orc, n, nbins):
+    # histogram_kernel! is generic in the element type (examples/histogram.jl:18); Julia's `rand(1:128, n)` is Int64.
+    # The Int64 path must give the counts of the pinned Int32 oracle on the same values, incl. out-of-range ones.
+    inp32 = orc.gen_bins_i32(n, 99, nbins + 3) - 1          # values 0 .. nbins+2: 0 and > nbins are ignored
+    want = np.zeros(nbins, dtype=np.int32)
+    orc.histogram(want, inp32, 256)
+    inp64 = inp32.astype(np.int64)
+    if n > 3:
+        inp64[1] = -5                                        # negative and huge values are out of range too
+        inp64[2] = (1 << 40) + 1
+        want[:] = 0
+        orc.histogram(want, np.where((inp64 >= 1) & (inp64 <= nbins), inp64, 0).astype(np.int32), 256)
+    d = KA.to_device(inp64)
+    bins = KA.ones(be, np.int64, nbins)                      # accumulates like the reference's +=
+    EX.histogram_(bins, d)
+    assert np.array_equal(KA.Array(bins), want.astype(np.int64) + 1)
+    if n > 8:                                                # 8-byte aligned but not 16-byte aligned input
+        bins2 = KA.zeros(be, np.int64, nbins)
+        EX.histogram_(bins2, d.view(1, (n - 1,)))
+        w2 = np.zeros(nbins, dtype=np.int32)
+        orc.histogram(w2, np.where((inp64[1:] >= 1) & (inp64[1:] <= nbins), inp64[1:], 0).astype(np.int32), 256)
+        assert np.array_equal(KA.Array(bins2), w2.astype(np.int64))
+
+
 # =====================================================================================================
 # host-buffer pipeline (b200_transpose_host / b200_histogram_i32_host): same bits as the oracle, host arrays in and out
 # =====================================================================================================

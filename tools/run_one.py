@@ -117,6 +117,12 @@ elif kind == "hist":
     d_in = KA.to_device(orc.gen_bins_i32(n, 1236, 256) if mode == 0 else np.full(n, 2, dtype=np.int32))
     bins = KA.zeros(be, np.int32, 256)
     run(lambda: _lib.call("b200_histogram_i32", C.c_void_p(bins.ptr), 256, C.c_void_p(d_in.ptr), n), 4.0 * n, "GB/s")
+elif kind == "hist64":
+    n = size or (1 << 29)
+    d32 = KA.rand_bins_(KA.allocate(be, np.int32, n), 1236, 256)
+    d_in = KA.to_device(KA.Array(d32).astype(np.int64))
+    bins = KA.zeros(be, np.int64, 256)
+    run(lambda: _lib.call("b200_histogram_i64", C.c_void_p(bins.ptr), 256, C.c_void_p(d_in.ptr), n), 8.0 * n, "GB/s")
 elif kind == "hist_fused":
     # the fused histogram + peer all-reduce kernel with a world of one rank (the exchange degenerates to local reductions)
     from b200ka import multigpu as mg
