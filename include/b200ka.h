@@ -153,6 +153,16 @@ typedef struct b200_arg {
 } b200_arg;
 
 b200_status b200_launch(const char *name, const b200_launch_desc *desc, const b200_arg *args, int32_t nargs);
+/* Run-time registration of precompiled kernels that live in the caller's own shared library -- the no-JIT counterpart of
+ * KI.kernel_function's compilation cache (reference src/pocl/backend.jl:151-154, src/pocl/compiler/execution.jl:190-217).
+ * `fn` receives the launch exactly as b200_launch got it, plus the calling thread's cudaStream_t (as void*) on which it must
+ * enqueue its kernel(s); it returns B200_OK or an error status (B200_ERR_BAD_ARGS for arguments it does not accept).
+ * include/b200ka_plugin.cuh holds the device-side index helpers (@index, __validindex) and the grid computation.
+ * Built-in names cannot be overridden.  Thread safe. */
+typedef b200_status (*b200_kernel_handler)(const b200_launch_desc *desc, const b200_arg *args, int32_t nargs,
+                                            void *cuda_stream, void *user);
+b200_status b200_register_kernel(const char *name, int32_t kind, b200_kernel_handler fn, void *user);
+b200_status b200_unregister_kernel(const char *name);
 b200_status b200_kernel_count(int32_t *count);
 const char *b200_kernel_name(int32_t index); /* NULL when out of range */
 /* KI.kernel_max_work_group_size (src/pocl/backend.jl:170-173; test/intrinsics.jl:95-96) */

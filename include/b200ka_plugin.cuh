@@ -1,0 +1,36 @@
+/* b200ka_plugin.cuh -- for authors of kernels registered with b200_register_kernel (include/b200ka.h).
+ *
+ * A KA `@kernel` launch is one-dimensional on the device: prod(blocks) CTAs of prod(workgroupsize) threads; the N-d indices
+ * are recovered per work-item (reference src/pocl/backend.jl:133-143, src/nditeration.jl:74-82,115-126).  This header gives a
+ * plug-in the same building blocks the built-in kernel twins use:
+ *   device:  b200::KaCtx, ka_global_linear / ka_local_linear / ka_group_linear, ka_expand, ka_valid (__validindex), ...
+ *   host:    b200_plugin_ctx(desc, &ctx, &groups, &items)  -- flatten a b200_launch_desc of kind B200_LAUNCH_KA
+ * A handler looks like
+ *   extern "C" int32_t my_handler(const b200_launch_desc *d, const b200_arg *a, int32_t n, void *stream, void *user) {
+ *       b200::KaCtx c; long long groups, items;
+ *       if (b200_plugin_ctx(d, &c, &groups, &items) != B200_OK || n != 2 || a[0].eltype != B200_T_F32) return B200_ERR_BAD_ARGS;
+ *       if (groups) my_kernel<<<(unsigned)groups, (unsigned)items, 0, (cudaStream_t)stream>>>(c, (float *)a[0].ptr, (float)a[1].fscalar);
+ *       return B200_OK;
+ *   }
+ */
+#pragma once
+#include "b200ka.h"
+#include "../kernelabstractions.jl_b200/csrc/ka_device.cuh"
+
+static inline int32_t b200_plugin_ctx(const b200_launch_desc *d, b200::KaCtx *c, long long *groups, long long *items) {
+    if (!d || d->kind != B200_LAUNCH_KA || d->ndim < 1 || d->ndim > b200::KA_MAX_NDIM) return B200_ERR_BAD_ARGS;
+    c->ndim = d->ndim;
+    c->dynamic_check = d->dynamic_check;
+    *groups = 1;
+    *items = 1;
+    for (int k = 0; k < b200::KA_MAX_NDIM; ++k) {
+        const bool in = k < d->ndim;
+        c->ndrange[k] = in ? d->ndrange[k] : 1;
+        c->wgs[k] = in ? d->wgs[k] : 1;
+        c->blocks[k] = in ? d->blocks[k] : 1;
+        *groups *= c->blocks[k];
+        *items *= c->wgs[k];
+    }
+    if (*items < 1 || *items > 1024 || *groups > 2147483647LL) return B200_ERR_LAUNCH_DIMS;
+    return B200_OK;
+}

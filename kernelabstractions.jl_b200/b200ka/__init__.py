@@ -13,7 +13,7 @@ from .backend import (CPU, Array, B200Array, B200Backend, CartesianIndex, Kernel
 from .backend import sum as sum  # noqa: A004 -- Base.sum for device arrays (KA.sum)
 from .kernel import (KIKernel, Kernel, KernelFunction, Val, check_launch_args, kernel_function,
                      kernel_max_work_group_size, ki_kernel, max_work_group_size, multiprocessor_count,
-                     registered_kernels)
+                     registered_kernels, register_kernel, unregister_kernel)
 from .ndrange import (DYNAMIC, DynamicCheck, DynamicSize, NDRange, NoDynamicCheck, StaticSize, expand, ka_partition,
                       nd_partition, threads_to_workgroupsize)
 from . import kernels, examples, multigpu  # noqa: E402

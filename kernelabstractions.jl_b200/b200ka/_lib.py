@@ -124,6 +124,8 @@ SIGNATURES = {
     "b200_event_elapsed_ms": (_I32, [_VP, _VP, C.POINTER(C.c_float)]),
     "b200_event_destroy": (_I32, [_VP]),
     "b200_launch": (_I32, [C.c_char_p, C.POINTER(LaunchDesc), C.POINTER(Arg), _I32]),
+    "b200_register_kernel": (_I32, [C.c_char_p, _I32, _VP, _VP]),
+    "b200_unregister_kernel": (_I32, [C.c_char_p]),
     "b200_kernel_count": (_I32, [_PI32]),
     "b200_kernel_name": (C.c_char_p, [_I32]),
     "b200_kernel_max_work_group_size": (_I32, [C.c_char_p, _I64, _PI64]),

@@ -245,3 +245,20 @@ def registered_kernels():
     n = C.c_int32(0)
     call("b200_kernel_count", C.byref(n))
     return [lib().b200_kernel_name(i).decode() for i in range(n.value)]
+
+
+def register_kernel(name: str, handler, kind: str = "ka", user=None) -> None:
+    """Add a precompiled kernel from the caller's own shared library to the catalogue (b200_register_kernel).
+    `name` is what b200_launch is called with: "gpu_" + function name for `@kernel`s (reference src/macros.jl:32), the
+    function name itself for `KI.@kernel`.  `handler` is the address of a native `b200_kernel_handler` (an int, a
+    ctypes function pointer, or a ctypes CFUNCTYPE object the caller keeps alive)."""
+    addr = handler if isinstance(handler, int) else C.cast(handler, C.c_void_p).value
+    call("b200_register_kernel", name.encode(), C.c_int32(_lib.B200_LAUNCH_KA if kind == "ka" else _lib.B200_LAUNCH_KI),
+         C.c_void_p(addr), C.c_void_p(user))
+
+
+def unregister_kernel(name: str) -> None:
+    st = lib().b200_unregister_kernel(name.encode())
+    if st == _lib.B200_ERR_UNKNOWN_KERNEL:
+        raise ErrorException(_lib.last_error())
+    _lib.check(st)

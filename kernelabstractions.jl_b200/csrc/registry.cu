@@ -11,6 +11,10 @@
 // runs its literal twin (kernels/twins.cu).  Both produce the same bits, so the choice is invisible.
 #include <cstring>
 
+#include <mutex>
+#include <string>
+#include <vector>
+
 #include "common.cuh"
 #include "kernels/twins.h"
 #include "tune.h"
@@ -461,23 +465,76 @@ static const Entry *find_entry(const char *name) {
     return nullptr;
 }
 
+// Kernels registered at run time (b200_register_kernel): precompiled sm_100a kernels that live in a user's own shared
+// library.  This is the no-JIT counterpart of KI.kernel_function's compilation cache (reference src/pocl/backend.jl:151-154,
+// src/pocl/compiler/execution.jl:190-217): the catalogue stays a table of native kernels, but it is open.
+struct UserEntry {
+    std::string name;
+    int kind;
+    b200_kernel_handler fn;
+    void *user;
+};
+static std::mutex g_user_mu;
+static std::vector<UserEntry> g_user;
+
+static bool find_user(const char *name, UserEntry *out) {
+    std::lock_guard<std::mutex> lk(g_user_mu);
+    for (const UserEntry &e : g_user)
+        if (e.name == name) {
+            if (out) *out = e;
+            return true;
+        }
+    return false;
+}
+
 }  // namespace b200
 
 using namespace b200;
 
 extern "C" b200_status b200_kernel_count(int32_t *count) {
     if (!count) return set_error(B200_ERR_INVALID_VALUE, "count is NULL");
-    *count = kNumEntries;
+    std::lock_guard<std::mutex> lk(g_user_mu);
+    *count = kNumEntries + (int32_t)g_user.size();
     return B200_OK;
 }
 
 extern "C" const char *b200_kernel_name(int32_t index) {
-    return (index >= 0 && index < kNumEntries) ? kTable[index].name : nullptr;
+    if (index >= 0 && index < kNumEntries) return kTable[index].name;
+    static thread_local std::string tmp;   // registered names may be unregistered concurrently: hand out a copy
+    std::lock_guard<std::mutex> lk(g_user_mu);
+    const int64_t u = (int64_t)index - kNumEntries;
+    if (u < 0 || u >= (int64_t)g_user.size()) return nullptr;
+    tmp = g_user[(size_t)u].name;
+    return tmp.c_str();
+}
+
+extern "C" b200_status b200_register_kernel(const char *name, int32_t kind, b200_kernel_handler fn, void *user) {
+    if (!name || !*name || !fn) return set_error(B200_ERR_INVALID_VALUE, "b200_register_kernel: NULL name or handler");
+    if (kind != B200_LAUNCH_KA && kind != B200_LAUNCH_KI)
+        return set_error(B200_ERR_INVALID_VALUE, "b200_register_kernel: kind must be B200_LAUNCH_KA or B200_LAUNCH_KI");
+    if (find_entry(name)) return set_error(B200_ERR_INVALID_VALUE, "b200_register_kernel: '%s' is a built-in kernel", name);
+    std::lock_guard<std::mutex> lk(g_user_mu);
+    for (const UserEntry &e : g_user)
+        if (e.name == name) return set_error(B200_ERR_INVALID_VALUE, "b200_register_kernel: '%s' is already registered", name);
+    g_user.push_back(UserEntry{name, kind, fn, user});
+    return B200_OK;
+}
+
+extern "C" b200_status b200_unregister_kernel(const char *name) {
+    if (!name) return set_error(B200_ERR_INVALID_VALUE, "b200_unregister_kernel: NULL name");
+    std::lock_guard<std::mutex> lk(g_user_mu);
+    for (size_t i = 0; i < g_user.size(); ++i)
+        if (g_user[i].name == name) {
+            g_user.erase(g_user.begin() + (long)i);
+            return B200_OK;
+        }
+    return set_error(B200_ERR_UNKNOWN_KERNEL, "b200_unregister_kernel: no registered kernel named '%s'", name);
 }
 
 extern "C" b200_status b200_kernel_max_work_group_size(const char *name, int64_t max_work_items, int64_t *out) {
     if (!name || !out) return set_error(B200_ERR_INVALID_VALUE, "NULL argument");
-    if (!find_entry(name)) return set_error(B200_ERR_UNKNOWN_KERNEL, "no precompiled kernel named '%s'", name);
+    if (!find_entry(name) && !find_user(name, nullptr))
+        return set_error(B200_ERR_UNKNOWN_KERNEL, "no precompiled kernel named '%s'", name);
     *out = max_work_items < 1024 ? max_work_items : 1024;  // reference src/pocl/backend.jl:170-173
     return B200_OK;
 }
@@ -524,9 +581,28 @@ extern "C" b200_status b200_launch(const char *name, const b200_launch_desc *des
         return set_error(B200_ERR_INVALID_VALUE, "b200_launch: unknown launch kind %d", desc->kind);
     }
     const Entry *e = find_entry(name);
-    if (!e)
-        return set_error(B200_ERR_UNKNOWN_KERNEL,
-                         "no precompiled sm_100a kernel named '%s' (B200Backend has no JIT; see b200_kernel_name)", name);
+    if (!e) {
+        UserEntry ue;
+        if (!find_user(name, &ue))
+            return set_error(B200_ERR_UNKNOWN_KERNEL,
+                             "no precompiled sm_100a kernel named '%s' (B200Backend has no JIT; see b200_kernel_name, "
+                             "b200_register_kernel)", name);
+        if (ue.kind != desc->kind)
+            return set_error(B200_ERR_BAD_ARGS, "kernel '%s' is registered as a %s kernel", name,
+                             ue.kind == B200_LAUNCH_KA ? "KA @kernel" : "KI.@kernel");
+        B200_TRY(current_stream(&L.st));
+        const int32_t st = ue.fn(desc, args, nargs, (void *)L.st, ue.user);   // the handler validates its own arguments
+        if (st == B200_OK) {
+            cudaError_t ce = cudaGetLastError();
+            if (ce != cudaSuccess) return set_error(B200_ERR_CUDA, "launch of registered kernel '%s' failed: %s", name, cudaGetErrorString(ce));
+            count_launch();
+        } else if (tls().err[0] == 0 || st != B200_ERR_BAD_ARGS) {
+            set_error(st, "registered kernel '%s' returned status %d", name, (int)st);
+        } else {
+            set_error(st, "registered kernel '%s' rejected its arguments", name);
+        }
+        return st;
+    }
     if (e->kind != desc->kind)
         return set_error(B200_ERR_BAD_ARGS, "kernel '%s' is a %s kernel", name,
                          e->kind == B200_LAUNCH_KA ? "KA @kernel" : "KI.@kernel");

@@ -350,6 +350,15 @@ function launch(name::String, desc::LaunchDesc, args)
     return nothing
 end
 
+# Run-time registration of a precompiled kernel from the user's own shared library (b200_register_kernel): `handler` is the
+# address of a native `b200_kernel_handler`, e.g. `Libdl.dlsym(Libdl.dlopen("libmykernels.so"), :my_handler)`.  `name` is
+# `"gpu_" * string(kernel function name)` for `@kernel`s (reference src/macros.jl:32), the function name for `KI.@kernel`.
+function register_kernel(name::AbstractString, handler::Ptr{Cvoid}; ki::Bool = false, user::Ptr{Cvoid} = C_NULL)
+    @b200 b200_register_kernel (Cstring, Int32, Ptr{Cvoid}, Ptr{Cvoid}) String(name) Int32(ki ? 1 : 0) handler user
+    return nothing
+end
+unregister_kernel(name::AbstractString) = (@b200 b200_unregister_kernel (Cstring,) String(name); nothing)
+
 function registered_kernels()
     n = Ref{Int32}(0)
     @b200 b200_kernel_count (Ptr{Int32},) n
