@@ -230,7 +230,8 @@ b200_status b200_matmul_f32_via_bf16(float *C, const float *A, const float *B, i
                                      int64_t N, int64_t lda, int64_t ldb, int64_t ldc, void *workspace);
 
 /* ---- device-array conveniences: what Base / LinearAlgebra give a CPU() user for free on plain Arrays ----------------
- * (SURVEY.md 8(f)-4).  These return a VALUE, so they wait for the calling thread's stream.  Arrays 16-byte aligned.
+ * (SURVEY.md 8(f)-4).  These return a VALUE, so they wait for the calling thread's stream.  Any element-aligned pointer
+ * (unaligned views take a scalar prologue; two operands vectorise when they are equally misaligned).
  *
  * maximum / minimum / sum over n elements (examples/histogram.jl:10,88-90 sizes the histogram with `maximum(input)`).
  * op: 0 = sum, 1 = maximum, 2 = minimum.  eltype: B200_T_I32/U32/I64/U64/F32/F64.  *result_host receives a value of the

@@ -31,6 +31,17 @@ __device__ __forceinline__ V ld_nc16(const V *p) {
     return *reinterpret_cast<V *>(&r);
 }
 
+// Unaligned views (B200Array.view, Base.view): `head` leading elements are handled one by one, the 128-bit loop starts at the
+// first 16-byte boundary; two operands vectorise together only when they are equally misaligned, else everything is scalar.
+template <typename T>
+__device__ __forceinline__ size_t head_elems(const T *a, const T *b, size_t n, bool *vec_ok) {
+    const uintptr_t ua = (uintptr_t)a, ub = b ? (uintptr_t)b : ua;
+    *vec_ok = ((ua ^ ub) & 15) == 0 && (ua % sizeof(T)) == 0;
+    if (!*vec_ok) return n;
+    const size_t h = ((16 - (ua & 15)) & 15) / sizeof(T);
+    return h < n ? h : n;
+}
+
 // ---- combine rules (Julia semantics: NaN propagates through maximum/minimum; max(-0.0, 0.0) == 0.0) ----
 template <typename T>
 __device__ __forceinline__ T jl_max(T a, T b) { return a > b ? a : b; }
@@ -160,9 +171,12 @@ __global__ void __launch_bounds__(THREADS) reduce_kernel(const T *__restrict__ x
     using Acc = typename R::Acc;
     constexpr int VEC = 16 / sizeof(T);
     struct alignas(16) V { T e[VEC]; };
-    const size_t nvec = n / VEC, tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+    bool vec_ok;
+    const size_t head = head_elems<T>(x, nullptr, n, &vec_ok);
+    const size_t nvec = (n - head) / VEC, tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
     Acc acc = OP == OP_SUM ? (Acc)0 : R::lift(x[0]);
-    const V *xv = reinterpret_cast<const V *>(x);
+    const V *xv = reinterpret_cast<const V *>(x + head);
+    for (size_t j = tid; j < head; j += stride) acc = R::comb(acc, R::lift(x[j]));
     size_t i = tid;
     for (; i + 3 * stride < nvec; i += 4 * stride) {
         V v[4];
@@ -178,7 +192,7 @@ __global__ void __launch_bounds__(THREADS) reduce_kernel(const T *__restrict__ x
 #pragma unroll
         for (int e = 0; e < VEC; ++e) acc = R::comb(acc, R::lift(v.e[e]));
     }
-    for (size_t j = nvec * VEC + tid; j < n; j += stride) acc = R::comb(acc, R::lift(x[j]));
+    for (size_t j = head + nvec * VEC + tid; j < n; j += stride) acc = R::comb(acc, R::lift(x[j]));
     __shared__ Acc sh[32];
     Acc blk[1];
     if (OP == OP_SUM) {   // lanes beyond the warp count must not contribute twice: plain two-level sum
@@ -206,9 +220,12 @@ __global__ void __launch_bounds__(THREADS) mismatch_kernel(const T *__restrict__
                                                            unsigned long long *result) {
     constexpr int VEC = 16 / sizeof(T);
     struct alignas(16) V { T e[VEC]; };
-    const size_t nvec = n / VEC, tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+    bool vec_ok;
+    const size_t head = head_elems<T>(a, b, n, &vec_ok);
+    const size_t nvec = (n - head) / VEC, tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
     unsigned long long bad = 0;
-    const V *av = reinterpret_cast<const V *>(a), *bv = reinterpret_cast<const V *>(b);
+    const V *av = reinterpret_cast<const V *>(a + head), *bv = reinterpret_cast<const V *>(b + head);
+    for (size_t j = tid; j < head; j += stride) bad += !(a[j] == b[j]);
     size_t i = tid;
     for (; i + stride < nvec; i += 2 * stride) {
         V x0 = ld_nc16(av + i), y0 = ld_nc16(bv + i), x1 = ld_nc16(av + i + stride), y1 = ld_nc16(bv + i + stride);
@@ -220,7 +237,7 @@ __global__ void __launch_bounds__(THREADS) mismatch_kernel(const T *__restrict__
 #pragma unroll
         for (int e = 0; e < VEC; ++e) bad += !(x0.e[e] == y0.e[e]);
     }
-    for (size_t j = nvec * VEC + tid; j < n; j += stride) bad += !(a[j] == b[j]);
+    for (size_t j = head + nvec * VEC + tid; j < n; j += stride) bad += !(a[j] == b[j]);
     __shared__ unsigned long long sh[32];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) bad += __shfl_xor_sync(0xffffffffu, bad, o);
@@ -238,9 +255,11 @@ __global__ void __launch_bounds__(THREADS) norms_kernel(const T *__restrict__ a,
                                                         unsigned int *ticket, double *result) {
     constexpr int VEC = 16 / sizeof(T);
     struct alignas(16) V { T e[VEC]; };
-    const size_t nvec = n / VEC, tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+    bool vec_ok;
+    const size_t head = head_elems<T>(a, b, n, &vec_ok);
+    const size_t nvec = (n - head) / VEC, tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
     double sd = 0, sx = 0, sy = 0;
-    const V *av = reinterpret_cast<const V *>(a), *bv = reinterpret_cast<const V *>(b);
+    const V *av = reinterpret_cast<const V *>(a + head), *bv = reinterpret_cast<const V *>(b + head);
     auto add = [&](T xe, T ye) {
         const double x = (double)xe, y = (double)ye, d = x - y;
         sd = fma(d, d, sd);
@@ -260,7 +279,8 @@ __global__ void __launch_bounds__(THREADS) norms_kernel(const T *__restrict__ a,
 #pragma unroll
         for (int e = 0; e < VEC; ++e) add(x0.e[e], y0.e[e]);
     }
-    for (size_t j = nvec * VEC + tid; j < n; j += stride) add(a[j], b[j]);
+    for (size_t j = tid; j < head; j += stride) add(a[j], b[j]);
+    for (size_t j = head + nvec * VEC + tid; j < n; j += stride) add(a[j], b[j]);
     __shared__ double sh[3][32];
     double v[3] = {sd, sx, sy};
 #pragma unroll
@@ -287,7 +307,8 @@ __device__ __forceinline__ uint32_t mix32(unsigned long long x) {
 }
 template <bool BINS>
 __global__ void __launch_bounds__(THREADS) gen_kernel(uint32_t *__restrict__ out, size_t n, unsigned long long base, uint32_t nbins, uint32_t recip) {
-    const size_t nvec = n / 4, tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+    const size_t head0 = ((16 - ((uintptr_t)out & 15)) & 15) / 4, head = head0 < n ? head0 : n;
+    const size_t nvec = (n - head) / 4, tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
     auto one = [&](size_t i) -> uint32_t {
         const uint32_t h = mix32(base + (unsigned long long)i);
         if (BINS && nbins == 1u) return 1u;
@@ -299,9 +320,12 @@ __global__ void __launch_bounds__(THREADS) gen_kernel(uint32_t *__restrict__ out
         }
         return __float_as_uint((float)(h >> 8) * (1.0f / 16777216.0f));
     };
-    for (size_t v = tid; v < nvec; v += stride)
-        reinterpret_cast<uint4 *>(out)[v] = make_uint4(one(4 * v), one(4 * v + 1), one(4 * v + 2), one(4 * v + 3));
-    for (size_t j = nvec * 4 + tid; j < n; j += stride) out[j] = one(j);
+    for (size_t j = tid; j < head; j += stride) out[j] = one(j);
+    for (size_t v = tid; v < nvec; v += stride) {
+        const size_t e = head + 4 * v;
+        reinterpret_cast<uint4 *>(out + head)[v] = make_uint4(one(e), one(e + 1), one(e + 2), one(e + 3));
+    }
+    for (size_t j = head + nvec * 4 + tid; j < n; j += stride) out[j] = one(j);
 }
 
 // ---- per-thread, per-device scratch: MAX_BLOCKS * 24 bytes of partials, a ticket, and a pinned 32-byte landing pad that
@@ -373,7 +397,6 @@ extern "C" b200_status b200_reduce(int32_t op, int32_t eltype, const void *x, si
         return B200_OK;
     }
     if (!x) return set_error(B200_ERR_INVALID_VALUE, "b200_reduce: NULL pointer");
-    if (((uintptr_t)x & 15) != 0) return set_error(B200_ERR_UNSUPPORTED, "b200_reduce: array must be 16-byte aligned");
     cudaStream_t st;
     B200_TRY(current_stream(&st));
     switch (eltype) {
@@ -393,8 +416,6 @@ extern "C" b200_status b200_count_mismatch(const void *a, const void *b, size_t 
     *count_host = 0;
     if (n == 0) return B200_OK;
     if (!a || !b) return set_error(B200_ERR_INVALID_VALUE, "b200_count_mismatch: NULL pointer");
-    if ((((uintptr_t)a | (uintptr_t)b) & 15) != 0)
-        return set_error(B200_ERR_UNSUPPORTED, "b200_count_mismatch: arrays must be 16-byte aligned");
     cudaStream_t st;
     B200_TRY(current_stream(&st));
     ao::Scratch *s;
@@ -431,7 +452,6 @@ extern "C" b200_status b200_norms(const void *x, const void *y, size_t n, int32_
     out3_host[0] = out3_host[1] = out3_host[2] = 0.0;
     if (n == 0) return B200_OK;
     if (!x || !y) return set_error(B200_ERR_INVALID_VALUE, "b200_norms: NULL pointer");
-    if ((((uintptr_t)x | (uintptr_t)y) & 15) != 0) return set_error(B200_ERR_UNSUPPORTED, "b200_norms: arrays must be 16-byte aligned");
     cudaStream_t st;
     B200_TRY(current_stream(&st));
     ao::Scratch *s;
@@ -448,7 +468,6 @@ extern "C" b200_status b200_norms(const void *x, const void *y, size_t n, int32_
 extern "C" b200_status b200_rand_uniform_f32(float *out, size_t n, uint64_t seed) {
     if (n == 0) return B200_OK;
     if (!out) return set_error(B200_ERR_INVALID_VALUE, "b200_rand_uniform_f32: NULL pointer");
-    if (((uintptr_t)out & 15) != 0) return set_error(B200_ERR_UNSUPPORTED, "b200_rand_uniform_f32: array must be 16-byte aligned");
     cudaStream_t st;
     B200_TRY(current_stream(&st));
     ao::gen_kernel<false><<<ao::grid_for(n / 4), ao::THREADS, 0, st>>>((uint32_t *)out, n, seed * 0x100000001B3ull, 1u, 0u);
@@ -460,7 +479,6 @@ extern "C" b200_status b200_rand_bins_i32(int32_t *out, size_t n, uint64_t seed,
     if (nbins <= 0) return set_error(B200_ERR_INVALID_VALUE, "b200_rand_bins_i32: nbins must be positive");
     if (n == 0) return B200_OK;
     if (!out) return set_error(B200_ERR_INVALID_VALUE, "b200_rand_bins_i32: NULL pointer");
-    if (((uintptr_t)out & 15) != 0) return set_error(B200_ERR_UNSUPPORTED, "b200_rand_bins_i32: array must be 16-byte aligned");
     cudaStream_t st;
     B200_TRY(current_stream(&st));
     ao::gen_kernel<true><<<ao::grid_for(n / 4), ao::THREADS, 0, st>>>((uint32_t *)out, n, seed * 0x100000001B3ull, (uint32_t)nbins,

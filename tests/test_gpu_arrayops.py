@@ -134,6 +134,25 @@ def test_device_generators_bit_identical_to_oracle(orc, n):
     assert np.array_equal(KA.Array(v), orc.gen_bins_i32(n, 1236, 256))
 
 
+@pytest.mark.parametrize("off", [1, 2, 3, 5])
+def test_unaligned_views(orc, off):
+    n = 100003
+    h = orc.gen_uniform_f32((n,), 3) - 0.5
+    d = KA.to_device(h)
+    v = d.view(off, (n - off,))                       # pointer is 4-byte but not 16-byte aligned
+    assert KA.maximum(v) == h[off:].max() and KA.minimum(v) == h[off:].min()
+    assert np.isclose(KA.sum(v), h[off:].astype(np.float64).sum(), rtol=1e-12)
+    e = KA.to_device(h)
+    assert KA.isequal(v, e.view(off, (n - off,)))     # equally misaligned: vector path with a scalar head
+    assert KA.isequal(v, KA.to_device(h[off:].copy()))   # differently aligned operands: scalar path
+    h2 = h.copy(); h2[off] += 1
+    assert not KA.isequal(v, KA.to_device(h2).view(off, (n - off,)))
+    assert KA.isapprox(v, KA.to_device(h[off:].copy()))
+    g = KA.allocate(be, np.float32, n)
+    KA.rand_uniform_(g.view(off, (n - off,)), 1234)
+    assert np.array_equal(KA.Array(g)[off:].view(np.uint32), orc.gen_uniform_f32((n - off,), 1234).view(np.uint32))
+
+
 def test_full_size_histogram_input_checks():
     # BASELINE config 3 input generated on the device: 2^30 values in 1..256; size-independent properties
     n = 1 << 30
