@@ -318,7 +318,8 @@ def main():
     suite = {}
     if not args.no_suite:
         del dA, dB
-        suite = run_suite(KA, _lib, EX, mg, orc, be, rank, world, dist, timed, peaks, min(args.steps, 50), warmup, barrier)
+        suite = run_suite(KA, _lib, EX, mg, orc, be, rank, world, dist, timed, peaks, min(args.steps, 50), warmup, barrier,
+                      cpu=(rank == 0 and world == 1 and not args.no_cpu_baseline))
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -343,8 +344,21 @@ def main():
     return 0
 
 
-def run_suite(KA, _lib, EX, mg, orc, be, rank, world, dist, timed, peaks, steps, warmup, barrier):
+def run_suite(KA, _lib, EX, mg, orc, be, rank, world, dist, timed, peaks, steps, warmup, barrier, cpu=False):
     out = {}
+
+    def cpu_time(fn, work, unit, scale, sample):
+        """best of up to 3 passes of the oracle's work-group-vectorised restatement on the host cores (reported, not a target)"""
+        best = float("inf")
+        t_all = time.perf_counter()
+        for _ in range(3):
+            t0 = time.perf_counter()
+            fn()
+            best = min(best, time.perf_counter() - t0)
+            if time.perf_counter() - t_all > 6.0:
+                break
+        return {"value": work / best / scale, "unit": unit, "cores": orc.threads(), "kind": "port", "sample": sample}
+
     # ---- copy 2^26 F32 (configs[0] size): alternate two buffer pairs so nothing is L2 resident ----
     try:
         n = N_COPY
@@ -363,6 +377,10 @@ def run_suite(KA, _lib, EX, mg, orc, be, rank, world, dist, timed, peaks, steps,
                                 "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm"], "frac": gbs / peaks["hbm"],
                                              "traffic": None}, "scaling": "weak"}
         del src, dst
+        if cpu:
+            hB, hA = orc.gen_uniform_f32((n,), 1234), np.zeros(n, dtype=np.float32)
+            out["copy_2^26_f32"]["cpu_baseline"] = cpu_time(lambda: orc.copy_wg(hA, hB, 1024), 8.0 * n, "GB/s", 1e9,
+                                                            "full 2^26 Float32 copy_kernel!, workgroup 1024, OpenMP over work-groups")
     except Exception as ex:
         out["copy_2^26_f32"] = {"error": str(ex)[:300]}
 
@@ -387,6 +405,10 @@ def run_suite(KA, _lib, EX, mg, orc, be, rank, world, dist, timed, peaks, steps,
                                  "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm"], "frac": gbs / peaks["hbm"],
                                               "traffic": None}, "scaling": "weak"}
         del X, Y, Z
+        if cpu:
+            hX, hY, hZ = orc.gen_uniform_f32((n,), 1300), orc.gen_uniform_f32((n,), 1310), np.zeros(n, dtype=np.float32)
+            out["saxpy_2^26_f32"]["cpu_baseline"] = cpu_time(lambda: orc.saxpy_wg(hZ, np.float32(2.0), hX, hY, 1024), 12.0 * n, "GB/s", 1e9,
+                                                             "full 2^26 Float32 saxpy_kernel!, workgroup 1024, OpenMP over work-groups")
     except Exception as ex:
         out["saxpy_2^26_f32"] = {"error": str(ex)[:300]}
 
@@ -445,6 +467,11 @@ def run_suite(KA, _lib, EX, mg, orc, be, rank, world, dist, timed, peaks, steps,
         if comm is not None:
             comm.destroy()
         del d_in, bins
+        if cpu:
+            hbins = np.zeros(256, dtype=np.int32)
+            out["histogram_2^30_i32_256bins"]["cpu_baseline"] = cpu_time(
+                lambda: orc.histogram(hbins, inp, 256), 4.0 * n, "GB/s", 1e9,
+                "full 2^30 Int32 histogram_kernel!, workgroup 256 (per-group local histogram + merge), OpenMP over work-groups")
     except Exception as ex:
         out["histogram_2^30_i32_256bins"] = {"error": str(ex)[:300]}
 
@@ -468,6 +495,13 @@ def run_suite(KA, _lib, EX, mg, orc, be, rank, world, dist, timed, peaks, steps,
         out["matmul_f32_8192"] = {"value": tf, "unit": "TFLOP/s", "ms_per_step": ms, "gpu_launches": launches, "scaling": "strong",
                                   "roofline": {"bound": "fma", "achieved": tf / world, "peak": fma_peak, "frac": tf / world / fma_peak,
                                                "peak_source": "148 SM x 128 lanes x 2 x sm_max_mhz"}}
+        if cpu:
+            ms_ = 2048
+            hA_, hB_ = orc.gen_uniform_f32((ms_, ms_), 1237), orc.gen_uniform_f32((ms_, ms_), 1238)
+            hC_ = np.zeros((ms_, ms_), dtype=np.float32, order="F")
+            out["matmul_f32_8192"]["cpu_baseline"] = cpu_time(
+                lambda: orc.coalesced_matmul(hC_, hA_, hB_), 2.0 * ms_ ** 3, "TFLOP/s", 1e12,
+                "2048^3 sample of coalesced_matmul_kernel! (16x16 local-memory tiles, reference summation order), OpenMP over work-groups")
         # ---- opt-in tensor-core paths, same A/C row-panel sharding (B replicated); reported only when a sampled parity
         # ---- check of THIS run's result passes (64 entries of C against float64 dot products, rtol 1e-2) ----
         hA, hB = KA.Array(Ap), KA.Array(dBm)

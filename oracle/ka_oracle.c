@@ -202,6 +202,30 @@ void orc_naive_transpose_wg_f32(const ka_ctx *c, float *a, const float *b, Int r
     }
 }
 
+/* Work-group-vectorised 1-d copy and saxpy, same idea: one bounds computation per group, the work-items of the group are the
+ * inner (vectorisable) loop -- how a CPU OpenCL runtime executes `A[I] = B[I]` (examples/memcopy.jl:4-7) and
+ * `Z[I] = a*X[I] + Y[I]` (benchmark/benchmarks.jl:29-32).  Identical results to orc_copy / orc_saxpy_f32 (checked in
+ * tests/test_oracle_golden.py); used only as timed CPU baselines. */
+void orc_copy_wg_f32(const ka_ctx *c, float *A, const float *B) {
+    const Int G = ka_num_groups(c), W = c->wgs[0], N = c->ndrange[0];
+#pragma omp parallel for schedule(static)
+    for (Int g = 0; g < G; ++g) {
+        const Int i0 = g * W, cnt = (i0 + W <= N) ? W : N - i0;
+        for (Int l = 0; l < cnt; ++l) A[i0 + l] = B[i0 + l];
+    }
+}
+void orc_saxpy_wg_f32(const ka_ctx *c, float *Z, float a, const float *X, const float *Y) {
+    const Int G = ka_num_groups(c), W = c->wgs[0], N = c->ndrange[0];
+#pragma omp parallel for schedule(static)
+    for (Int g = 0; g < G; ++g) {
+        const Int i0 = g * W, cnt = (i0 + W <= N) ? W : N - i0;
+        for (Int l = 0; l < cnt; ++l) {
+            const float p = a * X[i0 + l];
+            Z[i0 + l] = p + Y[i0 + l];
+        }
+    }
+}
+
 /* matmul_kernel!: tmp = zero(T); for k: tmp += a[i,k]*b[k,j]; output[i,j] = tmp
  * (reference examples/matmul.jl:5-15).  No @simd / @fastmath: separate multiply and add roundings,
  * so this file must be compiled with -ffp-contract=off. */

@@ -181,6 +181,20 @@ def naive_transpose_wg(a: np.ndarray, b: np.ndarray, workgroupsize=256) -> None:
     lib().orc_naive_transpose_wg_f32(C.byref(ctx), _p(_F(a)), _p(_F(b)), C.c_int64(a.shape[0]), C.c_int64(b.shape[0]))
 
 
+def copy_wg(A: np.ndarray, B: np.ndarray, workgroupsize=1024) -> None:
+    """Work-group-vectorised 1-d copy_kernel! (timed CPU baseline); float32 only."""
+    assert A.dtype == np.float32 and B.dtype == np.float32 and A.ndim == 1 and A.shape == B.shape
+    ctx = make_ctx(A.shape, workgroupsize)
+    lib().orc_copy_wg_f32(C.byref(ctx), _p(A), _p(B))
+
+
+def saxpy_wg(Z: np.ndarray, a, X: np.ndarray, Y: np.ndarray, workgroupsize=1024) -> None:
+    """Work-group-vectorised 1-d saxpy_kernel! (timed CPU baseline); float32 only."""
+    assert Z.dtype == X.dtype == Y.dtype == np.float32 and Z.ndim == 1
+    ctx = make_ctx(Z.shape, workgroupsize)
+    lib().orc_saxpy_wg_f32(C.byref(ctx), _p(Z), C.c_float(a), _p(X), _p(Y))
+
+
 def matmul_naive(out: np.ndarray, a: np.ndarray, b: np.ndarray, workgroupsize=None, max_threads=1024) -> None:
     """reference examples/matmul.jl:5-27 (dynamic workgroup -> threads_to_workgroupsize)"""
     ndrange = out.shape

@@ -174,6 +174,21 @@ def test_naive_transpose_example(orc):
     assert np.array_equal(a, b.T)
 
 
+def test_copy_and_saxpy_wg_equal_generic(orc):
+    # the work-group-vectorised forms timed as CPU baselines give the bits of the literal per-item forms
+    for n in (1, 1023, 1024, 4099):
+        B = orc.gen_uniform_f32((n,), 5)
+        A1, A2 = np.zeros(n, np.float32), np.zeros(n, np.float32)
+        orc.copy_kernel(A1, B, (n,), (1024,))
+        orc.copy_wg(A2, B, 1024)
+        assert np.array_equal(A1.view(np.uint32), A2.view(np.uint32)) and np.array_equal(A2, B)
+        X, Y = orc.gen_uniform_f32((n,), 6), orc.gen_uniform_f32((n,), 7)
+        Z1, Z2 = np.zeros(n, np.float32), np.zeros(n, np.float32)
+        orc.saxpy(Z1, np.float32(3.1415), X, Y, (n,), 1024)
+        orc.saxpy_wg(Z2, np.float32(3.1415), X, Y, 1024)
+        assert np.array_equal(Z1.view(np.uint32), Z2.view(np.uint32))
+
+
 def test_naive_transpose_wg_equals_generic(orc):
     for shape in [(300, 37), (512, 256), (1, 5)]:
         b = orc.gen_uniform_f32((shape[1], shape[0]), 3)
