@@ -76,9 +76,23 @@ template <> struct SumAcc<double> { using type = double; };
 template <> struct SumAcc<unsigned int> { using type = unsigned long long; };
 template <> struct SumAcc<unsigned long long> { using type = unsigned long long; };
 
+// identities: 0 for sum, the lowest / highest value of the type for maximum / minimum (-Inf / +Inf for floats, so NaN and signed
+// zeros still come out by Julia's rules)
+template <typename T> __device__ __forceinline__ T lowest_of() { return std::is_signed<T>::value ? (T)((T)1 << (sizeof(T) * 8 - 1)) : (T)0; }
+template <> __device__ __forceinline__ float lowest_of<float>() { return -__int_as_float(0x7f800000); }
+template <> __device__ __forceinline__ double lowest_of<double>() { return -__longlong_as_double(0x7ff0000000000000LL); }
+template <typename T> __device__ __forceinline__ T highest_of() { return std::is_signed<T>::value ? (T)~((T)1 << (sizeof(T) * 8 - 1)) : (T)~(T)0; }
+template <> __device__ __forceinline__ float highest_of<float>() { return __int_as_float(0x7f800000); }
+template <> __device__ __forceinline__ double highest_of<double>() { return __longlong_as_double(0x7ff0000000000000LL); }
+
 template <typename T, int OP>
 struct Red {
     using Acc = typename std::conditional<OP == OP_SUM, typename SumAcc<T>::type, T>::type;
+    __device__ static Acc identity() {
+        if (OP == OP_SUM) return (Acc)0;
+        if (OP == OP_MAX) return (Acc)lowest_of<T>();
+        return (Acc)highest_of<T>();
+    }
     __device__ static Acc lift(T v) { return (Acc)v; }
     __device__ static Acc comb(Acc a, Acc b) {
         if (OP == OP_SUM) return a + b;
@@ -127,7 +141,7 @@ __device__ __forceinline__ Acc block_reduce(Acc v, F comb, Acc *sh) {
 // Grid-wide finish: every block publishes Q partial values, the block that draws the last ticket folds all of them and
 // writes the Q results to `result` (a device-visible pinned host buffer), then re-arms the ticket for the next call.
 template <typename Acc, int Q, typename F>
-__device__ __forceinline__ void finish(const Acc (&v)[Q], Acc *partials, unsigned int *ticket, Acc *result, F comb, bool seed_from_first) {
+__device__ __forceinline__ void finish(const Acc (&v)[Q], Acc *partials, unsigned int *ticket, Acc *result, F comb, Acc identity) {
     __shared__ bool last;
     __shared__ Acc fold[Q][THREADS];
     if (threadIdx.x == 0) {
@@ -141,7 +155,7 @@ __device__ __forceinline__ void finish(const Acc (&v)[Q], Acc *partials, unsigne
     __threadfence();
     Acc acc[Q];
 #pragma unroll
-    for (int q = 0; q < Q; ++q) acc[q] = seed_from_first ? __ldcg(partials + q) : (Acc)0;
+    for (int q = 0; q < Q; ++q) acc[q] = identity;
     for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x)
 #pragma unroll
         for (int q = 0; q < Q; ++q) acc[q] = comb(acc[q], __ldcg(partials + Q * i + q));
@@ -162,8 +176,6 @@ __device__ __forceinline__ void finish(const Acc (&v)[Q], Acc *partials, unsigne
     }
 }
 
-// every thread starts from the first element it owns (so max/min need no identity); threads without an element
-// contribute `first` of the array (x[0]) for max/min and 0 for sum
 template <typename T, int OP>
 __global__ void __launch_bounds__(THREADS) reduce_kernel(const T *__restrict__ x, size_t n, typename Red<T, OP>::Acc *partials, unsigned int *ticket,
                                                          typename Red<T, OP>::Acc *result) {
@@ -174,7 +186,7 @@ __global__ void __launch_bounds__(THREADS) reduce_kernel(const T *__restrict__ x
     bool vec_ok;
     const size_t head = head_elems<T>(x, nullptr, n, &vec_ok);
     const size_t nvec = (n - head) / VEC, tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
-    Acc acc = OP == OP_SUM ? (Acc)0 : R::lift(x[0]);
+    Acc acc = R::identity();
     const V *xv = reinterpret_cast<const V *>(x + head);
     for (size_t j = tid; j < head; j += stride) acc = R::comb(acc, R::lift(x[j]));
     size_t i = tid;
@@ -211,7 +223,7 @@ __global__ void __launch_bounds__(THREADS) reduce_kernel(const T *__restrict__ x
     } else {
         blk[0] = block_reduce<Acc>(acc, [](Acc a, Acc b) { return R::comb(a, b); }, sh);
     }
-    finish<Acc, 1>(blk, partials, ticket, result, [](Acc a, Acc b) { return R::comb(a, b); }, OP != OP_SUM);
+    finish<Acc, 1>(blk, partials, ticket, result, [](Acc a, Acc b) { return R::comb(a, b); }, R::identity());
 }
 // ---- A == B: number of positions where !(a == b) (so NaN never equals, -0.0 == 0.0), bit patterns for opaque types ----
 template <typename T>
@@ -246,7 +258,7 @@ __global__ void __launch_bounds__(THREADS) mismatch_kernel(const T *__restrict__
     unsigned long long blk[1] = {0};
     if (threadIdx.x == 0)
         for (int w = 0; w < (int)(blockDim.x >> 5); ++w) blk[0] += sh[w];
-    finish<unsigned long long, 1>(blk, partials, ticket, result, [](unsigned long long x, unsigned long long y) { return x + y; }, false);
+    finish<unsigned long long, 1>(blk, partials, ticket, result, [](unsigned long long x, unsigned long long y) { return x + y; }, 0ull);
 }
 
 // ---- isapprox: sum (x-y)^2, sum x^2, sum y^2 in Float64 ----
@@ -295,7 +307,7 @@ __global__ void __launch_bounds__(THREADS) norms_kernel(const T *__restrict__ a,
 #pragma unroll
         for (int q = 0; q < 3; ++q)
             for (int w = 0; w < (int)(blockDim.x >> 5); ++w) blk[q] += sh[q][w];
-    finish<double, 3>(blk, partials, ticket, result, [](double x, double y) { return x + y; }, false);
+    finish<double, 3>(blk, partials, ticket, result, [](double x, double y) { return x + y; }, 0.0);
 }
 // ---- deterministic input streams: a splitmix-style counter hash (mix32), four elements per 16-byte store ----
 __device__ __forceinline__ uint32_t mix32(unsigned long long x) {
