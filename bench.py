@@ -383,7 +383,8 @@ def run_suite(KA, _lib, EX, mg, orc, be, rank, world, dist, timed, peaks, steps,
         gbs = 2 * 4 * n / (ms * 1e-3) / 1e9
         out["copy_2^26_f32"] = {"value": world * gbs, "unit": "GB/s", "ms_per_step": ms, "gpu_launches": launches,
                                 "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm"], "frac": gbs / peaks["hbm"],
-                                             "traffic": None}, "scaling": "weak"}
+                                             "traffic": traffic_from_profiles("capture:copy"), "algorithmic_bytes_per_launch": 8 * n},
+                                "scaling": "weak"}
         del src, dst
         if cpu:
             hB, hA = orc.gen_uniform_f32((n,), 1234), np.zeros(n, dtype=np.float32)
@@ -411,7 +412,8 @@ def run_suite(KA, _lib, EX, mg, orc, be, rank, world, dist, timed, peaks, steps,
         gbs = 3 * 4 * n / (ms * 1e-3) / 1e9
         out["saxpy_2^26_f32"] = {"value": world * gbs, "unit": "GB/s", "ms_per_step": ms, "gpu_launches": launches,
                                  "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm"], "frac": gbs / peaks["hbm"],
-                                              "traffic": None}, "scaling": "weak"}
+                                              "traffic": traffic_from_profiles("capture:saxpy"), "algorithmic_bytes_per_launch": 12 * n},
+                                 "scaling": "weak"}
         del X, Y, Z
         if cpu:
             hX, hY, hZ = orc.gen_uniform_f32((n,), 1300), orc.gen_uniform_f32((n,), 1310), np.zeros(n, dtype=np.float32)
@@ -458,7 +460,9 @@ def run_suite(KA, _lib, EX, mg, orc, be, rank, world, dist, timed, peaks, steps,
         out["histogram_2^30_i32_256bins"] = {"value": gbs, "unit": "GB/s", "ms_per_step": ms, "gpu_launches": launches,
                                              "sum_conserved": check, "scaling": "strong",
                                              "roofline": {"bound": "hbm", "achieved": gbs / world, "peak": peaks["hbm"],
-                                                          "frac": gbs / world / peaks["hbm"], "traffic": None},
+                                                          "frac": gbs / world / peaks["hbm"],
+                                                          "traffic": traffic_from_profiles("capture:hist") if world == 1 else None,
+                                                          "algorithmic_bytes_per_launch": 4 * (s1 - s0) + 1024},
                                              "collective": ("fused in the counting kernel: {count,tag} slot stores over NVLink peer memory "
                                                             "(b200_histogram_i32_allreduce), no NCCL launch") if world > 1 else None}
         if comm is not None:

@@ -92,7 +92,7 @@ elif kind == "saxpy":
     n = size or (1 << 26)
     x, y = KA.to_device(orc.gen_uniform_f32((n,), 2)), KA.to_device(orc.gen_uniform_f32((n,), 3))
     z = KA.zeros(be, np.float32, n)
-    run(lambda: _lib.call("b200_saxpy", C.c_void_p(z.ptr), C.c_double(3.1415), C.c_void_p(x.ptr), C.c_void_p(y.ptr), C.c_size_t(n), 4),
+    run(lambda: _lib.call("b200_saxpy", C.c_void_p(z.ptr), C.c_double(3.1415), C.c_void_p(x.ptr), C.c_void_p(y.ptr), C.c_size_t(n), 0),
         12.0 * n, "GB/s")
 elif kind in ("reduce_max", "reduce_sum", "mismatch", "norms", "gen_uniform", "gen_bins"):
     n = size or (1 << 28)

@@ -67,6 +67,7 @@ for f in sorted(os.listdir(GO)):
         tot = float(rd[0].replace(",", "")) * UNIT_SCALE.get(rd[1], 1.0) + float(wr[0].replace(",", "")) * UNIT_SCALE.get(wr[1], 1.0)
         short = kname.split("(")[0].replace("void ", "").split("<")[0].split("::")[-1]
         traffic[short] = tot
+        traffic[f"capture:{name}"] = tot   # keyed by capture too: both tensor-core GEMMs share one kernel template
         dur = d.get("gpu__time_duration.sum", ("?", ""))
         summary_lines.append(f"| {name} | `{short}` | {dur[0]} {dur[1]} | {tot / 1e9:.3f} GB | "
                              f"{d.get('gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', ('?',))[0]} | "
