@@ -109,6 +109,16 @@ b200_status b200_event_synchronize(void *event);
 b200_status b200_event_elapsed_ms(void *start, void *stop, float *ms);
 b200_status b200_event_destroy(void *event);
 
+/* CUDA graphs for launch-bound sequences (the reference waits after EVERY launch, src/pocl/backend.jl:144-145; here even the
+ * launch overhead of a recorded sequence collapses into one submission).  b200_graph_begin starts recording on the calling
+ * thread's stream; every stream-ordered call made by that thread until b200_graph_end is recorded instead of executed.
+ * Calls that wait for the stream (b200_synchronize, b200_reduce, synchronous copies ...) invalidate the recording.
+ * b200_graph_launch replays on the calling thread's stream (same argument pointers and values as recorded). */
+b200_status b200_graph_begin(void);
+b200_status b200_graph_end(void **graph);
+b200_status b200_graph_launch(void *graph);
+b200_status b200_graph_destroy(void *graph);
+
 /* ---- generic kernel launch ----------------------------------------------------------------
  * Replaces  clSetKernelArg* + clEnqueueNDRangeKernel  (src/pocl/nanoOpenCL.jl:1161-1283) for
  *   (obj::KA.Kernel{B})(args...; ndrange, workgroupsize)      src/pocl/backend.jl:117-147  (kind 0)

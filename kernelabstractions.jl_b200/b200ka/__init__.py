@@ -9,7 +9,7 @@ from ._lib import ArgumentError, B200Error, ErrorException, MethodError, build
 from .backend import (CPU, Array, B200Array, B200Backend, CartesianIndex, KernelData, adapt, allocate, copyto_,
                       device, device_, functional, get_backend, ndevices, ones, pagelock_, unpagelock_, priority_, similar,
                       supports_atomics, supports_float64, supports_unified, synchronize, to_device, unsafe_free_,
-                      zeros, maximum, minimum, isequal, isapprox, rand_uniform_, rand_bins_, mul_, matmul)
+                      zeros, maximum, minimum, isequal, isapprox, rand_uniform_, rand_bins_, mul_, matmul, Graph)
 from .backend import sum as sum  # noqa: A004 -- Base.sum for device arrays (KA.sum)
 from .kernel import (KIKernel, Kernel, KernelFunction, Val, check_launch_args, kernel_function,
                      kernel_max_work_group_size, ki_kernel, max_work_group_size, multiprocessor_count,

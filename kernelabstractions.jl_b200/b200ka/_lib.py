@@ -124,6 +124,10 @@ SIGNATURES = {
     "b200_event_elapsed_ms": (_I32, [_VP, _VP, C.POINTER(C.c_float)]),
     "b200_event_destroy": (_I32, [_VP]),
     "b200_launch": (_I32, [C.c_char_p, C.POINTER(LaunchDesc), C.POINTER(Arg), _I32]),
+    "b200_graph_begin": (_I32, []),
+    "b200_graph_end": (_I32, [_PVP]),
+    "b200_graph_launch": (_I32, [_VP]),
+    "b200_graph_destroy": (_I32, [_VP]),
     "b200_register_kernel": (_I32, [C.c_char_p, _I32, _VP, _VP]),
     "b200_unregister_kernel": (_I32, [C.c_char_p]),
     "b200_kernel_count": (_I32, [_PI32]),

@@ -423,3 +423,37 @@ def mul_(C_: B200Array, A: B200Array, B: B200Array) -> B200Array:
 def matmul(A: B200Array, B: B200Array) -> B200Array:
     """`A * B` (reference examples/matmul.jl:36 compares the kernel's output with it)."""
     return mul_(B200Array(A.dtype, (A.shape[0], B.shape[1])), A, B)
+
+
+class Graph:
+    """`with KA.Graph(backend) as g: <launches>` records the stream-ordered calls of the block (nothing executes), `g.launch()`
+    replays them with one submission.  For launch-bound sequences of small kernels (b200_graph_*)."""
+
+    def __init__(self, backend):
+        self.backend = backend
+        self.handle = C.c_void_p()
+
+    def __enter__(self):
+        call("b200_graph_begin")
+        return self
+
+    def __exit__(self, et, ev, tb):
+        if et is not None:                       # leave capture mode, drop the partial recording
+            h = C.c_void_p()
+            _lib.lib().b200_graph_end(C.byref(h))
+            if h:
+                _lib.lib().b200_graph_destroy(h)
+            return False
+        call("b200_graph_end", C.byref(self.handle))
+        return False
+
+    def launch(self) -> None:
+        call("b200_graph_launch", self.handle)
+
+    def __del__(self):
+        try:
+            if self.handle:
+                _lib.lib().b200_graph_destroy(self.handle)
+                self.handle = C.c_void_p()
+        except Exception:
+            pass

@@ -351,6 +351,49 @@ b200_status b200_event_destroy(void *event) {
     return B200_OK;
 }
 
+// ---- CUDA graphs: record a launch-bound sequence of stream-ordered calls once, replay it with one launch -----------------
+// Every b200 call that only ENQUEUES work (kernel launches, async copies, fills, events) may be recorded; calls that wait for
+// the stream (b200_synchronize, value-returning reductions, synchronous copies) fail while a capture is open.
+b200_status b200_graph_begin(void) {
+    cudaStream_t st;
+    B200_TRY(current_stream(&st));
+    B200_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+    return B200_OK;
+}
+
+b200_status b200_graph_end(void **graph) {
+    if (!graph) return set_error(B200_ERR_INVALID_VALUE, "b200_graph_end: graph is NULL");
+    *graph = nullptr;
+    cudaStream_t st;
+    B200_TRY(current_stream(&st));
+    cudaGraph_t g = nullptr;
+    cudaError_t e = cudaStreamEndCapture(st, &g);
+    if (e != cudaSuccess || !g) {
+        cudaGetLastError();
+        return set_error(B200_ERR_CUDA, "b200_graph_end: capture failed or was invalidated by a synchronising call: %s", cudaGetErrorString(e));
+    }
+    cudaGraphExec_t exec = nullptr;
+    e = cudaGraphInstantiate(&exec, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) return set_error(B200_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
+    *graph = (void *)exec;
+    return B200_OK;
+}
+
+b200_status b200_graph_launch(void *graph) {
+    if (!graph) return set_error(B200_ERR_INVALID_VALUE, "b200_graph_launch: NULL graph");
+    cudaStream_t st;
+    B200_TRY(current_stream(&st));
+    B200_CUDA(cudaGraphLaunch((cudaGraphExec_t)graph, st));
+    return B200_OK;
+}
+
+b200_status b200_graph_destroy(void *graph) {
+    if (!graph) return B200_OK;
+    B200_CUDA(cudaGraphExecDestroy((cudaGraphExec_t)graph));
+    return B200_OK;
+}
+
 b200_status b200_launch_counter(int64_t *count, int32_t reset) {
     if (count) *count = tls().launches;
     if (reset) tls().launches = 0;

@@ -350,6 +350,27 @@ function launch(name::String, desc::LaunchDesc, args)
     return nothing
 end
 
+# CUDA graphs for launch-bound sequences: `g = record(backend) do ... launches ... end; replay(g)` (b200_graph_*).
+mutable struct Graph
+    handle::Ptr{Cvoid}
+end
+function record(f::Function, ::B200Backend)
+    @b200 b200_graph_begin ()
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    try
+        f()
+    catch
+        ccall((:b200_graph_end, libb200ka), Int32, (Ptr{Ptr{Cvoid}},), h)      # leave capture mode, drop the partial recording
+        h[] != C_NULL && ccall((:b200_graph_destroy, libb200ka), Int32, (Ptr{Cvoid},), h[])
+        rethrow()
+    end
+    @b200 b200_graph_end (Ptr{Ptr{Cvoid}},) h
+    g = Graph(h[])
+    finalizer(x -> ccall((:b200_graph_destroy, libb200ka), Int32, (Ptr{Cvoid},), x.handle), g)
+    return g
+end
+replay(g::Graph) = (@b200 b200_graph_launch (Ptr{Cvoid},) g.handle; nothing)
+
 # Run-time registration of a precompiled kernel from the user's own shared library (b200_register_kernel): `handler` is the
 # address of a native `b200_kernel_handler`, e.g. `Libdl.dlsym(Libdl.dlopen("libmykernels.so"), :my_handler)`.  `name` is
 # `"gpu_" * string(kernel function name)` for `@kernel`s (reference src/macros.jl:32), the function name for `KI.@kernel`.
