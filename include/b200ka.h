@@ -214,7 +214,8 @@ b200_status b200_saxpy(void *Z, double a, const void *X, const void *Y, size_t n
  * mode 0: FP32 SIMT, summation order of the reference tiled kernel (16-wide k partials, k ascending,
  *         fused multiply-add) -> bit-identical to the oracle;
  * mode 1: FP32 SIMT, single running accumulator per output (k ascending). */
-enum { B200_MATMUL_TILE16 = 0, B200_MATMUL_RUNNING = 1 };
+enum { B200_MATMUL_TILE16 = 0, B200_MATMUL_RUNNING = 1,
+       B200_MATMUL_UNFUSED = 2 /* matmul_kernel! (examples/matmul.jl:5-15): tmp += a*b, product and sum rounded separately */ };
 b200_status b200_matmul_f32(float *C, const float *A, const float *B, int64_t M, int64_t K, int64_t N,
                             int64_t lda, int64_t ldb, int64_t ldc, int32_t mode);
 

@@ -37,7 +37,7 @@ B200_LAUNCH_KA, B200_LAUNCH_KI = 0, 1
 B200_ARG_ARRAY, B200_ARG_SCALAR, B200_ARG_VAL = 0, 1, 2
 (B200_T_OPAQUE, B200_T_I8, B200_T_U8, B200_T_I16, B200_T_U16, B200_T_I32, B200_T_U32, B200_T_I64, B200_T_U64,
  B200_T_F16, B200_T_BF16, B200_T_F32, B200_T_F64, B200_T_BOOL) = range(14)
-B200_MATMUL_TILE16, B200_MATMUL_RUNNING = 0, 1
+B200_MATMUL_TILE16, B200_MATMUL_RUNNING, B200_MATMUL_UNFUSED = 0, 1, 2
 B200_UNIQUE_ID_BYTES = 128
 B200_IPC_HANDLE_BYTES = 64
 

@@ -181,8 +181,10 @@ int sgemm_launch(float *C, const float *A, const float *B, int64_t M, int64_t K,
     if (M == 0 || N == 0) return B200_OK;
     if (M > INT32_MAX || N > INT32_MAX || K > INT32_MAX)
         return set_error(B200_ERR_UNSUPPORTED, "matmul: dimension exceeds 2^31-1");
-    if (mode != B200_MATMUL_TILE16 && mode != B200_MATMUL_RUNNING)
+    if (mode != B200_MATMUL_TILE16 && mode != B200_MATMUL_RUNNING && mode != B200_MATMUL_UNFUSED)
         return set_error(B200_ERR_INVALID_VALUE, "matmul: unknown mode %d", mode);
+    if (mode == B200_MATMUL_UNFUSED && !(tune_get("sgemm.engine", 1) == 1 && sgemm_tma_applicable(A, B, M, K, N, lda, ldb)))
+        return set_error(B200_ERR_UNSUPPORTED, "matmul: the unfused mode needs TMA-addressable operands (16-byte aligned, ld %% 4 == 0)");
     // engine 1 (default): TMA-fed warp-specialised kernel (matmul_f32_tma.cu); engine 0 or operands TMA cannot address
     // (leading dimension / base not 16-byte aligned, K == 0): the register-staged kernel below.  Same bits either way.
     if (tune_get("sgemm.engine", 1) == 1 && sgemm_tma_applicable(A, B, M, K, N, lda, ldb))

@@ -48,12 +48,27 @@ constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * STAGES * 8;
 // on an `empty` barrier.  The kernel is compiled for 384 threads (168 registers each); the producer group gives its
 // registers back (`setmaxnreg.dec 40`) and the consumer groups take them (`setmaxnreg.inc 232`): 8*32*232 + 4*32*40 = 64512.
 // PW = 0: thread 0 of consumer warp 0 produces with a lag of LAG tiles.
-template <bool TILE16, int NJ, int MI, int PW>
+// UNFUSED mode: round(a*b) and round(tmp + product) as TWO packed instructions.  ptxas 12.9 contracts `mul.rn.f32x2` followed by
+// `add.rn.f32x2` into one FFMA2 (scalar `mul.rn.f32` / `add.rn.f32` are left alone, as the PTX manual promises; the packed forms
+// are not -- the first two builds of this mode ran at FFMA2 speed and failed bit parity, /tmp experiment recorded in DESIGN.md).
+// Two FFMA2 with RUN-TIME constants cannot be folded or contracted and round identically:
+//     fma(a, b, -0.0) == round(a*b)   (adding -0.0 changes neither value nor sign of zero),   fma(p, 1.0, c) == round(p + c).
+// `one` and `negzero` arrive as kernel arguments so ptxas cannot see their values.
+__device__ __forceinline__ float2 mul_then_add(float2 a, float2 b, float2 c, float one, float negzero) {
+    const float2 p = __ffma2_rn(a, b, make_float2(negzero, negzero));
+    return __ffma2_rn(p, make_float2(one, one), c);
+}
+
+// MODE: B200_MATMUL_TILE16 (reference coalesced_matmul_kernel! order), B200_MATMUL_RUNNING (one fused running sum) or
+// B200_MATMUL_UNFUSED (matmul_kernel!, examples/matmul.jl:5-15: tmp = zero(T); tmp += a*b with the product and the sum rounded
+// separately, k ascending -- packed FMUL2 + FADD2, two pipe instructions per pair of MACs).
+template <int MODE, int NJ, int MI, int PW>
 __global__ void __launch_bounds__((consumer_warps(MI) + 4 * PW) * 32, 1)
     sgemm_tma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                      float *__restrict__ C, int M, int N, int64_t ldc, int ntiles, int tiles_m, int tiles_n, int group_m,
-                     int vec_ok) {
+                     int vec_ok, float one, float negzero) {
     using namespace pipe;
+    constexpr bool TILE16 = MODE == B200_MATMUL_TILE16, UNFUSED = MODE == B200_MATMUL_UNFUSED;
     constexpr int CONSUMER_WARPS = consumer_warps(MI);
     extern __shared__ __align__(1024) unsigned char smem[];
     uint64_t *full = (uint64_t *)(smem + STAGES * STAGE_BYTES);
@@ -184,7 +199,10 @@ __global__ void __launch_bounds__((consumer_warps(MI) + 4 * PW) * 32, 1)
                     for (int j = 0; j < NJ; ++j) {
                         const float bj = h ? b[cur][j].y : b[cur][j].x;
                         const float2 c = (TILE16 && kk == 0) ? make_float2(0.0f, 0.0f) : acc[i][j];  // out = zero(T)
-                        acc[i][j] = __ffma2_rn(a[i], make_float2(bj, bj), c);                         // out += a*b
+                        if (UNFUSED)
+                            acc[i][j] = mul_then_add(a[i], make_float2(bj, bj), c, one, negzero);     // tmp += (a*b), two roundings
+                        else
+                            acc[i][j] = __ffma2_rn(a[i], make_float2(bj, bj), c);                     // out += a*b
                     }
             }
         }
@@ -236,7 +254,7 @@ int sgemm_tma_applicable(const float *A, const float *B, int64_t M, int64_t K, i
            M < (1LL << 31) && N < (1LL << 31) && K < (1LL << 31);
 }
 
-template <bool TILE16, int NJ, int MI, int PW>
+template <int MODE, int NJ, int MI, int PW>
 static int sgemm_tma_launch_nj(float *C, const float *A, const float *B, int64_t M, int64_t K, int64_t N, int64_t lda,
                                int64_t ldb, int64_t ldc, cudaStream_t st) {
     using namespace sg;
@@ -252,9 +270,9 @@ static int sgemm_tma_launch_nj(float *C, const float *A, const float *B, int64_t
     const int ntiles = (int)cdiv(K, BK);
     const int group_m = tune_get("sgemm.group_m", 8);
     const int vec_ok = (ldc % 4 == 0) && (((uintptr_t)C & 15) == 0);
-    B200_CUDA(cudaFuncSetAttribute(sgemm_tma_kernel<TILE16, NJ, MI, PW>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    sgemm_tma_kernel<TILE16, NJ, MI, PW><<<grid, (consumer_warps(MI) + 4 * PW) * 32, SMEM_BYTES, st>>>(ta, tb, C, (int)M, (int)N, ldc, ntiles, tiles_m,
-                                                                         tiles_n, group_m, vec_ok);
+    B200_CUDA(cudaFuncSetAttribute(sgemm_tma_kernel<MODE, NJ, MI, PW>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    sgemm_tma_kernel<MODE, NJ, MI, PW><<<grid, (consumer_warps(MI) + 4 * PW) * 32, SMEM_BYTES, st>>>(ta, tb, C, (int)M, (int)N, ldc, ntiles, tiles_m,
+                                                                         tiles_n, group_m, vec_ok, 1.0f, -0.0f);
     B200_CHECK_LAUNCH("sgemm_tma_kernel");
     return B200_OK;
 }
@@ -281,14 +299,15 @@ int sgemm_tma_launch(float *C, const float *A, const float *B, int64_t M, int64_
                      int64_t ldb, int64_t ldc, int mode, cudaStream_t st) {
     const int nj = pick_nj(M, N, sm_count());
     const int mi = 2;   // MI = 1 (16 warps, thread tile 4 x nj) measured no faster (54.3 vs 54.5 TFLOP/s) and is not instantiated
-    const int pw = tune_get("sgemm.producer_warp", 1) != 0;
-#define B200_SGEMM_CASE(T16, NJ_, MI_, PW_) \
-    if ((mode == B200_MATMUL_TILE16) == T16 && nj == NJ_ && mi == MI_ && pw == PW_) \
-        return sgemm_tma_launch_nj<T16, NJ_, MI_, PW_>(C, A, B, M, K, N, lda, ldb, ldc, st);
-    B200_SGEMM_CASE(true, 8, 2, 1) B200_SGEMM_CASE(true, 7, 2, 1) B200_SGEMM_CASE(true, 6, 2, 1)
-    B200_SGEMM_CASE(false, 8, 2, 1) B200_SGEMM_CASE(false, 7, 2, 1) B200_SGEMM_CASE(false, 6, 2, 1)
-    B200_SGEMM_CASE(true, 8, 2, 0) B200_SGEMM_CASE(true, 7, 2, 0) B200_SGEMM_CASE(true, 6, 2, 0)
-    B200_SGEMM_CASE(false, 8, 2, 0) B200_SGEMM_CASE(false, 7, 2, 0) B200_SGEMM_CASE(false, 6, 2, 0)
+    const int pw = tune_get("sgemm.producer_warp", 1) != 0 || mode == B200_MATMUL_UNFUSED;   // UNFUSED is built for PW = 1 only
+#define B200_SGEMM_CASE(MODE_, NJ_, MI_, PW_) \
+    if (mode == MODE_ && nj == NJ_ && mi == MI_ && pw == PW_) \
+        return sgemm_tma_launch_nj<MODE_, NJ_, MI_, PW_>(C, A, B, M, K, N, lda, ldb, ldc, st);
+    B200_SGEMM_CASE(0, 8, 2, 1) B200_SGEMM_CASE(0, 7, 2, 1) B200_SGEMM_CASE(0, 6, 2, 1)
+    B200_SGEMM_CASE(1, 8, 2, 1) B200_SGEMM_CASE(1, 7, 2, 1) B200_SGEMM_CASE(1, 6, 2, 1)
+    B200_SGEMM_CASE(2, 8, 2, 1) B200_SGEMM_CASE(2, 7, 2, 1) B200_SGEMM_CASE(2, 6, 2, 1)
+    B200_SGEMM_CASE(0, 8, 2, 0) B200_SGEMM_CASE(0, 7, 2, 0) B200_SGEMM_CASE(0, 6, 2, 0)
+    B200_SGEMM_CASE(1, 8, 2, 0) B200_SGEMM_CASE(1, 7, 2, 0) B200_SGEMM_CASE(1, 6, 2, 0)
 #undef B200_SGEMM_CASE
     return set_error(B200_ERR_UNSUPPORTED, "sgemm: no kernel for nj=%d mi=%d pw=%d", nj, mi, pw);
 }

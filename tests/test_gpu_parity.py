@@ -336,6 +336,41 @@ def test_matmul_example_bit_exact(orc):
     assert np.array_equal(KA.Array(out64), ref64)
 
 
+@pytest.mark.parametrize("shape", [(256, 124, 48), (128, 16, 128), (132, 20, 260), (4, 4, 1), (512, 256, 1000)])
+def test_matmul_example_tiled_route_bit_exact(orc, shape):
+    # examples/matmul.jl:5-27 with TMA-addressable operands takes the tiled engine in its UNFUSED mode: same bits as the
+    # oracle's literal `tmp += a*b` (separate roundings, k ascending) and as the literal GPU twin
+    M, Kd, N = shape
+    a = orc.gen_uniform_f32((M, Kd), 1237) - 0.5
+    b = orc.gen_uniform_f32((Kd, N), 1238) - 0.5
+    dA, dB = KA.to_device(a), KA.to_device(b)
+    out = KA.allocate(be, np.float32, M, N).fill_(-7.0)
+    EX.matmul_(out, dA, dB)
+    ref = F((M, N), np.float32)
+    orc.matmul_naive(ref, a, b)
+    assert np.array_equal(KA.Array(out).view(np.uint32), ref.view(np.uint32))
+    tune(registry__force_twins=1)
+    out2 = KA.allocate(be, np.float32, M, N).fill_(-7.0)
+    EX.matmul_(out2, dA, dB)
+    tune(registry__force_twins=0)
+    assert KA.isequal(out, out2)
+
+
+def test_matmul_example_c4_size_route():
+    # 2048^3 through the tiled route against the literal twin (GPU vs GPU, every bit), and within rtol 1e-5 of Float64
+    n = 2048
+    dA = KA.rand_uniform_(KA.allocate(be, np.float32, n, n), 1237)
+    dB = KA.rand_uniform_(KA.allocate(be, np.float32, n, n), 1238)
+    out, out2 = KA.zeros(be, np.float32, n, n), KA.zeros(be, np.float32, n, n)
+    EX.matmul_(out, dA, dB)
+    tune(registry__force_twins=1)
+    EX.matmul_(out2, dA, dB)
+    tune(registry__force_twins=0)
+    assert KA.isequal(out, out2)
+    hA, hB = KA.Array(dA)[:64, :].astype(np.float64), KA.Array(dB)[:, :64].astype(np.float64)
+    assert np.allclose(KA.Array(out)[:64, :64], hA @ hB, rtol=1e-5, atol=0)
+
+
 @pytest.mark.parametrize("shape", [(1024, 512, 2048), (128, 16, 128), (256, 123, 45), (37, 29, 21), (130, 17, 129), (16, 16, 16)])
 @pytest.mark.parametrize("force_twins", [0, 1])
 def test_performant_matmul_bit_exact(orc, shape, force_twins):

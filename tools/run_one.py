@@ -160,6 +160,14 @@ elif kind in ("sgemm", "tcgemm"):
         _lib.call("b200_convert_f32_bf16", C.c_void_p(ws.ptr + 2 * m * n), C.c_void_p(B.ptr), n, n, n, 0)
         run(lambda: _lib.call("b200_matmul_bf16", C.c_void_p(Cd.ptr), C.c_void_p(ws.ptr), C.c_void_p(ws.ptr + 2 * m * n), m, n, n, m),
             2.0 * m * n * n, "TFLOP/s")
+elif kind == "matmul_naive":
+    # examples/matmul.jl through the registry: tiled UNFUSED route (mode 0) or the literal twin (mode 1)
+    from b200ka import examples as EXm
+    n = size or 4096
+    A, B = KA.rand_uniform_(KA.allocate(be, np.float32, n, n), 1237), KA.rand_uniform_(KA.allocate(be, np.float32, n, n), 1238)
+    Cd = KA.zeros(be, np.float32, n, n)
+    _lib.call("b200_tune_set", b"registry.force_twins", mode)
+    run(lambda: EXm.matmul_(Cd, A, B), 2.0 * n ** 3, "TFLOP/s")
 elif kind == "cublas_sgemm":
     # library reference point only (never on the product path): cuBLAS FP32 SIMT GEMM through torch
     import torch
