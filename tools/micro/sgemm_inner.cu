@@ -5,6 +5,7 @@
 //   V2: V1 with B taken from registers (only the A loads remain)
 //   V3: V1 with A taken from registers (only the B loads remain)
 //   V4: no shared-memory loads at all (operands rotate in registers)
+//   V5: 16 x 8 thread tile, running sum (A: 4 LDS.128 per k, B: 8 LDS.128 per 4 k; 10.7 FFMA2 per LDS.128)
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o sgemm_inner sgemm_inner.cu
 #include <cstdio>
 #include <cuda_runtime.h>
@@ -94,6 +95,91 @@ __global__ void __launch_bounds__(256, 1) inner(const float *in, float *out, int
     out[blockIdx.x * 256 + threadIdx.x] = s;
 }
 
+// V5: thread tile 16 (m) x 8 (n): acc[8][8] float2; CTA tile would be 256 x 128 with the same 8 warps
+__global__ void __launch_bounds__(256, 1) inner16(const float *in, float *out, int tiles) {
+    __shared__ __align__(16) float As_[BK * 256];
+    __shared__ __align__(16) float Bs_[BN * BK];
+    for (int i = threadIdx.x; i < BK * 256; i += 256) As_[i] = in[i % (BK * BM)];
+    for (int i = threadIdx.x; i < BN * BK; i += 256) Bs_[i] = in[BK * BM + i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int wm = warp & 1, wn = warp >> 1;
+    const int lx = (lane >> 1) & 7, ly = (lane & 1) | ((lane >> 4) << 1);
+    const float *As = As_ + wm * 128 + 4 * lx;
+    const float *Bs = Bs_ + (wn * 32 + ly) * BK;
+    float2 acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = make_float2(0.f, 0.f);
+    for (int kt = 0; kt < tiles; ++kt) {
+#pragma unroll
+        for (int k2 = 0; k2 < BK; k2 += 2) {
+            float2 b[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) b[j] = lds64(Bs + (4 * j) * BK + k2);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int kk = k2 + h;
+                float2 a[8];
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const float4 av = lds128(As + kk * 256 + 32 * g);
+                    a[2 * g] = make_float2(av.x, av.y);
+                    a[2 * g + 1] = make_float2(av.z, av.w);
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float bj = h ? b[j].y : b[j].x;
+                        acc[i][j] = __ffma2_rn(a[i], make_float2(bj, bj), acc[i][j]);
+                    }
+            }
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += acc[i][j].x + acc[i][j].y;
+    out[blockIdx.x * 256 + threadIdx.x] = s;
+}
+
+// V6: no loads, no scalar-broadcast operand: acc = ffma2(a_pair, b_pair, acc) with genuinely two-valued b pairs
+// V7: the same instruction count with the scalar-broadcast B form (b.x == b.y), for a like-for-like comparison
+template <int BROADCAST>
+__global__ void __launch_bounds__(256, 1) pairs(const float *in, float *out, int iters) {
+    float2 a[4], b[8], acc[4][8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[i] = make_float2(in[threadIdx.x + 32 * i], in[threadIdx.x + 32 * i + 7]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float x = in[threadIdx.x + 64 * j], y = in[threadIdx.x + 64 * j + 3];
+        b[j] = BROADCAST ? make_float2(x, x) : make_float2(x, y);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = make_float2(0.f, 0.f);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j] = __ffma2_rn(a[i], b[j], acc[i][j]);
+        float2 t = a[0];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) a[i] = a[i + 1];
+        a[3] = t;
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += acc[i][j].x + acc[i][j].y;
+    out[blockIdx.x * 256 + threadIdx.x] = s;
+}
+
 int main() {
     float *in, *out;
     cudaMalloc(&in, (BK * BM + BN * BK) * sizeof(float));
@@ -119,5 +205,29 @@ int main() {
             double flop = 2.0 * 64 * 256 * BK * (double)tiles * 148;
             if (rep == 1) printf("%-28s %.3f ms  %.2f TFLOP/s  (%.1f %% of 74.45) %s\n", names[v], ms, flop / ms * 1e-9, flop / ms * 1e-9 / 74.45 * 100, cudaGetErrorString(cudaGetLastError()));
         }
+    for (int v = 0; v < 2; ++v)
+        for (int rep = 0; rep < 2; ++rep) {
+            const int iters = 400000;
+            cudaEventRecord(e0);
+            if (v == 0) pairs<0><<<148, 256>>>(in, out, iters);
+            else pairs<1><<<148, 256>>>(in, out, iters);
+            cudaEventRecord(e1);
+            cudaEventSynchronize(e1);
+            float ms = 0;
+            cudaEventElapsedTime(&ms, e0, e1);
+            double flop = 2.0 * 64 * 256 * (double)iters * 148;
+            if (rep == 1) printf("%-28s %.3f ms  %.2f TFLOP/s  (%.1f %% of 74.45) %s\n", v == 0 ? "V6 pair x pair (no .F32)" : "V7 pair x broadcast (.F32)", ms, flop / ms * 1e-9,
+                                 flop / ms * 1e-9 / 74.45 * 100, cudaGetErrorString(cudaGetLastError()));
+        }
+    for (int rep = 0; rep < 2; ++rep) {
+        cudaEventRecord(e0);
+        inner16<<<148, 256>>>(in, out, tiles / 2);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        double flop = 2.0 * 128 * 256 * BK * (double)(tiles / 2) * 148;
+        if (rep == 1) printf("%-28s %.3f ms  %.2f TFLOP/s  (%.1f %% of 74.45) %s\n", "V5 16x8 tile, running sum", ms, flop / ms * 1e-9, flop / ms * 1e-9 / 74.45 * 100, cudaGetErrorString(cudaGetLastError()));
+    }
     return 0;
 }
