@@ -91,6 +91,8 @@ b200_status b200_host_unregister(void *ptr);
 b200_status b200_memcpy_h2d_async(void *dst, const void *src, size_t bytes);
 b200_status b200_memcpy_d2h_async(void *dst, const void *src, size_t bytes);
 b200_status b200_memcpy_d2d_async(void *dst, const void *src, size_t bytes);
+/* pitched device-to-device copy of `height` rows of `width_bytes` (column-major sub-matrix views: one row = one column) */
+b200_status b200_memcpy_2d_d2d_async(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width_bytes, size_t height);
 b200_status b200_memset_async(void *dst, int32_t byte, size_t bytes);
 
 /* ---- streams / synchronisation (KA.synchronize, KA.priority!; src/pocl/backend.jl:67,
@@ -282,6 +284,26 @@ b200_status b200_broadcast(void *comm, void *buf, size_t bytes, int32_t root);
 b200_status b200_sendrecv(void *comm, const void *sendbuf, int32_t dst_rank, void *recvbuf, int32_t src_rank,
                           size_t bytes);
 
+
+/* ---- symmetric device buffers + distributed transpose (fused tile transpose + all-to-all over NVLink peer memory) -----------
+ * b200_sym_alloc: `bytes` of device memory on the calling rank; export the 64-byte IPC handle, all-gather the handles with the
+ * launcher's own transport, b200_sym_connect maps every peer's buffer (<= 8 ranks of one NVLink domain, one process per GPU).
+ * b200_sym_ptr(handle, r): rank r's buffer as addressable from this rank (r == -1: the own buffer).
+ * b200_sym_barrier: stream-ordered barrier across the ranks of the buffer (system fence, one flag store per peer, spin) --
+ * everything this rank wrote to any peer before it is visible to a peer that has passed it.  Every rank must call it the
+ * same number of times.
+ * b200_transpose_alltoall: a = b^T for a GLOBAL N0 x N1 column-major matrix sharded by columns: the caller holds
+ * b_local = b[:, rank-th block of N1/world columns] (N0 x N1/world, ld N0); on return of the stream the symmetric buffer of
+ * every rank h holds a[:, h-th block of N0/world columns] (N1 x N0/world, ld N1).  One data kernel per rank whose stores go
+ * straight into the destination slabs, then b200_sym_barrier.  N0, N1 multiples of 64 x world; elsize 4 or 8.
+ * (the all-to-all the reference-style formulation would need, examples/mpi.jl:24-39 being its only exchange.) */
+b200_status b200_sym_alloc(void **handle, size_t bytes);
+b200_status b200_sym_export(void *handle, void *ipc64);
+b200_status b200_sym_connect(void *handle, int32_t world, int32_t rank, const void *all_handles /* world x 64 bytes */);
+b200_status b200_sym_ptr(void *handle, int32_t rank, void **ptr);
+b200_status b200_sym_barrier(void *handle);
+b200_status b200_sym_free(void *handle);
+b200_status b200_transpose_alltoall(void *a_sym, const void *b_local, int64_t N0, int64_t N1, int32_t elsize);
 
 /* ---- fused compute + collective over NVLink peer memory ------------------------------------------------------
  * One rank (process) per GPU of one NVLink/NVSwitch domain.  Each rank allocates a small symmetric buffer, the

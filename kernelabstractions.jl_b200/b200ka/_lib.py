@@ -124,6 +124,14 @@ SIGNATURES = {
     "b200_event_elapsed_ms": (_I32, [_VP, _VP, C.POINTER(C.c_float)]),
     "b200_event_destroy": (_I32, [_VP]),
     "b200_launch": (_I32, [C.c_char_p, C.POINTER(LaunchDesc), C.POINTER(Arg), _I32]),
+    "b200_memcpy_2d_d2d_async": (_I32, [_VP, _SZ, _VP, _SZ, _SZ, _SZ]),
+    "b200_sym_alloc": (_I32, [_PVP, _SZ]),
+    "b200_sym_export": (_I32, [_VP, _VP]),
+    "b200_sym_connect": (_I32, [_VP, _I32, _I32, _VP]),
+    "b200_sym_ptr": (_I32, [_VP, _I32, _PVP]),
+    "b200_sym_barrier": (_I32, [_VP]),
+    "b200_sym_free": (_I32, [_VP]),
+    "b200_transpose_alltoall": (_I32, [_VP, _VP, _I64, _I64, _I32]),
     "b200_graph_begin": (_I32, []),
     "b200_graph_end": (_I32, [_PVP]),
     "b200_graph_launch": (_I32, [_VP]),

@@ -62,6 +62,7 @@ class Comm:
         self.handle = C.c_void_p()
         buf = C.create_string_buffer(unique_id, _lib.B200_UNIQUE_ID_BYTES)
         _lib.call("b200_comm_init_rank", C.byref(self.handle), world_size, rank, buf)
+        self.world_size, self.rank = world_size, rank
 
     @staticmethod
     def unique_id() -> bytes:
@@ -130,3 +131,63 @@ def exchange_(comm: "Comm", backend, d_send_buf, d_recv_buf, src_rank: int, dst_
     d_recv_buf, stream ordered behind whatever produced d_send_buf; KA.synchronize(backend) completes it."""
     assert d_send_buf.nbytes == d_recv_buf.nbytes
     comm.sendrecv(d_send_buf.ptr, dst_rank, d_recv_buf.ptr, src_rank, d_send_buf.nbytes)
+
+
+class SymBuffer:
+    """A symmetric device buffer (b200_sym_*): every rank allocates `nbytes`, the IPC handles are all-gathered with `gather`
+    (see PeerGroup), and every rank maps its peers, so kernels can store straight into another GPU's memory over NVLink."""
+
+    def __init__(self, nbytes: int, world_size: int, rank: int, gather):
+        self.handle = C.c_void_p()
+        _lib.call("b200_sym_alloc", C.byref(self.handle), C.c_size_t(nbytes))
+        buf = C.create_string_buffer(_lib.B200_IPC_HANDLE_BYTES)
+        _lib.call("b200_sym_export", self.handle, buf)
+        handles = gather(buf.raw)
+        allh = C.create_string_buffer(b"".join(handles), world_size * _lib.B200_IPC_HANDLE_BYTES)
+        _lib.call("b200_sym_connect", self.handle, world_size, rank, allh)
+        self.world_size, self.rank, self.nbytes = world_size, rank, nbytes
+
+    def ptr(self, rank: int = -1) -> int:
+        p = C.c_void_p()
+        _lib.call("b200_sym_ptr", self.handle, C.c_int32(rank), C.byref(p))
+        return p.value
+
+    def array(self, dtype, shape):
+        """the own buffer as a (non-owning) B200Array view"""
+        from .backend import B200Array
+        return B200Array(dtype, shape, _ptr=self.ptr(), _owner=self)
+
+    def barrier(self) -> None:
+        _lib.call("b200_sym_barrier", self.handle)
+
+    def free(self) -> None:
+        if self.handle:
+            _lib.call("b200_sym_free", self.handle)
+            self.handle = C.c_void_p()
+
+
+def transpose_alltoall_(a_sym: SymBuffer, b_local, N0: int, N1: int) -> None:
+    """Distributed a = transpose(b) for a global N0 x N1 matrix sharded by columns (b_local: N0 x N1/world on this rank; afterwards
+    a_sym of rank h holds a[:, h-th block]: N1 x N0/world): the fused tile transpose + all-to-all of b200_transpose_alltoall."""
+    _lib.call("b200_transpose_alltoall", a_sym.handle, C.c_void_p(b_local.ptr), N0, N1, C.c_int32(b_local.dtype.itemsize))
+
+
+def transpose_alltoall_nccl_(comm: "Comm", backend, a_local, b_local, N0: int, N1: int, stage_send, stage_recv) -> None:
+    """The same result with library collectives, for comparison and as a parity check: pack each destination's block, exchange the
+    blocks pairwise with NCCL send/recv (world-1 rounds), transpose every received block locally into a_local."""
+    G, g = comm.world_size, comm.rank
+    rb, cb = N0 // G, N1 // G
+    es = b_local.dtype.itemsize
+    blk_bytes = rb * cb * es
+
+    for h in range(G):     # pack: contiguous rb x cb block for destination h  (copy of a strided sub-matrix = transpose of transpose ...)
+        _lib.call("b200_memcpy_2d_d2d_async", C.c_void_p(stage_send.ptr + h * blk_bytes), C.c_size_t(rb * es), C.c_void_p(b_local.ptr + h * rb * es),
+                  C.c_size_t(N0 * es), C.c_size_t(rb * es), C.c_size_t(cb))
+    for r in range(G):
+        dst, src = (g + r) % G, (g - r) % G
+        if r == 0:
+            _lib.call("b200_memcpy_d2d_async", C.c_void_p(stage_recv.ptr + g * blk_bytes), C.c_void_p(stage_send.ptr + g * blk_bytes), C.c_size_t(blk_bytes))
+        else:
+            comm.sendrecv(stage_send.ptr + dst * blk_bytes, dst, stage_recv.ptr + src * blk_bytes, src, blk_bytes)
+    for s in range(G):     # block from rank s (rb x cb) -> rows c1(s) of a_local (cb x rb block, ld N1)
+        _lib.call("b200_transpose", C.c_void_p(a_local.ptr + s * cb * es), C.c_void_p(stage_recv.ptr + s * blk_bytes), cb, rb, N1, rb, es)

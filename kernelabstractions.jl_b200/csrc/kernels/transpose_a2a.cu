@@ -1,0 +1,223 @@
+// transpose_a2a.cu -- distributed transpose: the tile transpose and the all-to-all it implies, in ONE data kernel over NVLink
+// peer memory (no NCCL, no staging buffer, no second pass over HBM).
+//
+// Setting ("all-to-all only if input were column-sharded"): a global N0 x N1 column-major matrix b is sharded
+// by COLUMNS over G ranks (rank g holds b_g = b[:, c1(g)], N0 x N1/G, ld = N0) and so is the result a = b^T (rank h holds
+// a_h = a[:, c0(h)], N1 x N0/G, ld = N1).  Element-wise  a_h[c1(g).start + i', j'] = b_g[c0(h).start + j', i'] : rank g owns,
+// for every destination h, the (N0/G) x (N1/G) block b_g[c0(h), :] and must deliver its transpose into rows c1(g) of rank h's
+// slab.  The reference has no multi-device code (examples/mpi.jl:24-39 is a host-staged ring); the NCCL formulation is an
+// all-to-all of the blocks followed by G local transposes, i.e. every byte crosses HBM three times on the receiver.
+//
+// Here every rank runs the swizzled 64 x 64 tile transpose of transpose.cu once over its whole slab with blockIdx.y = destination
+// rank: the 128-bit stores of a tile go straight into the destination's slab through its cudaIpc mapping (NVSwitch gives every
+// pair full bandwidth), so the exchange IS the store phase of the transpose.  Completion is signalled by a second, tiny kernel
+// (b200_sym_barrier): a system-scope fence, one flag store per peer, a spin on the own flags -- ordered behind the data kernel
+// on the stream, so a peer that sees the flag sees the data.
+//
+// Bound: NVLink egress for G > 1 -- (G-1)/G of the slab leaves the GPU -- and HBM for the local part.
+#include <cstring>
+
+#include "../common.cuh"
+#include "../tune.h"
+
+namespace b200 {
+
+constexpr int kSymMaxRanks = 8;
+constexpr size_t kSymFlagBytes = 256;   // [0..7]: arrival flags written by the peers, one 8-byte word each
+
+struct Sym {
+    void *local = nullptr;      // user bytes, then kSymFlagBytes of flags
+    size_t bytes = 0;
+    int world = 0, rank = -1;
+    void *peer[kSymMaxRanks] = {};
+    unsigned long long epoch = 0;
+};
+
+struct A2APeers {
+    void *dst[kSymMaxRanks];
+};
+
+template <typename T>
+struct alignas(16) V16 {
+    T e[16 / sizeof(T)];
+};
+template <typename T>
+__device__ __forceinline__ V16<T> ldg_v(const T *p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return *reinterpret_cast<V16<T> *>(&r);
+}
+
+// Rank g's data kernel.  src block for destination h: b_local + h * rows_blk (rows_blk = N0/G rows of every local column);
+// its transpose (cols_blk x rows_blk) goes to peers.dst[h] + row_off (row_off = g * cols_blk) with leading dimension ld_dst = N1.
+// Tile scheme and swizzle as transpose64_any_kernel (transpose.cu); rows_blk, cols_blk multiples of 64.
+template <typename T>
+__global__ void __launch_bounds__(256) transpose_a2a_kernel(A2APeers peers, const T *__restrict__ b_local, int64_t ld_src, int64_t ld_dst,
+                                                            int64_t rows_blk, int64_t row_off, int tiles_i, int tiles_j, int first_dst) {
+    constexpr int V = 16 / sizeof(T), CH = 64 / V, PASSES = CH * CH / 256, ROWS_PER_PASS = 256 / CH;
+    __shared__ V16<T> tile[64 * CH];
+    const int t = threadIdx.x;
+    // start with the own rank's block and walk the peers round-robin so that at any moment the ranks address different targets
+    const int h = (first_dst + (int)blockIdx.y) % (int)gridDim.y;
+    const int tj = blockIdx.x % tiles_j, ti = blockIdx.x / tiles_j;   // tj walks the source's contiguous dimension
+    // block-local coordinates: output tile rows i (0 .. cols_blk) = source columns, output tile columns j (0 .. rows_blk) = source rows
+    const int64_t i0 = (int64_t)ti * 64, j0 = (int64_t)tj * 64;
+    const T *src = b_local + (int64_t)h * rows_blk;                    // rows c0(h) of the local slab
+    T *dst = reinterpret_cast<T *>(peers.dst[h]) + row_off;            // rows c1(g) of rank h's slab
+    const int jq = t % CH;
+#pragma unroll
+    for (int p = 0; p < PASSES; ++p) {
+        const int iq = t / CH + (256 / CH) * p;
+        V16<T> blk[V];
+#pragma unroll
+        for (int r = 0; r < V; ++r) blk[r] = ldg_v(src + (j0 + V * jq) + (i0 + V * iq + r) * ld_src);
+#pragma unroll
+        for (int c = 0; c < V; ++c) {
+            V16<T> w;
+#pragma unroll
+            for (int r = 0; r < V; ++r) w.e[r] = blk[r].e[c];
+            tile[(V * jq + c) * CH + (iq ^ jq)] = w;
+        }
+    }
+    __syncthreads();
+    const int ic = t % CH, jr = t / CH;
+#pragma unroll
+    for (int sidx = 0; sidx < 64 / ROWS_PER_PASS; ++sidx) {
+        const int jl = jr + ROWS_PER_PASS * sidx;
+        const V16<T> w = tile[jl * CH + (ic ^ ((jl / V) & (CH - 1)))];
+        const uint4 r = *reinterpret_cast<const uint4 *>(&w);
+        T *p = dst + (i0 + V * ic) + (j0 + jl) * ld_dst;
+        asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(r.x), "r"(r.y), "r"(r.z), "r"(r.w) : "memory");
+    }
+}
+
+// One CTA: make everything this GPU wrote before visible system-wide, raise `epoch` in every peer's flag word for this rank,
+// wait until every peer has raised its word here.
+__global__ void sym_barrier_kernel(A2APeers flags, int world, int rank, unsigned long long epoch) {
+    __threadfence_system();
+    const int r = threadIdx.x;
+    if (r < world) {
+        unsigned long long *theirs = reinterpret_cast<unsigned long long *>(flags.dst[r]) + rank;
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(theirs), "l"(epoch) : "memory");
+        const unsigned long long *mine = reinterpret_cast<const unsigned long long *>(flags.dst[rank]) + r;
+        unsigned long long v;
+        do {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
+        } while (v < epoch);
+    }
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" b200_status b200_sym_alloc(void **handle, size_t bytes) {
+    if (!handle) return set_error(B200_ERR_INVALID_VALUE, "b200_sym_alloc: handle is NULL");
+    B200_TRY(ensure_device());
+    Sym *h = new Sym();
+    h->bytes = (bytes + 255) / 256 * 256;
+    cudaError_t e = cudaMalloc(&h->local, h->bytes + kSymFlagBytes);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        delete h;
+        return set_error(B200_ERR_OOM, "b200_sym_alloc: cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+    }
+    B200_CUDA(cudaMemset((char *)h->local + h->bytes, 0, kSymFlagBytes));
+    *handle = h;
+    return B200_OK;
+}
+
+extern "C" b200_status b200_sym_export(void *handle, void *ipc64) {
+    if (!handle || !ipc64) return set_error(B200_ERR_INVALID_VALUE, "NULL argument");
+    cudaIpcMemHandle_t ipc;
+    B200_CUDA(cudaIpcGetMemHandle(&ipc, ((Sym *)handle)->local));
+    memcpy(ipc64, &ipc, sizeof(ipc));
+    return B200_OK;
+}
+
+extern "C" b200_status b200_sym_connect(void *handle, int32_t world, int32_t rank, const void *all_handles) {
+    if (!handle || !all_handles) return set_error(B200_ERR_INVALID_VALUE, "NULL argument");
+    if (world < 1 || world > kSymMaxRanks || rank < 0 || rank >= world)
+        return set_error(B200_ERR_INVALID_VALUE, "b200_sym_connect: bad rank %d / world %d (1..8 ranks of one NVLink domain)", rank, world);
+    B200_TRY(ensure_device());
+    Sym *h = (Sym *)handle;
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) {
+            h->peer[r] = h->local;
+            continue;
+        }
+        cudaIpcMemHandle_t ipc;
+        memcpy(&ipc, (const char *)all_handles + (size_t)r * B200_IPC_HANDLE_BYTES, sizeof(ipc));
+        B200_CUDA(cudaIpcOpenMemHandle(&h->peer[r], ipc, cudaIpcMemLazyEnablePeerAccess));
+    }
+    h->world = world;
+    h->rank = rank;
+    return B200_OK;
+}
+
+extern "C" b200_status b200_sym_ptr(void *handle, int32_t rank, void **ptr) {
+    if (!handle || !ptr) return set_error(B200_ERR_INVALID_VALUE, "NULL argument");
+    Sym *h = (Sym *)handle;
+    if (rank == -1) rank = h->rank < 0 ? 0 : h->rank;
+    if (h->world < 1) {   // not connected yet: only the own buffer is known
+        *ptr = h->local;
+        return B200_OK;
+    }
+    if (rank < 0 || rank >= h->world) return set_error(B200_ERR_INVALID_VALUE, "b200_sym_ptr: rank %d out of range", rank);
+    *ptr = h->peer[rank];
+    return B200_OK;
+}
+
+extern "C" b200_status b200_sym_barrier(void *handle) {
+    if (!handle) return set_error(B200_ERR_INVALID_VALUE, "b200_sym_barrier: handle is NULL");
+    Sym *h = (Sym *)handle;
+    if (h->world < 1) return set_error(B200_ERR_INVALID_VALUE, "b200_sym_barrier: b200_sym_connect has not been called");
+    cudaStream_t st;
+    B200_TRY(current_stream(&st));
+    A2APeers flags;
+    for (int r = 0; r < kSymMaxRanks; ++r) flags.dst[r] = r < h->world ? (char *)h->peer[r] + h->bytes : nullptr;
+    sym_barrier_kernel<<<1, 32, 0, st>>>(flags, h->world, h->rank, ++h->epoch);
+    B200_CHECK_LAUNCH("sym_barrier_kernel");
+    return B200_OK;
+}
+
+extern "C" b200_status b200_sym_free(void *handle) {
+    if (!handle) return B200_OK;
+    Sym *h = (Sym *)handle;
+    B200_CUDA(cudaDeviceSynchronize());
+    for (int r = 0; r < h->world; ++r)
+        if (r != h->rank && h->peer[r]) (void)cudaIpcCloseMemHandle(h->peer[r]);
+    if (h->local) (void)cudaFree(h->local);
+    delete h;
+    return B200_OK;
+}
+
+extern "C" b200_status b200_transpose_alltoall(void *a_sym, const void *b_local, int64_t N0, int64_t N1, int32_t elsize) {
+    if (!a_sym || !b_local) return set_error(B200_ERR_INVALID_VALUE, "b200_transpose_alltoall: NULL argument");
+    Sym *h = (Sym *)a_sym;
+    const int G = h->world;
+    if (G < 1) return set_error(B200_ERR_INVALID_VALUE, "b200_transpose_alltoall: b200_sym_connect has not been called");
+    if (elsize != 4 && elsize != 8) return set_error(B200_ERR_UNSUPPORTED, "b200_transpose_alltoall: element size %d not in {4,8}", elsize);
+    if (N0 <= 0 || N1 <= 0 || N0 % (64 * G) != 0 || N1 % (64 * G) != 0)
+        return set_error(B200_ERR_UNSUPPORTED, "b200_transpose_alltoall: N0 and N1 must be positive multiples of 64 x world (got %lld, %lld)",
+                         (long long)N0, (long long)N1);
+    if ((size_t)(N1 * (N0 / G)) * (size_t)elsize > h->bytes)
+        return set_error(B200_ERR_INVALID_VALUE, "b200_transpose_alltoall: the symmetric output slab is smaller than N1 x N0/world elements");
+    if (((uintptr_t)b_local & 15) != 0) return set_error(B200_ERR_UNSUPPORTED, "b200_transpose_alltoall: b must be 16-byte aligned");
+    cudaStream_t st;
+    B200_TRY(current_stream(&st));
+    const int64_t rows_blk = N0 / G, cols_blk = N1 / G;   // a block of b_local: rows_blk x cols_blk; its transpose: cols_blk x rows_blk
+    A2APeers peers;
+    for (int r = 0; r < kSymMaxRanks; ++r) peers.dst[r] = r < G ? h->peer[r] : nullptr;
+    const int tiles_i = (int)(cols_blk / 64), tiles_j = (int)(rows_blk / 64);
+    if ((int64_t)tiles_i * tiles_j > INT32_MAX) return set_error(B200_ERR_UNSUPPORTED, "b200_transpose_alltoall: too many tiles");
+    const dim3 grid((unsigned)(tiles_i * tiles_j), (unsigned)G);
+    if (elsize == 4)
+        transpose_a2a_kernel<uint32_t><<<grid, 256, 0, st>>>(peers, (const uint32_t *)b_local, N0, N1, rows_blk, (int64_t)h->rank * cols_blk,
+                                                            tiles_i, tiles_j, h->rank);
+    else
+        transpose_a2a_kernel<uint64_t><<<grid, 256, 0, st>>>(peers, (const uint64_t *)b_local, N0, N1, rows_blk, (int64_t)h->rank * cols_blk,
+                                                            tiles_i, tiles_j, h->rank);
+    B200_CHECK_LAUNCH("transpose_a2a_kernel");
+    return b200_sym_barrier(a_sym);
+}

@@ -249,6 +249,17 @@ static int memcpy_async(void *dst, const void *src, size_t bytes, cudaMemcpyKind
     return B200_OK;
 }
 
+// strided (pitched) device-to-device copy: `height` rows of `width_bytes`, row pitches in bytes -- sub-matrix views
+b200_status b200_memcpy_2d_d2d_async(void *dst, size_t dpitch, const void *src, size_t spitch, size_t width_bytes, size_t height) {
+    if (width_bytes == 0 || height == 0) return B200_OK;
+    if (!dst || !src) return set_error(B200_ERR_INVALID_VALUE, "b200_memcpy_2d_d2d_async: NULL pointer");
+    if (dpitch < width_bytes || spitch < width_bytes) return set_error(B200_ERR_INVALID_VALUE, "b200_memcpy_2d_d2d_async: pitch < width");
+    cudaStream_t s;
+    B200_TRY(current_stream(&s));
+    B200_CUDA(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width_bytes, height, cudaMemcpyDeviceToDevice, s));
+    return B200_OK;
+}
+
 b200_status b200_memcpy_h2d_async(void *dst, const void *src, size_t bytes) {
     return memcpy_async(dst, src, bytes, cudaMemcpyHostToDevice);
 }

@@ -97,8 +97,75 @@ def main():
     assert np.array_equal(KA.Array(Cp), Cref[m0:m1, :])
     out["matmul_row_panels_bit_exact"] = True
 
+    # ---- distributed transpose: fused tile transpose + all-to-all over peer memory == definition == NCCL route ----
+    gather = mg.torch_gather(dist)
+    for (N0, N1, dt) in [(64 * world, 128 * world, np.float32), (256 * world, 64 * world, np.float64), (1024, 2048, np.float32)]:
+        if N0 % (64 * world) or N1 % (64 * world):
+            continue
+        rb, cb = N0 // world, N1 // world
+        rng = np.random.default_rng(N0 + N1)
+        whole = np.asfortranarray((rng.standard_normal((N0, N1)) * 100).astype(dt))      # every rank builds the same global b
+        b_loc = KA.to_device(np.asfortranarray(whole[:, rank * cb:(rank + 1) * cb]))
+        es = np.dtype(dt).itemsize
+        a_sym = mg.SymBuffer(N1 * rb * es, world, rank, gather)
+        a_view = a_sym.array(dt, (N1, rb))
+        a_view.fill_(0)
+        KA.synchronize(be)
+        dist.barrier()                                   # nobody stores into a slab that is still being zeroed
+        for _ in range(2):                               # twice: the flag epochs must keep working
+            mg.transpose_alltoall_(a_sym, b_loc, N0, N1)
+        KA.synchronize(be)
+        want = np.asfortranarray(whole.T[:, rank * rb:(rank + 1) * rb])                   # a[:, c0(rank)]
+        assert np.array_equal(KA.Array(a_view), want), f"fused distributed transpose mismatch on rank {rank} for {N0}x{N1}"
+        a_nccl = KA.zeros(be, dt, N1, rb)
+        st_s, st_r = KA.allocate(be, dt, rb * cb * world), KA.allocate(be, dt, rb * cb * world)
+        mg.transpose_alltoall_nccl_(comm, be, a_nccl, b_loc, N0, N1, st_s, st_r)
+        KA.synchronize(be)
+        assert np.array_equal(KA.Array(a_nccl), want), f"NCCL distributed transpose mismatch on rank {rank} for {N0}x{N1}"
+        dist.barrier()
+        a_sym.free()
+    out["distributed_transpose_fused_eq_nccl_eq_definition"] = True
+
     # ---- timing: NCCL route vs fused route at the C3 size ----
     if "--time" in sys.argv:
+        # distributed transpose of ONE 16384 x 16384 Float32 matrix sharded over the ranks (strong scaling)
+        N = 16384
+        rb = N // world
+        b_loc = KA.rand_uniform_(KA.allocate(be, np.float32, N, rb), 1235 + rank)
+        a_sym = mg.SymBuffer(N * rb * 4, world, rank, gather)
+        a_nccl = KA.zeros(be, np.float32, N, rb)
+        st_s, st_r = KA.allocate(be, np.float32, rb * rb * world), KA.allocate(be, np.float32, rb * rb * world)
+        ev0, ev1 = C.c_void_p(), C.c_void_p()
+        _lib.call("b200_event_create", C.byref(ev0))
+        _lib.call("b200_event_create", C.byref(ev1))
+
+        def timed_t(fn, steps=20, warm=3):
+            for _ in range(warm):
+                fn()
+            KA.synchronize(be)
+            dist.barrier()
+            _lib.call("b200_event_record", ev0)
+            for _ in range(steps):
+                fn()
+            _lib.call("b200_event_record", ev1)
+            KA.synchronize(be)
+            ms = C.c_float()
+            _lib.call("b200_event_elapsed_ms", ev0, ev1, C.byref(ms))
+            t = torch.tensor([ms.value / steps], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+
+        ms_f = timed_t(lambda: mg.transpose_alltoall_(a_sym, b_loc, N, N))
+        ms_n = timed_t(lambda: mg.transpose_alltoall_nccl_(comm, be, a_nccl, b_loc, N, N, st_s, st_r))
+        out["dist_transpose_16384_fused_ms"] = ms_f
+        out["dist_transpose_16384_fused_GBps"] = 2.0 * 4 * N * N / (ms_f * 1e-3) / 1e9
+        out["dist_transpose_16384_nccl_ms"] = ms_n
+        out["dist_transpose_16384_nccl_GBps"] = 2.0 * 4 * N * N / (ms_n * 1e-3) / 1e9
+        KA.synchronize(be)
+        dist.barrier()
+        a_sym.free()
+        del b_loc, a_nccl, st_s, st_r
+
         n = 1 << 30
         s0, s1 = mg.histogram_shard(n, world, rank)
         d_in = EX.move(be, orc.gen_bins_i32(s1 - s0, 1236 + rank, 256))
