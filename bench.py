@@ -422,6 +422,39 @@ def run_suite(KA, _lib, EX, mg, orc, be, rank, world, dist, timed, peaks, steps,
     except Exception as ex:
         out["saxpy_2^26_f32"] = {"error": str(ex)[:300]}
 
+    # ---- distributed transpose of ONE 16384^2 Float32 matrix, column-sharded in and out (strong scaling, N > 1 only):
+    # ---- the tile transpose and its all-to-all in one data kernel whose stores go to the peers' slabs over NVLink ----
+    if world > 1:
+        try:
+            n = N_T
+            rb = n // world
+            b_loc = KA.rand_uniform_(KA.allocate(be, np.float32, n, rb), 1235 + rank)
+            a_sym = mg.SymBuffer(n * rb * 4, world, rank, mg.torch_gather(dist))
+
+            def step_dt():
+                mg.transpose_alltoall_(a_sym, b_loc, n, n)
+
+            step_dt()
+            KA.synchronize(be)
+            barrier()
+            # property check on this rank's slab: a[:, c0(rank)] column j' == row (rank*rb + j') of the GLOBAL b; rows c1(rank) of it came
+            # from this rank's own b_loc, so  a_slab[rank*rb : (rank+1)*rb, :] == transpose(b_loc[rank*rb : (rank+1)*rb, :])
+            a_own = KA.Array(a_sym.array(np.float32, (n, rb)))[rank * rb:(rank + 1) * rb, :]
+            ok = bool(np.array_equal(a_own, KA.Array(b_loc)[rank * rb:(rank + 1) * rb, :].T))
+            ms, launches = timed(step_dt, steps, warmup)
+            gbs = 2.0 * 4 * n * n / (ms * 1e-3) / 1e9
+            out["distributed_transpose_16384_f32"] = {
+                "value": gbs, "unit": "GB/s", "ms_per_step": ms, "gpu_launches": launches, "scaling": "strong", "own_block_checked": ok,
+                "nvlink_egress_GBps_per_gpu": 4.0 * n * rb * (world - 1) / world / (ms * 1e-3) / 1e9,
+                "collective": "all-to-all fused into the transpose kernel's store phase (b200_transpose_alltoall: peer stores over NVLink + flag barrier), no NCCL",
+                "roofline": {"bound": "nvlink", "achieved": 4.0 * n * rb * (world - 1) / world / (ms * 1e-3) / 1e9, "peak": 900.0, "unit": "GB/s",
+                             "frac": 4.0 * n * rb * (world - 1) / world / (ms * 1e-3) / 1e9 / 900.0, "peak_source": "NVLink 5 nominal, per direction"}}
+            barrier()
+            a_sym.free()
+            del b_loc
+        except Exception as ex:
+            out["distributed_transpose_16384_f32"] = {"error": str(ex)[:300]}
+
     # ---- histogram 2^30 Int32 -> 256 bins, input slab per rank, one all-reduce of the bins (strong scaling) ----
     try:
         n = N_HIST

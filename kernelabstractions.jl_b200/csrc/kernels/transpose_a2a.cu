@@ -18,6 +18,7 @@
 #include <cstring>
 
 #include "../common.cuh"
+#include "../tma_pipe.cuh"
 #include "../tune.h"
 
 namespace b200 {
@@ -88,6 +89,54 @@ __global__ void __launch_bounds__(256) transpose_a2a_kernel(A2APeers peers, cons
         const uint4 r = *reinterpret_cast<const uint4 *>(&w);
         T *p = dst + (i0 + V * ic) + (j0 + jl) * ld_dst;
         asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(r.x), "r"(r.y), "r"(r.z), "r"(r.w) : "memory");
+    }
+}
+
+// The same data kernel with the store phase handed to TMA (opt-in, `a2a.tma_store`): the transposed tile is laid out densely and
+// ONE cp.async.bulk.tensor.2d store per tile moves it into the destination slab.  A 1-D bulk copy kernel reaches 697 GB/s over
+// NVLink on this box where cudaMemcpyPeer and 128-bit st.global reach ~550 (tools/p2p_bw.py); the 2-D tile stores -- 64 x 64 or
+// 256 x 16 tiles, i.e. 256-byte or 1-KiB destination runs -- stay at 550 as well, and capping the resident CTAs makes it slower,
+// so neither run length nor writer count is the limiter.  The dense layout costs bank conflicts on the transposing shared-memory
+// writes, which do not matter: a tile needs ~7000 cycles of NVLink time per SM.
+struct A2AMaps {
+    CUtensorMap m[kSymMaxRanks];
+};
+// Tile = TI (along the destination's contiguous dimension i) x TJ: 256 x 16 gives 1 KiB contiguous runs in the destination slab
+// (NVLink likes long runs: 64 x 64 tiles, i.e. 256-byte runs, stay at the 555 GB/s of plain stores), 64 x 64 is the fallback shape.
+template <typename T, int TI, int TJ>
+__global__ void __launch_bounds__(256) transpose_a2a_tma_kernel(const __grid_constant__ A2AMaps maps, const T *__restrict__ b_local,
+                                                                int64_t ld_src, int64_t rows_blk, int row_off, int tiles_j, int first_dst) {
+    constexpr int V = 16 / sizeof(T), CI = TI / V, CJ = TJ / V, PASSES = CI * CJ / 256;
+    static_assert(CI * CJ % 256 == 0 && 256 % CJ == 0, "tile must be a whole number of passes of 256 threads");
+    __shared__ __align__(128) V16<T> tile[TJ * CI];   // [j][chunk of i], dense: exactly the box the tensor map describes
+    const int t = threadIdx.x;
+    const int h = (first_dst + (int)blockIdx.y) % (int)gridDim.y;
+    const int tj = blockIdx.x % tiles_j, ti = blockIdx.x / tiles_j;
+    const int64_t i0 = (int64_t)ti * TI, j0 = (int64_t)tj * TJ;
+    const T *src = b_local + (int64_t)h * rows_blk;
+    const int jq = t % CJ;
+#pragma unroll
+    for (int p = 0; p < PASSES; ++p) {
+        const int iq = t / CJ + (256 / CJ) * p;
+        V16<T> blk[V];
+#pragma unroll
+        for (int r = 0; r < V; ++r) blk[r] = ldg_v(src + (j0 + V * jq) + (i0 + V * iq + r) * ld_src);
+#pragma unroll
+        for (int c = 0; c < V; ++c) {
+            V16<T> w;
+#pragma unroll
+            for (int r = 0; r < V; ++r) w.e[r] = blk[r].e[c];
+            tile[(V * jq + c) * CI + iq] = w;
+        }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the bulk engine
+    __syncthreads();
+    if (t == 0) {
+        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(&maps.m[h]),
+                     "r"(row_off + (int)i0), "r"((int)j0), "r"(pipe::smem_u32(tile))
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // the CTA may not retire (and free its smem) before the store
     }
 }
 
@@ -212,6 +261,30 @@ extern "C" b200_status b200_transpose_alltoall(void *a_sym, const void *b_local,
     const int tiles_i = (int)(cols_blk / 64), tiles_j = (int)(rows_blk / 64);
     if ((int64_t)tiles_i * tiles_j > INT32_MAX) return set_error(B200_ERR_UNSUPPORTED, "b200_transpose_alltoall: too many tiles");
     const dim3 grid((unsigned)(tiles_i * tiles_j), (unsigned)G);
+    // a2a.tma_store = 1 selects the TMA-store variant; measured equal to the plain stores (0.483 vs 0.486 ms for 16384^2 on two
+    // GPUs, both at the ~550 GB/s per direction that cudaMemcpyPeer reaches on this box), so the simpler kernel is the default
+    if (tune_get("a2a.tma_store", 0) != 0 && N1 < (1LL << 31) && rows_blk < (1LL << 31)) {
+        const bool wide = cols_blk % 256 == 0 && rows_blk % 16 == 0 && tune_get("a2a.wide_tiles", 1) != 0;
+        const int TI = wide ? 256 : 64, TJ = wide ? 16 : 64;
+        A2AMaps maps;
+        memset(&maps, 0, sizeof(maps));
+        for (int r = 0; r < G; ++r)   // rank r's slab: N1 (contiguous) x N0/G, box TI x TJ, no swizzle
+            B200_TRY(pipe::make_tmap_2d(&maps.m[r], elsize == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64, elsize,
+                                        h->peer[r], N1, rows_blk, N1, TI, TJ, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE));
+        const int tj_n = (int)(rows_blk / TJ);
+        const dim3 g2((unsigned)((cols_blk / TI) * tj_n), (unsigned)G);
+        const int roff = (int)(h->rank * cols_blk);
+        if (elsize == 4 && wide)
+            transpose_a2a_tma_kernel<uint32_t, 256, 16><<<g2, 256, 0, st>>>(maps, (const uint32_t *)b_local, N0, rows_blk, roff, tj_n, h->rank);
+        else if (elsize == 4)
+            transpose_a2a_tma_kernel<uint32_t, 64, 64><<<g2, 256, 0, st>>>(maps, (const uint32_t *)b_local, N0, rows_blk, roff, tj_n, h->rank);
+        else if (wide)
+            transpose_a2a_tma_kernel<uint64_t, 256, 16><<<g2, 256, 0, st>>>(maps, (const uint64_t *)b_local, N0, rows_blk, roff, tj_n, h->rank);
+        else
+            transpose_a2a_tma_kernel<uint64_t, 64, 64><<<g2, 256, 0, st>>>(maps, (const uint64_t *)b_local, N0, rows_blk, roff, tj_n, h->rank);
+        B200_CHECK_LAUNCH("transpose_a2a_tma_kernel");
+        return b200_sym_barrier(a_sym);
+    }
     if (elsize == 4)
         transpose_a2a_kernel<uint32_t><<<grid, 256, 0, st>>>(peers, (const uint32_t *)b_local, N0, N1, rows_blk, (int64_t)h->rank * cols_blk,
                                                             tiles_i, tiles_j, h->rank);

@@ -37,6 +37,9 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     _lib.call("b200_set_device", local)
     be = KA.B200Backend()
+    for kv in filter(None, os.environ.get("B200_TUNE", "").split(",")):     # e.g. B200_TUNE=a2a.tma_store=0
+        k, v = kv.rsplit("=", 1)
+        _lib.call("b200_tune_set", k.encode(), int(v))
     out = {"world": world}
 
     uid = torch.zeros(_lib.B200_UNIQUE_ID_BYTES, dtype=torch.uint8, device="cuda")
@@ -99,7 +102,8 @@ def main():
 
     # ---- distributed transpose: fused tile transpose + all-to-all over peer memory == definition == NCCL route ----
     gather = mg.torch_gather(dist)
-    for (N0, N1, dt) in [(64 * world, 128 * world, np.float32), (256 * world, 64 * world, np.float64), (1024, 2048, np.float32)]:
+    for (N0, N1, dt) in [(64 * world, 128 * world, np.float32), (256 * world, 64 * world, np.float64), (1024, 2048, np.float32),
+                         (64 * world, 256 * world, np.float64), (192 * world, 512 * world, np.float32)]:
         if N0 % (64 * world) or N1 % (64 * world):
             continue
         rb, cb = N0 // world, N1 // world
@@ -112,11 +116,16 @@ def main():
         a_view.fill_(0)
         KA.synchronize(be)
         dist.barrier()                                   # nobody stores into a slab that is still being zeroed
-        for _ in range(2):                               # twice: the flag epochs must keep working
-            mg.transpose_alltoall_(a_sym, b_loc, N0, N1)
-        KA.synchronize(be)
         want = np.asfortranarray(whole.T[:, rank * rb:(rank + 1) * rb])                   # a[:, c0(rank)]
-        assert np.array_equal(KA.Array(a_view), want), f"fused distributed transpose mismatch on rank {rank} for {N0}x{N1}"
+        for tma in (0, 1, 0):                            # plain-store and TMA-store variants; repeated: the flag epochs must keep working
+            _lib.call("b200_tune_set", b"a2a.tma_store", tma)
+            a_view.fill_(0)
+            KA.synchronize(be)
+            dist.barrier()
+            mg.transpose_alltoall_(a_sym, b_loc, N0, N1)
+            KA.synchronize(be)
+            assert np.array_equal(KA.Array(a_view), want), f"fused distributed transpose (tma_store={tma}) mismatch on rank {rank} for {N0}x{N1}"
+            dist.barrier()
         a_nccl = KA.zeros(be, dt, N1, rb)
         st_s, st_r = KA.allocate(be, dt, rb * cb * world), KA.allocate(be, dt, rb * cb * world)
         mg.transpose_alltoall_nccl_(comm, be, a_nccl, b_loc, N0, N1, st_s, st_r)
