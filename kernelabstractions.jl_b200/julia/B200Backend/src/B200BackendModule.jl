@@ -350,6 +350,35 @@ function launch(name::String, desc::LaunchDesc, args)
     return nothing
 end
 
+# Symmetric device buffers + distributed transpose (b200_sym_*, b200_transpose_alltoall): one process per GPU (MPI.jl), the
+# 64-byte IPC handles are exchanged with the launcher's transport, e.g. `all = MPI.Allgather(export_handle(s), comm)`.
+mutable struct SymBuffer
+    handle::Ptr{Cvoid}
+    nbytes::Int
+end
+function SymBuffer(nbytes::Integer)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    @b200 b200_sym_alloc (Ptr{Ptr{Cvoid}}, Csize_t) h nbytes
+    return SymBuffer(h[], nbytes)
+end
+function export_handle(s::SymBuffer)
+    blob = Vector{UInt8}(undef, 64)
+    GC.@preserve blob @b200 b200_sym_export (Ptr{Cvoid}, Ptr{Cvoid}) s.handle pointer(blob)
+    return blob
+end
+connect!(s::SymBuffer, all_handles::Vector{UInt8}, world::Integer, rank::Integer) =
+    (GC.@preserve all_handles @b200 b200_sym_connect (Ptr{Cvoid}, Int32, Int32, Ptr{Cvoid}) s.handle Int32(world) Int32(rank) pointer(all_handles); s)
+function Base.unsafe_wrap(::Type{B200Array{T, N}}, s::SymBuffer, dims::Dims{N}) where {T, N}      # the own slab as a non-owning array
+    p = Ref{Ptr{Cvoid}}(C_NULL)
+    @b200 b200_sym_ptr (Ptr{Cvoid}, Int32, Ptr{Ptr{Cvoid}}) s.handle Int32(-1) p
+    return B200Array{T, N}(Ptr{T}(p[]), dims, false, s)
+end
+barrier(s::SymBuffer) = (@b200 b200_sym_barrier (Ptr{Cvoid},) s.handle; nothing)
+Base.close(s::SymBuffer) = (@b200 b200_sym_free (Ptr{Cvoid},) s.handle; s.handle = C_NULL; nothing)
+# a = transpose(b) for a global N0 x N1 matrix sharded by columns: b_local is N0 x N1/world, the slab of `a_sym` N1 x N0/world
+transpose_alltoall!(a_sym::SymBuffer, b_local::B200Array{T, 2}, N0::Integer, N1::Integer) where {T} =
+    (@b200 b200_transpose_alltoall (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Int32) a_sym.handle b_local.ptr N0 N1 Int32(sizeof(T)); nothing)
+
 # CUDA graphs for launch-bound sequences: `g = record(backend) do ... launches ... end; replay(g)` (b200_graph_*).
 mutable struct Graph
     handle::Ptr{Cvoid}
