@@ -166,6 +166,16 @@ class SymBuffer:
             self.handle = C.c_void_p()
 
 
+def transpose_alltoall_blocks(N0: int, N1: int, world_size: int, rank: int):
+    """The block plan of the distributed transpose (pure host logic, tested on CPU): for every destination h the tuple
+    (h, first source row in b_local, first destination row in rank h's slab); a block is N0/world x N1/world in b_local and its
+    transpose N1/world x N0/world lands at that row of a_h (all columns)."""
+    if N0 % world_size or N1 % world_size:
+        raise _lib.ArgumentError("transpose_alltoall: N0 and N1 must be multiples of the world size")
+    rb, cb = N0 // world_size, N1 // world_size
+    return [(h, h * rb, rank * cb) for h in range(world_size)]
+
+
 def transpose_alltoall_(a_sym: SymBuffer, b_local, N0: int, N1: int) -> None:
     """Distributed a = transpose(b) for a global N0 x N1 matrix sharded by columns (b_local: N0 x N1/world on this rank; afterwards
     a_sym of rank h holds a[:, h-th block]: N1 x N0/world): the fused tile transpose + all-to-all of b200_transpose_alltoall."""

@@ -130,3 +130,20 @@ def test_slabs_tile_the_range(ws):
         assert edges[0][0] == 0 and edges[-1][1] == n
         for (a0, a1), (b0, b1) in zip(edges, edges[1:]):
             assert a1 == b0 and a1 > a0
+
+
+def test_distributed_transpose_block_plan():
+    # numpy model of b200_transpose_alltoall: every rank applies its block plan; the slabs then hold a = b^T column-sharded
+    from b200ka import multigpu as mg
+    for (N0, N1, G) in [(8, 12, 2), (12, 8, 4), (16, 16, 8), (6, 6, 1)]:
+        b = np.arange(N0 * N1, dtype=np.float64).reshape(N0, N1)
+        rb, cb = N0 // G, N1 // G
+        slabs = [np.full((N1, rb), -1.0) for _ in range(G)]                       # a_h = a[:, h-th block of N0/G columns]
+        for g in range(G):
+            b_loc = b[:, g * cb:(g + 1) * cb]                                      # b_g = b[:, g-th block of N1/G columns]
+            for (h, src_row, dst_row) in mg.transpose_alltoall_blocks(N0, N1, G, g):
+                slabs[h][dst_row:dst_row + cb, :] = b_loc[src_row:src_row + rb, :].T
+        a = np.concatenate(slabs, axis=1)
+        assert np.array_equal(a, b.T)
+    with pytest.raises(KA.ArgumentError):
+        mg.transpose_alltoall_blocks(10, 8, 4, 0)
