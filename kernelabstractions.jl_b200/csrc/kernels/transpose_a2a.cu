@@ -8,8 +8,8 @@
 // slab.  The reference has no multi-device code (examples/mpi.jl:24-39 is a host-staged ring); the NCCL formulation is an
 // all-to-all of the blocks followed by G local transposes, i.e. every byte crosses HBM three times on the receiver.
 //
-// Here every rank runs the swizzled 64 x 64 tile transpose of transpose.cu once over its whole slab with blockIdx.y = destination
-// rank: the 128-bit stores of a tile go straight into the destination's slab through its cudaIpc mapping (NVSwitch gives every
+// Here every rank runs the swizzled 64 x 64 tile transpose of transpose.cu once over its whole slab, destinations interleaved over
+// consecutive CTAs: the 128-bit stores of a tile go straight into the destination's slab through its cudaIpc mapping (NVSwitch gives every
 // pair full bandwidth), so the exchange IS the store phase of the transpose.  Completion is signalled by a second, tiny kernel
 // (b200_sym_barrier): a system-scope fence, one flag store per peer, a spin on the own flags -- ordered behind the data kernel
 // on the stream, so a peer that sees the flag sees the data.
@@ -54,13 +54,18 @@ __device__ __forceinline__ V16<T> ldg_v(const T *p) {
 // Tile scheme and swizzle as transpose64_any_kernel (transpose.cu); rows_blk, cols_blk multiples of 64.
 template <typename T>
 __global__ void __launch_bounds__(256) transpose_a2a_kernel(A2APeers peers, const T *__restrict__ b_local, int64_t ld_src, int64_t ld_dst,
-                                                            int64_t rows_blk, int64_t row_off, int tiles_i, int tiles_j, int first_dst) {
+                                                            int64_t rows_blk, int64_t row_off, int tiles_i, int tiles_j, int first_dst, int order, int world) {
     constexpr int V = 16 / sizeof(T), CH = 64 / V, PASSES = CH * CH / 256, ROWS_PER_PASS = 256 / CH;
     __shared__ V16<T> tile[64 * CH];
     const int t = threadIdx.x;
-    // start with the own rank's block and walk the peers round-robin so that at any moment the ranks address different targets
-    const int h = (first_dst + (int)blockIdx.y) % (int)gridDim.y;
-    const int tj = blockIdx.x % tiles_j, ti = blockIdx.x / tiles_j;   // tj walks the source's contiguous dimension
+    // Destinations are INTERLEAVED over consecutive CTAs (a 1-d grid of world x tiles): the local tiles run at HBM speed, the
+    // remote ones at NVLink speed, and a grid that did one destination after the other (blockIdx.y) finished the local block
+    // first and only then started to use the links -- 0.481 ms instead of 0.40 ms for 16384^2 on two GPUs.
+    const int h = (first_dst + (int)(blockIdx.x % (unsigned)world)) % world;
+    const unsigned tile_id = blockIdx.x / (unsigned)world;
+    // order 0: consecutive CTAs walk j (the source's contiguous dimension); order 1: they walk i (the DESTINATION's contiguous
+    // dimension), so the CTAs in flight write neighbouring runs instead of runs one leading dimension apart
+    const int tj = order ? tile_id / tiles_i : tile_id % tiles_j, ti = order ? tile_id % tiles_i : tile_id / tiles_j;
     // block-local coordinates: output tile rows i (0 .. cols_blk) = source columns, output tile columns j (0 .. rows_blk) = source rows
     const int64_t i0 = (int64_t)ti * 64, j0 = (int64_t)tj * 64;
     const T *src = b_local + (int64_t)h * rows_blk;                    // rows c0(h) of the local slab
@@ -93,11 +98,10 @@ __global__ void __launch_bounds__(256) transpose_a2a_kernel(A2APeers peers, cons
 }
 
 // The same data kernel with the store phase handed to TMA (opt-in, `a2a.tma_store`): the transposed tile is laid out densely and
-// ONE cp.async.bulk.tensor.2d store per tile moves it into the destination slab.  A 1-D bulk copy kernel reaches 697 GB/s over
-// NVLink on this box where cudaMemcpyPeer and 128-bit st.global reach ~550 (tools/p2p_bw.py); the 2-D tile stores -- 64 x 64 or
-// 256 x 16 tiles, i.e. 256-byte or 1-KiB destination runs -- stay at 550 as well, and capping the resident CTAs makes it slower,
-// so neither run length nor writer count is the limiter.  The dense layout costs bank conflicts on the transposing shared-memory
-// writes, which do not matter: a tile needs ~7000 cycles of NVLink time per SM.
+// ONE cp.async.bulk.tensor.2d store per tile (64 x 64, or 256 x 16 for 1-KiB destination runs) moves it into the destination slab.
+// Measured the same as the plain 128-bit stores (tools/a2a_time.py): linear copies to a peer reach 699 GB/s with either store
+// type (tools/p2p_bw.py; cudaMemcpyPeer: 544), this kernel 681.  The dense layout costs bank conflicts on the transposing
+// shared-memory writes, which do not matter: a tile needs ~7000 cycles of NVLink time per SM.
 struct A2AMaps {
     CUtensorMap m[kSymMaxRanks];
 };
@@ -105,13 +109,15 @@ struct A2AMaps {
 // (NVLink likes long runs: 64 x 64 tiles, i.e. 256-byte runs, stay at the 555 GB/s of plain stores), 64 x 64 is the fallback shape.
 template <typename T, int TI, int TJ>
 __global__ void __launch_bounds__(256) transpose_a2a_tma_kernel(const __grid_constant__ A2AMaps maps, const T *__restrict__ b_local,
-                                                                int64_t ld_src, int64_t rows_blk, int row_off, int tiles_j, int first_dst) {
+                                                                int64_t ld_src, int64_t rows_blk, int row_off, int tiles_i, int tiles_j, int first_dst,
+                                                                int order, int world) {
     constexpr int V = 16 / sizeof(T), CI = TI / V, CJ = TJ / V, PASSES = CI * CJ / 256;
     static_assert(CI * CJ % 256 == 0 && 256 % CJ == 0, "tile must be a whole number of passes of 256 threads");
     __shared__ __align__(128) V16<T> tile[TJ * CI];   // [j][chunk of i], dense: exactly the box the tensor map describes
     const int t = threadIdx.x;
-    const int h = (first_dst + (int)blockIdx.y) % (int)gridDim.y;
-    const int tj = blockIdx.x % tiles_j, ti = blockIdx.x / tiles_j;
+    const int h = (first_dst + (int)(blockIdx.x % (unsigned)world)) % world;   // destinations interleaved over consecutive CTAs
+    const unsigned tile_id = blockIdx.x / (unsigned)world;
+    const int tj = order ? tile_id / tiles_i : tile_id % tiles_j, ti = order ? tile_id % tiles_i : tile_id / tiles_j;
     const int64_t i0 = (int64_t)ti * TI, j0 = (int64_t)tj * TJ;
     const T *src = b_local + (int64_t)h * rows_blk;
     const int jq = t % CJ;
@@ -259,10 +265,11 @@ extern "C" b200_status b200_transpose_alltoall(void *a_sym, const void *b_local,
     A2APeers peers;
     for (int r = 0; r < kSymMaxRanks; ++r) peers.dst[r] = r < G ? h->peer[r] : nullptr;
     const int tiles_i = (int)(cols_blk / 64), tiles_j = (int)(rows_blk / 64);
-    if ((int64_t)tiles_i * tiles_j > INT32_MAX) return set_error(B200_ERR_UNSUPPORTED, "b200_transpose_alltoall: too many tiles");
-    const dim3 grid((unsigned)(tiles_i * tiles_j), (unsigned)G);
-    // a2a.tma_store = 1 selects the TMA-store variant; measured equal to the plain stores (0.483 vs 0.486 ms for 16384^2 on two
-    // GPUs, both at the ~550 GB/s per direction that cudaMemcpyPeer reaches on this box), so the simpler kernel is the default
+    if ((int64_t)tiles_i * tiles_j * G > INT32_MAX) return set_error(B200_ERR_UNSUPPORTED, "b200_transpose_alltoall: too many tiles");
+    const dim3 grid((unsigned)(tiles_i * tiles_j * G));
+    const int order = tune_get("a2a.order", 1);
+    // a2a.tma_store = 1 selects the TMA-store variant; measured equal to the plain stores (0.3944 vs 0.3945 ms for 16384^2 on two
+    // GPUs = 681 GB/s of NVLink egress, where a linear copy kernel reaches 699 and cudaMemcpyPeer 544), so the simpler kernel is the default
     if (tune_get("a2a.tma_store", 0) != 0 && N1 < (1LL << 31) && rows_blk < (1LL << 31)) {
         const bool wide = cols_blk % 256 == 0 && rows_blk % 16 == 0 && tune_get("a2a.wide_tiles", 1) != 0;
         const int TI = wide ? 256 : 64, TJ = wide ? 16 : 64;
@@ -272,25 +279,26 @@ extern "C" b200_status b200_transpose_alltoall(void *a_sym, const void *b_local,
             B200_TRY(pipe::make_tmap_2d(&maps.m[r], elsize == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64, elsize,
                                         h->peer[r], N1, rows_blk, N1, TI, TJ, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE));
         const int tj_n = (int)(rows_blk / TJ);
-        const dim3 g2((unsigned)((cols_blk / TI) * tj_n), (unsigned)G);
+        if ((cols_blk / TI) * tj_n * G > INT32_MAX) return set_error(B200_ERR_UNSUPPORTED, "b200_transpose_alltoall: too many tiles");
+        const dim3 g2((unsigned)((cols_blk / TI) * tj_n * G));
         const int roff = (int)(h->rank * cols_blk);
         if (elsize == 4 && wide)
-            transpose_a2a_tma_kernel<uint32_t, 256, 16><<<g2, 256, 0, st>>>(maps, (const uint32_t *)b_local, N0, rows_blk, roff, tj_n, h->rank);
+            transpose_a2a_tma_kernel<uint32_t, 256, 16><<<g2, 256, 0, st>>>(maps, (const uint32_t *)b_local, N0, rows_blk, roff, (int)(cols_blk / TI), tj_n, h->rank, order, G);
         else if (elsize == 4)
-            transpose_a2a_tma_kernel<uint32_t, 64, 64><<<g2, 256, 0, st>>>(maps, (const uint32_t *)b_local, N0, rows_blk, roff, tj_n, h->rank);
+            transpose_a2a_tma_kernel<uint32_t, 64, 64><<<g2, 256, 0, st>>>(maps, (const uint32_t *)b_local, N0, rows_blk, roff, (int)(cols_blk / TI), tj_n, h->rank, order, G);
         else if (wide)
-            transpose_a2a_tma_kernel<uint64_t, 256, 16><<<g2, 256, 0, st>>>(maps, (const uint64_t *)b_local, N0, rows_blk, roff, tj_n, h->rank);
+            transpose_a2a_tma_kernel<uint64_t, 256, 16><<<g2, 256, 0, st>>>(maps, (const uint64_t *)b_local, N0, rows_blk, roff, (int)(cols_blk / TI), tj_n, h->rank, order, G);
         else
-            transpose_a2a_tma_kernel<uint64_t, 64, 64><<<g2, 256, 0, st>>>(maps, (const uint64_t *)b_local, N0, rows_blk, roff, tj_n, h->rank);
+            transpose_a2a_tma_kernel<uint64_t, 64, 64><<<g2, 256, 0, st>>>(maps, (const uint64_t *)b_local, N0, rows_blk, roff, (int)(cols_blk / TI), tj_n, h->rank, order, G);
         B200_CHECK_LAUNCH("transpose_a2a_tma_kernel");
         return b200_sym_barrier(a_sym);
     }
     if (elsize == 4)
         transpose_a2a_kernel<uint32_t><<<grid, 256, 0, st>>>(peers, (const uint32_t *)b_local, N0, N1, rows_blk, (int64_t)h->rank * cols_blk,
-                                                            tiles_i, tiles_j, h->rank);
+                                                            tiles_i, tiles_j, h->rank, order, G);
     else
         transpose_a2a_kernel<uint64_t><<<grid, 256, 0, st>>>(peers, (const uint64_t *)b_local, N0, N1, rows_blk, (int64_t)h->rank * cols_blk,
-                                                            tiles_i, tiles_j, h->rank);
+                                                            tiles_i, tiles_j, h->rank, order, G);
     B200_CHECK_LAUNCH("transpose_a2a_kernel");
     return b200_sym_barrier(a_sym);
 }

@@ -26,11 +26,14 @@ def timed(fn, steps=20):
     ms = C.c_float(); _lib.call("b200_event_elapsed_ms", e0, e1, C.byref(ms))
     t = torch.tensor([ms.value / steps], dtype=torch.float64, device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
-for tma in (1, 0):
-    _lib.call("b200_tune_set", b"a2a.tma_store", tma)
-    ms = timed(lambda: mg.transpose_alltoall_(a_sym, b_loc, N, N))
-    remote = N * rb * 4 * (world - 1) / world
-    if rank == 0:
-        print(f"world {world} tma_store={tma}: {ms:.4f} ms/step, NVLink egress {remote / ms / 1e6:.0f} GB/s per GPU", flush=True)
+for order in (0, 1):
+    for tma in (0, 1):
+        _lib.call("b200_tune_set", b"a2a.tma_store", tma)
+        _lib.call("b200_tune_set", b"a2a.order", order)
+        ms = timed(lambda: mg.transpose_alltoall_(a_sym, b_loc, N, N))
+        remote = N * rb * 4 * (world - 1) / world
+        if rank == 0:
+            print(f"world {world} order={order} tma_store={tma}: {ms:.4f} ms/step, NVLink egress {remote / ms / 1e6:.0f} GB/s per GPU", flush=True)
 _lib.call("b200_tune_set", b"a2a.tma_store", 0)
+_lib.call("b200_tune_set", b"a2a.order", 1)
 KA.synchronize(be); dist.barrier(); a_sym.free(); dist.destroy_process_group()

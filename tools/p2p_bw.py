@@ -26,6 +26,14 @@ def timed(fn, steps=20):
     return ms.value / steps
 ms = timed(lambda: _lib.call("b200_memcpy_d2d_async", C.c_void_p(peer), C.c_void_p(src.ptr), C.c_size_t(nbytes)))
 print(rank, "cudaMemcpyAsync to peer (all ranks at once, ring):", round(nbytes / ms / 1e6, 1), "GB/s", flush=True)
-ms = timed(lambda: _lib.call("b200_copy", C.c_void_p(peer), C.c_void_p(src.ptr), C.c_size_t(nbytes)))
-print(rank, "b200_copy (TMA bulk kernel) to peer:", round(nbytes / ms / 1e6, 1), "GB/s", flush=True)
+for knobs in ({"copy.impl": 1, "copy.bulk_stage_kb": 16}, {"copy.impl": 1, "copy.bulk_stage_kb": 4, "copy.bulk_stages": 8},
+              {"copy.impl": 1, "copy.bulk_stage_kb": 1, "copy.bulk_stages": 8}, {"copy.impl": 1, "copy.bulk_stage_kb": 32, "copy.bulk_stages": 4},
+              {"copy.impl": 1, "copy.bulk_stage_kb": 16, "copy.bulk_ctas_per_sm": 2}, {"copy.impl": 0}):
+    for k, v in knobs.items():
+        _lib.call("b200_tune_set", k.encode(), v)
+    ms = timed(lambda: _lib.call("b200_copy", C.c_void_p(peer), C.c_void_p(src.ptr), C.c_size_t(nbytes)))
+    if rank == 0:
+        print(rank, "b200_copy to peer", knobs, ":", round(nbytes / ms / 1e6, 1), "GB/s", flush=True)
+    for k in knobs:
+        _lib.call("b200_tune_set", k.encode(), {"copy.impl": 1, "copy.bulk_stage_kb": 16, "copy.bulk_stages": 4, "copy.bulk_ctas_per_sm": 1}[k])
 KA.synchronize(be); dist.barrier(); sym.free(); dist.destroy_process_group()
