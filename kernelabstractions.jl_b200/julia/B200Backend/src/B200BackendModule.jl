@@ -17,6 +17,7 @@ module B200BackendModule
 import KernelAbstractions as KA
 import KernelAbstractions.KernelIntrinsics as KI
 import Adapt
+import LinearAlgebra
 
 export B200Backend, B200Array
 
@@ -136,10 +137,7 @@ Base.Broadcast.materialize!(A::B200Array, bc::Base.Broadcast.Broadcasted{<:Any, 
 # device (csrc/kernels/arrayops.cu) so the examples run without host round trips.  Mixed host/device operands fall back
 # to a host copy.
 # ---------------------------------------------------------------------------------------------------------
-eltype_code(::Type{Int32}) = Int32(5);  eltype_code(::Type{UInt32}) = Int32(6)
-eltype_code(::Type{Int64}) = Int32(7);  eltype_code(::Type{UInt64}) = Int32(8)
-eltype_code(::Type{Float32}) = Int32(11); eltype_code(::Type{Float64}) = Int32(12)
-eltype_code(::Type{Bool}) = Int32(13);  eltype_code(::Type) = Int32(0)
+# (eltype_code(T): the B200_T_* code of an element type, defined with the argument marshalling below)
 const Reducible = Union{Int32, UInt32, Int64, UInt64, Float32, Float64}
 sumtype(::Type{T}) where {T <: Signed} = Int64
 sumtype(::Type{T}) where {T <: Unsigned} = UInt64
@@ -180,7 +178,7 @@ Base.isapprox(A::B200Array, B::AbstractArray; kw...) = isapprox(Array(A), B isa 
 Base.isapprox(A::AbstractArray, B::B200Array; kw...) = isapprox(B, A; kw...)
 
 # LinearAlgebra.mul!(C, A, B) / A * B -> the FP32 SIMT GEMM in the reference kernel's summation order (mode 0)
-function mul!(C::B200Array{Float32, 2}, A::B200Array{Float32, 2}, B::B200Array{Float32, 2})
+function LinearAlgebra.mul!(C::B200Array{Float32, 2}, A::B200Array{Float32, 2}, B::B200Array{Float32, 2})
     (size(A, 2) == size(B, 1) && size(C) == (size(A, 1), size(B, 2))) || throw(DimensionMismatch("mul!"))
     M, K, N = size(A, 1), size(A, 2), size(B, 2)
     (M == 0 || N == 0) && return C
@@ -188,7 +186,7 @@ function mul!(C::B200Array{Float32, 2}, A::B200Array{Float32, 2}, B::B200Array{F
     @b200 b200_matmul_f32 (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Int64, Int64, Int64, Int64, Int32) C.ptr A.ptr B.ptr M K N M K M Int32(0)
     return C
 end
-Base.:*(A::B200Array{Float32, 2}, B::B200Array{Float32, 2}) = mul!(B200Array{Float32, 2}(undef, (size(A, 1), size(B, 2))), A, B)
+Base.:*(A::B200Array{Float32, 2}, B::B200Array{Float32, 2}) = LinearAlgebra.mul!(B200Array{Float32, 2}(undef, (size(A, 1), size(B, 2))), A, B)
 
 # opt-in tensor-core products (no reference twin): C = A * B with TF32 / BF16 tcgen05 arithmetic, FP32 storage
 function matmul_tf32!(C::B200Array{Float32, 2}, A::B200Array{Float32, 2}, B::B200Array{Float32, 2})

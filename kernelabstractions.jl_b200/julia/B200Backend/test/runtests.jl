@@ -12,8 +12,8 @@ include(joinpath(pkgdir(KernelAbstractions), "test", "testsuite.jl"))
         Testsuite.testsuite(
             B200Backend, "B200", B200BackendModule, B200Array, B200Array;
             skip_tests = Set([
-                "Const", "Reflection", "Printing", "SpecialFunctions", "Convert", "sparse",
-                "fallback test: callable types", "unaliased",
+                "Const", "Reflection", "Printing", "sparse",       # need Julia IR / device printf / SparseArrays adaptors
+                "fallback test: callable types",                     # a kernel defined on a callable type has no name to dispatch on
             ]),
         )
     else
