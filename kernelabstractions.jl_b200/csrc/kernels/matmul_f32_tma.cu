@@ -34,7 +34,7 @@ namespace b200 {
 namespace sg {
 
 constexpr int BM = 128, BN = 128, BK = 16;
-constexpr int STAGES = 8;
+constexpr int STAGES = 8;                    // measured with the producer warp group: 6 stages 57.2, 8 stages 57.3, 12 stages 56.5 TFLOP/s
 constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4, STAGE_BYTES = A_BYTES + B_BYTES;
 // MI = float4 row groups per thread: 2 -> 8 warps (2 x 4), thread tile 8 x nj; 1 -> 16 warps (4 x 4), thread tile 4 x nj
 constexpr int consumer_warps(int MI) { return 16 / MI; }
