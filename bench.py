@@ -511,6 +511,28 @@ def run_suite(KA, _lib, EX, mg, orc, be, rank, world, dist, timed, peaks, steps,
             peers.free()
         if comm is not None:
             comm.destroy()
+        if world == 1:
+            try:   # e2e: Int32 input in pinned HOST memory, bins back on the host; h2d | counting overlapped by slabs (b200_histogram_i32_host)
+                hp = C.c_void_p()
+                _lib.call("b200_host_alloc", C.byref(hp), 4 * n)
+                h_in = np.ctypeslib.as_array((C.c_int32 * n).from_address(hp.value))
+                h_in[...] = inp
+                h_bins = np.zeros(256, dtype=np.int32)
+                EX.histogram_host_(be, h_bins, h_in)
+                KA.synchronize(be)
+                ok_e = bool(np.array_equal(h_bins, got))
+                t0 = time.perf_counter()
+                for _ in range(3):
+                    h_bins[:] = 0
+                    EX.histogram_host_(be, h_bins, h_in)
+                    KA.synchronize(be)
+                dt = (time.perf_counter() - t0) / 3
+                out["histogram_2^30_i32_256bins"]["e2e"] = {"value": 4.0 * n / dt / 1e9, "unit": "GB/s", "h2d_bytes_per_step": 4 * n,
+                                                            "d2h_bytes_per_step": 1024, "ms_per_step": dt * 1e3, "steps": 3, "result_checked": ok_e,
+                                                            "path": "EX.histogram_host_ -> b200_histogram_i32_host: pinned host input, slab-wise h2d | counting"}
+                _lib.call("b200_host_free", hp)
+            except Exception as ex:
+                out["histogram_2^30_i32_256bins"]["e2e"] = {"value": None, "error": str(ex)[:200]}
         del d_in, bins
         if cpu:
             hbins = np.zeros(256, dtype=np.int32)
@@ -540,6 +562,36 @@ def run_suite(KA, _lib, EX, mg, orc, be, rank, world, dist, timed, peaks, steps,
         out["matmul_f32_8192"] = {"value": tf, "unit": "TFLOP/s", "ms_per_step": ms, "gpu_launches": launches, "scaling": "strong",
                                   "roofline": {"bound": "fma", "achieved": tf / world, "peak": fma_peak, "frac": tf / world / fma_peak,
                                                "peak_source": "148 SM x 128 lanes x 2 x sm_max_mhz"}}
+        if world == 1:
+            try:   # e2e: A, B in pinned HOST memory, C back to the host: copyto! in, performant_matmul!, copyto! out, synchronize
+                hp = [C.c_void_p() for _ in range(3)]
+                for q in hp:
+                    _lib.call("b200_host_alloc", C.byref(q), 4 * n * n)
+                hA_, hB_, hC_e = (np.ctypeslib.as_array((C.c_float * (n * n)).from_address(q.value)).reshape((n, n), order="F") for q in hp)
+                hA_[...] = KA.Array(Ap)
+                hB_[...] = KA.Array(dBm)
+
+                def step_mm_e2e():
+                    KA.copyto_(be, Ap, hA_)
+                    KA.copyto_(be, dBm, hB_)
+                    EX.performant_matmul_(dC, Ap, dBm)
+                    KA.copyto_(be, hC_e, dC)
+                    KA.synchronize(be)
+
+                step_mm_e2e()
+                t0 = time.perf_counter()
+                for _ in range(2):
+                    step_mm_e2e()
+                dt = (time.perf_counter() - t0) / 2
+                truth_row = hA_[7, :].astype(np.float64) @ hB_[:, :64].astype(np.float64)
+                out["matmul_f32_8192"]["e2e"] = {"value": 2.0 * n ** 3 / dt / 1e12, "unit": "TFLOP/s", "h2d_bytes_per_step": 8 * n * n,
+                                                 "d2h_bytes_per_step": 4 * n * n, "ms_per_step": dt * 1e3, "steps": 2,
+                                                 "result_checked": bool(np.allclose(hC_e[7, :64], truth_row, rtol=1e-5)),
+                                                 "path": "KA.copyto! (pinned host -> device) x2, EX.performant_matmul_, KA.copyto! (device -> host), KA.synchronize"}
+                for q in hp:
+                    _lib.call("b200_host_free", q)
+            except Exception as ex:
+                out["matmul_f32_8192"]["e2e"] = {"value": None, "error": str(ex)[:200]}
         if cpu:
             ms_ = 2048
             hA_, hB_ = orc.gen_uniform_f32((ms_, ms_), 1237), orc.gen_uniform_f32((ms_, ms_), 1238)
