@@ -272,6 +272,10 @@ b200_status b200_rand_bins_i32(int32_t *out, size_t n, uint64_t seed, int32_t nb
 b200_status b200_transpose_host(void *a_host, const void *b_host, int64_t m, int64_t n, int64_t lda, int64_t ldb,
                                 int32_t elsize);
 b200_status b200_histogram_i32_host(int32_t *bins_host, int64_t nbins, const int32_t *input_host, int64_t n);
+/* C = A * B on HOST arrays (FP32, column-major, `mode` as b200_matmul_f32): B is uploaded once, A row panels stream in and
+ * C row panels stream out while the panels in between are multiplied.  Same bits as the device-resident product. */
+b200_status b200_matmul_f32_host(float *C_host, const float *A_host, const float *B_host, int64_t M, int64_t K, int64_t N,
+                                 int64_t lda, int64_t ldb, int64_t ldc, int32_t mode);
 
 /* ---- multi-GPU plumbing (pattern: examples/mpi.jl:24-39; NCCL over NVLink) ------------------ */
 #define B200_UNIQUE_ID_BYTES 128

@@ -161,6 +161,7 @@ SIGNATURES = {
     "b200_rand_uniform_f32": (_I32, [_VP, _SZ, C.c_uint64]),
     "b200_rand_bins_i32": (_I32, [_VP, _SZ, C.c_uint64, _I32]),
     "b200_transpose_host": (_I32, [_VP, _VP, _I64, _I64, _I64, _I64, _I32]),
+    "b200_matmul_f32_host": (_I32, [_VP, _VP, _VP, _I64, _I64, _I64, _I64, _I64, _I64, _I32]),
     "b200_histogram_i32_host": (_I32, [_VP, _I64, _VP, _I64]),
     "b200_comm_unique_id": (_I32, [_VP]),
     "b200_comm_init_rank": (_I32, [_PVP, _I32, _I32, _VP]),

@@ -170,3 +170,18 @@ def histogram_host_(backend: B200Backend, histogram_output: np.ndarray, input: n
         raise _lib.ArgumentError("histogram_host_: Int32 input and bins only")
     _lib.call("b200_histogram_i32_host", C.c_void_p(histogram_output.ctypes.data), histogram_output.size,
               C.c_void_p(np.ascontiguousarray(input).ctypes.data), input.size)
+
+
+def performant_matmul_host_(backend: B200Backend, C_: np.ndarray, A: np.ndarray, B: np.ndarray, mode: int = _lib.B200_MATMUL_TILE16) -> None:
+    """reference examples/performant_matmul.jl:79-92 on host Arrays (Float32, column-major): B is uploaded once, row panels of
+    A stream in and row panels of C stream out while the panels in between are multiplied; stream ordered."""
+    for name, x in (("C", C_), ("A", A), ("B", B)):
+        _host_f(x, name)
+        if x.dtype != np.float32 or x.ndim != 2:
+            raise _lib.ArgumentError("performant_matmul_host_: Float32 matrices only")
+    M, K = A.shape
+    N = B.shape[1]
+    if B.shape[0] != K or C_.shape != (M, N):
+        raise _lib.ArgumentError("performant_matmul_host_: shapes do not conform")
+    _lib.call("b200_matmul_f32_host", C.c_void_p(C_.ctypes.data), C.c_void_p(A.ctypes.data), C.c_void_p(B.ctypes.data), M, K, N, M, K, M,
+              C.c_int32(mode))

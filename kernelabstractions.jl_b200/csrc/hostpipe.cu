@@ -18,6 +18,8 @@ namespace b200 {
 
 int transpose_launch(void *a, const void *b, int64_t m, int64_t n, int64_t lda, int64_t ldb, int elsize, cudaStream_t st);
 int histogram_launch(int32_t *bins, int64_t nbins, const int32_t *input, int64_t n, cudaStream_t st);
+int sgemm_launch(float *C, const float *A, const float *B, int64_t M, int64_t K, int64_t N, int64_t lda, int64_t ldb, int64_t ldc, int mode,
+                 cudaStream_t st);
 
 namespace {
 
@@ -175,5 +177,59 @@ extern "C" b200_status b200_histogram_i32_host(int32_t *bins_host, int64_t nbins
     B200_CUDA(cudaMemcpyAsync(bins_host, d_bins, (size_t)nbins * 4, cudaMemcpyDeviceToHost, p->s_k));
     B200_CUDA(cudaEventRecord(p->out_done[0], p->s_k));
     B200_CUDA(cudaStreamWaitEvent(user, p->out_done[0], 0));
+    return B200_OK;
+}
+
+// C (M x N, ldc) = A (M x K, lda) * B (K x N, ldb), all in host memory, FP32, summation order `mode` of b200_matmul_f32
+// (coalesced_matmul_kernel!, examples/performant_matmul.jl:79-92, on plain host Arrays).  B goes to the device once; A is streamed
+// as row panels (pitched h2d into a dense panel), each panel's product is computed while the next panel arrives and the
+// previous C panel leaves (pitched d2h).  k is never split, so every bit equals the one-shot device product.
+extern "C" b200_status b200_matmul_f32_host(float *C_host, const float *A_host, const float *B_host, int64_t M, int64_t K, int64_t N,
+                                            int64_t lda, int64_t ldb, int64_t ldc, int32_t mode) {
+    if (M < 0 || N < 0 || K < 0 || lda < M || ldb < K || ldc < M) return set_error(B200_ERR_INVALID_VALUE, "b200_matmul_f32_host: bad shape");
+    if (M == 0 || N == 0) return B200_OK;
+    if (!C_host || (K > 0 && (!A_host || !B_host))) return set_error(B200_ERR_INVALID_VALUE, "b200_matmul_f32_host: NULL pointer");
+    cudaStream_t user;
+    B200_TRY(current_stream(&user));
+    // panel height: a multiple of 128 rows (the GEMM's tile), sized so that a panel's A and C pieces are ~hostpipe.slab_mib MiB
+    const int64_t target = (int64_t)tune_get("hostpipe.slab_mib", 32) << 20;
+    int64_t mp = target / (4 * (K > N ? K : N));
+    mp = mp / 128 * 128;
+    if (mp < 128) mp = 128;
+    if (mp > M) mp = M;
+    const int64_t npanels = cdiv(M, mp);
+    const int64_t kpad = (K + 3) / 4 * 4;                                  // device B with ld % 4 == 0 keeps the TMA engine eligible
+    const size_t b_bytes = align_up((size_t)kpad * (size_t)N * 4, 256);
+    const size_t a_bytes = align_up((size_t)mp * (size_t)(K ? K : 1) * 4, 256), c_bytes = align_up((size_t)mp * (size_t)N * 4, 256);
+    HostPipe *p = nullptr;
+    B200_TRY(get_pipe(&p, b_bytes + NBUF * (a_bytes + c_bytes)));
+    float *dB = (float *)p->ws;
+    char *abuf = (char *)p->ws + b_bytes, *cbuf = abuf + NBUF * a_bytes;
+
+    B200_CUDA(cudaEventRecord(p->start, user));
+    B200_CUDA(cudaStreamWaitEvent(p->s_in, p->start, 0));
+    B200_CUDA(cudaStreamWaitEvent(p->s_k, p->start, 0));
+    B200_CUDA(cudaStreamWaitEvent(p->s_out, p->start, 0));
+    if (K > 0) {
+        if (kpad != K) B200_CUDA(cudaMemsetAsync(dB, 0, (size_t)kpad * (size_t)N * 4, p->s_in));   // padding rows never enter a product
+        B200_CUDA(cudaMemcpy2DAsync(dB, (size_t)kpad * 4, B_host, (size_t)ldb * 4, (size_t)K * 4, (size_t)N, cudaMemcpyHostToDevice, p->s_in));
+    }
+    for (int64_t s = 0; s < npanels; ++s) {
+        const int i = (int)(s % NBUF);
+        const int64_t m0 = s * mp, mh = (m0 + mp <= M) ? mp : M - m0;
+        float *dA = (float *)(abuf + (size_t)i * a_bytes), *dC = (float *)(cbuf + (size_t)i * c_bytes);
+        if (s >= NBUF) B200_CUDA(cudaStreamWaitEvent(p->s_in, p->k_done[i], 0));
+        if (K > 0)   // rows [m0, m0+mh) of A: K columns of mh floats, host pitch lda -> dense panel (ld = mp keeps 16-byte aligned columns)
+            B200_CUDA(cudaMemcpy2DAsync(dA, (size_t)mp * 4, A_host + m0, (size_t)lda * 4, (size_t)mh * 4, (size_t)K, cudaMemcpyHostToDevice, p->s_in));
+        B200_CUDA(cudaEventRecord(p->in_done[i], p->s_in));
+        B200_CUDA(cudaStreamWaitEvent(p->s_k, p->in_done[i], 0));
+        if (s >= NBUF) B200_CUDA(cudaStreamWaitEvent(p->s_k, p->out_done[i], 0));
+        B200_TRY(sgemm_launch(dC, dA, dB, mh, K, N, mp, kpad, mp, mode, p->s_k));
+        B200_CUDA(cudaEventRecord(p->k_done[i], p->s_k));
+        B200_CUDA(cudaStreamWaitEvent(p->s_out, p->k_done[i], 0));
+        B200_CUDA(cudaMemcpy2DAsync(C_host + m0, (size_t)ldc * 4, dC, (size_t)mp * 4, (size_t)mh * 4, (size_t)N, cudaMemcpyDeviceToHost, p->s_out));
+        B200_CUDA(cudaEventRecord(p->out_done[i], p->s_out));
+    }
+    B200_CUDA(cudaStreamWaitEvent(user, p->out_done[(npanels - 1) % NBUF], 0));
     return B200_OK;
 }

@@ -188,6 +188,23 @@ function LinearAlgebra.mul!(C::B200Array{Float32, 2}, A::B200Array{Float32, 2}, 
 end
 Base.:*(A::B200Array{Float32, 2}, B::B200Array{Float32, 2}) = LinearAlgebra.mul!(B200Array{Float32, 2}(undef, (size(A, 1), size(B, 2))), A, B)
 
+# host-array forms (csrc/hostpipe.cu): plain Arrays in and out, slabs streamed through the GPU with h2d | kernel | d2h overlapped;
+# stream ordered -- KA.synchronize(B200Backend()) completes them; page-lock the arrays (KA.pagelock!) for full PCIe speed
+function transpose_host!(a::Matrix{T}, b::Matrix{T}) where {T}
+    size(a) == reverse(size(b)) || (println("Matrix size mismatch!"); return nothing)      # examples/naive_transpose.jl:12-15
+    GC.@preserve a b @b200 b200_transpose_host (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Int64, Int64, Int32) pointer(a) pointer(b) size(a, 1) size(a, 2) size(a, 1) size(b, 1) Int32(sizeof(T))
+    return nothing
+end
+function histogram_host!(bins::Vector{Int32}, input::Vector{Int32})
+    GC.@preserve bins input @b200 b200_histogram_i32_host (Ptr{Int32}, Int64, Ptr{Int32}, Int64) pointer(bins) length(bins) pointer(input) length(input)
+    return nothing
+end
+function matmul_host!(C::Matrix{Float32}, A::Matrix{Float32}, B::Matrix{Float32}; mode::Integer = 0)
+    (size(A, 2) == size(B, 1) && size(C) == (size(A, 1), size(B, 2))) || throw(DimensionMismatch("matmul_host!"))
+    GC.@preserve C A B @b200 b200_matmul_f32_host (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Int64, Int64, Int64, Int64, Int32) pointer(C) pointer(A) pointer(B) size(A, 1) size(A, 2) size(B, 2) size(A, 1) size(B, 1) size(C, 1) Int32(mode)
+    return nothing
+end
+
 # opt-in tensor-core products (no reference twin): C = A * B with TF32 / BF16 tcgen05 arithmetic, FP32 storage
 function matmul_tf32!(C::B200Array{Float32, 2}, A::B200Array{Float32, 2}, B::B200Array{Float32, 2})
     M, K, N = size(A, 1), size(A, 2), size(B, 2)

@@ -488,6 +488,35 @@ def test_histogram_int64_matches_int32_oracle(orc, n, nbins):
         assert np.array_equal(KA.Array(bins2), w2.astype(np.int64))
 
 
+@pytest.mark.parametrize("shape,slab_mib", [((256, 64, 128), 32), ((1000, 300, 260), 1), ((130, 17, 129), 1), ((2048, 512, 1024), 1), ((129, 1, 3), 32)])
+def test_matmul_host_pipeline_matches_oracle_and_device(orc, shape, slab_mib):
+    # performant_matmul! on host Arrays: B uploaded once, A / C row panels streamed; every bit equal to the device-resident product
+    M, Kd, N = shape
+    tune(hostpipe__slab_mib=slab_mib)
+    try:
+        A = orc.gen_uniform_f32((M, Kd), 1237) - 0.5
+        B = orc.gen_uniform_f32((Kd, N), 1238) - 0.5
+        Ch = np.full((M, N), -7.0, dtype=np.float32, order="F")
+        KA.pagelock_(be, A)
+        EX.performant_matmul_host_(be, Ch, A, B)
+        KA.synchronize(be)
+        dC = KA.zeros(be, np.float32, M, N)
+        EX.performant_matmul_(dC, KA.to_device(A), KA.to_device(B))
+        assert np.array_equal(Ch.view(np.uint32), KA.Array(dC).view(np.uint32))
+        if M * Kd * N <= 1 << 26:
+            ref = F((M, N), np.float32)
+            orc.coalesced_matmul(ref, A, B)
+            assert np.array_equal(Ch.view(np.uint32), ref.view(np.uint32))
+        Ch2 = np.zeros((M, N), dtype=np.float32, order="F")       # a second call right behind the first reuses the workspace
+        EX.performant_matmul_host_(be, Ch2, A, B)
+        EX.performant_matmul_host_(be, Ch, A, B)
+        KA.synchronize(be)
+        assert np.array_equal(Ch2, Ch)
+    finally:
+        KA.unpagelock_(be, A)
+        tune(hostpipe__slab_mib=32)
+
+
 # =====================================================================================================
 # host-buffer pipeline (b200_transpose_host / b200_histogram_i32_host): same bits as the oracle, host arrays in and out
 # =====================================================================================================
