@@ -153,6 +153,7 @@ SIGNATURES = {
     "b200_matmul_f32": (_I32, [_VP, _VP, _VP, _I64, _I64, _I64, _I64, _I64, _I64, _I32]),
     "b200_matmul_bf16": (_I32, [_VP, _VP, _VP, _I64, _I64, _I64, _I64]),
     "b200_matmul_tf32": (_I32, [_VP, _VP, _VP, _I64, _I64, _I64, _I64, _I64, _I64]),
+    "b200_matmul_f32_tf32x3": (_I32, [_VP, _VP, _VP, _I64, _I64, _I64, _I64, _I64, _I64, _VP]),
     "b200_convert_f32_bf16": (_I32, [_VP, _VP, _I64, _I64, _I64, _I32]),
     "b200_matmul_f32_via_bf16": (_I32, [_VP, _VP, _VP, _I64, _I64, _I64, _I64, _I64, _I64, _VP]),
     "b200_reduce": (_I32, [_I32, _I32, _VP, _SZ, _VP]),

@@ -143,6 +143,17 @@ def matmul_tf32_(C_: B200Array, A: B200Array, B: B200Array) -> None:
     _lib.call("b200_matmul_tf32", C.c_void_p(C_.ptr), C.c_void_p(A.ptr), C.c_void_p(B.ptr), M, K, N, M, K, M)
 
 
+def matmul_tf32x3_(C_: B200Array, A: B200Array, B: B200Array, workspace: B200Array = None) -> None:
+    """Opt-in FP32-grade tensor-core product ("3xTF32", no reference twin): split operands, three tcgen05 MMAs per k step, K
+    accumulated in chunks that are added to C in FP32.  rtol 1e-5 against Float64 for the examples' inputs, not bit-exact."""
+    M, K = A.shape
+    N = B.shape[1]
+    if B.shape[0] != K or C_.shape != (M, N):
+        raise _lib.ArgumentError("matmul_tf32x3_: shapes do not conform")
+    ws = workspace if workspace is not None else allocate(B200Backend(), np.float32, (M * K + K * N,))
+    _lib.call("b200_matmul_f32_tf32x3", C.c_void_p(C_.ptr), C.c_void_p(A.ptr), C.c_void_p(B.ptr), M, K, N, M, K, M, C.c_void_p(ws.ptr))
+
+
 # ---- host-array forms: what `naive_transpose!(a, b)` / `histogram!(out, in)` are for a CPU() user -- plain host
 # ---- arrays in and out -- executed by B200Backend as a slab pipeline (h2d | kernel | d2h overlapped).
 def _host_f(arr: np.ndarray, name: str) -> np.ndarray:

@@ -182,22 +182,30 @@ __device__ __forceinline__ void umma_pair(uint32_t tmem_d, uint64_t desc_a, uint
 // NCTA = 1: one CTA per 128 x bn tile.  NCTA = 2: a CTA pair (cluster of 2, one TPC) per 256 x bn tile -- each CTA stages
 // its own 128 rows of A and HALF of the tile's B columns; the leader's tcgen05.mma.cta_group::2 (M = 256) reads both
 // halves, so every SM pulls 16 + 16 KiB per k block through L2 instead of 16 + 32, and six stages fit instead of four.
-template <int NCTA>
+// X3 = 1 ("3xTF32", b200_matmul_f32_tf32x3): every operand is split into its TF32 head (what the tensor core reads from the FP32
+// word anyway) and the TF32 head of the remainder, A = A_hi + A_lo, B = B_hi + B_lo, and each k step issues A_lo*B_hi, A_hi*B_lo
+// and A_hi*B_hi into the same accumulator (the lo*lo term is below FP32 resolution).  A stage then holds four operand tiles.
+// The tensor core truncates when it accumulates, an error that grows linearly with k, so K is processed in chunks of
+// kb_chunk k blocks: each chunk is accumulated in TMEM and the epilogue adds it to C in FP32 with round-to-nearest.
+template <int NCTA, int X3>
 struct PipeCfg {
-    static constexpr int STAGES = NCTA == 2 ? 6 : 4;
-    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES / NCTA;
+    static constexpr int STAGES = X3 ? (NCTA == 2 ? 3 : 2) : (NCTA == 2 ? 6 : 4);
+    static constexpr int STAGE_BYTES = (1 + X3) * (A_BYTES + B_BYTES / NCTA);
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <bool TF32, int NCTA>
+template <bool TF32, int NCTA, int X3>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
     gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                        const __grid_constant__ CUtensorMap tmap_alo, const __grid_constant__ CUtensorMap tmap_blo,
                         float *__restrict__ C, int64_t ldc, int M, int N, int tiles_m, int tiles_n, int num_kb,
-                        int group_m, int bn) {
+                        int group_m, int bn, int kb_chunk) {
+    static_assert(!X3 || TF32, "the split-operand mode is a TF32 mode");
     // bn = columns per output tile (multiple of 16 NCTA, <= BN): chosen by the host so that the tile count fills whole
     // rounds of the persistent grid (pick_bn); shared-memory stages and TMEM accumulators stay sized for BN.
     constexpr int KB = TF32 ? BK_TF32 : BK;   // k elements per stage
-    constexpr int STAGES = PipeCfg<NCTA>::STAGES, STAGE_BYTES = PipeCfg<NCTA>::STAGE_BYTES;
+    constexpr int STAGES = PipeCfg<NCTA, X3>::STAGES, STAGE_BYTES = PipeCfg<NCTA, X3>::STAGE_BYTES;
+    constexpr int LO_OFF = A_BYTES + B_BYTES / NCTA;   // X3: the lo tiles follow the hi tiles inside a stage
     extern __shared__ unsigned char smem_raw[];
     // SWIZZLE_128B operands need 1024-byte aligned stage bases (the dynamic window starts at the same offset in both
     // CTAs of a pair, so the aligned bases coincide as the pair MMA requires)
@@ -269,17 +277,29 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
                     unsigned char *sb = sa + A_BYTES;
                     if (NCTA == 2) {
                         const uint32_t lead_full = mapa_u32(smem_u32(&full[stage]), 0);
-                        if (rank == 0) mbar_expect_tx(&full[stage], 2 * (A_BYTES + bnh * 128));
+                        if (rank == 0) mbar_expect_tx(&full[stage], (1 + X3) * 2 * (A_BYTES + bnh * 128));
                         if (TF32) {
 #pragma unroll
                             for (int g = 0; g < BM / 32; ++g)
                                 tma_load_2d_pair(sa + g * 4096, &tmap_a, m_base + 32 * g, kb * KB, lead_full);
+                            if (X3) {
+#pragma unroll
+                                for (int g = 0; g < BM / 32; ++g)
+                                    tma_load_2d_pair(sa + LO_OFF + g * 4096, &tmap_alo, m_base + 32 * g, kb * KB, lead_full);
+                                tma_load_2d_pair(sb + LO_OFF, &tmap_blo, kb * KB, n_base, lead_full);
+                            }
                         } else {
                             tma_load_2d_pair(sa, &tmap_a, kb * KB, m_base, lead_full);
                         }
                         tma_load_2d_pair(sb, &tmap_b, kb * KB, n_base, lead_full);
                     } else {
-                        mbar_expect_tx(&full[stage], A_BYTES + bn * 128);
+                        mbar_expect_tx(&full[stage], (1 + X3) * (A_BYTES + bn * 128));
+                        if (X3) {
+#pragma unroll
+                            for (int g = 0; g < BM / 32; ++g)
+                                tma_load_2d(sa + LO_OFF + g * 4096, &tmap_alo, m_base + 32 * g, kb * KB, &full[stage]);
+                            tma_load_2d(sb + LO_OFF, &tmap_blo, kb * KB, n_base, &full[stage]);
+                        }
                         if (TF32) {
 #pragma unroll
                             for (int g = 0; g < BM / 32; ++g)   // A slabs [k][32 m]: coordinates (m, k) of column-major A
@@ -303,13 +323,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            for (int tile = unit; tile < num_tiles; tile += num_units, ++it) {
+            for (int tile = unit; tile < num_tiles; tile += num_units) {
+              for (int kb0 = 0; kb0 < num_kb; kb0 += kb_chunk, ++it) {   // one TMEM accumulator per (tile, k chunk)
                 const int acc = it & 1;
                 const uint32_t acc_phase = (uint32_t)(it >> 1) & 1;
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
-                for (int kb = 0; kb < num_kb; ++kb) {
+                const int kb1 = min(kb0 + kb_chunk, num_kb);
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
@@ -318,14 +340,33 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
                     // TF32: A's next group of 8 k = +1024 B = 64 units; K-major operands: +32 B inside the 128-byte
                     // swizzle row = 2 units per MMA (UMMA_K * 2 bytes for BF16, UMMA_K_TF32 * 4 bytes for TF32)
                     constexpr int a_step = TF32 ? 64 : 2;
+                    const uint32_t first = (uint32_t)(kb - kb0);
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        if (NCTA == 2) {
-                            umma_pair<TF32>(tmem_d, da + (uint64_t)(a_step * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                        const uint64_t dak = da + (uint64_t)(a_step * k), dbk = db + (uint64_t)(2 * k);
+                        if (X3) {
+                            // The tensor core truncates on every accumulation, relative to the accumulator's magnitude.  The two
+                            // correction terms therefore get an accumulator of their own (columns +128 of the same buffer; bn <= 128
+                            // in this mode): their sum is ~2^-11 of the main term, so their truncation is invisible, and the
+                            // main accumulator sees one truncation per k step instead of three.
+                            const uint64_t dalk = make_desc_mn128(sa + LO_OFF) + (uint64_t)(a_step * k);
+                            const uint64_t dblk = make_desc_k128(sa + LO_OFF + A_BYTES) + (uint64_t)(2 * k);
+                            const uint32_t tmem_s = tmem_d + (uint32_t)(BN / 2);
+                            if (NCTA == 2) {
+                                umma_pair<true>(tmem_s, dalk, dbk, idesc, (first | k) != 0);
+                                umma_pair<true>(tmem_s, dak, dblk, idesc, 1u);
+                                umma_pair<true>(tmem_d, dak, dbk, idesc, (first | k) != 0);
+                            } else {
+                                umma_tf32(tmem_s, dalk, dbk, idesc, (first | k) != 0);
+                                umma_tf32(tmem_s, dak, dblk, idesc, 1u);
+                                umma_tf32(tmem_d, dak, dbk, idesc, (first | k) != 0);
+                            }
+                        } else if (NCTA == 2) {
+                            umma_pair<TF32>(tmem_d, dak, dbk, idesc, (first | k) != 0);
                         } else if (TF32) {
-                            umma_tf32(tmem_d, da + (uint64_t)(a_step * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                            umma_tf32(tmem_d, dak, dbk, idesc, (first | k) != 0);
                         } else {
-                            umma_bf16(tmem_d, da + (uint64_t)(a_step * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                            umma_bf16(tmem_d, dak, dbk, idesc, (first | k) != 0);
                         }
                     }
                     if (NCTA == 2) umma_commit_pair(&empty[stage]); else umma_commit(&empty[stage]);  // stage reusable once read
@@ -335,6 +376,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
                     }
                 }
                 if (NCTA == 2) umma_commit_pair(&tmem_full[acc]); else umma_commit(&tmem_full[acc]);  // accumulator complete
+              }
             }
         }
     } else {
@@ -342,9 +384,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
         const int lane_grp = warp & 3;
         const uint32_t lead_empty0 = NCTA == 2 ? mapa_u32(smem_u32(&tmem_empty[0]), 0) : 0u;
         int it = 0;
-        for (int tile = unit; tile < num_tiles; tile += num_units, ++it) {
-            int tm, tn;
-            tile_coords(tile, tm, tn);
+        for (int tile = unit; tile < num_tiles; tile += num_units) {
+          int tm, tn;
+          tile_coords(tile, tm, tn);
+          for (int kb0 = 0; kb0 < num_kb; kb0 += kb_chunk, ++it) {
             const int acc = it & 1;
             const uint32_t acc_phase = (uint32_t)(it >> 1) & 1;
             mbar_wait(&tmem_full[acc], acc_phase);
@@ -354,17 +397,35 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
             float *crow = C + m + (int64_t)n0 * ldc;
             const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(acc * BN);
             const bool full_tile = (int64_t)(tm * NCTA + (int)rank + 1) * BM <= M && n0 + bn <= N && (bn & 31) == 0;
+            const bool add = kb0 != 0;   // later k chunks are added to what the first one stored (FP32, round to nearest)
 #pragma unroll 1
             for (int c = 0; c < bn; c += 32) {
                 uint32_t r[32];
                 tmem_ld32(taddr + (uint32_t)c, r);   // warp-collective: every lane takes part, stores are predicated
-                if (full_tile) {
+                if (X3) {   // main accumulator + correction accumulator, in FP32 with round to nearest
+                    uint32_t rs[32];
+                    tmem_ld32(taddr + (uint32_t)(BN / 2) + (uint32_t)c, rs);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) crow[(int64_t)(c + j) * ldc] = __uint_as_float(r[j]);
+                    for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(rs[j]));
+                }
+                if (full_tile) {
+                    if (add) {   // all 32 loads first: with a run-time ldc the compiler must assume the stores alias the next load
+                        float old[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) old[j] = __ldcg(crow + (int64_t)(c + j) * ldc);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) crow[(int64_t)(c + j) * ldc] = old[j] + __uint_as_float(r[j]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) crow[(int64_t)(c + j) * ldc] = __uint_as_float(r[j]);
+                    }
                 } else if (m < M) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
-                        if (c + j < bn && n0 + c + j < N) crow[(int64_t)(c + j) * ldc] = __uint_as_float(r[j]);
+                        if (c + j < bn && n0 + c + j < N) {
+                            float *pc = crow + (int64_t)(c + j) * ldc;
+                            *pc = add ? *pc + __uint_as_float(r[j]) : __uint_as_float(r[j]);
+                        }
                 }
             }
             tc_fence_before();
@@ -372,6 +433,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
             if (lane == 0) {   // this warp has drained its quarter of the accumulator
                 if (NCTA == 2) mbar_arrive_cluster(lead_empty0 + (uint32_t)(acc * 8)); else mbar_arrive(&tmem_empty[acc]);
             }
+          }
         }
     }
     __syncwarp();   // role branches diverged inside the warp; the cluster barrier is warp-aligned
@@ -503,19 +565,19 @@ static int pick_bn(int64_t M, int64_t N, int units, int ncta) {
 
 // One persistent CTA per SM; NCTA = 2 launches clusters of two (a CTA pair shares a TPC) -- chosen when the matrix has
 // more than one 128-row tile (`tcgemm.cta2` = 0 forces single CTAs).
-template <bool TF32, int NCTA>
-static int launch_tcgen05(const CUtensorMap &ta, const CUtensorMap &tb, float *C, int64_t ldc, int64_t M, int64_t N, int num_kb,
-                          int bn, cudaStream_t st) {
+template <bool TF32, int NCTA, int X3>
+static int launch_tcgen05(const CUtensorMap &ta, const CUtensorMap &tb, const CUtensorMap &talo, const CUtensorMap &tblo, float *C, int64_t ldc,
+                          int64_t M, int64_t N, int num_kb, int bn, int kb_chunk, cudaStream_t st) {
     using namespace tc;
     const int tiles_m = (int)cdiv(M, BM * NCTA), tiles_n = (int)cdiv(N, bn);
     int grid = sm_count() / NCTA * NCTA;
     if ((int64_t)grid > (int64_t)tiles_m * tiles_n * NCTA) grid = tiles_m * tiles_n * NCTA;
-    auto kfn = gemm_tcgen05_kernel<TF32, NCTA>;
-    B200_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, PipeCfg<NCTA>::SMEM_BYTES));
+    auto kfn = gemm_tcgen05_kernel<TF32, NCTA, X3>;
+    B200_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, PipeCfg<NCTA, X3>::SMEM_BYTES));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);
     cfg.blockDim = dim3(NUM_THREADS);
-    cfg.dynamicSmemBytes = PipeCfg<NCTA>::SMEM_BYTES;
+    cfg.dynamicSmemBytes = PipeCfg<NCTA, X3>::SMEM_BYTES;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -524,9 +586,9 @@ static int launch_tcgen05(const CUtensorMap &ta, const CUtensorMap &tb, float *C
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    B200_CUDA(cudaLaunchKernelEx(&cfg, kfn, ta, tb, C, ldc, (int)M, (int)N, tiles_m, tiles_n, num_kb,
-                                 tune_get("tcgemm.group_m", NCTA == 2 ? 8 : 16), bn));
-    B200_CHECK_LAUNCH(TF32 ? "gemm_tcgen05_kernel<tf32>" : "gemm_tcgen05_kernel<bf16>");
+    B200_CUDA(cudaLaunchKernelEx(&cfg, kfn, ta, tb, talo, tblo, C, ldc, (int)M, (int)N, tiles_m, tiles_n, num_kb,
+                                 tune_get("tcgemm.group_m", NCTA == 2 ? 8 : 16), bn, kb_chunk > 0 ? kb_chunk : num_kb));
+    B200_CHECK_LAUNCH(X3 ? "gemm_tcgen05_kernel<tf32x3>" : (TF32 ? "gemm_tcgen05_kernel<tf32>" : "gemm_tcgen05_kernel<bf16>"));
     return B200_OK;
 }
 static int use_cta_pairs(int64_t M) { return tune_get("tcgemm.cta2", 1) != 0 && M > tc::BM; }
@@ -551,8 +613,8 @@ int gemm_bf16_launch(float *C, const uint16_t *A, const uint16_t *B, int64_t M, 
     const int bn = pick_bn(M, N, sm_count() / ncta, ncta);
     B200_TRY(make_tmap_bf16_kmajor(&ta, A, M, K, BM));
     B200_TRY(make_tmap_bf16_kmajor(&tb, B, N, K, bn / ncta));
-    if (ncta == 2) return launch_tcgen05<false, 2>(ta, tb, C, ldc, M, N, (int)cdiv(K, BK), bn, st);
-    return launch_tcgen05<false, 1>(ta, tb, C, ldc, M, N, (int)cdiv(K, BK), bn, st);
+    if (ncta == 2) return launch_tcgen05<false, 2, 0>(ta, tb, ta, tb, C, ldc, M, N, (int)cdiv(K, BK), bn, 0, st);
+    return launch_tcgen05<false, 1, 0>(ta, tb, ta, tb, C, ldc, M, N, (int)cdiv(K, BK), bn, 0, st);
 }
 
 // FP32 operands straight from HBM: A (M x K, lda) column-major -> boxes of 32 m x 32 k; B (K x N, ldb) -> 32 k x 256 n
@@ -571,8 +633,54 @@ int gemm_tf32_launch(float *C, const float *A, const float *B, int64_t M, int64_
                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B));
     B200_TRY(pipe::make_tmap_2d(&tb, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, B, K, N, ldb, BK_TF32, bn / ncta, CU_TENSOR_MAP_SWIZZLE_128B,
                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B));
-    if (ncta == 2) return launch_tcgen05<true, 2>(ta, tb, C, ldc, M, N, (int)cdiv(K, BK_TF32), bn, st);
-    return launch_tcgen05<true, 1>(ta, tb, C, ldc, M, N, (int)cdiv(K, BK_TF32), bn, st);
+    if (ncta == 2) return launch_tcgen05<true, 2, 0>(ta, tb, ta, tb, C, ldc, M, N, (int)cdiv(K, BK_TF32), bn, 0, st);
+    return launch_tcgen05<true, 1, 0>(ta, tb, ta, tb, C, ldc, M, N, (int)cdiv(K, BK_TF32), bn, 0, st);
+}
+
+// ---- 3xTF32: FP32-grade products on the tensor cores -------------------------------------------------------------------
+// lo = x - (x with the 13 low mantissa bits cleared): the part of x the tensor core drops when it reads x as TF32; exact in FP32.
+__global__ void __launch_bounds__(256) split_tf32_lo_kernel(float4 *__restrict__ lo, const float4 *__restrict__ x, int64_t n4) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 v = ld_nc_v4(x + i);
+        float4 r;
+        r.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+        r.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+        r.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+        r.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+        lo[i] = r;
+    }
+}
+
+int gemm_tf32x3_launch(float *C, const float *A, const float *B, int64_t M, int64_t K, int64_t N, int64_t lda, int64_t ldb,
+                       int64_t ldc, float *workspace, cudaStream_t st) {
+    using namespace tc;
+    if (M <= 0 || N <= 0 || K <= 0 || M > INT32_MAX || N > INT32_MAX || K > INT32_MAX)
+        return set_error(B200_ERR_UNSUPPORTED, "b200_matmul_f32_tf32x3: M, N, K must be positive (got %lld, %lld, %lld)", (long long)M,
+                         (long long)K, (long long)N);
+    if ((lda % 4) || (ldb % 4) || ((((uintptr_t)A | (uintptr_t)B | (uintptr_t)workspace) & 15) != 0))
+        return set_error(B200_ERR_UNSUPPORTED, "b200_matmul_f32_tf32x3: TMA needs 16-byte aligned operands and leading dimensions that are multiples of 4");
+    float *Alo = workspace, *Blo = workspace + lda * K;   // same shapes and leading dimensions as A and B
+    const int sgrid = sm_count() * 8;
+    split_tf32_lo_kernel<<<sgrid, 256, 0, st>>>((float4 *)Alo, (const float4 *)A, lda * K / 4);
+    B200_CHECK_LAUNCH("split_tf32_lo_kernel");
+    split_tf32_lo_kernel<<<sgrid, 256, 0, st>>>((float4 *)Blo, (const float4 *)B, ldb * N / 4);
+    B200_CHECK_LAUNCH("split_tf32_lo_kernel");
+    CUtensorMap ta, tb, talo, tblo;
+    const int ncta = use_cta_pairs(M) ? 2 : 1;
+    const int bn = BN / 2;   // two TMEM accumulators (main + correction) per buffer, two buffers: 4 x 128 of the 512 columns
+    for (int lo = 0; lo < 2; ++lo) {
+        B200_TRY(pipe::make_tmap_2d(lo ? &talo : &ta, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, lo ? Alo : A, M, K, lda, 32, BK_TF32,
+                                    CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B));
+        B200_TRY(pipe::make_tmap_2d(lo ? &tblo : &tb, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, lo ? Blo : B, K, N, ldb, BK_TF32, bn / ncta,
+                                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B));
+    }
+    // k blocks (of 32) per accumulation chunk: the tensor core's truncating accumulation is restarted every chunk
+    // measured at 8192^3, uniform [0,1) inputs (max element-wise error vs Float64 / TFLOP/s): 512 -> 4e-6 / 219, 1024 -> 7e-6 / 229,
+    // none -> 239; the main accumulator loses ~7.4e-9 per k (one truncation of half an ulp per 8 k)
+    int kb_chunk = tune_get("tcgemm.x3_chunk_k", 512) / BK_TF32;
+    if (kb_chunk < 1) kb_chunk = 1;
+    if (ncta == 2) return launch_tcgen05<true, 2, 1>(ta, tb, talo, tblo, C, ldc, M, N, (int)cdiv(K, BK_TF32), bn, kb_chunk, st);
+    return launch_tcgen05<true, 1, 1>(ta, tb, talo, tblo, C, ldc, M, N, (int)cdiv(K, BK_TF32), bn, kb_chunk, st);
 }
 
 int convert_bf16_launch(uint16_t *out, const float *in, int64_t rows, int64_t cols, int64_t ld, int transpose,
@@ -627,6 +735,17 @@ extern "C" b200_status b200_matmul_tf32(float *C, const float *A, const float *B
     cudaStream_t st;
     B200_TRY(current_stream(&st));
     return gemm_tf32_launch(C, A, B, M, K, N, lda, ldb, ldc, st);
+}
+
+extern "C" b200_status b200_matmul_f32_tf32x3(float *C, const float *A, const float *B, int64_t M, int64_t K, int64_t N,
+                                              int64_t lda, int64_t ldb, int64_t ldc, void *workspace) {
+    if (M < 0 || N < 0 || K < 0 || lda < M || ldb < K || ldc < M)
+        return set_error(B200_ERR_INVALID_VALUE, "b200_matmul_f32_tf32x3: bad shape");
+    if (M == 0 || N == 0) return B200_OK;
+    if (!C || !A || !B || !workspace) return set_error(B200_ERR_INVALID_VALUE, "b200_matmul_f32_tf32x3: NULL pointer");
+    cudaStream_t st;
+    B200_TRY(current_stream(&st));
+    return gemm_tf32x3_launch(C, A, B, M, K, N, lda, ldb, ldc, (float *)workspace, st);
 }
 
 extern "C" b200_status b200_convert_f32_bf16(uint16_t *out, const float *in, int64_t rows, int64_t cols, int64_t ld,

@@ -211,6 +211,12 @@ function matmul_tf32!(C::B200Array{Float32, 2}, A::B200Array{Float32, 2}, B::B20
     @b200 b200_matmul_tf32 (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Int64, Int64, Int64, Int64) C.ptr A.ptr B.ptr M K N M K M
     return C
 end
+function matmul_tf32x3!(C::B200Array{Float32, 2}, A::B200Array{Float32, 2}, B::B200Array{Float32, 2};      # FP32-grade, rtol 1e-5
+                        workspace::B200Array{Float32, 1} = B200Array{Float32, 1}(undef, (length(A) + length(B),)))
+    M, K, N = size(A, 1), size(A, 2), size(B, 2)
+    @b200 b200_matmul_f32_tf32x3 (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Int64, Int64, Int64, Int64, Ptr{Cvoid}) C.ptr A.ptr B.ptr M K N M K M workspace.ptr
+    return C
+end
 function matmul_bf16!(C::B200Array{Float32, 2}, A::B200Array{Float32, 2}, B::B200Array{Float32, 2};
                       workspace::B200Array{UInt16, 1} = B200Array{UInt16, 1}(undef, (length(A) + length(B),)))
     M, K, N = size(A, 1), size(A, 2), size(B, 2)

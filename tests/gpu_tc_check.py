@@ -101,6 +101,33 @@ for (M, K, N) in [(200, 104, 300), (129, 72, 257)]:
     print(f"bf16 gemm ragged {M}x{K}x{N}: max_rel_err_vs_fp64_truth={err:.3e}", flush=True)
     ok = ok and err < 1e-4
 
+# ---- 3xTF32: FP32-grade accuracy on the tensor cores (split operands, chunked accumulation) ----
+for (M, K, N) in [(128, 32, 256), (256, 512, 512), (200, 100, 300), (129, 40, 257), (512, 8192, 512), (1024, 4100, 768)]:
+    A = orc.gen_uniform_f32((M, K), 1237)            # uniform [0,1) like rand(Float32, ...) in examples/performant_matmul.jl:82-83
+    B = orc.gen_uniform_f32((K, N), 1238)
+    lda, ldb = (M + 3) // 4 * 4, (K + 3) // 4 * 4
+    Ap = np.zeros((lda, K), dtype=np.float32, order="F")
+    Ap[:M] = A
+    Bp = np.zeros((ldb, N), dtype=np.float32, order="F")
+    Bp[:K] = B
+    dA, dB = KA.to_device(Ap), KA.to_device(Bp)
+    dC = KA.allocate(be, np.float32, M, N).fill_(-7.0)
+    ws = KA.allocate(be, np.float32, lda * K + ldb * N)
+    _lib.call("b200_matmul_f32_tf32x3", C.c_void_p(dC.ptr), C.c_void_p(dA.ptr), C.c_void_p(dB.ptr), M, K, N, lda, ldb, M, C.c_void_p(ws.ptr))
+    KA.synchronize(be)
+    got = KA.Array(dC)
+    truth = orc.matmul_f64_truth(np.asfortranarray(A), np.asfortranarray(B))
+    rel = np.abs(got - truth) / np.abs(truth)
+    As, Bs = A - 0.5, B - 0.5                          # signed inputs: norm-wise error (cancellation makes element-wise rtol meaningless)
+    KA.copyto_(be, dA, np.asfortranarray(np.vstack([As, np.zeros((lda - M, K), np.float32)])))
+    KA.copyto_(be, dB, np.asfortranarray(np.vstack([Bs, np.zeros((ldb - K, N), np.float32)])))
+    _lib.call("b200_matmul_f32_tf32x3", C.c_void_p(dC.ptr), C.c_void_p(dA.ptr), C.c_void_p(dB.ptr), M, K, N, lda, ldb, M, C.c_void_p(ws.ptr))
+    KA.synchronize(be)
+    ts = orc.matmul_f64_truth(np.asfortranarray(As), np.asfortranarray(Bs))
+    nrm = np.linalg.norm(KA.Array(dC) - ts) / np.linalg.norm(ts)
+    print(f"tf32x3 gemm {M}x{K}x{N}: max element-wise rel err vs fp64 = {rel.max():.3e} (rtol 1e-5 bar), signed inputs norm-wise = {nrm:.3e}", flush=True)
+    ok = ok and rel.max() < 1e-5 and nrm < 1e-5
+
 # ---- every tile width the wave-filling heuristic may choose (tcgemm.bn pinned), both kinds, ragged N ----
 M, K, N = 256, 256, 1000
 A = orc.gen_uniform_f32((M, K), 1237) - 0.5

@@ -139,6 +139,14 @@ elif kind == "tf32gemm":
     Cd = KA.zeros(be, np.float32, m, n)
     run(lambda: _lib.call("b200_matmul_tf32", C.c_void_p(Cd.ptr), C.c_void_p(A.ptr), C.c_void_p(B.ptr), m, n, n, m, n, m),
         2.0 * m * n * n, "TFLOP/s")
+elif kind == "tf32x3gemm":
+    n = size or 8192
+    m = int(os.environ.get("RUN_M", n))
+    A, B = KA.to_device(orc.gen_uniform_f32((m, n), 1237)), KA.to_device(orc.gen_uniform_f32((n, n), 1238))
+    Cd = KA.zeros(be, np.float32, m, n)
+    ws = KA.allocate(be, np.float32, m * n + n * n)
+    run(lambda: _lib.call("b200_matmul_f32_tf32x3", C.c_void_p(Cd.ptr), C.c_void_p(A.ptr), C.c_void_p(B.ptr), m, n, n, m, n, m, C.c_void_p(ws.ptr)),
+        2.0 * m * n * n, "TFLOP/s")
 elif kind in ("sgemm", "tcgemm"):
     n = size or 8192
     m = int(os.environ.get("RUN_M", n))      # rows of A / C (a row panel of the sharded problem)
