@@ -643,7 +643,7 @@ def run_suite(KA, _lib, EX, mg, orc, be, rank, world, dist, timed, peaks, steps,
                 ("matmul_bf16_tcgen05_8192_from_f32", step_tc_e2e, peaks["bf16"], "FP32 operands in HBM: FP32->BF16 conversion passes + GEMM per step", 1e-2),
                 ("matmul_tf32_tcgen05_8192", step_tf32, peaks["bf16"] / 2, "FP32 operands read directly by TMA (no conversion pass); peak = half the measured BF16 peak", 1e-2),
                 ("matmul_f32_tf32x3_tcgen05_8192", step_tf32x3, peaks["bf16"] / 6,
-                 "FP32-grade product on the tensor cores: operands split into two TF32 terms, 3 MMAs per k step, K accumulated in chunks of 512 "
+                 "FP32-grade product on the tensor cores: operands split into two TF32 terms, 3 MMAs per k step, K accumulated in chunks of 256 "
                  "(split pass included); sampled parity at rtol 1e-5; peak = measured BF16 peak / 6", 1e-5)):
             dC.fill_(0)
             fn()

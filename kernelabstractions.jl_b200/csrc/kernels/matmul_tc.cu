@@ -194,6 +194,15 @@ struct PipeCfg {
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 template <bool TF32, int NCTA, int X3>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
     gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -383,6 +392,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
         // ===== epilogue warps 2..5: TMEM lane group = warp % 4 (own 128 rows of the tile) =====
         const int lane_grp = warp & 3;
         const uint32_t lead_empty0 = NCTA == 2 ? mapa_u32(smem_u32(&tmem_empty[0]), 0) : 0u;
+        float accr[X3 ? BN / 2 : 1];   // X3: this thread's row of the tile, carried across the k chunks
         int it = 0;
         for (int tile = unit; tile < num_tiles; tile += num_units) {
           int tm, tn;
@@ -397,17 +407,35 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
             float *crow = C + m + (int64_t)n0 * ldc;
             const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(acc * BN);
             const bool full_tile = (int64_t)(tm * NCTA + (int)rank + 1) * BM <= M && n0 + bn <= N && (bn & 31) == 0;
-            const bool add = kb0 != 0;   // later k chunks are added to what the first one stored (FP32, round to nearest)
+            const bool add = kb0 != 0;   // later k chunks are added to what the first one produced (FP32, round to nearest)
+            if (X3) {
+                // 3xTF32: bn == BN / 2.  The chunk sums live in registers (128 per thread) until the last chunk of the tile -- adding
+                // them to C in global memory instead cost 8 GB of read-modify-write traffic per 8192^3 product (219 -> 236 TFLOP/s).
+#pragma unroll
+                for (int c = 0; c < BN / 2; c += 16) {   // 16 columns at a time: 128 carried sums + 32 in flight fit the register file
+                    uint32_t r[16], rs[16];
+                    tmem_ld16(taddr + (uint32_t)c, r);
+                    tmem_ld16(taddr + (uint32_t)(BN / 2) + (uint32_t)c, rs);   // the correction accumulator
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float v = __uint_as_float(r[j]) + __uint_as_float(rs[j]);
+                        accr[X3 ? c + j : 0] = add ? accr[X3 ? c + j : 0] + v : v;
+                    }
+                }
+                if (kb0 + kb_chunk >= num_kb && m < M) {   // last chunk: the only write of C
+                    float *pc = crow;
+                    const int ncols = min(BN / 2, N - n0);
+#pragma unroll
+                    for (int c = 0; c < BN / 2; ++c) {
+                        if (c < ncols) *pc = accr[X3 ? c : 0];
+                        pc += ldc;
+                    }
+                }
+            } else {
 #pragma unroll 1
             for (int c = 0; c < bn; c += 32) {
                 uint32_t r[32];
                 tmem_ld32(taddr + (uint32_t)c, r);   // warp-collective: every lane takes part, stores are predicated
-                if (X3) {   // main accumulator + correction accumulator, in FP32 with round to nearest
-                    uint32_t rs[32];
-                    tmem_ld32(taddr + (uint32_t)(BN / 2) + (uint32_t)c, rs);
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(rs[j]));
-                }
                 if (full_tile) {
                     if (add) {   // all 32 loads first: with a run-time ldc the compiler must assume the stores alias the next load
                         float old[32];
@@ -427,6 +455,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
                             *pc = add ? *pc + __uint_as_float(r[j]) : __uint_as_float(r[j]);
                         }
                 }
+            }
             }
             tc_fence_before();
             __syncwarp();
@@ -675,9 +704,9 @@ int gemm_tf32x3_launch(float *C, const float *A, const float *B, int64_t M, int6
                                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B));
     }
     // k blocks (of 32) per accumulation chunk: the tensor core's truncating accumulation is restarted every chunk
-    // measured at 8192^3, uniform [0,1) inputs (max element-wise error vs Float64 / TFLOP/s): 512 -> 4e-6 / 219, 1024 -> 7e-6 / 229,
-    // none -> 239; the main accumulator loses ~7.4e-9 per k (one truncation of half an ulp per 8 k)
-    int kb_chunk = tune_get("tcgemm.x3_chunk_k", 512) / BK_TF32;
+    // measured at 8192^3, uniform [0,1) inputs (max element-wise error vs Float64 / TFLOP/s): 256 -> 2e-6 / 230, 512 -> 3.6e-6 / 236,
+    // 1024 -> 7e-6 / 239; the main accumulator loses ~7.4e-9 per k (one truncation of half an ulp per 8 k)
+    int kb_chunk = tune_get("tcgemm.x3_chunk_k", 256) / BK_TF32;
     if (kb_chunk < 1) kb_chunk = 1;
     if (ncta == 2) return launch_tcgen05<true, 2, 1>(ta, tb, talo, tblo, C, ldc, M, N, (int)cdiv(K, BK_TF32), bn, kb_chunk, st);
     return launch_tcgen05<true, 1, 1>(ta, tb, talo, tblo, C, ldc, M, N, (int)cdiv(K, BK_TF32), bn, kb_chunk, st);
