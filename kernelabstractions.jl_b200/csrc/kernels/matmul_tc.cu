@@ -409,7 +409,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
             const bool full_tile = (int64_t)(tm * NCTA + (int)rank + 1) * BM <= M && n0 + bn <= N && (bn & 31) == 0;
             const bool add = kb0 != 0;   // later k chunks are added to what the first one produced (FP32, round to nearest)
             if (X3) {
-                // 3xTF32: bn == BN / 2.  The chunk sums live in registers (128 per thread) until the last chunk of the tile -- adding
+                // 3xTF32: bn <= BN / 2.  The chunk sums live in registers (128 per thread) until the last chunk of the tile -- adding
                 // them to C in global memory instead cost 8 GB of read-modify-write traffic per 8192^3 product (219 -> 236 TFLOP/s).
 #pragma unroll
                 for (int c = 0; c < BN / 2; c += 16) {   // 16 columns at a time: 128 carried sums + 32 in flight fit the register file
@@ -424,7 +424,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
                 }
                 if (kb0 + kb_chunk >= num_kb && m < M) {   // last chunk: the only write of C
                     float *pc = crow;
-                    const int ncols = min(BN / 2, N - n0);
+                    const int ncols = min(bn, N - n0);
 #pragma unroll
                     for (int c = 0; c < BN / 2; ++c) {
                         if (c < ncols) *pc = accr[X3 ? c : 0];
@@ -575,13 +575,14 @@ __global__ void __launch_bounds__(256) convert_bf16_transpose64_kernel(__nv_bflo
 // 2 rounds either way, 148 tiles of 256 x 224 instead of 128 tiles of 256 x 256.  Ties keep the widest tile (fewest
 // re-reads of A); `tcgemm.bn` pins a value.  bn is a multiple of 16 per CTA of the unit.
 static int pick_bn(int64_t M, int64_t N, int units, int ncta) {
+    const int max_bn = tc::BN;
     const int step = 16 * ncta;
     const int forced = tune_get("tcgemm.bn", 0);
-    if (forced >= step && forced <= tc::BN && forced % step == 0) return forced;
+    if (forced >= step && forced <= max_bn && forced % step == 0) return forced;
     const int64_t tiles_m = cdiv(M, tc::BM * ncta);
-    int best = tc::BN;
+    int best = max_bn;
     int64_t best_cost = INT64_MAX;
-    for (int bn = tc::BN; bn >= 128; bn -= step) {
+    for (int bn = max_bn; bn >= max_bn / 2; bn -= step) {
         const int64_t tiles = tiles_m * cdiv(N, bn);
         const int64_t cost = cdiv(tiles, units) * (bn + 8);   // + 8: per-tile fixed cost (pipeline refill, epilogue hand-over)
         if (cost < best_cost) {
@@ -696,7 +697,10 @@ int gemm_tf32x3_launch(float *C, const float *A, const float *B, int64_t M, int6
     B200_CHECK_LAUNCH("split_tf32_lo_kernel");
     CUtensorMap ta, tb, talo, tblo;
     const int ncta = use_cta_pairs(M) ? 2 : 1;
-    const int bn = BN / 2;   // two TMEM accumulators (main + correction) per buffer, two buffers: 4 x 128 of the 512 columns
+    // two TMEM accumulators (main + correction) per buffer, two buffers: 4 x 128 of the 512 columns -> tiles at most 128 wide.
+    // Narrower wave-filling widths do not pay here (1024 x 8192 panel: bn 64 -> 113 TFLOP/s against 175 with 128): `tcgemm.bn` only.
+    const int forced_bn = tune_get("tcgemm.bn", 0);
+    const int bn = (forced_bn >= 16 * ncta && forced_bn <= BN / 2 && forced_bn % (16 * ncta) == 0) ? forced_bn : BN / 2;
     for (int lo = 0; lo < 2; ++lo) {
         B200_TRY(pipe::make_tmap_2d(lo ? &talo : &ta, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, lo ? Alo : A, M, K, lda, 32, BK_TF32,
                                     CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B));
