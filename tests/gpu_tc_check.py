@@ -147,7 +147,18 @@ for bn in range(128, 257, 16):
     _lib.call("b200_matmul_tf32", C.c_void_p(dC.ptr), C.c_void_p(dA.ptr), C.c_void_p(dB.ptr), M, K, N, M, K, M)
     KA.synchronize(be)
     worst["tf32"] = max(worst["tf32"], np.abs(KA.Array(dC) - truth_tf).max() / np.abs(truth_tf).max())
+worst["tf32x3"] = 0.0
+ws3 = KA.allocate(be, np.float32, M * K + K * N)
+truth_x3 = orc.matmul_f64_truth(np.asfortranarray(A), np.asfortranarray(B))
+for bn in (64, 96, 128):
+    _lib.call("b200_tune_set", b"tcgemm.bn", bn)
+    dC = KA.allocate(be, np.float32, M, N).fill_(-7.0)
+    _lib.call("b200_matmul_f32_tf32x3", C.c_void_p(dC.ptr), C.c_void_p(dA.ptr), C.c_void_p(dB.ptr), M, K, N, M, K, M, C.c_void_p(ws3.ptr))
+    KA.synchronize(be)
+    worst["tf32x3"] = max(worst["tf32x3"], np.abs(KA.Array(dC) - truth_x3).max() / np.abs(truth_x3).max())
 _lib.call("b200_tune_set", b"tcgemm.bn", 0)
+print(f"tf32x3 tile widths 64/96/128 on {M}x{K}x{N}: worst max_rel_err {worst['tf32x3']:.3e}", flush=True)
+ok = ok and worst["tf32x3"] < 1e-5
 print(f"tile widths 128..256 step 16 on {M}x{K}x{N}: worst max_rel_err bf16={worst['bf16']:.3e} tf32={worst['tf32']:.3e}", flush=True)
 ok = ok and worst["bf16"] < 1e-4 and worst["tf32"] < 1e-4
 sys.exit(0 if ok else 1)
