@@ -189,8 +189,9 @@ __device__ __forceinline__ void umma_pair(uint32_t tmem_d, uint64_t desc_a, uint
 // kb_chunk k blocks: each chunk is accumulated in TMEM and the epilogue adds it to C in FP32 with round-to-nearest.
 template <int NCTA, int X3>
 struct PipeCfg {
-    static constexpr int STAGES = X3 ? (NCTA == 2 ? 3 : 2) : (NCTA == 2 ? 6 : 4);
-    static constexpr int STAGE_BYTES = (1 + X3) * (A_BYTES + B_BYTES / NCTA);
+    static constexpr int B_STAGE = (X3 ? B_BYTES / 2 : B_BYTES) / NCTA;   // X3 tiles are at most BN / 2 wide
+    static constexpr int STAGES = X3 ? (NCTA == 2 ? 4 : 3) : (NCTA == 2 ? 6 : 4);
+    static constexpr int STAGE_BYTES = (1 + X3) * (A_BYTES + B_STAGE);
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
@@ -214,7 +215,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     // rounds of the persistent grid (pick_bn); shared-memory stages and TMEM accumulators stay sized for BN.
     constexpr int KB = TF32 ? BK_TF32 : BK;   // k elements per stage
     constexpr int STAGES = PipeCfg<NCTA, X3>::STAGES, STAGE_BYTES = PipeCfg<NCTA, X3>::STAGE_BYTES;
-    constexpr int LO_OFF = A_BYTES + B_BYTES / NCTA;   // X3: the lo tiles follow the hi tiles inside a stage
+    constexpr int LO_OFF = A_BYTES + PipeCfg<NCTA, X3>::B_STAGE;   // X3: the lo tiles follow the hi tiles inside a stage
     extern __shared__ unsigned char smem_raw[];
     // SWIZZLE_128B operands need 1024-byte aligned stage bases (the dynamic window starts at the same offset in both
     // CTAs of a pair, so the aligned bases coincide as the pair MMA requires)

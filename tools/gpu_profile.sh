@@ -21,6 +21,7 @@ run_ncu hist hist_atomic hist 1073741824 0 3
 run_ncu copy copy_bulk copy 67108864 0 3
 run_ncu tcgemm gemm_tcgen05 tcgemm 8192 0 3
 run_ncu tf32gemm gemm_tcgen05 tf32gemm 8192 0 3
+run_ncu tf32x3gemm gemm_tcgen05 tf32x3gemm 8192 0 3
 run_ncu saxpy saxpy saxpy 67108864 0 3
 $P bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_plain.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
