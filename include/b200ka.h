@@ -235,7 +235,8 @@ b200_status b200_matmul_tf32(float *C, const float *A, const float *B, int64_t M
 /* "3xTF32": FP32-grade C = A*B on the tensor cores.  Every operand is split into its TF32 head and the TF32 head of the
  * remainder; A_lo*B_hi + A_hi*B_lo + A_hi*B_hi are accumulated per k step, K in chunks whose TMEM sums are added to C in FP32
  * (the tensor core's own accumulation truncates).  Same operand rules as b200_matmul_tf32; workspace: (lda*K + ldb*N) floats,
- * 16-byte aligned.  Not the reference's summation order: parity is "rtol 1e-5 against Float64" (measured ~1e-6), not bit-exact. */
+ * 16-byte aligned.  Not the reference's summation order: parity is "rtol 1e-5 against Float64" (measured 2e-6), not bit-exact.
+ * Finite operands only: an Inf operand makes its row / column of C non-finite (Inf, or NaN where it meets a zero remainder). */
 b200_status b200_matmul_f32_tf32x3(float *C, const float *A, const float *B, int64_t M, int64_t K, int64_t N,
                                    int64_t lda, int64_t ldb, int64_t ldc, void *workspace);
 /* float32 column-major (rows x cols, ld) -> bf16; transpose!=0 writes the cols x rows... see DESIGN.md:

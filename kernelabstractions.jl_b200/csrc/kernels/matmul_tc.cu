@@ -673,11 +673,15 @@ int gemm_tf32_launch(float *C, const float *A, const float *B, int64_t M, int64_
 __global__ void __launch_bounds__(256) split_tf32_lo_kernel(float4 *__restrict__ lo, const float4 *__restrict__ x, int64_t n4) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
         const float4 v = ld_nc_v4(x + i);
+        auto lo_of = [](float x) {   // Inf / NaN keep a zero remainder, so they propagate through the head term only (Inf - Inf would be NaN)
+            const float d = x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+            return (__float_as_uint(x) & 0x7F800000u) == 0x7F800000u ? 0.0f : d;
+        };
         float4 r;
-        r.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
-        r.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
-        r.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
-        r.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+        r.x = lo_of(v.x);
+        r.y = lo_of(v.y);
+        r.z = lo_of(v.z);
+        r.w = lo_of(v.w);
         lo[i] = r;
     }
 }

@@ -147,6 +147,21 @@ for bn in range(128, 257, 16):
     _lib.call("b200_matmul_tf32", C.c_void_p(dC.ptr), C.c_void_p(dA.ptr), C.c_void_p(dB.ptr), M, K, N, M, K, M)
     KA.synchronize(be)
     worst["tf32"] = max(worst["tf32"], np.abs(KA.Array(dC) - truth_tf).max() / np.abs(truth_tf).max())
+# 3xTF32 with an Inf in A: the affected row of C is non-finite (Inf, or NaN where the Inf meets a zero remainder of B in a
+# correction term -- documented deviation from plain FP32), every other row finite
+Ainf = A.copy()
+Ainf[5, 7] = np.inf
+dAi = KA.to_device(np.asfortranarray(Ainf))
+dCi = KA.allocate(be, np.float32, M, N).fill_(-7.0)
+ws_i = KA.allocate(be, np.float32, M * K + K * N)
+Bpos = np.abs(B) + 0.25
+dBp = KA.to_device(np.asfortranarray(Bpos))
+_lib.call("b200_matmul_f32_tf32x3", C.c_void_p(dCi.ptr), C.c_void_p(dAi.ptr), C.c_void_p(dBp.ptr), M, K, N, M, K, M, C.c_void_p(ws_i.ptr))
+KA.synchronize(be)
+gi = KA.Array(dCi)
+inf_ok = bool(not np.any(np.isfinite(gi[5, :])) and np.all(np.isfinite(np.delete(gi, 5, axis=0))))
+print(f"tf32x3 with an Inf operand: its row is non-finite and the rest finite = {inf_ok}", flush=True)
+ok = ok and inf_ok
 worst["tf32x3"] = 0.0
 ws3 = KA.allocate(be, np.float32, M * K + K * N)
 truth_x3 = orc.matmul_f64_truth(np.asfortranarray(A), np.asfortranarray(B))
