@@ -1,5 +1,5 @@
-// matmul_tc.cu -- opt-in tensor-core GEMM: tcgen05.mma (BF16 in, FP32 accumulate in TMEM), TMA operand
-// staging, mbarrier pipelines, warp-specialised persistent CTAs.
+// matmul_tc.cu -- opt-in tensor-core GEMMs: tcgen05.mma (BF16, TF32 or split-TF32 operands, FP32 accumulate in TMEM), TMA operand
+// staging, mbarrier pipelines, warp-specialised persistent CTAs and CTA pairs.
 //
 // Reference: there is none -- KernelAbstractions' only dense contraction is the FP32 SIMT kernel of
 // examples/performant_matmul.jl:15-77.  north_star asks for an opt-in BF16 tensor-core path for it; parity is
@@ -21,12 +21,15 @@
 // formats = TF32; each tcgen05.mma.kind::tf32 consumes K = 8 (two 4-k atoms, +1024 B per step).  The tensor core reads the FP32 words and
 // uses their top 19 bits.  Edge tiles: TMA zero-fills out-of-range rows/columns/k, the epilogue predicates its stores.
 //
-// CTA (192 threads, 1 per SM, persistent over 128x256 output tiles):
-//   warp 0   : TMA producer   -- cp.async.bulk.tensor.2d A(128x64) + B(256x64) per stage, 4 stages (192 KiB)
-//   warp 1   : TMEM allocator + MMA issuer -- one elected lane issues 4 x tcgen05.mma 128x256x16 per stage,
+// CTA (192 threads, 1 per SM, persistent over its share of the output tiles):
+//   warp 0   : TMA producer   -- cp.async.bulk.tensor.2d operand boxes per stage into a ring (completion on `full` mbarriers)
+//   warp 1   : TMEM allocator + MMA issuer -- one elected lane issues 4 tcgen05.mma per stage (12 in the 3xTF32 mode),
 //              tcgen05.commit releases the stage / publishes the accumulator
 //   warps 2-5: epilogue       -- tcgen05.ld 32 lanes x 32 columns -> registers -> coalesced st.global
-//   TMEM     : 2 accumulators x 256 columns, so the epilogue of tile i overlaps the MMAs of tile i+1.
+//   TMEM     : 2 accumulator buffers of 256 columns, so the epilogue of one (tile, k chunk) overlaps the MMAs of the next.
+// Variants (template parameters): NCTA = 2 runs CTA pairs (cta_group::2, 256 x bn tiles, B split across the pair, 6 stages instead
+// of 4); X3 = 1 is the split-operand FP32-grade mode with its correction accumulator and K chunks (see PipeCfg below); the tile
+// width bn and the k-chunk length are run-time arguments.
 #include <cuda.h>
 #include <cuda_bf16.h>
 
