@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Small-shape pass over every hot kernel, meant to run under `compute-sanitizer --tool memcheck` (and racecheck)."""
+"""Small-shape pass over every hot kernel through the public API with on-device checks only (no oracle): a 2-second
+"is the library alive" run for a fresh box.  (compute-sanitizer is closed on this pool; bounds are checked by the parity tests.)"""
 import ctypes as C
 import os
 import sys
@@ -40,4 +41,4 @@ for (M, K, N) in [(256, 64, 224), (130, 40, 70), (384, 32, 112)]:
         EX.matmul_bf16_(Bf, A, B)
         assert KA.isapprox(Bf, ref, rtol=1e-2)
 KA.synchronize(be)
-print("sanitize_smoke ok")
+print("smoke_all ok")
