@@ -196,7 +196,7 @@ b200_status b200_copy(void *dst, const void *src, size_t bytes);
 b200_status b200_fill(void *dst, size_t count, int32_t elsize, const void *value);
 
 /* naive_transpose_kernel!: a[i,j] = b[j,i]  (examples/naive_transpose.jl:4-7).
- * a is m x n (leading dim lda >= m), b is n x m (ldb >= n), column-major, elsize 4 or 8. */
+ * a is m x n (leading dim lda >= m), b is n x m (ldb >= n), column-major, elsize in {1,2,4,8,16} (4: the tuned tile kernel). */
 b200_status b200_transpose(void *a, const void *b, int64_t m, int64_t n, int64_t lda, int64_t ldb,
                            int32_t elsize);
 

@@ -168,8 +168,8 @@ def naive_transpose_host_(backend: B200Backend, a: np.ndarray, b: np.ndarray):
     if a.shape[0] != b.shape[1] or a.shape[1] != b.shape[0]:
         print("Matrix size mismatch!")
         return None
-    if a.dtype != b.dtype or a.dtype.itemsize not in (4, 8):
-        raise _lib.ArgumentError("naive_transpose_host_: element types must match and be 4 or 8 bytes wide")
+    if a.dtype != b.dtype or a.dtype.itemsize not in (1, 2, 4, 8, 16):
+        raise _lib.ArgumentError("naive_transpose_host_: element types must match and be 1, 2, 4, 8 or 16 bytes wide")
     m, n = a.shape
     _lib.call("b200_transpose_host", C.c_void_p(a.ctypes.data), C.c_void_p(b.ctypes.data), m, n, m, n, a.dtype.itemsize)
     return None

@@ -86,8 +86,8 @@ extern "C" b200_status b200_transpose_host(void *a_host, const void *b_host, int
     if (m < 0 || n < 0 || lda < m || ldb < n)
         return set_error(B200_ERR_INVALID_VALUE, "b200_transpose_host: bad shape m=%lld n=%lld lda=%lld ldb=%lld",
                          (long long)m, (long long)n, (long long)lda, (long long)ldb);
-    if (elsize != 4 && elsize != 8)
-        return set_error(B200_ERR_UNSUPPORTED, "b200_transpose_host: element size %d not in {4,8}", elsize);
+    if (elsize != 1 && elsize != 2 && elsize != 4 && elsize != 8 && elsize != 16)
+        return set_error(B200_ERR_UNSUPPORTED, "b200_transpose_host: element size %d not in {1,2,4,8,16}", elsize);
     if (m == 0 || n == 0) return B200_OK;
     if (!a_host || !b_host) return set_error(B200_ERR_INVALID_VALUE, "b200_transpose_host: NULL pointer");
     cudaStream_t user;

@@ -13,7 +13,7 @@
 //     contiguous dimension and stored.  Per 16 bytes moved: 1 LDG.128 + 1 STS.128 + 1 LDS.128 + 1 STG.128.
 //   any-shape path (4-byte elements, any m,n; 16-byte aligned bases, leading dimensions multiples of 4 words): the same
 //     scheme; edge tiles are predicated, interior tiles are not (6.2 TB/s at 10000 x 7000, 6.0 at 16388^2).
-//   generic path (8-byte elements, unaligned rows): 32x32 padded tile, scalar accesses, predicated edges (6.6 TB/s for
+//   generic path (1-, 2-, 8-, 16-byte elements, unaligned rows): 32x32 padded tile, scalar accesses, predicated edges (6.6 TB/s for
 //     Float64: 32 lanes x 8 bytes are full 256-byte requests already; 4.6 TB/s for 4-byte words).
 //
 // HBM bound: 2*elsize bytes of traffic per element; algorithmic bytes for 16384^2 F32 = 2^31.
@@ -161,7 +161,10 @@ __global__ void __launch_bounds__(256) transpose64_any_kernel(T *__restrict__ a,
     }
 }
 
-// Generic tile transpose with bounds checks; T is a 4- or 8-byte word type.
+// Generic tile transpose with bounds checks; T is a 1-, 2-, 4-, 8- or 16-byte word type.
+struct alignas(16) Word16 {
+    uint64_t lo, hi;
+};
 template <typename T>
 __global__ void __launch_bounds__(256) transpose32_generic_kernel(T *__restrict__ a, const T *__restrict__ b,
                                                                   int64_t m, int64_t n, int64_t lda, int64_t ldb,
@@ -218,14 +221,21 @@ int transpose_launch(void *a, const void *b, int64_t m, int64_t n, int64_t lda, 
         return set_error(B200_ERR_UNSUPPORTED, "transpose: %lld x %lld too large for the generic path", (long long)m,
                          (long long)n);
     unsigned grid = (unsigned)(tiles_i * tiles_j);
-    if (elsize == 4)
-        transpose32_generic_kernel<uint32_t>
-            <<<grid, 256, 0, st>>>((uint32_t *)a, (const uint32_t *)b, m, n, lda, ldb, tiles_j);
-    else if (elsize == 8)
-        transpose32_generic_kernel<uint64_t>
-            <<<grid, 256, 0, st>>>((uint64_t *)a, (const uint64_t *)b, m, n, lda, ldb, tiles_j);
-    else
-        return set_error(B200_ERR_UNSUPPORTED, "transpose: element size %d not in {4,8}", elsize);
+    if (elsize == 16 && ((((uintptr_t)a | (uintptr_t)b) & 15) != 0))
+        return set_error(B200_ERR_UNSUPPORTED, "transpose: 16-byte elements need 16-byte aligned arrays");
+#define B200_T32_CASE(BYTES, T)                                                                                       \
+    case BYTES:                                                                                                       \
+        transpose32_generic_kernel<T><<<grid, 256, 0, st>>>((T *)a, (const T *)b, m, n, lda, ldb, tiles_j);           \
+        break;
+    switch (elsize) {   // a pure permutation of elsize-byte words: any isbits element type of these sizes
+        B200_T32_CASE(1, uint8_t)
+        B200_T32_CASE(2, uint16_t)
+        B200_T32_CASE(4, uint32_t)
+        B200_T32_CASE(8, uint64_t)
+        B200_T32_CASE(16, Word16)
+        default: return set_error(B200_ERR_UNSUPPORTED, "transpose: element size %d not in {1,2,4,8,16}", elsize);
+    }
+#undef B200_T32_CASE
     B200_CHECK_LAUNCH("transpose32_generic_kernel");
     return B200_OK;
 }

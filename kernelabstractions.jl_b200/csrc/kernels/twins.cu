@@ -79,12 +79,17 @@ __global__ void transpose_twin_kernel(KaCtx c, T *__restrict__ a, const T *__res
 int twin_transpose(const KaCtx &c, void *a, const void *b, long long rows_a, long long rows_b, int elsize,
                    cudaStream_t st) {
     KA_LAUNCH_1D(c, groups, items);
-    if (elsize == 4)
-        transpose_twin_kernel<uint32_t><<<(unsigned)groups, (unsigned)items, 0, st>>>(c, (uint32_t *)a, (const uint32_t *)b, rows_a, rows_b);
-    else if (elsize == 8)
-        transpose_twin_kernel<uint64_t><<<(unsigned)groups, (unsigned)items, 0, st>>>(c, (uint64_t *)a, (const uint64_t *)b, rows_a, rows_b);
-    else
-        return set_error(B200_ERR_UNSUPPORTED, "naive_transpose_kernel!: element size %d", elsize);
+    switch (elsize) {
+        case 1: transpose_twin_kernel<uint8_t><<<(unsigned)groups, (unsigned)items, 0, st>>>(c, (uint8_t *)a, (const uint8_t *)b, rows_a, rows_b); break;
+        case 2: transpose_twin_kernel<uint16_t><<<(unsigned)groups, (unsigned)items, 0, st>>>(c, (uint16_t *)a, (const uint16_t *)b, rows_a, rows_b); break;
+        case 4: transpose_twin_kernel<uint32_t><<<(unsigned)groups, (unsigned)items, 0, st>>>(c, (uint32_t *)a, (const uint32_t *)b, rows_a, rows_b); break;
+        case 8: transpose_twin_kernel<uint64_t><<<(unsigned)groups, (unsigned)items, 0, st>>>(c, (uint64_t *)a, (const uint64_t *)b, rows_a, rows_b); break;
+        case 16:
+            if ((((uintptr_t)a | (uintptr_t)b) & 15) != 0) return set_error(B200_ERR_UNSUPPORTED, "naive_transpose_kernel!: 16-byte elements need 16-byte aligned arrays");
+            transpose_twin_kernel<ulonglong2><<<(unsigned)groups, (unsigned)items, 0, st>>>(c, (ulonglong2 *)a, (const ulonglong2 *)b, rows_a, rows_b);
+            break;
+        default: return set_error(B200_ERR_UNSUPPORTED, "naive_transpose_kernel!: element size %d not in {1,2,4,8,16}", elsize);
+    }
     B200_CHECK_LAUNCH("transpose_twin_kernel");
     return B200_OK;
 }

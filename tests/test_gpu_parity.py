@@ -183,6 +183,36 @@ def test_transpose_any_shape_vector_path(shape, dtype):
     assert np.array_equal(g[:m, :], b.T) and np.all(g[m:, :] == 7)
 
 
+@pytest.mark.parametrize("dtype", [np.int8, np.float16, np.complex128])
+@pytest.mark.parametrize("shape", [(64, 64), (37, 300), (1, 9), (1000, 129)])
+@pytest.mark.parametrize("twins", [0, 1])
+def test_transpose_other_element_sizes(orc, shape, dtype, twins):
+    """naive_transpose_kernel! is a permutation of isbits elements: 1-, 2- and 16-byte element types (Int8, Float16, ComplexF64)
+    through the tile kernel and the literal twin, against the oracle's byte-wise restatement, incl. a partial ndrange."""
+    m, n = shape
+    rng = np.random.default_rng(m * 7 + n)
+    raw = rng.integers(0, 256, size=n * m * np.dtype(dtype).itemsize, dtype=np.uint8)
+    b = np.asfortranarray(raw.view(dtype).reshape((n, m), order="F"))
+    a_ref = np.zeros((m, n), dtype=dtype, order="F")
+    orc.naive_transpose(a_ref, b)
+    assert bits_equal(a_ref, np.asfortranarray(b.T))
+    tune(registry__force_twins=twins)
+    try:
+        dA = KA.zeros(be, dtype, m, n)
+        dB = KA.to_device(b)
+        EX.naive_transpose_(dA, dB)
+        assert bits_equal(KA.Array(dA), a_ref)
+        if m > 8 and n > 8:
+            part = (m - 5, n - 3)
+            dA = KA.zeros(be, dtype, m, n)
+            K.naive_transpose_kernel_(be, 256)(dA, dB, ndrange=part)
+            ref = np.zeros((m, n), dtype=dtype, order="F")
+            orc.naive_transpose(ref, b, ndrange=part)
+            assert bits_equal(KA.Array(dA), ref)
+    finally:
+        tune(registry__force_twins=0)
+
+
 def test_transpose_variants(orc):
     b = orc.gen_uniform_f32((256, 192), 5)
     a_ref = F((192, 256), np.float32)
@@ -525,7 +555,8 @@ def bits_equal(x, y):
 
 
 @pytest.mark.parametrize("shape,dtype,slab_mib", [((256, 128), np.float32, 32), ((300, 1000), np.float32, 1), ((1000, 333), np.float64, 1),
-                                                  ((4096, 2048), np.float32, 4), ((64, 64), np.float32, 32), ((1, 7), np.float32, 32)])
+                                                  ((4096, 2048), np.float32, 4), ((64, 64), np.float32, 32), ((1, 7), np.float32, 32),
+                                                  ((515, 260), np.int16, 1), ((130, 70), np.complex128, 1)])
 def test_transpose_host_pipeline_matches_oracle(orc, shape, dtype, slab_mib):
     tune(hostpipe__slab_mib=slab_mib)
     b = None
