@@ -28,8 +28,8 @@
 //   warps 2-5: epilogue       -- tcgen05.ld 32 lanes x 32 columns -> registers -> coalesced st.global
 //   TMEM     : 2 accumulator buffers of 256 columns, so the epilogue of one (tile, k chunk) overlaps the MMAs of the next.
 // Variants (template parameters): NCTA = 2 runs CTA pairs (cta_group::2, 256 x bn tiles, B split across the pair, 6 stages instead
-// of 4); X3 = 1 is the split-operand FP32-grade mode with its correction accumulator and K chunks (see PipeCfg below); the tile
-// width bn and the k-chunk length are run-time arguments.
+// of 4); X3 = 1 / 2 is the split-operand FP32-grade mode with its correction accumulator and K chunks (see PipeCfg below; 2 = 256-wide
+// tiles, one TMEM buffer, 8 epilogue warps = 320 threads); the tile width bn and the k-chunk length are run-time arguments.
 #include <cuda.h>
 #include <cuda_bf16.h>
 
@@ -190,12 +190,22 @@ __device__ __forceinline__ void umma_pair(uint32_t tmem_d, uint64_t desc_a, uint
 // and A_hi*B_hi into the same accumulator (the lo*lo term is below FP32 resolution).  A stage then holds four operand tiles.
 // The tensor core truncates when it accumulates, an error that grows linearly with k, so K is processed in chunks of
 // kb_chunk k blocks: each chunk is accumulated in TMEM and the epilogue adds it to C in FP32 with round-to-nearest.
+// X3 = 2 is the same arithmetic on 256-wide tiles (CTA pairs only): main accumulator in TMEM columns [0, 256), correction
+// accumulator in [256, 512), i.e. ONE buffer -- the MMAs of a chunk wait for the epilogue of the previous one -- and eight epilogue
+// warps (two per TMEM lane group, 128 columns each) because a thread can carry 128 chunk sums, not 256.  Why: with 128-wide tiles
+// shared memory is the limit -- per k block TMA writes 48 KiB and the twelve MMAs read 12 x (4 + 2) KiB, 120 KiB in the 768 clocks the
+// tensor core needs = 156 B/clk against 128 B/clk (plain TF32 at bn = 128 measures the same 0.70 of its bn = 256 rate); 256-wide tiles
+// move 64 + 96 KiB per 1536 clocks = 104 B/clk.
 template <int NCTA, int X3>
 struct PipeCfg {
-    static constexpr int B_STAGE = (X3 ? B_BYTES / 2 : B_BYTES) / NCTA;   // X3 tiles are at most BN / 2 wide
-    static constexpr int STAGES = X3 ? (NCTA == 2 ? 4 : 3) : (NCTA == 2 ? 6 : 4);
-    static constexpr int STAGE_BYTES = (1 + X3) * (A_BYTES + B_STAGE);
+    static constexpr int SPLIT = X3 ? 1 : 0;
+    static constexpr int B_STAGE = (X3 == 1 ? B_BYTES / 2 : B_BYTES) / NCTA;   // X3 = 1 tiles are at most BN / 2 wide
+    static constexpr int STAGES = X3 == 2 ? 3 : X3 ? (NCTA == 2 ? 4 : 3) : (NCTA == 2 ? 6 : 4);
+    static constexpr int STAGE_BYTES = (1 + SPLIT) * (A_BYTES + B_STAGE);
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int EPI_WARPS = X3 == 2 ? 8 : 4;
+    static constexpr int THREADS = 64 + 32 * EPI_WARPS;
+    static constexpr int CORR_OFF = X3 == 2 ? BN : BN / 2;   // TMEM column offset of the correction accumulator
 };
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
@@ -208,7 +218,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
 }
 
 template <bool TF32, int NCTA, int X3>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(PipeCfg<NCTA, X3>::THREADS, 1)
     gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                         const __grid_constant__ CUtensorMap tmap_alo, const __grid_constant__ CUtensorMap tmap_blo,
                         float *__restrict__ C, int64_t ldc, int M, int N, int tiles_m, int tiles_n, int num_kb,
@@ -219,6 +229,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     constexpr int KB = TF32 ? BK_TF32 : BK;   // k elements per stage
     constexpr int STAGES = PipeCfg<NCTA, X3>::STAGES, STAGE_BYTES = PipeCfg<NCTA, X3>::STAGE_BYTES;
     constexpr int LO_OFF = A_BYTES + PipeCfg<NCTA, X3>::B_STAGE;   // X3: the lo tiles follow the hi tiles inside a stage
+    constexpr int SPLIT = PipeCfg<NCTA, X3>::SPLIT, CORR_OFF = PipeCfg<NCTA, X3>::CORR_OFF;
+    constexpr bool WIDE = X3 == 2;                                 // one accumulator buffer, eight epilogue warps
+    static_assert(!WIDE || NCTA == 2, "the 256-wide split-operand tiles are a CTA-pair layout");
     extern __shared__ unsigned char smem_raw[];
     // SWIZZLE_128B operands need 1024-byte aligned stage bases (the dynamic window starts at the same offset in both
     // CTAs of a pair, so the aligned bases coincide as the pair MMA requires)
@@ -244,7 +257,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tmem_full[a], 1);
-            mbar_init(&tmem_empty[a], 4 * NCTA);   // one arrive per epilogue warp of every CTA of the pair
+            mbar_init(&tmem_empty[a], PipeCfg<NCTA, X3>::EPI_WARPS * NCTA);   // one arrive per epilogue warp of every CTA of the pair
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -290,7 +303,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
                     unsigned char *sb = sa + A_BYTES;
                     if (NCTA == 2) {
                         const uint32_t lead_full = mapa_u32(smem_u32(&full[stage]), 0);
-                        if (rank == 0) mbar_expect_tx(&full[stage], (1 + X3) * 2 * (A_BYTES + bnh * 128));
+                        if (rank == 0) mbar_expect_tx(&full[stage], (1 + SPLIT) * 2 * (A_BYTES + bnh * 128));
                         if (TF32) {
 #pragma unroll
                             for (int g = 0; g < BM / 32; ++g)
@@ -306,7 +319,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
                         }
                         tma_load_2d_pair(sb, &tmap_b, kb * KB, n_base, lead_full);
                     } else {
-                        mbar_expect_tx(&full[stage], (1 + X3) * (A_BYTES + bn * 128));
+                        mbar_expect_tx(&full[stage], (1 + SPLIT) * (A_BYTES + bn * 128));
                         if (X3) {
 #pragma unroll
                             for (int g = 0; g < BM / 32; ++g)
@@ -338,10 +351,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
             int it = 0;
             for (int tile = unit; tile < num_tiles; tile += num_units) {
               for (int kb0 = 0; kb0 < num_kb; kb0 += kb_chunk, ++it) {   // one TMEM accumulator per (tile, k chunk)
-                const int acc = it & 1;
-                const uint32_t acc_phase = (uint32_t)(it >> 1) & 1;
-                mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
-                tc_fence_after();
+                const int acc = WIDE ? 0 : (it & 1);
+                const uint32_t acc_phase = (uint32_t)(WIDE ? it : (it >> 1)) & 1;
+                // WIDE: only the MAIN accumulator is handed to the epilogue at a chunk boundary, so the correction MMAs around the boundary
+                // keep the tensor core busy while the epilogue drains -- the last k block of a chunk issues main, commit, corrections; the
+                // first block of the next chunk corrections, wait for the drain, main.  (First chunk of a tile: the epilogue of the previous
+                // tile still reads the correction accumulator, so wait before anything.)
+                if (!WIDE || kb0 == 0) {
+                    mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                    tc_fence_after();
+                }
                 const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
                 const int kb1 = min(kb0 + kb_chunk, num_kb);
                 for (int kb = kb0; kb < kb1; ++kb) {
@@ -354,6 +373,39 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
                     // swizzle row = 2 units per MMA (UMMA_K * 2 bytes for BF16, UMMA_K_TF32 * 4 bytes for TF32)
                     constexpr int a_step = TF32 ? 64 : 2;
                     const uint32_t first = (uint32_t)(kb - kb0);
+                    if (WIDE) {
+                        const uint64_t dal = make_desc_mn128(sa + LO_OFF), dbl = make_desc_k128(sa + LO_OFF + A_BYTES);
+                        const uint32_t tmem_s = tmem_d + (uint32_t)CORR_OFF;
+                        const bool lead = kb0 != 0 && kb == kb0, tail = kb1 != num_kb && kb == kb1 - 1;
+                        auto corr = [&](int k) {   // A_lo * B_hi + A_hi * B_lo; restarted once per TILE, not per chunk (~2^-11 of the main term)
+                            umma_pair<true>(tmem_s, dal + (uint64_t)(a_step * k), db + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+                            umma_pair<true>(tmem_s, da + (uint64_t)(a_step * k), dbl + (uint64_t)(2 * k), idesc, 1u);
+                        };
+                        auto mainm = [&](int k) {
+                            umma_pair<true>(tmem_d, da + (uint64_t)(a_step * k), db + (uint64_t)(2 * k), idesc, (uint32_t)((first | (uint32_t)k) != 0));
+                        };
+                        if (lead) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) corr(k);
+                            mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+                            tc_fence_after();
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) mainm(k);
+                            if (tail) umma_commit_pair(&tmem_full[acc]);
+                        } else if (tail) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) mainm(k);
+                            umma_commit_pair(&tmem_full[acc]);   // covers every main MMA of the chunk; the corrections below run under the drain
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) corr(k);
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                corr(k);
+                                mainm(k);
+                            }
+                        }
+                    } else
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const uint64_t dak = da + (uint64_t)(a_step * k), dbk = db + (uint64_t)(2 * k);
@@ -364,9 +416,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
                             // main accumulator sees one truncation per k step instead of three.
                             const uint64_t dalk = make_desc_mn128(sa + LO_OFF) + (uint64_t)(a_step * k);
                             const uint64_t dblk = make_desc_k128(sa + LO_OFF + A_BYTES) + (uint64_t)(2 * k);
-                            const uint32_t tmem_s = tmem_d + (uint32_t)(BN / 2);
+                            const uint32_t tmem_s = tmem_d + (uint32_t)CORR_OFF;
+                            // WIDE: the correction accumulator is NOT restarted per k chunk -- it is ~2^-11 of the main one, so its own
+                            // truncation stays ~2^-25 of the result over any K -- and the epilogue reads it once per tile.
                             if (NCTA == 2) {
-                                umma_pair<true>(tmem_s, dalk, dbk, idesc, (first | k) != 0);
+                                umma_pair<true>(tmem_s, dalk, dbk, idesc, WIDE ? (uint32_t)((kb | k) != 0) : (uint32_t)((first | k) != 0));
                                 umma_pair<true>(tmem_s, dak, dblk, idesc, 1u);
                                 umma_pair<true>(tmem_d, dak, dbk, idesc, (first | k) != 0);
                             } else {
@@ -388,13 +442,17 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
                         phase ^= 1;
                     }
                 }
-                if (NCTA == 2) umma_commit_pair(&tmem_full[acc]); else umma_commit(&tmem_full[acc]);  // accumulator complete
+                if (!WIDE || kb1 == num_kb) {   // (WIDE: inner chunks committed after their last main MMA above)
+                    if (NCTA == 2) umma_commit_pair(&tmem_full[acc]); else umma_commit(&tmem_full[acc]);  // accumulator complete
+                }
               }
             }
         }
     } else {
-        // ===== epilogue warps 2..5: TMEM lane group = warp % 4 (own 128 rows of the tile) =====
+        // ===== epilogue warps 2..5 (2..9 when WIDE): TMEM lane group = warp % 4 (own 128 rows of the tile); WIDE: warps 2..5 take
+        // columns [0, 128) of the tile, warps 6..9 columns [128, 256) =====
         const int lane_grp = warp & 3;
+        const int col_off = WIDE ? ((warp - 2) >> 2) * (BN / 2) : 0;
         const uint32_t lead_empty0 = NCTA == 2 ? mapa_u32(smem_u32(&tmem_empty[0]), 0) : 0u;
         float accr[X3 ? BN / 2 : 1];   // X3: this thread's row of the tile, carried across the k chunks
         int it = 0;
@@ -402,8 +460,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
           int tm, tn;
           tile_coords(tile, tm, tn);
           for (int kb0 = 0; kb0 < num_kb; kb0 += kb_chunk, ++it) {
-            const int acc = it & 1;
-            const uint32_t acc_phase = (uint32_t)(it >> 1) & 1;
+            const int acc = WIDE ? 0 : (it & 1);
+            const uint32_t acc_phase = (uint32_t)(WIDE ? it : (it >> 1)) & 1;
             mbar_wait(&tmem_full[acc], acc_phase);
             tc_fence_after();
             const int64_t m = (int64_t)(tm * NCTA + (int)rank) * BM + lane_grp * 32 + lane;
@@ -412,14 +470,45 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
             const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(acc * BN);
             const bool full_tile = (int64_t)(tm * NCTA + (int)rank + 1) * BM <= M && n0 + bn <= N && (bn & 31) == 0;
             const bool add = kb0 != 0;   // later k chunks are added to what the first one produced (FP32, round to nearest)
-            if (X3) {
+            if (WIDE) {
+                // 256-wide 3xTF32 tiles: this warp's 128 columns of the main accumulator per k chunk (the MMAs of the next chunk wait for
+                // this drain, so it is four 32-column loads, not sixteen dependent ld + wait pairs), the correction accumulator once.
+                const bool last = kb0 + kb_chunk >= num_kb;
+#pragma unroll
+                for (int c = 0; c < BN / 2; c += 32) {
+                    uint32_t r[32];
+                    tmem_ld32(taddr + (uint32_t)(col_off + c), r);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) accr[X3 ? c + j : 0] = add ? accr[X3 ? c + j : 0] + __uint_as_float(r[j]) : __uint_as_float(r[j]);
+                }
+                if (last) {
+#pragma unroll
+                    for (int c = 0; c < BN / 2; c += 32) {
+                        uint32_t r[32];
+                        tmem_ld32(taddr + (uint32_t)(CORR_OFF + col_off + c), r);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) accr[X3 ? c + j : 0] += __uint_as_float(r[j]);
+                    }
+                    if (m < M) {   // the only write of C
+                        int64_t ld = ldc;
+                        asm volatile("" : "+l"(ld));   // opaque here: keeps the 128 store addresses from being hoisted (and spilled)
+                        float *pc = crow + (int64_t)col_off * ld;
+                        const int ncols = min(bn, N - n0) - col_off;
+#pragma unroll
+                        for (int c = 0; c < BN / 2; ++c) {
+                            if (c < ncols) *pc = accr[X3 ? c : 0];
+                            pc += ld;
+                        }
+                    }
+                }
+            } else if (X3) {
                 // 3xTF32: bn <= BN / 2.  The chunk sums live in registers (128 per thread) until the last chunk of the tile -- adding
                 // them to C in global memory instead cost 8 GB of read-modify-write traffic per 8192^3 product (219 -> 236 TFLOP/s).
 #pragma unroll
                 for (int c = 0; c < BN / 2; c += 16) {   // 16 columns at a time: 128 carried sums + 32 in flight fit the register file
                     uint32_t r[16], rs[16];
-                    tmem_ld16(taddr + (uint32_t)c, r);
-                    tmem_ld16(taddr + (uint32_t)(BN / 2) + (uint32_t)c, rs);   // the correction accumulator
+                    tmem_ld16(taddr + (uint32_t)(col_off + c), r);
+                    tmem_ld16(taddr + (uint32_t)(CORR_OFF + col_off + c), rs);   // the correction accumulator
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                         const float v = __uint_as_float(r[j]) + __uint_as_float(rs[j]);
@@ -427,12 +516,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
                     }
                 }
                 if (kb0 + kb_chunk >= num_kb && m < M) {   // last chunk: the only write of C
-                    float *pc = crow;
-                    const int ncols = min(bn, N - n0);
+                    int64_t ld = ldc;
+                    asm volatile("" : "+l"(ld));   // opaque here: keeps the 128 store addresses from being hoisted out of the chunk loop (and spilled)
+                    float *pc = crow + (int64_t)col_off * ld;
+                    const int ncols = min(bn, N - n0) - col_off;
 #pragma unroll
                     for (int c = 0; c < BN / 2; ++c) {
                         if (c < ncols) *pc = accr[X3 ? c : 0];
-                        pc += ldc;
+                        pc += ld;
                     }
                 }
             } else {
@@ -610,7 +701,7 @@ static int launch_tcgen05(const CUtensorMap &ta, const CUtensorMap &tb, const CU
     B200_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, PipeCfg<NCTA, X3>::SMEM_BYTES));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.blockDim = dim3(PipeCfg<NCTA, X3>::THREADS);
     cfg.dynamicSmemBytes = PipeCfg<NCTA, X3>::SMEM_BYTES;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
@@ -705,10 +796,15 @@ int gemm_tf32x3_launch(float *C, const float *A, const float *B, int64_t M, int6
     B200_CHECK_LAUNCH("split_tf32_lo_kernel");
     CUtensorMap ta, tb, talo, tblo;
     const int ncta = use_cta_pairs(M) ? 2 : 1;
-    // two TMEM accumulators (main + correction) per buffer, two buffers: 4 x 128 of the 512 columns -> tiles at most 128 wide.
-    // Narrower wave-filling widths do not pay here (1024 x 8192 panel: bn 64 -> 113 TFLOP/s against 175 with 128): `tcgemm.bn` only.
+    // CTA pairs: 256-wide tiles, one (main + correction) accumulator pair filling the 512 TMEM columns (X3 = 2; `tcgemm.x3_wide` = 0
+    // goes back to the narrow layout).  Single CTAs (M <= 128): two buffers of 128 + 128 columns -> tiles at most 128 wide (X3 = 1);
+    // narrower wave-filling widths do not pay there (1024 x 8192 panel: bn 64 -> 113 TFLOP/s against 175 with 128): `tcgemm.bn` only.
+    const bool wide = ncta == 2 && tune_get("tcgemm.x3_wide", 1) != 0;
     const int forced_bn = tune_get("tcgemm.bn", 0);
-    const int bn = (forced_bn >= 16 * ncta && forced_bn <= BN / 2 && forced_bn % (16 * ncta) == 0) ? forced_bn : BN / 2;
+    const int max_bn = wide ? BN : BN / 2;
+    const int bn = (forced_bn >= 16 * ncta && forced_bn <= max_bn && forced_bn % (16 * ncta) == 0) ? forced_bn
+                   : wide                                                                         ? pick_bn(M, N, sm_count() / ncta, ncta)
+                                                                                                  : max_bn;
     for (int lo = 0; lo < 2; ++lo) {
         B200_TRY(pipe::make_tmap_2d(lo ? &talo : &ta, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, lo ? Alo : A, M, K, lda, 32, BK_TF32,
                                     CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B));
@@ -720,6 +816,7 @@ int gemm_tf32x3_launch(float *C, const float *A, const float *B, int64_t M, int6
     // 1024 -> 7e-6 / 239; the main accumulator loses ~7.4e-9 per k (one truncation of half an ulp per 8 k)
     int kb_chunk = tune_get("tcgemm.x3_chunk_k", 256) / BK_TF32;
     if (kb_chunk < 1) kb_chunk = 1;
+    if (wide) return launch_tcgen05<true, 2, 2>(ta, tb, talo, tblo, C, ldc, M, N, (int)cdiv(K, BK_TF32), bn, kb_chunk, st);
     if (ncta == 2) return launch_tcgen05<true, 2, 1>(ta, tb, talo, tblo, C, ldc, M, N, (int)cdiv(K, BK_TF32), bn, kb_chunk, st);
     return launch_tcgen05<true, 1, 1>(ta, tb, talo, tblo, C, ldc, M, N, (int)cdiv(K, BK_TF32), bn, kb_chunk, st);
 }

@@ -165,15 +165,26 @@ ok = ok and inf_ok
 worst["tf32x3"] = 0.0
 ws3 = KA.allocate(be, np.float32, M * K + K * N)
 truth_x3 = orc.matmul_f64_truth(np.asfortranarray(A), np.asfortranarray(B))
-for bn in (64, 96, 128):
-    _lib.call("b200_tune_set", b"tcgemm.bn", bn)
-    dC = KA.allocate(be, np.float32, M, N).fill_(-7.0)
-    _lib.call("b200_matmul_f32_tf32x3", C.c_void_p(dC.ptr), C.c_void_p(dA.ptr), C.c_void_p(dB.ptr), M, K, N, M, K, M, C.c_void_p(ws3.ptr))
-    KA.synchronize(be)
-    worst["tf32x3"] = max(worst["tf32x3"], np.abs(KA.Array(dC) - truth_x3).max() / np.abs(truth_x3).max())
+x3_ref = None                                         # the tile width must not change a bit of C (same per-element arithmetic)
+x3_same = True
+for wide, widths in ((1, (64, 96, 128, 160, 224, 256)), (0, (64, 96, 128))):
+    _lib.call("b200_tune_set", b"tcgemm.x3_wide", wide)
+    x3_ref = None                                     # (the two layouts differ in how often the correction accumulator is read)
+    for bn in widths:
+        _lib.call("b200_tune_set", b"tcgemm.bn", bn)
+        dC = KA.allocate(be, np.float32, M, N).fill_(-7.0)
+        _lib.call("b200_matmul_f32_tf32x3", C.c_void_p(dC.ptr), C.c_void_p(dA.ptr), C.c_void_p(dB.ptr), M, K, N, M, K, M, C.c_void_p(ws3.ptr))
+        KA.synchronize(be)
+        got = KA.Array(dC)
+        worst["tf32x3"] = max(worst["tf32x3"], np.abs(got - truth_x3).max() / np.abs(truth_x3).max())
+        if x3_ref is None:
+            x3_ref = got
+        x3_same = x3_same and np.array_equal(got.view(np.uint32), x3_ref.view(np.uint32))
 _lib.call("b200_tune_set", b"tcgemm.bn", 0)
-print(f"tf32x3 tile widths 64/96/128 on {M}x{K}x{N}: worst max_rel_err {worst['tf32x3']:.3e}", flush=True)
-ok = ok and worst["tf32x3"] < 1e-5
+_lib.call("b200_tune_set", b"tcgemm.x3_wide", 1)
+print(f"tf32x3 tile widths 64..256 (wide layout) and 64..128 (narrow) on {M}x{K}x{N}: worst max_rel_err {worst['tf32x3']:.3e}, "
+      f"bit-identical within a layout = {x3_same}", flush=True)
+ok = ok and worst["tf32x3"] < 1e-5 and x3_same
 print(f"tile widths 128..256 step 16 on {M}x{K}x{N}: worst max_rel_err bf16={worst['bf16']:.3e} tf32={worst['tf32']:.3e}", flush=True)
 ok = ok and worst["bf16"] < 1e-4 and worst["tf32"] < 1e-4
 sys.exit(0 if ok else 1)
