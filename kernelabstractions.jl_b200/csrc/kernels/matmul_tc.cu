@@ -796,10 +796,12 @@ int gemm_tf32x3_launch(float *C, const float *A, const float *B, int64_t M, int6
     B200_CHECK_LAUNCH("split_tf32_lo_kernel");
     CUtensorMap ta, tb, talo, tblo;
     const int ncta = use_cta_pairs(M) ? 2 : 1;
-    // CTA pairs: 256-wide tiles, one (main + correction) accumulator pair filling the 512 TMEM columns (X3 = 2; `tcgemm.x3_wide` = 0
-    // goes back to the narrow layout).  Single CTAs (M <= 128): two buffers of 128 + 128 columns -> tiles at most 128 wide (X3 = 1);
+    // CTA pairs: 256-wide tiles, one (main + correction) accumulator pair filling the 512 TMEM columns (X3 = 2; `tcgemm.x3_wide` = 0 / 1
+    // pins the narrow / wide layout).  Single CTAs (M <= 128): two buffers of 128 + 128 columns -> tiles at most 128 wide (X3 = 1);
     // narrower wave-filling widths do not pay there (1024 x 8192 panel: bn 64 -> 113 TFLOP/s against 175 with 128): `tcgemm.bn` only.
-    const bool wide = ncta == 2 && tune_get("tcgemm.x3_wide", 1) != 0;
+    // (too few 256-wide tiles to occupy the CTA pairs -> the narrow layout: 256 x 8192 x 8192 measures 131 against 112 TFLOP/s)
+    const int wide_knob = tune_get("tcgemm.x3_wide", -1);
+    const bool wide = ncta == 2 && (wide_knob < 0 ? 2 * cdiv(M, 2 * BM) * cdiv(N, BN) >= sm_count() / 2 : wide_knob != 0);
     const int forced_bn = tune_get("tcgemm.bn", 0);
     const int max_bn = wide ? BN : BN / 2;
     const int bn = (forced_bn >= 16 * ncta && forced_bn <= max_bn && forced_bn % (16 * ncta) == 0) ? forced_bn

@@ -181,7 +181,7 @@ for wide, widths in ((1, (64, 96, 128, 160, 224, 256)), (0, (64, 96, 128))):
             x3_ref = got
         x3_same = x3_same and np.array_equal(got.view(np.uint32), x3_ref.view(np.uint32))
 _lib.call("b200_tune_set", b"tcgemm.bn", 0)
-_lib.call("b200_tune_set", b"tcgemm.x3_wide", 1)
+_lib.call("b200_tune_set", b"tcgemm.x3_wide", -1)
 print(f"tf32x3 tile widths 64..256 (wide layout) and 64..128 (narrow) on {M}x{K}x{N}: worst max_rel_err {worst['tf32x3']:.3e}, "
       f"bit-identical within a layout = {x3_same}", flush=True)
 ok = ok and worst["tf32x3"] < 1e-5 and x3_same
