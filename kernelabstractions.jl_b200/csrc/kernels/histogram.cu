@@ -31,6 +31,18 @@ __device__ __forceinline__ int4 ldg_stream_i4(const int4 *p) {
     return r;
 }
 
+// CTA b counts the int4 units [slice_cut(b), slice_cut(b + 1)).  The cuts fall on 512-byte lines of the INPUT ADDRESS (32 units = one
+// warp-wide LDG.128), so that no warp request straddles a line: with cuts at n4 * b / grid every warp of a CTA with an odd cut read
+// 17 sectors per request and the shared sectors came from DRAM twice -- ncu: 142.8 M DRAM sectors for 134.2 M of input (+6.4 %),
+// i.e. the kernel already moved 7.0 TB/s for 6.55 TB/s of input.
+__device__ __forceinline__ int64_t slice_cut(const int4 *in4, int64_t n4, unsigned b) {
+    if (b == 0) return 0;
+    if (b >= gridDim.x) return n4;
+    const int64_t off = (int64_t)(((uintptr_t)in4 >> 4) & 31);   // units between the previous 512-byte line and in4
+    const int64_t u = ((n4 * (int64_t)b / gridDim.x + off) & ~(int64_t)31) - off;
+    return u < 0 ? 0 : u;
+}
+
 // ---------------------------------------------------------------------------------------------
 // impl 0: thread-private byte counters
 // ---------------------------------------------------------------------------------------------
@@ -103,8 +115,7 @@ __global__ void __launch_bounds__(T, 1) hist256_bytes_kernel(int32_t *__restrict
     const uint32_t base = (uint32_t)((warp >> 2) * 128 + lane * 4 + (warp & 3));
     uint32_t acc = 0;
 
-    const int64_t u0 = n4 * (int64_t)blockIdx.x / gridDim.x;
-    const int64_t u1 = n4 * (int64_t)(blockIdx.x + 1) / gridDim.x;
+    const int64_t u0 = slice_cut(in4, n4, blockIdx.x), u1 = slice_cut(in4, n4, blockIdx.x + 1);
     // batch k covers units u0 + k*P*T + p*T + t, p = 0..P-1
     const int64_t nbatch = (u1 - u0 + (int64_t)P * T - 1) / ((int64_t)P * T);
     int4 cur[P], nxt[P];
@@ -157,8 +168,7 @@ __device__ __noinline__ void hist_count_phase(uint32_t *sh, uint32_t nbins, cons
         uint32_t b = (uint32_t)v - 1u;
         if (b < nbins) atomicAdd(mine + b, 1u);
     };
-    const int64_t u0 = n4 * (int64_t)blockIdx.x / gridDim.x;
-    const int64_t u1 = n4 * (int64_t)(blockIdx.x + 1) / gridDim.x;
+    const int64_t u0 = slice_cut(in4, n4, blockIdx.x), u1 = slice_cut(in4, n4, blockIdx.x + 1);
     const int64_t nbatch = (u1 - u0 + (int64_t)P * T - 1) / ((int64_t)P * T);
     int4 cur[P], nxt[P];
     auto load_batch = [&](int64_t k, int4 *buf) {
@@ -426,8 +436,7 @@ __global__ void __launch_bounds__(T) hist64_atomic_kernel(long long *__restrict_
         const unsigned long long b = (((unsigned long long)(uint32_t)hi << 32) | (uint32_t)lo) - 1ull;
         if (b < (unsigned long long)nbins) atomicAdd(mine + (uint32_t)b, 1u);
     };
-    const int64_t u0 = n4 * (int64_t)blockIdx.x / gridDim.x;
-    const int64_t u1 = n4 * (int64_t)(blockIdx.x + 1) / gridDim.x;
+    const int64_t u0 = slice_cut(in4, n4, blockIdx.x), u1 = slice_cut(in4, n4, blockIdx.x + 1);
     const int64_t nbatch = (u1 - u0 + (int64_t)P * T - 1) / ((int64_t)P * T);
     int4 cur[P], nxt[P];
     auto load_batch = [&](int64_t k, int4 *buf) {
