@@ -147,3 +147,26 @@ def test_distributed_transpose_block_plan():
         assert np.array_equal(a, b.T)
     with pytest.raises(KA.ArgumentError):
         mg.transpose_alltoall_blocks(10, 8, 4, 0)
+
+
+def test_histogram_slice_cuts_model():
+    """Python restatement of `slice_cut` (csrc/kernels/histogram.cu): the int4 units [cut(b), cut(b+1)) of CTA b tile [0, n4),
+    and every interior cut falls on a 512-byte line of the input ADDRESS (32 units), whatever the 16-byte alignment of the input."""
+    def cut(off, n4, grid, b):
+        if b == 0:
+            return 0
+        if b >= grid:
+            return n4
+        u = ((n4 * b // grid + off) & ~31) - off
+        return max(u, 0)
+
+    rng = np.random.default_rng(7)
+    cases = [(0, 2 ** 28, 148), (5, 2 ** 28 - 3, 148), (31, 1000, 148), (17, 33, 148), (0, 0, 148), (9, 1, 1), (3, 10 ** 6 + 7, 7)]
+    cases += [(int(rng.integers(0, 32)), int(rng.integers(0, 1 << 20)), int(rng.integers(1, 300))) for _ in range(200)]
+    for off, n4, grid in cases:
+        cuts = [cut(off, n4, grid, b) for b in range(grid + 1)]
+        assert cuts[0] == 0 and cuts[-1] == n4
+        assert all(a <= b for a, b in zip(cuts, cuts[1:]))
+        assert all((c + off) % 32 == 0 for c in cuts[1:-1] if c > 0)
+        per = n4 / grid                                   # no slice grows by more than one line over its fair share
+        assert all(b - a <= per + 32 for a, b in zip(cuts, cuts[1:]))
