@@ -44,7 +44,6 @@ constexpr int BM = 128, BN = 256, BK = 64;   // BF16: 64 k per stage, 16 per MMA
 constexpr int BK_TF32 = 32;                  // TF32: 32 k per stage,  8 per MMA (same bytes, 4 MMAs per stage)
 constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2;
 static_assert(BM * BK_TF32 * 4 == A_BYTES && BN * BK_TF32 * 4 == B_BYTES, "both variants use 128-byte operand rows");
-constexpr int NUM_THREADS = 192;
 constexpr int TMEM_COLS = 512;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
