@@ -161,8 +161,12 @@ template <int T, int P>
 __device__ __noinline__ void hist_count_phase(uint32_t *sh, uint32_t nbins, const int4 *__restrict__ in4, int64_t n4,
                                               const int32_t *__restrict__ tail, int ntail, int copies) {
     const int t = threadIdx.x, warp = t >> 5;
+    // Programmatic dependent launch (see launch_pdl): the next kernel of the stream may be scheduled as SMs drain; our own set-up
+    // runs before we wait for the previous kernel's memory.  Back-to-back steps on input shards hide ~2 us of the ~9 us a launch costs.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     for (uint32_t i = t; i < nbins * (uint32_t)copies; i += T) sh[i] = 0;
     __syncthreads();
+    asm volatile("griddepcontrol.wait;" ::: "memory");   // everything before us in the stream is complete and visible
     uint32_t *mine = sh + (uint32_t)(warp % copies) * nbins;
     auto bump = [&](int v) {
         uint32_t b = (uint32_t)v - 1u;
@@ -320,6 +324,25 @@ __global__ void hist_global_kernel(int32_t *__restrict__ bins, uint64_t nbins, c
     }
 }
 
+// Launch with the programmatic-stream-serialization attribute (`hist.pdl` = 0 turns it off): the kernel may START before the previous
+// kernel of the stream has finished IF that kernel executed griddepcontrol.launch_dependents (only this library's copy / fill / histogram
+// kernels do); it touches global memory only after its own griddepcontrol.wait, which returns when the previous grid is complete.
+template <typename... KArgs, typename... Args>
+static int launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = tune_get("hist.pdl", 1) != 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    B200_CUDA(cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...));
+    return B200_OK;
+}
+
 template <int T, int P, int ILP>
 static int launch_bytes(int32_t *bins, uint32_t nbins, const int4 *in4, int64_t n4, const int32_t *tail, int ntail,
                         int grid, cudaStream_t st) {
@@ -338,7 +361,7 @@ static int launch_atomic(int32_t *bins, uint32_t nbins, const int4 *in4, int64_t
     if (smem > 48 * 1024)
         B200_CUDA(cudaFuncSetAttribute(hist_atomic_kernel<T, P>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem));
-    hist_atomic_kernel<T, P><<<grid, T, smem, st>>>(bins, nbins, in4, n4, tail, ntail, copies);
+    B200_TRY(launch_pdl(hist_atomic_kernel<T, P>, grid, T, smem, st, bins, nbins, in4, n4, tail, ntail, copies));
     B200_CHECK_LAUNCH("hist_atomic_kernel");
     return B200_OK;
 }
@@ -548,8 +571,8 @@ int histogram_allreduce_launch(P2P *h, int32_t *bins, int64_t nbins, const int32
     const size_t smem = (size_t)nbins * copies * 4 + 16;   // + the ticket word of fused_exchange
     if (smem > 48 * 1024)
         B200_CUDA(cudaFuncSetAttribute(hist_allreduce_kernel<T, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    hist_allreduce_kernel<T, P><<<grid, T, smem, st>>>(bins, (uint32_t)nbins, reinterpret_cast<const int4 *>(input), n4,
-                                                      input + n4 * 4, tail_n, copies, peer);
+    B200_TRY(launch_pdl(hist_allreduce_kernel<T, P>, grid, T, smem, st, bins, (uint32_t)nbins, reinterpret_cast<const int4 *>(input), n4,
+                        input + n4 * 4, tail_n, copies, peer));
     B200_CHECK_LAUNCH("hist_allreduce_kernel");
     return B200_OK;
 }
