@@ -320,7 +320,9 @@ def main():
     roofline = {"bound": "hbm", "achieved": per_gpu, "peak": peaks["hbm"], "unit": "GB/s", "frac": per_gpu / peaks["hbm"],
                 "traffic": traffic_from_profiles("transpose64_f32_kernel"), "peak_source": peaks["source"],
                 "frac_of_nominal_8000": per_gpu / 8000.0, "kernel": "transpose64_f32_kernel",
-                "algorithmic_bytes_per_launch": BYTES_T}
+                "algorithmic_bytes_per_launch": BYTES_T,
+                "note": "peak = driver-measured copy; independent read + write streams reach 6.7 TB/s of total traffic on this part, "
+                        "one direction alone 7.2-7.5 (tools/micro/hbm_stream.cu, profiles/r04_hbm_stream.txt)"}
 
     # ---------------- suite: the other north-star kernels ----------------
     suite = {}
@@ -495,7 +497,9 @@ def run_suite(KA, _lib, EX, mg, orc, be, rank, world, dist, timed, peaks, steps,
                                              "roofline": {"bound": "hbm", "achieved": gbs / world, "peak": peaks["hbm"],
                                                           "frac": gbs / world / peaks["hbm"],
                                                           "traffic": traffic_from_profiles("capture:hist") if world == 1 else None,
-                                                          "algorithmic_bytes_per_launch": 4 * (s1 - s0) + 1024},
+                                                          "algorithmic_bytes_per_launch": 4 * (s1 - s0) + 1024,
+                                                          "note": "read-only stream: the measured peak is a copy (mixed traffic); read-only ceiling "
+                                                                  "7.2-7.5 TB/s (profiles/r04_hbm_stream.txt), so frac can exceed 1"},
                                              "collective": ("fused in the counting kernel: {count,tag} slot stores over NVLink peer memory "
                                                             "(b200_histogram_i32_allreduce), no NCCL launch") if world > 1 else None}
         if comm is not None:
