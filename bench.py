@@ -10,8 +10,12 @@ Headline workload (configs[1]): naive_transpose 16384 x 16384 Float32 through B2
             FP32 SIMT matmul 8192^3 [row-panel sharded], opt-in BF16 tcgen05 matmul), each with its own roofline fraction
 
 `--impl reference` times the reference's own algorithm on the host CPU (the oracle port: the Julia/PoCL reference
-cannot run here -- no Julia toolchain), same config/metric/unit.  N>1 (torchrun): one rank per GPU, slabs of the
-problem per rank (weak scaling for the headline), barrier + max-over-ranks timing.
+cannot run here -- no Julia toolchain), same config/metric/unit/steps, on every host core it may use.
+N>1 (torchrun): one rank per GPU; the headline is STRONG scaling of the ONE 16384^2 matrix of configs[1] in the
+partition of SURVEY.md 8(e): rank g owns the output columns a[:, g n/G : (g+1) n/G) and holds rows g n/G ... of b as an
+(n/G) x n column-major slab -- an ordinary (n/G) x n -> n x (n/G) transpose per GPU, no collective; barrier +
+max-over-ranks timing, value = 2*4*n^2 bytes / that time.  A compact per-kernel summary of the suite is repeated under
+roofline.suite.
 """
 from __future__ import annotations
 
@@ -54,12 +58,15 @@ def measured_peaks():
     return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, sm_max_mhz=1965.0, source="fallback")
 
 
-def traffic_from_profiles(kernel_key):
-    """dram bytes per launch from the committed ncu capture (profiles/traffic.json), or None."""
+def traffic_from_profiles(kernel_key, scale=1.0):
+    """dram bytes per launch from the committed `ncu --set full` capture of the same kernel at the 1-GPU size
+    (profiles/traffic.json, written by tools/summarize_profiles.py from the .ncu-rep), scaled to the launch timed here
+    when that is a slab of it; None when the kernel has no capture."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(p):
         try:
-            return json.load(open(p)).get(kernel_key)
+            v = json.load(open(p)).get(kernel_key)
+            return None if v is None else float(v) * scale
         except Exception:
             return None
     return None
@@ -123,43 +130,88 @@ class ClockSampler:
 # =================================================================================================
 # reference arm / cpu baseline: the oracle port of the reference CPU() algorithm
 # =================================================================================================
-def cpu_transpose_baseline(budget_s=12.0, max_passes=3):
+METRIC = "naive_transpose HBM GB/s (16384x16384 Float32)"
+
+
+def bench_config(world):
+    """The `config` object of the JSON line -- the SAME for the B200 arm and the reference arm (the driver compares them)."""
+    return {"workload": "naive_transpose 16384x16384 Float32 (examples/naive_transpose.jl), one matrix per step",
+            "l2": "inputs larger than L2 (1 GiB in, 1 GiB out per step; 128 MiB + 128 MiB per GPU at 8 GPUs)",
+            "parallelism": f"row-of-b slabs over {world} GPU(s), no collective (SURVEY.md 8(e))" if world > 1 else "1 GPU"}
+
+
+def host_cores():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def load_oracle(all_cores=True):
+    """The CPU oracle (test infrastructure: imported here only for input generation, the cpu_baseline leg and the reference arm).
+    torchrun exports OMP_NUM_THREADS=1 to its ranks; the CPU arm must use every core it may, so the OpenMP thread count is set
+    before libgomp initialises AND through omp_set_num_threads afterwards."""
+    if all_cores:
+        os.environ["OMP_NUM_THREADS"] = str(host_cores())
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import ka_oracle as orc
+    if all_cores:
+        orc.set_threads(host_cores())
+    return orc
 
+
+def cpu_transpose_baseline(steps=3, warmup=1, budget_s=12.0):
+    """`warmup` untimed + `steps` timed passes of the reference CPU() algorithm (oracle restatement: OpenMP over work-groups,
+    work-items as inner loops; workgroup (256,1), ndrange (n,n) -- the launch shape of examples/naive_transpose.jl:18-19).
+    A pass is the full 16384^2 matrix unless (warmup + steps) full passes would exceed `budget_s`: then every pass is the
+    first `cols` output columns (a bounded sample of the same workload; bytes counted for the sample only)."""
+    orc = load_oracle()
     n = N_T
     b = orc.gen_uniform_f32((n, n), 1235)
     a = np.zeros((n, n), dtype=np.float32, order="F")
+    t0 = time.perf_counter()
+    orc.naive_transpose_wg(a, b)                       # calibration pass (untimed; also first-touches `a`)
+    t_full = time.perf_counter() - t0
+    cols = n
+    while cols > 1024 and (steps + warmup) * t_full * cols / n > budget_s:
+        cols //= 2
+    a_s, b_s = (a, b) if cols == n else (a[:, :cols], b[:cols, :])
+    if cols != n:   # contiguous column-major slabs of the same matrices
+        a_s, b_s = np.asfortranarray(a_s), np.asfortranarray(b_s)
+    for _ in range(warmup):
+        orc.naive_transpose_wg(a_s, b_s)
     times = []
-    t_all = time.perf_counter()
-    for _ in range(max_passes):
+    for _ in range(steps):
         t0 = time.perf_counter()
-        orc.naive_transpose_wg(a, b)  # workgroup (256,1), ndrange (n,n): the launch shape of examples/naive_transpose.jl:18-19
+        orc.naive_transpose_wg(a_s, b_s)
         times.append(time.perf_counter() - t0)
-        if time.perf_counter() - t_all > budget_s:
-            break
-    best = min(times)
-    return dict(value=BYTES_T / best / 1e9, unit="GB/s", cores=orc.threads(), kind="port",
-                sample=f"full {n}x{n} Float32 naive_transpose (oracle restatement of KA CPU(): OpenMP over work-groups, work-items as inner loops), "
-                       f"best of {len(times)} passes", seconds=best)
+    ok = bool(np.array_equal(a_s[5, :64], b_s[:64, 5]))
+    mean = float(np.mean(times))
+    nbytes = 2 * 4 * n * cols
+    sample = (f"full {n}x{n} Float32 naive_transpose" if cols == n else
+              f"first {cols} of {n} output columns of the {n}x{n} Float32 naive_transpose ({nbytes >> 20} MiB of traffic per pass)")
+    return dict(value=nbytes / mean / 1e9, unit="GB/s", cores=orc.threads(), kind="port",
+                sample=sample + f" (oracle restatement of KA CPU(): OpenMP over work-groups, work-items as inner loops), "
+                                f"mean of {steps} timed passes after {warmup} warm-up", seconds=mean, best_seconds=float(min(times)),
+                result_checked=ok)
 
 
 def run_reference(args):
     rank = env_int("RANK", 0)
     if rank != 0:
         return 0
-    steps = max(1, min(args.steps, 3))
     t0 = time.perf_counter()
-    base = cpu_transpose_baseline(budget_s=4.0 * steps, max_passes=max(1, args.warmup and 1) + steps)
+    base = cpu_transpose_baseline(steps=args.steps, warmup=args.warmup, budget_s=150.0)
     line = {
-        "impl": "reference", "metric": "naive_transpose HBM GB/s (16384x16384 Float32)", "value": base["value"], "unit": "GB/s",
-        "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": base["seconds"] * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "naive_transpose 16384x16384 Float32 (examples/naive_transpose.jl), reference CPU() algorithm "
-                               "restated in C (oracle port; Julia/PoCL reference not runnable here)", "l2": "inputs larger than L2"},
+        "impl": "reference", "metric": METRIC, "value": base["value"], "unit": "GB/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": base["seconds"] * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": bench_config(args.gpus),
+        "impl_detail": "reference CPU() algorithm restated in C (oracle port; the Julia/PoCL reference is not runnable here), "
+                       f"{base['cores']} OpenMP threads on rank 0's host",
         "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": base["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0, "wall_s": time.perf_counter() - t0,
+        "gpu_launches": 0, "result_checked": base["result_checked"], "wall_s": time.perf_counter() - t0,
     }
     print(json.dumps(line))
     return 0
@@ -220,6 +272,9 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def all_ranks(flag):
+        return bool(max_over_ranks(0.0 if flag else 1.0) == 0.0)
+
     def new_event():
         e = C.c_void_p()
         _lib.call("b200_event_create", C.byref(e))
@@ -245,106 +300,142 @@ def main():
         barrier()
         return max_over_ranks(ms.value) / steps, int(cnt.value)
 
-    peaks = measured_peaks()
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import ka_oracle as orc  # input generation + cpu_baseline leg only
+    def graphed(fn):
+        """One step recorded into a CUDA graph through the backend's own record/replay API (b200_graph_*): at 8 GPUs a step is
+        ~45 us of device work, less than what the Python mirror needs to issue a launch; the replay is one submission."""
+        fn()
+        KA.synchronize(be)
+        g = KA.Graph(be)
+        with g:
+            fn()
+        return g.launch, g
 
-    # ---------------- headline: transpose 16384^2 F32, one full problem per GPU (weak scaling) ----------------
+    peaks = measured_peaks()
+    orc = load_oracle(all_cores=(world == 1))  # input generation + cpu_baseline leg only
+
+    # ---------------- headline: ONE transpose 16384^2 F32, rows-of-b slab per GPU (strong scaling, no collective) ----------------
     n = N_T
-    hb = orc.gen_uniform_f32((n, n), 1235 + rank)
+    j0, j1 = mg.transpose_shard(n, world, rank)
+    rb = j1 - j0
+    hb_full = orc.gen_uniform_f32((n, n), 1235)
+    hb = np.asfortranarray(hb_full[j0:j1, :]) if world > 1 else hb_full        # (rb x n, ld = rb): rows j0..j1 of b
+    del hb_full
     dB = KA.to_device(hb)
-    dA = KA.zeros(be, np.float32, n, n)
+    dA = KA.zeros(be, np.float32, n, rb)                                        # a[:, j0:j1]
 
     def step_transpose():
         EX.naive_transpose_(dA, dB)
 
+    step_transpose()
+    KA.synchronize(be)
+    slab_ok = all_ranks(bool(np.array_equal(KA.Array(dA), hb.T)))              # the whole slab, every rank, bit for bit
+    use_graph = world > 1 and os.environ.get("B200_BENCH_GRAPH", "1") != "0"
+    step_fn, graph_keep = (graphed(step_transpose) if use_graph else (step_transpose, None))
     with ClockSampler(local_rank) as clk:
-        ms_step, launches = timed(step_transpose, args.steps, warmup)
-    value = world * BYTES_T / (ms_step * 1e-3) / 1e9
-    per_gpu = BYTES_T / (ms_step * 1e-3) / 1e9
+        ms_step, launches = timed(step_fn, args.steps, warmup)
+    value = BYTES_T / (ms_step * 1e-3) / 1e9                 # whole job: the one matrix / max-over-ranks time
+    per_gpu = value / world
+    plain = None
+    if use_graph:                                            # the same step issued launch by launch from the Python mirror
+        ms_plain, _ = timed(step_transpose, args.steps, warmup)
+        plain = {"value": BYTES_T / (ms_plain * 1e-3) / 1e9, "ms_per_step": ms_plain}
 
     # ---------------- e2e: host buffers, copies inside the timed region ----------------
     e2e = None
     try:
         hp_in, hp_out = C.c_void_p(), C.c_void_p()
-        nbytes = 4 * n * n
+        nbytes = 4 * n * rb
         _lib.call("b200_host_alloc", C.byref(hp_in), nbytes)
         _lib.call("b200_host_alloc", C.byref(hp_out), nbytes)
-        h_in = np.ctypeslib.as_array((C.c_float * (n * n)).from_address(hp_in.value)).reshape((n, n), order="F")
-        h_out = np.ctypeslib.as_array((C.c_float * (n * n)).from_address(hp_out.value)).reshape((n, n), order="F")
+        h_in = np.ctypeslib.as_array((C.c_float * (n * rb)).from_address(hp_in.value)).reshape((rb, n), order="F")
+        h_out = np.ctypeslib.as_array((C.c_float * (n * rb)).from_address(hp_out.value)).reshape((n, rb), order="F")
         h_in[...] = hb
 
-        def step_e2e():
+        def step_pipe():
             # the public host-array call: slabs of b go host -> device, are transposed, and come back device -> host,
             # with the three legs of consecutive slabs overlapped (csrc/hostpipe.cu)
             EX.naive_transpose_host_(be, h_out, h_in)
 
-        e2e_steps = max(1, min(args.e2e_steps, args.steps))
-        for _ in range(2):
-            step_e2e()
-        barrier()
-        e2e_launches0 = C.c_int64()
-        _lib.call("b200_launch_counter", C.byref(e2e_launches0), 1)
-        _lib.call("b200_event_record", ev0)
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            step_e2e()
-        _lib.call("b200_event_record", ev1)
-        KA.synchronize(be)
-        wall = time.perf_counter() - t0
-        ms = C.c_float()
-        _lib.call("b200_event_elapsed_ms", ev0, ev1, C.byref(ms))
-        dt = max_over_ranks(max(ms.value * 1e-3, wall)) / e2e_steps   # device events and host clock agree; keep the larger
-        ok = bool(np.array_equal(h_out[5, :64], hb[:64, 5]) and np.array_equal(h_out[n - 3, n - 64:], hb[n - 64:, n - 3]))
-        e2e = {"value": world * BYTES_T / dt / 1e9, "unit": "GB/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
-               "ms_per_step": dt * 1e3, "steps": e2e_steps, "result_checked": ok,
-               "path": "EX.naive_transpose_host_ -> b200_transpose_host: pinned host in/out, 32 MiB slabs, h2d | kernel | d2h overlapped"}
-        # the same step without the slab pipeline (copyto! in, kernel, copyto! out on one stream), for comparison
         def step_seq():
+            # copyto! in, kernel, copyto! out on one stream
             KA.copyto_(be, dB, h_in)
             EX.naive_transpose_(dA, dB)
             KA.copyto_(be, h_out, dA)
 
-        step_seq()
+        def time_e2e(fn, k):
+            for _ in range(2):
+                fn()
+            barrier()
+            _lib.call("b200_launch_counter", None, 1)
+            _lib.call("b200_event_record", ev0)
+            t0 = time.perf_counter()
+            for _ in range(k):
+                fn()
+            _lib.call("b200_event_record", ev1)
+            KA.synchronize(be)
+            wall = time.perf_counter() - t0
+            ms = C.c_float()
+            _lib.call("b200_event_elapsed_ms", ev0, ev1, C.byref(ms))
+            barrier()
+            return max_over_ranks(max(ms.value * 1e-3, wall)) / k   # device events and host clock agree; keep the larger
+
+        e2e_steps = max(1, min(args.e2e_steps, args.steps))
+        dt_pipe = time_e2e(step_pipe, e2e_steps)
+        h_out[...] = 0
+        dt_seq = time_e2e(step_seq, e2e_steps)
+        ok_seq = bool(np.array_equal(h_out[5, :64], hb[:64, 5]) and np.array_equal(h_out[n - 3, rb - 64:], hb[rb - 64:, n - 3]))
+        # the route a user gets is the faster of the two on this host (with 8 ranks sharing one host the 3-stream slab
+        # pipeline can lose to the plain in-order copies); both are reported
+        h_out[...] = 0
+        best_fn, best_dt, best_name = (step_pipe, dt_pipe, "pipelined") if dt_pipe <= dt_seq else (step_seq, dt_seq, "in-order")
+        best_fn()
         KA.synchronize(be)
-        t0 = time.perf_counter()
-        for _ in range(2):
-            step_seq()
-        KA.synchronize(be)
-        e2e["unpipelined_value"] = world * BYTES_T / (max_over_ranks(time.perf_counter() - t0) / 2) / 1e9
+        ok = all_ranks(bool(np.array_equal(h_out, hb.T)))
+        e2e = {"value": BYTES_T / best_dt / 1e9, "unit": "GB/s", "h2d_bytes_per_step": nbytes * world, "d2h_bytes_per_step": nbytes * world,
+               "ms_per_step": best_dt * 1e3, "steps": e2e_steps, "result_checked": ok and ok_seq, "route": best_name,
+               "pipelined_value": BYTES_T / dt_pipe / 1e9, "unpipelined_value": BYTES_T / dt_seq / 1e9,
+               "path": "pipelined = EX.naive_transpose_host_ -> b200_transpose_host (pinned host in/out, 32 MiB slabs, h2d | kernel | d2h "
+                       "overlapped); in-order = KA.copyto! in, naive_transpose!, KA.copyto! out on one stream; every rank moves its own "
+                       "slab of the one matrix; bytes are whole-job totals"}
         _lib.call("b200_host_free", hp_in)
         _lib.call("b200_host_free", hp_out)
     except Exception as ex:  # keep the headline line even if pinned allocation fails
         e2e = {"value": None, "unit": "GB/s", "error": str(ex)[:200]}
 
+    slab_bytes = 2 * 4 * n * rb
     roofline = {"bound": "hbm", "achieved": per_gpu, "peak": peaks["hbm"], "unit": "GB/s", "frac": per_gpu / peaks["hbm"],
-                "traffic": traffic_from_profiles("transpose64_f32_kernel"), "peak_source": peaks["source"],
+                "traffic": traffic_from_profiles("transpose64_f32_kernel", slab_bytes / BYTES_T), "peak_source": peaks["source"],
                 "frac_of_nominal_8000": per_gpu / 8000.0, "kernel": "transpose64_f32_kernel",
-                "algorithmic_bytes_per_launch": BYTES_T,
-                "note": "peak = driver-measured copy; independent read + write streams reach 6.7 TB/s of total traffic on this part, "
-                        "one direction alone 7.2-7.5 (tools/micro/hbm_stream.cu, profiles/r04_hbm_stream.txt)"}
+                "algorithmic_bytes_per_launch": slab_bytes,
+                "note": "per GPU: slab bytes / max-over-ranks step time.  peak = driver-measured copy; independent read + write streams "
+                        "reach 6.7 TB/s of total traffic on this part, one direction alone 7.2-7.5 (tools/micro/hbm_stream.cu, "
+                        "profiles/r04_hbm_stream.txt)"}
 
     # ---------------- suite: the other north-star kernels ----------------
     suite = {}
     if not args.no_suite:
-        del dA, dB
-        suite = run_suite(KA, _lib, EX, mg, orc, be, rank, world, dist, timed, peaks, min(args.steps, 50), warmup, barrier,
-                      cpu=(rank == 0 and world == 1 and not args.no_cpu_baseline))
+        del dA, dB, graph_keep
+        suite = run_suite(KA, _lib, EX, mg, orc, be, rank, world, dist, timed, graphed, all_ranks, peaks, min(args.steps, 50), warmup, barrier,
+                          cpu=(rank == 0 and world == 1 and not args.no_cpu_baseline))
+        roofline["suite"] = {k: {"value": v.get("value"), "unit": v.get("unit"), "ms": v.get("ms_per_step"),
+                                 "frac": (v.get("roofline") or {}).get("frac"), "scaling": v.get("scaling")}
+                             for k, v in suite.items() if isinstance(v, dict) and "value" in v}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        base = cpu_transpose_baseline()
+        base = cpu_transpose_baseline(steps=3, warmup=1, budget_s=12.0)
         cpu_baseline = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     if rank == 0:
         line = {
-            "metric": "naive_transpose HBM GB/s (16384x16384 Float32)", "value": value, "unit": "GB/s", "n_gpus": world,
-            "steps": args.steps, "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world,
+            "steps": args.steps, "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "naive_transpose 16384x16384 Float32 (examples/naive_transpose.jl) via B200Backend; "
-                                   "one full matrix per GPU" + (" (slabs of a 16384 x 16384*N problem, no collective)" if world > 1 else ""),
-                       "l2": "inputs larger than L2 (1 GiB in, 1 GiB out per step)", "parallelism": f"slab{world}"},
+            "config": bench_config(world),
+            "impl_detail": "B200Backend: EX.naive_transpose_ -> b200_launch -> transpose64_f32_kernel on the rank's slab"
+                           + ("; one step = one CUDA-graph replay (b200_graph_launch) of that launch" if use_graph else ""),
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches,
+            "result_checked": slab_ok, "launch_by_launch": plain,
             "clocks": clk.summary(), "suite": suite,
         }
         print(json.dumps(line))
@@ -354,7 +445,7 @@ def main():
     return 0
 
 
-def run_suite(KA, _lib, EX, mg, orc, be, rank, world, dist, timed, peaks, steps, warmup, barrier, cpu=False):
+def run_suite(KA, _lib, EX, mg, orc, be, rank, world, dist, timed, graphed, all_ranks, peaks, steps, warmup, barrier, cpu=False):
     out = {}
 
     def cpu_time(fn, work, unit, scale, sample):
@@ -369,25 +460,57 @@ def run_suite(KA, _lib, EX, mg, orc, be, rank, world, dist, timed, peaks, steps,
                 break
         return {"value": work / best / scale, "unit": unit, "cores": orc.threads(), "kind": "port", "sample": sample}
 
-    # ---- copy 2^26 F32 (configs[0] size): alternate two buffer pairs so nothing is L2 resident ----
+    # ---- copy 2^26 F32 (configs[0] size), contiguous element slabs per rank (strong scaling, no collective).  Buffer pairs are
+    # ---- rotated so that nothing is L2 resident: at 8 GPUs a slab pair is 64 MiB, so 8 pairs (512 MiB) go round ----
     try:
         n = N_COPY
-        src = [KA.to_device(orc.gen_uniform_f32((n,), 1234 + i)) for i in range(2)]
-        dst = [KA.zeros(be, np.float32, n) for _ in range(2)]
+        c0, c1 = mg.copy_shard(n, world, rank)
+        ns = c1 - c0
+        npairs = max(2, min(8, (512 << 20) // (8 * ns)))
+        src = [KA.rand_uniform_(KA.allocate(be, np.float32, ns), 1234 + i) for i in range(npairs)]
+        dst = [KA.zeros(be, np.float32, ns) for _ in range(npairs)]
         state = {"i": 0}
 
         def step_copy():
-            i = state["i"] & 1
+            i = state["i"] % npairs
             EX.mycopy_(dst[i], src[i])
             state["i"] += 1
 
-        ms, launches = timed(step_copy, steps, warmup)
-        gbs = 2 * 4 * n / (ms * 1e-3) / 1e9
-        out["copy_2^26_f32"] = {"value": world * gbs, "unit": "GB/s", "ms_per_step": ms, "gpu_launches": launches,
-                                "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm"], "frac": gbs / peaks["hbm"],
-                                             "traffic": traffic_from_profiles("capture:copy"), "algorithmic_bytes_per_launch": 8 * n},
-                                "scaling": "weak"}
-        del src, dst
+        for _ in range(npairs):
+            step_copy()
+        KA.synchronize(be)
+        ok = all_ranks(all(KA.isequal(d, s_) for d, s_ in zip(dst, src)))
+        fn, keep = step_copy, None
+        if world > 1:      # npairs consecutive steps in one graph (keeps the buffer rotation); a "step" stays one copy
+            def cycle():
+                for _ in range(npairs):
+                    step_copy()
+            fn, keep = graphed(cycle)
+        k = max(1, steps // npairs) if world > 1 else steps
+        ms, launches = timed(fn, k, warmup)
+        if world > 1:
+            ms /= npairs
+        gbs = 2 * 4 * n / (ms * 1e-3) / 1e9          # whole job: 2^26 elements / max-over-ranks time
+        out["copy_2^26_f32"] = {"value": gbs, "unit": "GB/s", "ms_per_step": ms, "gpu_launches": launches, "result_checked": ok,
+                                "roofline": {"bound": "hbm", "achieved": gbs / world, "peak": peaks["hbm"], "frac": gbs / world / peaks["hbm"],
+                                             "traffic": traffic_from_profiles("copy_bulk_kernel", 1.0 / world),
+                                             "algorithmic_bytes_per_launch": 8 * ns},
+                                "scaling": "strong", "buffer_pairs_rotated": npairs,
+                                "launch": "CUDA-graph replay of one rotation" if world > 1 else "launch by launch"}
+        if world == 1:
+            # the literal twin (generic NDRange -> grid mapping of csrc/ka_device.cuh) against the routed tuned kernel
+            _lib.call("b200_tune_set", b"registry.force_twins", 1)
+            try:
+                ms_t, _ = timed(step_copy, steps, warmup)
+            finally:
+                _lib.call("b200_tune_set", b"registry.force_twins", 0)
+            gbs_t = 2 * 4 * n / (ms_t * 1e-3) / 1e9
+            out["copy_2^26_f32_literal_twin"] = {"value": gbs_t, "unit": "GB/s", "ms_per_step": ms_t, "scaling": "strong",
+                                                 "of_tuned": gbs_t / gbs,
+                                                 "note": "registry.force_twins=1: gpu_copy_kernel! through the generic @index(Global, Linear) "
+                                                         "lowering (strength-reduced expand/__validindex), no routing to b200_copy",
+                                                 "roofline": {"bound": "hbm", "achieved": gbs_t, "peak": peaks["hbm"], "frac": gbs_t / peaks["hbm"]}}
+        del src, dst, keep
         if cpu:
             hB, hA = orc.gen_uniform_f32((n,), 1234), np.zeros(n, dtype=np.float32)
             out["copy_2^26_f32"]["cpu_baseline"] = cpu_time(lambda: orc.copy_wg(hA, hB, 1024), 8.0 * n, "GB/s", 1e9,
@@ -439,14 +562,23 @@ def run_suite(KA, _lib, EX, mg, orc, be, rank, world, dist, timed, peaks, steps,
             step_dt()
             KA.synchronize(be)
             barrier()
-            # property check on this rank's slab: a[:, c0(rank)] column j' == row (rank*rb + j') of the GLOBAL b; rows c1(rank) of it came
-            # from this rank's own b_loc, so  a_slab[rank*rb : (rank+1)*rb, :] == transpose(b_loc[rank*rb : (rank+1)*rb, :])
-            a_own = KA.Array(a_sym.array(np.float32, (n, rb)))[rank * rb:(rank + 1) * rb, :]
-            ok = bool(np.array_equal(a_own, KA.Array(b_loc)[rank * rb:(rank + 1) * rb, :].T))
+            # every block of this rank's slab against its source, regenerated here from the peer's seed:
+            # a_slab[s*rb:(s+1)*rb, :] == transpose(b_loc of rank s [rank*rb:(rank+1)*rb, :]) -- for s != rank those bytes crossed NVLink
+            a_host = KA.Array(a_sym.array(np.float32, (n, rb)))
+            tmp = KA.allocate(be, np.float32, n, rb)
+            ok, peer_ok = True, True
+            for s_ in range(world):
+                blk = KA.Array(KA.rand_uniform_(tmp, 1235 + s_))[rank * rb:(rank + 1) * rb, :].T
+                same = bool(np.array_equal(a_host[s_ * rb:(s_ + 1) * rb, :], blk))
+                ok = ok and same
+                if s_ != rank:
+                    peer_ok = peer_ok and same
+            del tmp, a_host
+            ok, peer_ok = all_ranks(ok), all_ranks(peer_ok)
             ms, launches = timed(step_dt, steps, warmup)
             gbs = 2.0 * 4 * n * n / (ms * 1e-3) / 1e9
             out["distributed_transpose_16384_f32"] = {
-                "value": gbs, "unit": "GB/s", "ms_per_step": ms, "gpu_launches": launches, "scaling": "strong", "own_block_checked": ok,
+                "value": gbs, "unit": "GB/s", "ms_per_step": ms, "gpu_launches": launches, "scaling": "strong", "slab_checked": ok, "peer_block_checked": peer_ok,
                 "nvlink_egress_GBps_per_gpu": 4.0 * n * rb * (world - 1) / world / (ms * 1e-3) / 1e9,
                 "collective": "all-to-all fused into the transpose kernel's store phase (b200_transpose_alltoall: peer stores over NVLink + flag barrier), no NCCL",
                 "roofline": {"bound": "nvlink", "achieved": 4.0 * n * rb * (world - 1) / world / (ms * 1e-3) / 1e9, "peak": 900.0, "unit": "GB/s",

@@ -103,6 +103,14 @@ b200_status b200_device_synchronize(void);
 b200_status b200_set_priority(int32_t priority); /* -1 :low, 0 :normal, 1 :high */
 b200_status b200_get_stream(void **cuda_stream);
 b200_status b200_set_stream(void *cuda_stream);  /* adopt an external cudaStream_t (NULL = back to own) */
+/* Explicit stream handles for hosts whose unit of execution is a TASK, not an OS thread.  The reference keeps device and
+ * queue in task_local_storage (src/pocl/pocl.jl:12-41) and Julia tasks migrate between OS threads at every yield point
+ * (KA.synchronize itself yields), so the Julia layer owns one stream per (task, device, priority) and calls b200_bind
+ * before every other entry point: set the calling OS thread's device and adopt the stream in one call (NULL = the
+ * thread's own stream).  b200_stream_create makes a non-blocking stream on the calling thread's current device. */
+b200_status b200_stream_create(void **cuda_stream, int32_t priority);
+b200_status b200_stream_destroy(void *cuda_stream);
+b200_status b200_bind(int32_t device, void *cuda_stream);
 
 /* CUDA events on the calling thread's stream (device-side timing for bench.py). */
 b200_status b200_event_create(void **event);
@@ -307,6 +315,8 @@ b200_status b200_sendrecv(void *comm, const void *sendbuf, int32_t dst_rank, voi
  * b_local = b[:, rank-th block of N1/world columns] (N0 x N1/world, ld N0); on return of the stream the symmetric buffer of
  * every rank h holds a[:, h-th block of N0/world columns] (N1 x N0/world, ld N1).  One data kernel per rank whose stores go
  * straight into the destination slabs, then b200_sym_barrier.  N0, N1 multiples of 64 x world; elsize 4 or 8.
+ * Back-to-back calls are safe without a barrier in between: every rank announces at the start of its call that its slab
+ * may be overwritten (its stream has finished whatever read the previous result) and stores into a slab wait for that.
  * (the all-to-all the reference-style formulation would need, examples/mpi.jl:24-39 being its only exchange.) */
 b200_status b200_sym_alloc(void **handle, size_t bytes);
 b200_status b200_sym_export(void *handle, void *ipc64);
@@ -332,6 +342,8 @@ b200_status b200_p2p_free(void *handle);
 /* diagnostic: four %globaltimer stamps (ns) of the last fused launch (slowest CTA left the counting loop, local counts
  * merged, slots sent, all ranks' slots summed) */
 b200_status b200_p2p_debug(void *handle, uint64_t *stamps4);
+/* the same plus [4] fastest CTA left the counting loop, [5] first CTA resident (six stamps) */
+b200_status b200_p2p_timeline(void *handle, uint64_t *stamps6);
 b200_status b200_histogram_i32_allreduce(void *handle, int32_t *bins, int64_t nbins, const int32_t *input, int64_t n);
 
 #ifdef __cplusplus

@@ -118,6 +118,9 @@ SIGNATURES = {
     "b200_set_priority": (_I32, [_I32]),
     "b200_get_stream": (_I32, [_PVP]),
     "b200_set_stream": (_I32, [_VP]),
+    "b200_stream_create": (_I32, [_PVP, _I32]),
+    "b200_stream_destroy": (_I32, [_VP]),
+    "b200_bind": (_I32, [_I32, _VP]),
     "b200_event_create": (_I32, [_PVP]),
     "b200_event_record": (_I32, [_VP]),
     "b200_event_synchronize": (_I32, [_VP]),
@@ -174,6 +177,7 @@ SIGNATURES = {
     "b200_p2p_export": (_I32, [_VP, _VP]),
     "b200_p2p_connect": (_I32, [_VP, _I32, _I32, _VP]),
     "b200_p2p_free": (_I32, [_VP]),
+    "b200_p2p_timeline": (_I32, [_VP, C.POINTER(C.c_uint64)]),
     "b200_p2p_debug": (_I32, [_VP, _VP]),
     "b200_histogram_i32_allreduce": (_I32, [_VP, _VP, _I64, _VP, _I64]),
 }

@@ -8,6 +8,7 @@ of GPU backends (docs/src/implementations.md:3-11).
 from __future__ import annotations
 
 import ctypes as C
+import threading
 import time
 from typing import Optional, Sequence, Tuple
 
@@ -63,7 +64,23 @@ class CPU:
         return hash("CPU")
 
 
-_pending_host_refs = []  # host buffers of in-flight async copies (caller-preserve rule, KernelAbstractions.jl:127-142)
+# Host buffers of in-flight async copies (caller-preserve rule, KernelAbstractions.jl:127-142), keyed by the stream the copy
+# was enqueued on: synchronize() waits for ONE stream (the calling thread's, on its current device) and releases only that
+# stream's references -- a copy still in flight on another thread's stream or on another device keeps its buffer.
+_pending_host_refs: dict = {}
+_pending_lock = threading.Lock()
+
+
+def _stream_key() -> int:
+    s = C.c_void_p()
+    call("b200_get_stream", C.byref(s))
+    return s.value or 0
+
+
+def _hold(ref) -> None:
+    key = _stream_key()
+    with _pending_lock:
+        _pending_host_refs.setdefault(key, []).append(ref)
 
 
 class B200Array:
@@ -179,8 +196,11 @@ def ones(backend, T, *dims, **kw) -> B200Array:
 
 
 def _host_ptr(a: np.ndarray):
-    if not (a.flags.f_contiguous or a.flags.c_contiguous):
-        raise ArgumentError("host arrays must be contiguous")
+    """Device arrays are column-major (Julia layout); a host array's bytes are copied as they lie, so a matrix must be
+    Fortran-ordered (vectors are both)."""
+    if not a.flags.f_contiguous:
+        raise ArgumentError("host arrays of more than one dimension must be column-major (np.asfortranarray): device arrays "
+                            "are column-major and copyto! moves raw bytes")
     return a.ctypes.data_as(C.c_void_p)
 
 
@@ -203,17 +223,24 @@ def copyto_(backend, A, B):
     if a_dev and isinstance(B, np.ndarray):
         if A.size != B.size:
             raise ErrorException("Arrays must match in length")
+        # element (i, j, ...) of the host array must land on element (i, j, ...) of the column-major device array: a C-ordered
+        # matrix (numpy's default) is re-laid out first; the temporary stays alive until the stream has been waited for
         src = B if B.dtype == A.dtype else B.astype(A.dtype)
+        if not src.flags.f_contiguous:
+            src = np.asfortranarray(src)
         call("b200_memcpy_h2d_async", C.c_void_p(A.ptr), _host_ptr(src), C.c_size_t(A.nbytes))
-        _pending_host_refs.append(src)
+        _hold(src)
         return A
     if isinstance(A, np.ndarray) and b_dev:
         if A.size != B.size:
             raise ErrorException("Arrays must match in length")
         if A.dtype != B.dtype:
             raise ErrorException("copyto!: host destination must have the device array's eltype")
+        if not A.flags.f_contiguous:
+            raise ArgumentError("copyto!: a host destination of more than one dimension must be column-major "
+                                "(np.asfortranarray / order='F'); the device array's bytes are copied as they lie")
         call("b200_memcpy_d2h_async", _host_ptr(A), C.c_void_p(B.ptr), C.c_size_t(B.nbytes))
-        _pending_host_refs.append(A)
+        _hold(A)
         return A
     raise MethodError("copyto!(::B200Backend, A, B): at least one side must be a B200Array")
 
@@ -232,7 +259,9 @@ def synchronize(backend) -> None:
             _lib.check(st)
         spins += 1
         time.sleep(0 if spins < 2000 else 50e-6)
-    _pending_host_refs.clear()
+    key = _stream_key()
+    with _pending_lock:
+        _pending_host_refs.pop(key, None)      # only the stream that was waited for
 
 
 def get_backend(A):
@@ -251,12 +280,14 @@ def functional(backend) -> bool:
 
 def pagelock_(backend, x: np.ndarray) -> None:
     """KA.pagelock! (reference src/KernelAbstractions.jl:166)"""
-    call("b200_host_register", _host_ptr(x), C.c_size_t(x.nbytes))
+    if not (x.flags.f_contiguous or x.flags.c_contiguous):
+        raise ArgumentError("pagelock!: host arrays must be contiguous")
+    call("b200_host_register", x.ctypes.data_as(C.c_void_p), C.c_size_t(x.nbytes))
 
 
 def unpagelock_(backend, x: np.ndarray) -> None:
     """Undo pagelock_ before the host array is freed (the registration outlives the Python object otherwise)."""
-    call("b200_host_unregister", _host_ptr(x))
+    call("b200_host_unregister", x.ctypes.data_as(C.c_void_p))
 
 
 def supports_float64(backend) -> bool:

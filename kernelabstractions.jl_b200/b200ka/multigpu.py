@@ -111,6 +111,14 @@ class PeerGroup:
         _lib.call("b200_p2p_debug", self.handle, buf)
         return [int(buf[i]) - int(buf[0]) for i in (1, 2, 3)]
 
+    def timeline(self):
+        """ns timeline of the last fused launch relative to the moment its FASTEST CTA left the counting loop (b200_p2p_timeline)."""
+        buf = (C.c_uint64 * 6)()
+        _lib.call("b200_p2p_timeline", self.handle, buf)
+        t0 = int(buf[4])
+        return {"first_cta_resident": int(buf[5]) - t0, "slowest_cta_done": int(buf[0]) - t0, "counts_merged": int(buf[1]) - int(buf[0]),
+                "slots_sent": int(buf[2]) - int(buf[0]), "all_summed": int(buf[3]) - int(buf[0])}
+
     def free(self) -> None:
         if self.handle:
             _lib.call("b200_p2p_free", self.handle)

@@ -157,9 +157,13 @@ __global__ void __launch_bounds__(T, 1) hist256_bytes_kernel(int32_t *__restrict
 // histogram + all-reduce kernel, so both run exactly the same SASS for the hot loop: inlined into the larger fused
 // kernel, ptxas scheduled the four in-flight LDG.128 differently and the loop lost 13 % (745 us instead of 650 us for
 // 2^30 elements; profiles/r02_hist_fused_notes.md).
+// `tail`/`ntail`: the scalar leftovers, counted by CTA 0 -- the n % 4 elements behind the int4 body and, when the input is not
+// 16-byte aligned, the (< 4) head elements in front of it: both lie in ONE array of <= 6 words when head + body + tail are
+// contiguous, so the callers pass the head through `head`/`nhead`.
 template <int T, int P>
 __device__ __noinline__ void hist_count_phase(uint32_t *sh, uint32_t nbins, const int4 *__restrict__ in4, int64_t n4,
-                                              const int32_t *__restrict__ tail, int ntail, int copies) {
+                                              const int32_t *__restrict__ tail, int ntail, int copies,
+                                              const int32_t *__restrict__ head = nullptr, int nhead = 0) {
     const int t = threadIdx.x, warp = t >> 5;
     // Programmatic dependent launch (see launch_pdl): the next kernel of the stream may be scheduled as SMs drain; our own set-up
     // runs before we wait for the previous kernel's memory.  Back-to-back steps on input shards hide ~2 us of the ~9 us a launch costs.
@@ -196,6 +200,7 @@ __device__ __noinline__ void hist_count_phase(uint32_t *sh, uint32_t nbins, cons
         for (int p = 0; p < P; ++p) cur[p] = nxt[p];
     }
     if (blockIdx.x == 0 && t < ntail) bump(tail[t]);
+    if (blockIdx.x == 0 && t >= 32 && t < 32 + nhead) bump(head[t - 32]);
     __syncthreads();
 }
 
@@ -222,8 +227,17 @@ __global__ void __launch_bounds__(T) hist_atomic_kernel(int32_t *__restrict__ bi
 // data and "it has arrived" travel together and no fence, flag or atomic crosses NVLink (the LL idea of NCCL): a
 // system-scope fence alone costs ~7 us on this box (b200_p2p_debug timeline), more than a whole NCCL all-reduce of 1 KiB.
 // tag = step + 1; slots are double-buffered by step parity, which is race-free because a rank can start step e+2 only
-// after every rank has finished step e+1, hence has long read its step-e slots.  Sums are taken in rank order: integer
-// adds, bit-identical to b200_histogram_i32 + b200_allreduce_sum_i32.  One launch per step, no NCCL kernel.
+// after every rank has finished step e+1, hence has long read its step-e slots.  Integer adds: bit-identical to
+// b200_histogram_i32 + b200_allreduce_sum_i32 in any order.  One launch per step, no NCCL kernel.
+//
+// What is on the critical path after the slowest CTA of the slowest rank has left the counting loop (r05): fold of the private
+// copies -> red.global into the partial -> fence + ticket -> [last CTA] partial -> slot stores over NVLink -> poll -> bins.
+// The poll used to walk the 8 sources of a bin one after the other, every step a dependent ~0.7 us system-scope load: ~5 us
+// for 8 ranks.  Now the (bin, source) pairs are spread over all threads of the CTA -- 8 consecutive lanes hold the 8 sources of
+// one bin, every thread has all its slot loads in flight at once, and the sources are summed with three shuffles -- so the
+// poll costs one round trip (plus re-polls of slots that have not landed).  The last CTA also skips the round trip of its own
+// counts through the partial (they are still in its shared memory) and the ticket is taken with one acq_rel atomic instead of
+// atomic + two fences.
 struct HistPeer {
     int world;
     int rank;
@@ -231,8 +245,10 @@ struct HistPeer {
     uint32_t nbins_max;               // slot stride
     uint32_t *counter;                // local ticket counter (zero between launches)
     uint32_t *partial;                // local per-bin partial (zero between launches)
-    unsigned long long *stamps;       // %globaltimer stamps of the last launch (b200_p2p_debug)
+    unsigned long long *stamps;       // %globaltimer stamps of the last launch (b200_p2p_debug / b200_p2p_timeline)
     unsigned long long *slots[8];     // rank r's slot array: [2 halves][8 source ranks][nbins_max] x {count, tag}
+    uint32_t *error_flag;             // pinned host word (zero-copy): set when the poll below gives up
+    unsigned long long timeout_ns;    // 0 = wait for ever
 };
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
@@ -251,9 +267,12 @@ template <int T>
 __device__ __noinline__ void fused_exchange(uint32_t *sh, uint32_t nbins, int copies, int32_t *__restrict__ bins,
                                             const HistPeer &peer) {
     const int t = threadIdx.x, warp = t >> 5;
-    if (t == 0) atomicMax(peer.stamps + 0, globaltimer_ns());                          // slowest CTA leaves the counting loop
-    // Fold the private copies into copy 0, then let ONE warp publish the CTA's counts, fence and take the ticket (a
-    // device-scope fence waits for the warp's outstanding atomics; one fencing warp per CTA is enough).
+    if (t == 0) {
+        const unsigned long long now = globaltimer_ns();
+        atomicMax(peer.stamps + 0, now);                                                 // slowest CTA leaves the counting loop
+        atomicMin(peer.stamps + 4, now);                                                 // fastest CTA leaves the counting loop
+    }
+    // Fold the private copies into copy 0.
     for (uint32_t b = t; b < nbins; b += T) {
         uint32_t s = 0;
         for (int c = 0; c < copies; ++c) s += sh[(uint32_t)c * nbins + b];
@@ -261,43 +280,93 @@ __device__ __noinline__ void fused_exchange(uint32_t *sh, uint32_t nbins, int co
     }
     uint32_t &ticket = sh[nbins * (uint32_t)copies];   // one spare word behind the private copies (dynamic smem)
     __syncthreads();
-    if (warp == 0) {
-        for (uint32_t b = t; b < nbins; b += 32) {
-            const uint32_t s = sh[b];
-            if (s) atomicAdd(peer.partial + b, s);
+    // Draw the ticket FIRST (relaxed: it only orders the CTAs): the CTA that draws the last one keeps its counts in shared
+    // memory, every other CTA publishes them (red.global) and then raises `published` with a release at device scope.
+    if (t == 0) ticket = atomicAdd(peer.counter, 1u);
+    __syncthreads();
+    const bool last = ticket == gridDim.x - 1;
+    uint32_t *published = peer.counter + 1;
+    if (!last) {
+        if (warp == 0) {
+            for (uint32_t b = t; b < nbins; b += 32) {
+                const uint32_t s = sh[b];
+                if (s) atomicAdd(peer.partial + b, s);
+            }
+            __threadfence();                           // every lane: its reds are performed before the count below is visible
+            __syncwarp();
+            if (t == 0) atomicAdd(published, 1u);
         }
-        __threadfence();
-        __syncwarp();
-        if (t == 0) {
-            ticket = atomicAdd(peer.counter, 1u);
-            __threadfence();
-        }
+        return;
+    }
+    // ---- last CTA of this GPU ----
+    if (t == 0) {
+        peer.stamps[1] = globaltimer_ns();                                               // local counting done (ticket drawn)
+        uint32_t seen;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(published) : "memory");
+        } while (seen != gridDim.x - 1);
+        peer.counter[0] = 0;                                                             // ready for the next launch
+        peer.counter[1] = 0;
     }
     __syncthreads();
-    if (ticket != gridDim.x - 1) return;   // only the last CTA of this GPU goes on
-    if (t == 0) {
-        peer.stamps[1] = globaltimer_ns();                                               // local counting done
-        *peer.counter = 0;                                                               // ready for the next launch
-    }
     const uint32_t tag = peer.epoch + 1u;
     const size_t half = (size_t)(peer.epoch & 1u) * 8u * peer.nbins_max;
     for (uint32_t b = t; b < nbins; b += T) {
-        const uint32_t v = __ldcg(peer.partial + b);
+        const uint32_t v = __ldcg(peer.partial + b) + sh[b];
         peer.partial[b] = 0;
         for (int r = 0; r < peer.world; ++r) st_slot(peer.slots[r] + half + (size_t)peer.rank * peer.nbins_max + b, v, tag);
     }
     if (t == 0) peer.stamps[2] = globaltimer_ns();                                       // slots sent
+    // Poll: pair index q = b * 8 + src (8 consecutive lanes = the 8 possible sources of bin b).  A thread owns pairs
+    // q = t, t + T, ... ; all of its loads are issued before any is checked.
     const unsigned long long *mine = peer.slots[peer.rank] + half;
-    for (uint32_t b = t; b < nbins; b += T) {
-        uint32_t sum = 0;
-        for (int src = 0; src < peer.world; ++src) {
-            uint32_t v, g;
-            do {
-                ld_slot(mine + (size_t)src * peer.nbins_max + b, v, g);
-            } while (g != tag);
-            sum += v;
+    const unsigned long long t_start = globaltimer_ns();
+    const int src = t & 7;
+    const bool src_on = src < peer.world;
+    bool gave_up = false;
+    for (uint32_t b0 = 0; b0 < nbins; b0 += 4 * (T / 8)) {       // 4 bins per thread and pass
+        uint32_t v[4], g[4];
+        const unsigned long long *p[4];
+        bool want[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t b = b0 + (uint32_t)k * (T / 8) + (uint32_t)(t >> 3);
+            want[k] = src_on && b < nbins;
+            p[k] = mine + (size_t)src * peer.nbins_max + (want[k] ? b : 0);
+            v[k] = 0;
+            g[k] = tag;
         }
-        bins[b] += (int32_t)sum;                                                         // accumulate like the reference's +=
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (want[k]) ld_slot(p[k], v[k], g[k]);
+        uint32_t spins = 0;
+        while (true) {
+            bool pending = false;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (want[k] && g[k] != tag) {
+                    ld_slot(p[k], v[k], g[k]);
+                    pending = pending || g[k] != tag;
+                }
+            if (!pending) break;
+            if (peer.timeout_ns && (++spins & 1023u) == 0 && globaltimer_ns() - t_start > peer.timeout_ns) {
+                gave_up = true;                      // a peer never arrived (failed launch / validation on that rank)
+                break;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            uint32_t sum = (want[k] && g[k] == tag) ? v[k] : 0u;
+            sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+            sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+            sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+            const uint32_t b = b0 + (uint32_t)k * (T / 8) + (uint32_t)(t >> 3);
+            if (src == 0 && b < nbins) bins[b] += (int32_t)sum;                          // accumulate like the reference's +=
+        }
+    }
+    if (gave_up) {
+        *reinterpret_cast<volatile uint32_t *>(peer.error_flag) = tag;                   // bins are incomplete: the host reports it
+        __threadfence_system();
     }
     __syncthreads();
     if (t == 0) peer.stamps[3] = globaltimer_ns();                                       // every rank's slots summed
@@ -307,10 +376,12 @@ template <int T, int P>
 __global__ void __launch_bounds__(T) hist_allreduce_kernel(int32_t *__restrict__ bins, uint32_t nbins,
                                                            const int4 *__restrict__ in4, int64_t n4,
                                                            const int32_t *__restrict__ tail, int ntail, int copies,
+                                                           const int32_t *__restrict__ head, int nhead,
                                                            const __grid_constant__ HistPeer peer) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t *sh = reinterpret_cast<uint32_t *>(smem_raw);
-    hist_count_phase<T, P>(sh, nbins, in4, n4, tail, ntail, copies);
+    if (blockIdx.x == 0 && threadIdx.x == 0) peer.stamps[5] = globaltimer_ns();          // first CTA resident
+    hist_count_phase<T, P>(sh, nbins, in4, n4, tail, ntail, copies, head, nhead);
     fused_exchange<T>(sh, nbins, copies, bins, peer);
 }
 
@@ -532,7 +603,7 @@ int histogram64_launch(long long *bins, int64_t nbins, const long long *input, i
 // symmetric peer buffers (cudaIpc) for the fused histogram + all-reduce
 // ---------------------------------------------------------------------------------------------
 constexpr uint32_t kP2PMaxBins = 14336;
-constexpr size_t kP2PCounterOff = 0, kP2PStampsOff = 8, kP2PPartialOff = 128;
+constexpr size_t kP2PCounterOff = 0 /* ticket, published */, kP2PStampsOff = 8 /* 8 x u64 */, kP2PPartialOff = 128;
 constexpr size_t kP2PSlotsOff = (kP2PPartialOff + (size_t)kP2PMaxBins * 4 + 255) / 256 * 256;
 constexpr size_t kP2PBytes = kP2PSlotsOff + 2 * 8 * (size_t)kP2PMaxBins * 8;
 
@@ -541,26 +612,39 @@ struct P2P {
     int world = 0, rank = -1;
     void *peer[8] = {};
     uint32_t epoch = 0;
+    uint32_t *error_host = nullptr;   // pinned, mapped: the kernel's "a peer never arrived" flag
+    uint32_t *error_dev = nullptr;
 };
 
 int histogram_allreduce_launch(P2P *h, int32_t *bins, int64_t nbins, const int32_t *input, int64_t n, cudaStream_t st) {
     if (h->world < 1) return set_error(B200_ERR_INVALID_VALUE, "b200_histogram_i32_allreduce: b200_p2p_connect has not been called");
     if (nbins > kP2PMaxBins || nbins < 1)
         return set_error(B200_ERR_UNSUPPORTED, "b200_histogram_i32_allreduce: nbins must be 1..%u", kP2PMaxBins);
-    if (((uintptr_t)input & 15) != 0)
-        return set_error(B200_ERR_UNSUPPORTED, "b200_histogram_i32_allreduce: input must be 16-byte aligned");
+    if (((uintptr_t)input & 3) != 0)
+        return set_error(B200_ERR_INVALID_VALUE, "b200_histogram_i32_allreduce: input must be 4-byte aligned");
+    if (h->error_host && *h->error_host != 0) {
+        const uint32_t step = *h->error_host;
+        return set_error(B200_ERR_CUDA, "b200_histogram_i32_allreduce: step %u timed out waiting for a peer's counts (a rank skipped the "
+                         "collective or its launch failed); the communicator is out of step -- free it and connect again", step);
+    }
     HistPeer peer;
     peer.world = h->world;
     peer.rank = h->rank;
-    peer.epoch = h->epoch++;
+    peer.epoch = h->epoch;           // advanced only after a successful launch: a rank whose launch fails stays in step
     peer.nbins_max = kP2PMaxBins;
     peer.counter = (uint32_t *)((char *)h->local + kP2PCounterOff);
     peer.stamps = (unsigned long long *)((char *)h->local + kP2PStampsOff);
     peer.partial = (uint32_t *)((char *)h->local + kP2PPartialOff);
+    peer.error_flag = h->error_dev;
+    peer.timeout_ns = (unsigned long long)tune_get("hist.fused_timeout_ms", 10000) * 1000000ull;
     for (int r = 0; r < 8; ++r)
         peer.slots[r] = r < h->world ? (unsigned long long *)((char *)h->peer[r] + kP2PSlotsOff) : nullptr;
-    const int64_t n4 = n / 4;
-    const int tail_n = (int)(n - n4 * 4);
+    // [unaligned head (< 4 elements) | 16-byte aligned int4 body | tail (< 4 elements)]: head and tail are counted by CTA 0
+    int64_t head = ((uintptr_t)input & 15) ? (int64_t)((16 - ((uintptr_t)input & 15)) / 4) : 0;
+    if (head > n) head = n;
+    const int32_t *body = input + head;
+    const int64_t n4 = (n - head) / 4;
+    const int tail_n = (int)((n - head) - n4 * 4);
     constexpr int T = 1024, P = 4;
     int copies = (int)((48 * 1024 - 16) / (nbins * 4));
     if (copies > T / 32) copies = T / 32;
@@ -571,9 +655,10 @@ int histogram_allreduce_launch(P2P *h, int32_t *bins, int64_t nbins, const int32
     const size_t smem = (size_t)nbins * copies * 4 + 16;   // + the ticket word of fused_exchange
     if (smem > 48 * 1024)
         B200_CUDA(cudaFuncSetAttribute(hist_allreduce_kernel<T, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    B200_TRY(launch_pdl(hist_allreduce_kernel<T, P>, grid, T, smem, st, bins, (uint32_t)nbins, reinterpret_cast<const int4 *>(input), n4,
-                        input + n4 * 4, tail_n, copies, peer));
+    B200_TRY(launch_pdl(hist_allreduce_kernel<T, P>, grid, T, smem, st, bins, (uint32_t)nbins, reinterpret_cast<const int4 *>(body), n4,
+                        body + n4 * 4, tail_n, copies, input, (int)head, peer));
     B200_CHECK_LAUNCH("hist_allreduce_kernel");
+    h->epoch++;
     return B200_OK;
 }
 
@@ -592,6 +677,10 @@ extern "C" b200_status b200_p2p_alloc(void **handle) {
         return set_error(B200_ERR_OOM, "b200_p2p_alloc: cudaMalloc failed: %s", cudaGetErrorString(e));
     }
     B200_CUDA(cudaMemset(h->local, 0, kP2PBytes));
+    B200_CUDA(cudaMemset((char *)h->local + kP2PStampsOff + 4 * 8, 0xff, 8));   // stamp 4 is an atomicMin
+    B200_CUDA(cudaHostAlloc((void **)&h->error_host, 64, cudaHostAllocMapped | cudaHostAllocPortable));
+    *h->error_host = 0;
+    B200_CUDA(cudaHostGetDevicePointer((void **)&h->error_dev, h->error_host, 0));
     *handle = h;
     return B200_OK;
 }
@@ -636,6 +725,19 @@ extern "C" b200_status b200_p2p_debug(void *handle, uint64_t *stamps4) {
     B200_CUDA(cudaStreamSynchronize(st));
     B200_CUDA(cudaMemcpy(stamps6, (char *)((P2P *)handle)->local + kP2PStampsOff, 32, cudaMemcpyDeviceToHost));
     B200_CUDA(cudaMemset((char *)((P2P *)handle)->local + kP2PStampsOff, 0, 8));   // stamp 0 is an atomicMax
+    B200_CUDA(cudaMemset((char *)((P2P *)handle)->local + kP2PStampsOff + 4 * 8, 0xff, 8));   // stamp 4 is an atomicMin
+    return B200_OK;
+}
+
+// Six stamps: [0..3] as b200_p2p_debug, [4] fastest CTA left the counting loop, [5] CTA 0 became resident.
+extern "C" b200_status b200_p2p_timeline(void *handle, uint64_t *stamps6) {
+    if (!handle || !stamps6) return set_error(B200_ERR_INVALID_VALUE, "NULL argument");
+    cudaStream_t st;
+    B200_TRY(current_stream(&st));
+    B200_CUDA(cudaStreamSynchronize(st));
+    B200_CUDA(cudaMemcpy(stamps6, (char *)((P2P *)handle)->local + kP2PStampsOff, 48, cudaMemcpyDeviceToHost));
+    B200_CUDA(cudaMemset((char *)((P2P *)handle)->local + kP2PStampsOff, 0, 8));
+    B200_CUDA(cudaMemset((char *)((P2P *)handle)->local + kP2PStampsOff + 4 * 8, 0xff, 8));
     return B200_OK;
 }
 
@@ -646,6 +748,7 @@ extern "C" b200_status b200_p2p_free(void *handle) {
     for (int r = 0; r < h->world; ++r)
         if (r != h->rank && h->peer[r]) (void)cudaIpcCloseMemHandle(h->peer[r]);
     if (h->local) (void)cudaFree(h->local);
+    if (h->error_host) (void)cudaFreeHost(h->error_host);
     delete h;
     return B200_OK;
 }

@@ -24,7 +24,8 @@
 namespace b200 {
 
 constexpr int kSymMaxRanks = 8;
-constexpr size_t kSymFlagBytes = 256;   // [0..7]: arrival flags written by the peers, one 8-byte word each
+constexpr size_t kSymFlagBytes = 256;   // words [0..7]: arrival flags of b200_sym_barrier, [8..15]: "slab may be overwritten" flags
+                                        // of b200_transpose_alltoall -- written by the peers, one 8-byte word per source rank
 
 struct Sym {
     void *local = nullptr;      // user bytes, then kSymFlagBytes of flags
@@ -32,6 +33,7 @@ struct Sym {
     int world = 0, rank = -1;
     void *peer[kSymMaxRanks] = {};
     unsigned long long epoch = 0;
+    unsigned long long a2a_calls = 0;   // b200_transpose_alltoall calls so far (the value of the "ready" flags)
 };
 
 struct A2APeers {
@@ -49,15 +51,38 @@ __device__ __forceinline__ V16<T> ldg_v(const T *p) {
     return *reinterpret_cast<V16<T> *>(&r);
 }
 
+// Write-after-read guard of the distributed transpose.  Rank h's slab may still be read by the kernels h enqueued after the
+// PREVIOUS call; h's stream reaches its own call k only when they are done, and the first thing that call does is to raise
+// "ready = k" in every peer's flag area (words 8 + h).  A CTA that is about to store into h's slab waits for that word -- in
+// steady state it was raised long ago and the wait is one L2 read hidden behind the tile's loads.  No deadlock: a rank raises
+// its flags without waiting for anybody.
+__device__ __forceinline__ void a2a_post_ready(const A2APeers &flags, int world, int rank, unsigned long long call) {
+    if (blockIdx.x < (unsigned)world && threadIdx.x == 0) {
+        unsigned long long *theirs = reinterpret_cast<unsigned long long *>(flags.dst[blockIdx.x]) + 8 + rank;
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(theirs), "l"(call) : "memory");
+    }
+}
+__device__ __forceinline__ void a2a_wait_ready(const A2APeers &flags, int rank, int h, unsigned long long call) {
+    if (threadIdx.x == 0) {
+        const unsigned long long *mine = reinterpret_cast<const unsigned long long *>(flags.dst[rank]) + 8 + h;
+        unsigned long long v;
+        do {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
+        } while (v < call);
+    }
+}
+
 // Rank g's data kernel.  src block for destination h: b_local + h * rows_blk (rows_blk = N0/G rows of every local column);
 // its transpose (cols_blk x rows_blk) goes to peers.dst[h] + row_off (row_off = g * cols_blk) with leading dimension ld_dst = N1.
 // Tile scheme and swizzle as transpose64_any_kernel (transpose.cu); rows_blk, cols_blk multiples of 64.
 template <typename T>
 __global__ void __launch_bounds__(256) transpose_a2a_kernel(A2APeers peers, const T *__restrict__ b_local, int64_t ld_src, int64_t ld_dst,
-                                                            int64_t rows_blk, int64_t row_off, int tiles_i, int tiles_j, int first_dst, int order, int world) {
+                                                            int64_t rows_blk, int64_t row_off, int tiles_i, int tiles_j, int first_dst, int order, int world,
+                                                            A2APeers flags, unsigned long long call) {
     constexpr int V = 16 / sizeof(T), CH = 64 / V, PASSES = CH * CH / 256, ROWS_PER_PASS = 256 / CH;
     __shared__ V16<T> tile[64 * CH];
     const int t = threadIdx.x;
+    a2a_post_ready(flags, world, first_dst, call);
     // Destinations are INTERLEAVED over consecutive CTAs (a 1-d grid of world x tiles): the local tiles run at HBM speed, the
     // remote ones at NVLink speed, and a grid that did one destination after the other (blockIdx.y) finished the local block
     // first and only then started to use the links -- 0.481 ms instead of 0.40 ms for 16384^2 on two GPUs.
@@ -85,6 +110,7 @@ __global__ void __launch_bounds__(256) transpose_a2a_kernel(A2APeers peers, cons
             tile[(V * jq + c) * CH + (iq ^ jq)] = w;
         }
     }
+    a2a_wait_ready(flags, first_dst, h, call);   // thread 0, before the barrier: nobody stores into h's slab earlier
     __syncthreads();
     const int ic = t % CH, jr = t / CH;
 #pragma unroll
@@ -110,11 +136,12 @@ struct A2AMaps {
 template <typename T, int TI, int TJ>
 __global__ void __launch_bounds__(256) transpose_a2a_tma_kernel(const __grid_constant__ A2AMaps maps, const T *__restrict__ b_local,
                                                                 int64_t ld_src, int64_t rows_blk, int row_off, int tiles_i, int tiles_j, int first_dst,
-                                                                int order, int world) {
+                                                                int order, int world, A2APeers flags, unsigned long long call) {
     constexpr int V = 16 / sizeof(T), CI = TI / V, CJ = TJ / V, PASSES = CI * CJ / 256;
     static_assert(CI * CJ % 256 == 0 && 256 % CJ == 0, "tile must be a whole number of passes of 256 threads");
     __shared__ __align__(128) V16<T> tile[TJ * CI];   // [j][chunk of i], dense: exactly the box the tensor map describes
     const int t = threadIdx.x;
+    a2a_post_ready(flags, world, first_dst, call);
     const int h = (first_dst + (int)(blockIdx.x % (unsigned)world)) % world;   // destinations interleaved over consecutive CTAs
     const unsigned tile_id = blockIdx.x / (unsigned)world;
     const int tj = order ? tile_id / tiles_i : tile_id % tiles_j, ti = order ? tile_id % tiles_i : tile_id / tiles_j;
@@ -137,6 +164,7 @@ __global__ void __launch_bounds__(256) transpose_a2a_tma_kernel(const __grid_con
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the bulk engine
     __syncthreads();
+    a2a_wait_ready(flags, first_dst, h, call);
     if (t == 0) {
         asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(&maps.m[h]),
                      "r"(row_off + (int)i0), "r"((int)j0), "r"(pipe::smem_u32(tile))
@@ -262,8 +290,12 @@ extern "C" b200_status b200_transpose_alltoall(void *a_sym, const void *b_local,
     cudaStream_t st;
     B200_TRY(current_stream(&st));
     const int64_t rows_blk = N0 / G, cols_blk = N1 / G;   // a block of b_local: rows_blk x cols_blk; its transpose: cols_blk x rows_blk
-    A2APeers peers;
-    for (int r = 0; r < kSymMaxRanks; ++r) peers.dst[r] = r < G ? h->peer[r] : nullptr;
+    A2APeers peers, flags;
+    for (int r = 0; r < kSymMaxRanks; ++r) {
+        peers.dst[r] = r < G ? h->peer[r] : nullptr;
+        flags.dst[r] = r < G ? (char *)h->peer[r] + h->bytes : nullptr;
+    }
+    const unsigned long long call = ++h->a2a_calls;
     const int tiles_i = (int)(cols_blk / 64), tiles_j = (int)(rows_blk / 64);
     if ((int64_t)tiles_i * tiles_j * G > INT32_MAX) return set_error(B200_ERR_UNSUPPORTED, "b200_transpose_alltoall: too many tiles");
     const dim3 grid((unsigned)(tiles_i * tiles_j * G));
@@ -283,22 +315,22 @@ extern "C" b200_status b200_transpose_alltoall(void *a_sym, const void *b_local,
         const dim3 g2((unsigned)((cols_blk / TI) * tj_n * G));
         const int roff = (int)(h->rank * cols_blk);
         if (elsize == 4 && wide)
-            transpose_a2a_tma_kernel<uint32_t, 256, 16><<<g2, 256, 0, st>>>(maps, (const uint32_t *)b_local, N0, rows_blk, roff, (int)(cols_blk / TI), tj_n, h->rank, order, G);
+            transpose_a2a_tma_kernel<uint32_t, 256, 16><<<g2, 256, 0, st>>>(maps, (const uint32_t *)b_local, N0, rows_blk, roff, (int)(cols_blk / TI), tj_n, h->rank, order, G, flags, call);
         else if (elsize == 4)
-            transpose_a2a_tma_kernel<uint32_t, 64, 64><<<g2, 256, 0, st>>>(maps, (const uint32_t *)b_local, N0, rows_blk, roff, (int)(cols_blk / TI), tj_n, h->rank, order, G);
+            transpose_a2a_tma_kernel<uint32_t, 64, 64><<<g2, 256, 0, st>>>(maps, (const uint32_t *)b_local, N0, rows_blk, roff, (int)(cols_blk / TI), tj_n, h->rank, order, G, flags, call);
         else if (wide)
-            transpose_a2a_tma_kernel<uint64_t, 256, 16><<<g2, 256, 0, st>>>(maps, (const uint64_t *)b_local, N0, rows_blk, roff, (int)(cols_blk / TI), tj_n, h->rank, order, G);
+            transpose_a2a_tma_kernel<uint64_t, 256, 16><<<g2, 256, 0, st>>>(maps, (const uint64_t *)b_local, N0, rows_blk, roff, (int)(cols_blk / TI), tj_n, h->rank, order, G, flags, call);
         else
-            transpose_a2a_tma_kernel<uint64_t, 64, 64><<<g2, 256, 0, st>>>(maps, (const uint64_t *)b_local, N0, rows_blk, roff, (int)(cols_blk / TI), tj_n, h->rank, order, G);
+            transpose_a2a_tma_kernel<uint64_t, 64, 64><<<g2, 256, 0, st>>>(maps, (const uint64_t *)b_local, N0, rows_blk, roff, (int)(cols_blk / TI), tj_n, h->rank, order, G, flags, call);
         B200_CHECK_LAUNCH("transpose_a2a_tma_kernel");
         return b200_sym_barrier(a_sym);
     }
     if (elsize == 4)
         transpose_a2a_kernel<uint32_t><<<grid, 256, 0, st>>>(peers, (const uint32_t *)b_local, N0, N1, rows_blk, (int64_t)h->rank * cols_blk,
-                                                            tiles_i, tiles_j, h->rank, order, G);
+                                                            tiles_i, tiles_j, h->rank, order, G, flags, call);
     else
         transpose_a2a_kernel<uint64_t><<<grid, 256, 0, st>>>(peers, (const uint64_t *)b_local, N0, N1, rows_blk, (int64_t)h->rank * cols_blk,
-                                                            tiles_i, tiles_j, h->rank, order, G);
+                                                            tiles_i, tiles_j, h->rank, order, G, flags, call);
     B200_CHECK_LAUNCH("transpose_a2a_kernel");
     return b200_sym_barrier(a_sym);
 }

@@ -328,6 +328,40 @@ b200_status b200_set_stream(void *cuda_stream) {
     return B200_OK;
 }
 
+// Explicit stream handles for hosts whose unit of execution is not the OS thread (Julia tasks migrate between threads at
+// every yield point; the reference keeps its queue in task_local_storage, src/pocl/pocl.jl:12-41): the host owns the
+// handles, keeps (device, stream) per task and binds them to the OS thread it is on before each call.
+b200_status b200_stream_create(void **cuda_stream, int32_t priority) {
+    if (!cuda_stream) return set_error(B200_ERR_INVALID_VALUE, "cuda_stream is NULL");
+    *cuda_stream = nullptr;
+    if (priority < -1 || priority > 1)
+        return set_error(B200_ERR_INVALID_VALUE, "priority must be -1 (:low), 0 (:normal) or 1 (:high)");
+    B200_TRY(ensure_device());
+    int lo = 0, hi = 0;  // numerically lower == higher priority
+    B200_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    const int prio = priority > 0 ? hi : (priority < 0 ? lo : (lo + hi) / 2);
+    cudaStream_t s = nullptr;
+    B200_CUDA(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, prio));
+    *cuda_stream = (void *)s;
+    return B200_OK;
+}
+
+b200_status b200_stream_destroy(void *cuda_stream) {
+    if (!cuda_stream) return B200_OK;
+    ThreadState &t = tls();
+    if (t.use_external && t.external == (cudaStream_t)cuda_stream) {
+        t.external = nullptr;
+        t.use_external = false;
+    }
+    B200_CUDA(cudaStreamDestroy((cudaStream_t)cuda_stream));   // returns at once; resources go when the stream drains
+    return B200_OK;
+}
+
+b200_status b200_bind(int32_t device, void *cuda_stream) {
+    B200_TRY(b200_set_device(device));
+    return b200_set_stream(cuda_stream);
+}
+
 // ---- events -------------------------------------------------------------------------------
 b200_status b200_event_create(void **event) {
     if (!event) return set_error(B200_ERR_INVALID_VALUE, "event is NULL");
@@ -365,10 +399,19 @@ b200_status b200_event_destroy(void *event) {
 // ---- CUDA graphs: record a launch-bound sequence of stream-ordered calls once, replay it with one launch -----------------
 // Every b200 call that only ENQUEUES work (kernel launches, async copies, fills, events) may be recorded; calls that wait for
 // the stream (b200_synchronize, value-returning reductions, synchronous copies) fail while a capture is open.
+namespace {
+struct GraphRec {           // what a b200 graph handle points to
+    cudaGraphExec_t exec;
+    int64_t launches;       // device kernels recorded (added to the thread's launch counter on every replay)
+};
+thread_local int64_t g_capture_base = 0;
+}  // namespace
+
 b200_status b200_graph_begin(void) {
     cudaStream_t st;
     B200_TRY(current_stream(&st));
     B200_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeRelaxed));
+    g_capture_base = tls().launches;
     return B200_OK;
 }
 
@@ -379,6 +422,8 @@ b200_status b200_graph_end(void **graph) {
     B200_TRY(current_stream(&st));
     cudaGraph_t g = nullptr;
     cudaError_t e = cudaStreamEndCapture(st, &g);
+    const int64_t recorded = tls().launches - g_capture_base;
+    tls().launches = g_capture_base;      // recorded launches did not run
     if (e != cudaSuccess || !g) {
         cudaGetLastError();
         return set_error(B200_ERR_CUDA, "b200_graph_end: capture failed or was invalidated by a synchronising call: %s", cudaGetErrorString(e));
@@ -387,7 +432,7 @@ b200_status b200_graph_end(void **graph) {
     e = cudaGraphInstantiate(&exec, g, 0);
     cudaGraphDestroy(g);
     if (e != cudaSuccess) return set_error(B200_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
-    *graph = (void *)exec;
+    *graph = (void *)new GraphRec{exec, recorded};
     return B200_OK;
 }
 
@@ -395,13 +440,18 @@ b200_status b200_graph_launch(void *graph) {
     if (!graph) return set_error(B200_ERR_INVALID_VALUE, "b200_graph_launch: NULL graph");
     cudaStream_t st;
     B200_TRY(current_stream(&st));
-    B200_CUDA(cudaGraphLaunch((cudaGraphExec_t)graph, st));
+    GraphRec *r = (GraphRec *)graph;
+    B200_CUDA(cudaGraphLaunch(r->exec, st));
+    count_launch((int)r->launches);
     return B200_OK;
 }
 
 b200_status b200_graph_destroy(void *graph) {
     if (!graph) return B200_OK;
-    B200_CUDA(cudaGraphExecDestroy((cudaGraphExec_t)graph));
+    GraphRec *r = (GraphRec *)graph;
+    cudaError_t e = cudaGraphExecDestroy(r->exec);
+    delete r;
+    B200_CUDA(e);
     return B200_OK;
 }
 

@@ -5,9 +5,13 @@
 # (`@kernel`, `@index`, `@localmem`, `@private`, `@synchronize`, `@Const`), `KA.partition` and NDIteration are
 # reused UNCHANGED; only the methods a backend must provide are defined here.
 #
-# NOTE: there is no Julia toolchain in the build environment of this repository, so this file is verified by
-# reading, not by execution; its behaviour is pinned through the Python mirror (kernelabstractions.jl_b200/b200ka),
-# which implements the same methods over the same C ABI and runs the ported testsuite on a B200.
+# NOTE: there is no Julia toolchain in the build environment of this repository, so this file is not executed there.
+# It is checked mechanically instead (tests/test_julia_binding.py): every ccall against include/b200ka.h (symbol, arity,
+# argument and return types, record layouts, constants), every method of the backend interface against the template
+# src/pocl/backend.jl, every host-side name the reference's tests and examples call, and the KI.@kernel expansion
+# (src/intrinsics.jl:352-360) statement by statement.  Behaviour is pinned through the Python mirror
+# (kernelabstractions.jl_b200/b200ka), which implements the same methods over the same C ABI and runs the ported
+# testsuite on a B200.
 #
 # There is no JIT.  A `@kernel` launched on B200Backend is dispatched BY NAME (`nameof(obj.f)`, i.e.
 # `:gpu_<kernel name>`, reference src/macros.jl:32) to a precompiled sm_100a kernel inside the library; an
@@ -51,8 +55,49 @@ function check(status::Int32)
     throw(B200Error(status, msg))
 end
 
+# ---------------------------------------------------------------------------------------------------------
+# Task-local runtime state (twin of the task-local platform/device/context/queue, reference src/pocl/pocl.jl:12-41).
+# The library keeps "current device" and "current stream" per OS thread, but a Julia task migrates between OS threads at
+# every yield point -- and KA.synchronize itself yields.  So device, priority and the stream handles live in
+# `task_local_storage()`, and every checked call first binds them to whatever OS thread the task is running on right now
+# (`b200_bind`: cudaSetDevice + adopt the stream).  There is no yield point between the bind and the ccall that follows it.
+# ---------------------------------------------------------------------------------------------------------
+mutable struct TaskState
+    device::Int32                                        # 0-based
+    priority::Int32                                      # -1 :low, 0 :normal, 1 :high
+    streams::Dict{Tuple{Int32, Int32}, Ptr{Cvoid}}       # (device, priority) -> cudaStream_t owned by this task
+end
+
+function destroy_streams(st::TaskState)
+    for s in values(st.streams)
+        ccall((:b200_stream_destroy, libb200ka), Int32, (Ptr{Cvoid},), s)     # waits for nothing: cudaStreamDestroy defers
+    end
+    empty!(st.streams)
+    return nothing
+end
+
+function task_state()
+    return get!(task_local_storage(), :B200State) do
+        finalizer(destroy_streams, TaskState(Int32(0), Int32(0), Dict{Tuple{Int32, Int32}, Ptr{Cvoid}}()))
+    end::TaskState
+end
+
+function bind!()
+    st = task_state()
+    s = get(st.streams, (st.device, st.priority), C_NULL)
+    if s == C_NULL
+        r = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:b200_bind, libb200ka), Int32, (Int32, Ptr{Cvoid}), st.device, C_NULL))
+        check(ccall((:b200_stream_create, libb200ka), Int32, (Ptr{Ptr{Cvoid}}, Int32), r, st.priority))
+        s = st.streams[(st.device, st.priority)] = r[]
+    end
+    check(ccall((:b200_bind, libb200ka), Int32, (Int32, Ptr{Cvoid}), st.device, s))
+    return nothing
+end
+
 macro b200(name, argtypes, args...)
     return quote
+        bind!()
         check(ccall(($(QuoteNode(name)), libb200ka), Int32, $(esc(argtypes)), $(map(esc, args)...)))
     end
 end
@@ -255,14 +300,16 @@ function KA.copyto!(::B200Backend, A::B200Array{T}, B::B200Array{T}) where {T}
     @b200 b200_copy (Ptr{Cvoid}, Ptr{Cvoid}, Csize_t) A.ptr B.ptr (length(A) * sizeof(T))
     return A
 end
+# host legs: the arrays are preserved for the duration of the ENQUEUE (reference src/intrinsics.jl:353,
+# src/pocl/compiler/execution.jl:63); the caller keeps them alive until synchronize (src/KernelAbstractions.jl:127-142)
 function KA.copyto!(::B200Backend, A::B200Array{T}, B::Array{T}) where {T}
     length(A) == length(B) || error("Arrays must match in length")
-    @b200 b200_memcpy_h2d_async (Ptr{Cvoid}, Ptr{Cvoid}, Csize_t) A.ptr pointer(B) sizeof(B)
+    GC.@preserve A B @b200 b200_memcpy_h2d_async (Ptr{Cvoid}, Ptr{Cvoid}, Csize_t) A.ptr pointer(B) sizeof(B)
     return A
 end
 function KA.copyto!(::B200Backend, A::Array{T}, B::B200Array{T}) where {T}
     length(A) == length(B) || error("Arrays must match in length")
-    @b200 b200_memcpy_d2h_async (Ptr{Cvoid}, Ptr{Cvoid}, Csize_t) pointer(A) B.ptr sizeof(A)
+    GC.@preserve A B @b200 b200_memcpy_d2h_async (Ptr{Cvoid}, Ptr{Cvoid}, Csize_t) pointer(A) B.ptr sizeof(A)
     return A
 end
 
@@ -280,6 +327,7 @@ KA.supports_unified(::B200Backend) = true
 # (reference docs/src/implementations.md:3-11; examples/mpi.jl:30 relies on it).
 function KA.synchronize(::B200Backend)
     while true
+        bind!()                                   # the task may have moved to another OS thread during the last yield
         st = ccall((:b200_stream_query, libb200ka), Int32, ())
         st == B200_OK && break
         st == B200_NOT_READY || check(st)
@@ -290,23 +338,20 @@ end
 
 function KA.priority!(::B200Backend, prio::Symbol)
     prio in (:high, :normal, :low) || error("priority must be one of :high, :normal, :low")   # KernelAbstractions.jl:658-663
-    @b200 b200_set_priority (Int32,) Int32(prio === :high ? 1 : (prio === :low ? -1 : 0))
+    # task local like the reference's queue: later launches of THIS task go to its stream of that priority
+    task_state().priority = Int32(prio === :high ? 1 : (prio === :low ? -1 : 0))
     return nothing
 end
 
 function KA.ndevices(::B200Backend)
     n = Ref{Int32}(0)
-    @b200 b200_device_count (Ptr{Int32},) n
+    check(ccall((:b200_device_count, libb200ka), Int32, (Ptr{Int32},), n))
     return Int(n[])
 end
-function KA.device(::B200Backend)
-    d = Ref{Int32}(0)
-    @b200 b200_get_device (Ptr{Int32},) d
-    return Int(d[]) + 1
-end
+KA.device(::B200Backend) = Int(task_state().device) + 1
 function KA.device!(backend::B200Backend, id::Int)
     (1 <= id <= KA.ndevices(backend)) || throw(ArgumentError("Device id $id out of bounds."))   # KernelAbstractions.jl:686-691
-    @b200 b200_set_device (Int32,) Int32(id - 1)
+    task_state().device = Int32(id - 1)           # bound to the OS thread by the next call (bind!)
     return nothing
 end
 
@@ -355,10 +400,17 @@ carg(A::B200Array{T, N}) where {T, N} = CArg(0, eltype_code(T), sizeof(T), N, pa
 carg(x::Integer) = CArg(1, eltype_code(Int64), 8, 0, pad4(()), C_NULL, Int64(x), Float64(x))
 carg(x::AbstractFloat) = CArg(1, eltype_code(typeof(x)), sizeof(x), 0, pad4(()), C_NULL, isinteger(x) ? Int64(x) : 0, Float64(x))
 carg(::Val{x}) where {x} = CArg(2, eltype_code(Int64), 8, 0, pad4(()), C_NULL, Int64(x), Float64(x))
-carg(::Type{T}) where {T} = CArg(2, eltype_code(T), sizeof(T), 0, pad4(()), C_NULL, Int64(eltype_code(T)), 0.0)
+# type arguments (convert_kernel!(A, B, ::Type{T})): only the eltype code travels; abstract / union types have no size
+carg(::Type{T}) where {T} = CArg(2, eltype_code(T), (isconcretetype(T) && isbitstype(T)) ? sizeof(T) : 0, 0, pad4(()), C_NULL, Int64(eltype_code(T)), 0.0)
+# function-valued ARGUMENTS of a kernel (init_kernel(arr, f, T), src/KernelAbstractions.jl:869-872): only zero / one have a twin
 carg(f::Function) = f === zero ? carg(0) : f === one ? carg(1) : error("Don't know how to convert function $f for Kernel{B200Backend}")
 carg(x) = error("Don't know how to convert arguments of type $(typeof(x)) for Kernel{B200Backend}")
 KA.argconvert(::KA.Kernel{B200Backend}, arg) = carg(arg)
+# KI.@kernel calls argconvert on the kernel FUNCTION first (reference src/intrinsics.jl:354; src/pocl/backend.jl:149 passes it
+# through clconvert unchanged) and hands the result to kernel_function: the function must come back as itself -- its NAME
+# selects the precompiled kernel.  Every other value becomes its C record (only the types are used by the macro, :355-356;
+# the launch receives the ORIGINAL arguments, :358).
+KI.argconvert(::B200Backend, f::F) where {F <: Function} = f
 KI.argconvert(::B200Backend, arg) = carg(arg)
 
 function launch(name::String, desc::LaunchDesc, args)
@@ -509,8 +561,14 @@ struct B200Function
     name::String
 end
 
+kernel_name(f::Function) = String(nameof(f))
+kernel_name(f::B200Function) = f.name
+kernel_name(f::Union{AbstractString, Symbol}) = String(f)
+
+# `f` is the kernel function itself (see KI.argconvert above); `name` is accepted for interface parity but cannot rename a
+# precompiled kernel, so the catalogue lookup always uses the function's own name.
 function KI.kernel_function(::B200Backend, f::F, tt::TT = Tuple{}; name = nothing, kwargs...) where {F, TT}
-    kname = name === nothing ? String(nameof(f)) : String(name)
+    kname = kernel_name(f)
     out = Ref{Int64}(0)
     @b200 b200_kernel_max_work_group_size (Cstring, Int64, Ptr{Int64}) kname Int64(MAX_WORK_GROUP_SIZE) out   # existence check
     return KI.Kernel{B200Backend, B200Function}(B200Backend(), B200Function(kname))

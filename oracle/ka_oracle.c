@@ -42,6 +42,15 @@ int ka_oracle_threads(void) {
 #endif
 }
 
+/* launchers such as torchrun export OMP_NUM_THREADS=1; the timed CPU baseline sets its thread count explicitly */
+void ka_oracle_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 /* ------------------------------------------------------------------------------------------
  * NDIteration.partition  (reference src/nditeration.jl:143-164)
  *   workgroupsize padded with ones up to length(ndrange) (a 0 entry also becomes 1);

@@ -66,6 +66,11 @@ def threads() -> int:
     return int(lib().ka_oracle_threads())
 
 
+def set_threads(n: int) -> None:
+    """OpenMP thread count of the timed CPU baseline (torchrun exports OMP_NUM_THREADS=1 to its ranks)."""
+    lib().ka_oracle_set_threads(C.c_int(int(n)))
+
+
 def _i64arr(vals: Sequence[int]):
     return (C.c_int64 * max(len(vals), 1))(*[int(v) for v in vals])
 

@@ -100,6 +100,26 @@ def main():
     assert np.array_equal(KA.Array(Cp), Cref[m0:m1, :])
     out["matmul_row_panels_bit_exact"] = True
 
+    # ---- slab copy and slab transpose (contiguous element slabs; rows-of-b slabs, no collective) ----
+    nc = 1 << 20
+    whole_c = orc.gen_uniform_f32((nc,), 1234)
+    c0, c1 = mg.copy_shard(nc, world, rank)
+    d_dst = KA.zeros(be, np.float32, c1 - c0)
+    EX.mycopy_(d_dst, KA.to_device(np.ascontiguousarray(whole_c[c0:c1])))
+    nt = 512 * world
+    whole_b = orc.gen_uniform_f32((nt, nt), 1235)
+    j0, j1 = mg.transpose_shard(nt, world, rank)
+    d_a = KA.zeros(be, np.float32, nt, j1 - j0)
+    EX.naive_transpose_(d_a, KA.to_device(np.asfortranarray(whole_b[j0:j1, :])))     # (n/G) x n slab -> n x (n/G) slab
+    KA.synchronize(be)
+    # reassemble on every rank and compare with the single-device definition
+    parts_c, parts_t = [None] * world, [None] * world
+    dist.all_gather_object(parts_c, KA.Array(d_dst))
+    dist.all_gather_object(parts_t, KA.Array(d_a))
+    assert np.array_equal(np.concatenate(parts_c), whole_c)
+    assert np.array_equal(np.concatenate(parts_t, axis=1), whole_b.T)
+    out["slab_copy_and_transpose_bit_exact"] = True
+
     # ---- distributed transpose: fused tile transpose + all-to-all over peer memory == definition == NCCL route ----
     gather = mg.torch_gather(dist)
     for (N0, N1, dt) in [(64 * world, 128 * world, np.float32), (256 * world, 64 * world, np.float64), (1024, 2048, np.float32),
@@ -134,6 +154,32 @@ def main():
         dist.barrier()
         a_sym.free()
     out["distributed_transpose_fused_eq_nccl_eq_definition"] = True
+
+    # ---- back-to-back calls with a consumer of the slab in between and NO barrier from the caller: the kernel's own
+    # ---- write-after-read guard ("slab may be overwritten" flags) must keep call k+1 out of a slab that call k's consumer reads ----
+    N0 = N1 = 2048 if 2048 % (64 * world) == 0 else 64 * world * 4
+    rb, cb = N0 // world, N1 // world
+    a_sym = mg.SymBuffer(N1 * rb * 4, world, rank, gather)
+    a_view = a_sym.array(np.float32, (N1, rb))
+    keep = [KA.allocate(be, np.float32, N1, rb) for _ in range(6)]
+    wholes, b_locs = [], []
+    for k in range(6):
+        rng = np.random.default_rng(900 + k)
+        whole = np.asfortranarray(rng.standard_normal((N0, N1)).astype(np.float32))
+        wholes.append(whole)
+        b_locs.append(KA.to_device(np.asfortranarray(whole[:, rank * cb:(rank + 1) * cb])))   # kept alive: freeing would synchronise
+    KA.synchronize(be)
+    dist.barrier()
+    for k in range(6):
+        mg.transpose_alltoall_(a_sym, b_locs[k], N0, N1)
+        for _ in range(1 + 7 * (rank == 0)):       # rank 0 is a slow consumer: its peers reach call k+1 first
+            KA.copyto_(be, keep[k], a_view)
+    KA.synchronize(be)
+    for k in range(6):
+        assert np.array_equal(KA.Array(keep[k]), wholes[k].T[:, rank * rb:(rank + 1) * rb]), f"back-to-back call {k} on rank {rank}"
+    dist.barrier()
+    a_sym.free()
+    out["distributed_transpose_back_to_back"] = True
 
     # ---- timing: NCCL route vs fused route at the C3 size ----
     if "--time" in sys.argv:
@@ -214,7 +260,7 @@ def main():
             out[f"hist_{name}_ms"] = ms
             out[f"hist_{name}_GBps"] = 4.0 * n / (ms * 1e-3) / 1e9
             if name == "fused":
-                stamps = peers.debug_stamps()
+                stamps = peers.timeline()
                 gathered = [None] * world
                 dist.all_gather_object(gathered, stamps)
                 out["fused_timeline_ns_per_rank"] = gathered

@@ -124,6 +124,54 @@ def test_copyto():
     assert np.array_equal(a, hb)
 
 
+def test_copyto_matrix_layout():
+    """Device arrays are column-major: a C-ordered host matrix (numpy's default) must arrive element for element, not byte for
+    byte, and a C-ordered host destination is refused instead of being filled with permuted data."""
+    be = backend()
+    h = np.arange(6 * 4, dtype=np.float32).reshape(6, 4)          # C order
+    assert not h.flags.f_contiguous
+    dA = ArrayT(np.float32, 6, 4)
+    KA.copyto_(be, dA, h)
+    KA.synchronize(be)
+    assert np.array_equal(KA.Array(dA), h)
+    out_f = np.empty((6, 4), dtype=np.float32, order="F")
+    KA.copyto_(be, out_f, dA)
+    KA.synchronize(be)
+    assert np.array_equal(out_f, h)
+    with pytest.raises(KA.ArgumentError, match="column-major"):
+        KA.copyto_(be, np.empty((6, 4), dtype=np.float32), dA)
+
+
+def test_pending_host_refs_are_per_stream():
+    """synchronize() releases only the references of the stream it waited for (another thread's in-flight copy keeps its buffer)."""
+    import threading
+
+    from b200ka import backend as B
+
+    be = backend()
+    dA = ArrayT(np.float32, 1 << 16)
+    h = np.ones(1 << 16, dtype=np.float32)
+    KA.copyto_(be, dA, h)
+    main_key = B._stream_key()
+    assert main_key in B._pending_host_refs
+    seen = {}
+
+    def other():
+        d2 = ArrayT(np.float32, 16)
+        KA.copyto_(be, d2, np.zeros(16, dtype=np.float32))
+        seen["key"] = B._stream_key()
+        KA.synchronize(be)
+        seen["main_still_held"] = main_key in B._pending_host_refs
+        seen["own_released"] = seen["key"] not in B._pending_host_refs
+
+    t = threading.Thread(target=other)
+    t.start()
+    t.join()
+    assert seen["key"] != main_key and seen["main_still_held"] and seen["own_released"]
+    KA.synchronize(be)
+    assert main_key not in B._pending_host_refs
+
+
 def test_copyto_device_checks():
     be = backend()
     A = ArrayT(np.float32, 100)
