@@ -498,18 +498,28 @@ def run_suite(KA, _lib, EX, mg, orc, be, rank, world, dist, timed, graphed, all_
                                 "scaling": "strong", "buffer_pairs_rotated": npairs,
                                 "launch": "CUDA-graph replay of one rotation" if world > 1 else "launch by launch"}
         if world == 1:
-            # the literal twin (generic NDRange -> grid mapping of csrc/ka_device.cuh) against the routed tuned kernel
-            _lib.call("b200_tune_set", b"registry.force_twins", 1)
-            try:
-                ms_t, _ = timed(step_copy, steps, warmup)
-            finally:
-                _lib.call("b200_tune_set", b"registry.force_twins", 0)
-            gbs_t = 2 * 4 * n / (ms_t * 1e-3) / 1e9
-            out["copy_2^26_f32_literal_twin"] = {"value": gbs_t, "unit": "GB/s", "ms_per_step": ms_t, "scaling": "strong",
-                                                 "of_tuned": gbs_t / gbs,
-                                                 "note": "registry.force_twins=1: gpu_copy_kernel! through the generic @index(Global, Linear) "
-                                                         "lowering (strength-reduced expand/__validindex), no routing to b200_copy",
-                                                 "roofline": {"bound": "hbm", "achieved": gbs_t, "peak": peaks["hbm"], "frac": gbs_t / peaks["hbm"]}}
+            # the literal twin (generic NDRange -> grid lowering of csrc/ka_device.cuh, no routing to b200_copy) in its three forms:
+            # 128-bit vectorised, one work-item per thread with the strength-reduced index arithmetic, and one work-item per
+            # thread with the reference's 64-bit div/mod per dimension (src/nditeration.jl:115-126)
+            for key, knobs, note in (
+                    ("copy_2^26_f32_literal_twin", {"registry.twin_vec": 1, "registry.ka_mode": -1},
+                     "registry.force_twins=1: gpu_copy_kernel! through the generic lowering, 16 bytes (4 work-items) per thread"),
+                    ("copy_2^26_f32_literal_twin_scalar", {"registry.twin_vec": 0, "registry.ka_mode": -1},
+                     "registry.force_twins=1, registry.twin_vec=0: one work-item per thread, native-grid / multiply-high index arithmetic"),
+                    ("copy_2^26_f32_literal_twin_div64", {"registry.twin_vec": 0, "registry.ka_mode": 2},
+                     "registry.force_twins=1, registry.twin_vec=0, registry.ka_mode=2: one work-item per thread, the reference's Int64 div/mod")):
+                _lib.call("b200_tune_set", b"registry.force_twins", 1)
+                for k_, v_ in knobs.items():
+                    _lib.call("b200_tune_set", k_.encode(), v_)
+                try:
+                    ms_t, _ = timed(step_copy, steps, warmup)
+                finally:
+                    _lib.call("b200_tune_set", b"registry.force_twins", 0)
+                    _lib.call("b200_tune_set", b"registry.twin_vec", 1)
+                    _lib.call("b200_tune_set", b"registry.ka_mode", -1)
+                gbs_t = 2 * 4 * n / (ms_t * 1e-3) / 1e9
+                out[key] = {"value": gbs_t, "unit": "GB/s", "ms_per_step": ms_t, "scaling": "strong", "of_tuned": gbs_t / gbs, "note": note,
+                            "roofline": {"bound": "hbm", "achieved": gbs_t, "peak": peaks["hbm"], "frac": gbs_t / peaks["hbm"]}}
         del src, dst, keep
         if cpu:
             hB, hA = orc.gen_uniform_f32((n,), 1234), np.zeros(n, dtype=np.float32)

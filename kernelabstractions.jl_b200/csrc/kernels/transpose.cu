@@ -42,6 +42,10 @@ __global__ void __launch_bounds__(256) transpose64_f32_kernel(float *__restrict_
                                                               int tiles_i, int tiles_j, int64_t lda, int64_t ldb) {
     __shared__ __align__(16) float tile[64 * 64];  // [j][i], 16-byte chunk index XOR ((j >> 2) & 15)
     const int t = threadIdx.x;
+    // Programmatic dependent launch (launch attribute set by transpose_launch): the next PDL-aware kernel of the stream may
+    // become resident while this grid drains; nothing here touches global memory before the previous grid has completed.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     int ti, tj;
     if (ORDER == 0) {
         tj = blockIdx.x % tiles_j;
@@ -195,10 +199,24 @@ int transpose_launch(void *a, const void *b, int64_t m, int64_t n, int64_t lda, 
     if (fast) {
         int tiles_i = (int)(m / 64), tiles_j = (int)(n / 64);
         unsigned grid = (unsigned)((int64_t)tiles_i * tiles_j);
-        if (tune_get("transpose.order", 0) == 0)
-            transpose64_f32_kernel<0><<<grid, 256, 0, st>>>((float *)a, (const float *)b, tiles_i, tiles_j, lda, ldb);
-        else
-            transpose64_f32_kernel<1><<<grid, 256, 0, st>>>((float *)a, (const float *)b, tiles_i, tiles_j, lda, ldb);
+        // `transpose.ctas_per_sm` (0 = as many as fit: 8) caps the resident CTAs per SM with unused dynamic shared memory: a
+        // CTA lives for (bytes in flight per SM) / (bandwidth per SM), and a launch pays about one CTA lifetime of ramp + drain
+        const int cps = tune_get("transpose.ctas_per_sm", 0);
+        size_t dyn = 0;
+        if (cps > 0 && cps < 8) dyn = (size_t)(227 * 1024) / (size_t)cps - 16 * 1024 - 1024;
+        auto kern = tune_get("transpose.order", 0) == 0 ? transpose64_f32_kernel<0> : transpose64_f32_kernel<1>;
+        if (dyn > 32 * 1024) B200_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(256);
+        cfg.dynamicSmemBytes = dyn;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = tune_get("transpose.pdl", 1) != 0;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        B200_CUDA(cudaLaunchKernelEx(&cfg, kern, (float *)a, (const float *)b, tiles_i, tiles_j, lda, ldb));
         B200_CHECK_LAUNCH("transpose64_f32_kernel");
         return B200_OK;
     }

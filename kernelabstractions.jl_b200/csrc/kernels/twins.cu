@@ -9,10 +9,16 @@
 // everything else here, so results never depend on which one ran.
 #include "twins.h"
 
+#include <cstring>
+
 #include "../common.cuh"
+#include "../tune.h"
 
 namespace b200 {
 
+// Launch geometry of a KA launch (ka_device.cuh): a native <=3-d grid of <=3-d blocks when the limits allow (group / item ids are
+// blockIdx / threadIdx, no division), else the reference's 1-d launch with multiply-high unravelling.  ka_grid x ka_block is
+// prod(blocks) groups of prod(wgs) items either way.
 #define KA_LAUNCH_1D(ctx, groups, items)                                                               \
     long long groups = 1, items = 1;                                                                   \
     for (int d = 0; d < (ctx).ndim; ++d) {                                                             \
@@ -22,25 +28,92 @@ namespace b200 {
     if (groups == 0) return B200_OK; /* reference src/pocl/backend.jl:136-138 */                       \
     if (items > 1024 || items < 1)                                                                     \
         return set_error(B200_ERR_LAUNCH_DIMS, "workgroup of %lld items exceeds 1024", items);         \
-    if (groups > 2147483647LL) return set_error(B200_ERR_LAUNCH_DIMS, "%lld groups exceed 2^31-1", groups);
+    if (groups > 2147483647LL) return set_error(B200_ERR_LAUNCH_DIMS, "%lld groups exceed 2^31-1", groups); \
+    dim3 ka_grid, ka_block;                                                                            \
+    ka_launch_dims((ctx), &ka_grid, &ka_block);
+
+// ---- 128-bit vectorised lowering of the element-wise kernels on @index(Global, Linear) -------------------------------
+// copy_kernel!, init_kernel and saxpy_kernel! are `A[I] = f(B[I], ...)` with I the global linear id, no @localmem and no
+// @synchronize: the work-items are independent of their grouping.  When the valid work-items of the launch are exactly
+// I = 1..n (a 1-d ndrange, or an N-d one without ragged dimensions -- then @index(Global, Linear) enumerates a contiguous
+// range) one CUDA thread executes the 16 / sizeof(T) consecutive work-items that share a 16-byte word, four such words in
+// flight per thread: one work-item per thread keeps only 8 KiB of loads in flight per SM, a quarter of what a B200 needs to
+// cover its HBM latency (measured: 0.73 TB/s for the reference's div/mod lowering, r05 bench).
+// `registry.twin_vec = 0` keeps the scalar one-item-per-thread form.  Same bits either way.
+constexpr int KA_VEC_U = 4;   // 16-byte words in flight per thread
+
+static inline bool ka_vectorisable(const KaCtx &c, long long *n_valid) {
+    long long total = 1, nd = 1;
+    for (int d = 0; d < c.ndim; ++d) {
+        total *= c.blocks[d] * c.wgs[d];
+        nd *= c.ndrange[d];
+    }
+    if (c.ndim == 1) {
+        *n_valid = c.dynamic_check && c.ndrange[0] < total ? c.ndrange[0] : total;
+        return true;
+    }
+    if (c.ragged != 0) return false;
+    *n_valid = c.dynamic_check ? nd : total;
+    return true;
+}
+static inline bool twin_vec_enabled() { return tune_get("registry.twin_vec", 1) != 0; }
+__device__ __forceinline__ uint4 ka_ldg16(const void *p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void ka_stg16(void *p, const uint4 &v) {
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// bytes [0, nbytes) = work-items 1..n; CTA b owns 16-byte words [b * 256 * U, (b + 1) * 256 * U); the last CTA also moves the
+// (< 16) bytes behind the last whole word
+__global__ void __launch_bounds__(256) copy_twin_vec_kernel(char *__restrict__ A, const char *__restrict__ B, long long nvec, int tail_bytes) {
+    const long long v0 = (long long)blockIdx.x * (256 * KA_VEC_U) + threadIdx.x;
+    uint4 w[KA_VEC_U];
+#pragma unroll
+    for (int u = 0; u < KA_VEC_U; ++u)
+        if (v0 + u * 256 < nvec) w[u] = ka_ldg16(B + 16 * (v0 + u * 256));
+#pragma unroll
+    for (int u = 0; u < KA_VEC_U; ++u)
+        if (v0 + u * 256 < nvec) ka_stg16(A + 16 * (v0 + u * 256), w[u]);
+    if (blockIdx.x == gridDim.x - 1 && (int)threadIdx.x < tail_bytes) A[16 * nvec + threadIdx.x] = B[16 * nvec + threadIdx.x];
+}
+__global__ void __launch_bounds__(256) init_twin_vec_kernel(char *__restrict__ A, uint4 pattern, long long nvec, int tail_bytes) {
+    const long long v0 = (long long)blockIdx.x * (256 * KA_VEC_U) + threadIdx.x;
+#pragma unroll
+    for (int u = 0; u < KA_VEC_U; ++u)
+        if (v0 + u * 256 < nvec) ka_stg16(A + 16 * (v0 + u * 256), pattern);
+    if (blockIdx.x == gridDim.x - 1 && (int)threadIdx.x < tail_bytes)
+        A[16 * nvec + threadIdx.x] = reinterpret_cast<const char *>(&pattern)[threadIdx.x];   // tail starts on a 16-byte word: same phase
+}
 
 // ---- copy_kernel / copy_kernel!  (src/KernelAbstractions.jl:874-877, examples/memcopy.jl:4-7) ----
 template <typename T>
 __global__ void copy_twin_kernel(KaCtx c, T *__restrict__ A, const T *__restrict__ B) {
     const bool active = ka_valid(c);
     if (active) {
-        const long long I = ka_global_linear();
+        const long long I = ka_global_linear(c);
         A[I - 1] = B[I - 1];
     }
 }
 int twin_copy(const KaCtx &c, void *A, const void *B, int elsize, cudaStream_t st) {
     KA_LAUNCH_1D(c, groups, items);
+    long long n_valid = 0;
+    if (twin_vec_enabled() && ka_vectorisable(c, &n_valid) && ((((uintptr_t)A | (uintptr_t)B) & 15) == 0) && 16 % elsize == 0) {
+        if (n_valid <= 0) return B200_OK;
+        const long long bytes = n_valid * elsize, nvec = bytes / 16;
+        const long long ctas = (nvec + 256 * KA_VEC_U - 1) / (256 * KA_VEC_U);
+        copy_twin_vec_kernel<<<(unsigned)(ctas < 1 ? 1 : ctas), 256, 0, st>>>((char *)A, (const char *)B, nvec, (int)(bytes - 16 * nvec));
+        B200_CHECK_LAUNCH("copy_twin_vec_kernel");
+        return B200_OK;
+    }
     switch (elsize) {
-        case 1: copy_twin_kernel<uint8_t><<<(unsigned)groups, (unsigned)items, 0, st>>>(c, (uint8_t *)A, (const uint8_t *)B); break;
-        case 2: copy_twin_kernel<uint16_t><<<(unsigned)groups, (unsigned)items, 0, st>>>(c, (uint16_t *)A, (const uint16_t *)B); break;
-        case 4: copy_twin_kernel<uint32_t><<<(unsigned)groups, (unsigned)items, 0, st>>>(c, (uint32_t *)A, (const uint32_t *)B); break;
-        case 8: copy_twin_kernel<uint64_t><<<(unsigned)groups, (unsigned)items, 0, st>>>(c, (uint64_t *)A, (const uint64_t *)B); break;
-        case 16: copy_twin_kernel<uint4><<<(unsigned)groups, (unsigned)items, 0, st>>>(c, (uint4 *)A, (const uint4 *)B); break;
+        case 1: copy_twin_kernel<uint8_t><<<ka_grid, ka_block, 0, st>>>(c, (uint8_t *)A, (const uint8_t *)B); break;
+        case 2: copy_twin_kernel<uint16_t><<<ka_grid, ka_block, 0, st>>>(c, (uint16_t *)A, (const uint16_t *)B); break;
+        case 4: copy_twin_kernel<uint32_t><<<ka_grid, ka_block, 0, st>>>(c, (uint32_t *)A, (const uint32_t *)B); break;
+        case 8: copy_twin_kernel<uint64_t><<<ka_grid, ka_block, 0, st>>>(c, (uint64_t *)A, (const uint64_t *)B); break;
+        case 16: copy_twin_kernel<uint4><<<ka_grid, ka_block, 0, st>>>(c, (uint4 *)A, (const uint4 *)B); break;
         default: return set_error(B200_ERR_UNSUPPORTED, "copy_kernel: element size %d", elsize);
     }
     B200_CHECK_LAUNCH("copy_twin_kernel");
@@ -50,15 +123,28 @@ int twin_copy(const KaCtx &c, void *A, const void *B, int elsize, cudaStream_t s
 // ---- init_kernel  (src/KernelAbstractions.jl:869-872) ----
 template <typename T>
 __global__ void init_twin_kernel(KaCtx c, T *__restrict__ arr, T value) {
-    if (ka_valid(c)) arr[ka_global_linear() - 1] = value;
+    if (ka_valid(c)) arr[ka_global_linear(c) - 1] = value;
 }
 int twin_init(const KaCtx &c, void *arr, const void *value, int elsize, cudaStream_t st) {
     KA_LAUNCH_1D(c, groups, items);
+    long long n_valid = 0;
+    if (twin_vec_enabled() && ka_vectorisable(c, &n_valid) && (((uintptr_t)arr & 15) == 0) && 16 % elsize == 0) {
+        if (n_valid <= 0) return B200_OK;
+        unsigned char pat[16];
+        for (int k = 0; k < 16; ++k) pat[k] = ((const unsigned char *)value)[k % elsize];
+        uint4 pattern;
+        memcpy(&pattern, pat, 16);
+        const long long bytes = n_valid * elsize, nvec = bytes / 16;
+        const long long ctas = (nvec + 256 * KA_VEC_U - 1) / (256 * KA_VEC_U);
+        init_twin_vec_kernel<<<(unsigned)(ctas < 1 ? 1 : ctas), 256, 0, st>>>((char *)arr, pattern, nvec, (int)(bytes - 16 * nvec));
+        B200_CHECK_LAUNCH("init_twin_vec_kernel");
+        return B200_OK;
+    }
     switch (elsize) {
-        case 1: init_twin_kernel<uint8_t><<<(unsigned)groups, (unsigned)items, 0, st>>>(c, (uint8_t *)arr, *(const uint8_t *)value); break;
-        case 2: init_twin_kernel<uint16_t><<<(unsigned)groups, (unsigned)items, 0, st>>>(c, (uint16_t *)arr, *(const uint16_t *)value); break;
-        case 4: init_twin_kernel<uint32_t><<<(unsigned)groups, (unsigned)items, 0, st>>>(c, (uint32_t *)arr, *(const uint32_t *)value); break;
-        case 8: init_twin_kernel<uint64_t><<<(unsigned)groups, (unsigned)items, 0, st>>>(c, (uint64_t *)arr, *(const uint64_t *)value); break;
+        case 1: init_twin_kernel<uint8_t><<<ka_grid, ka_block, 0, st>>>(c, (uint8_t *)arr, *(const uint8_t *)value); break;
+        case 2: init_twin_kernel<uint16_t><<<ka_grid, ka_block, 0, st>>>(c, (uint16_t *)arr, *(const uint16_t *)value); break;
+        case 4: init_twin_kernel<uint32_t><<<ka_grid, ka_block, 0, st>>>(c, (uint32_t *)arr, *(const uint32_t *)value); break;
+        case 8: init_twin_kernel<uint64_t><<<ka_grid, ka_block, 0, st>>>(c, (uint64_t *)arr, *(const uint64_t *)value); break;
         default: return set_error(B200_ERR_UNSUPPORTED, "init_kernel: element size %d", elsize);
     }
     B200_CHECK_LAUNCH("init_twin_kernel");
@@ -80,13 +166,13 @@ int twin_transpose(const KaCtx &c, void *a, const void *b, long long rows_a, lon
                    cudaStream_t st) {
     KA_LAUNCH_1D(c, groups, items);
     switch (elsize) {
-        case 1: transpose_twin_kernel<uint8_t><<<(unsigned)groups, (unsigned)items, 0, st>>>(c, (uint8_t *)a, (const uint8_t *)b, rows_a, rows_b); break;
-        case 2: transpose_twin_kernel<uint16_t><<<(unsigned)groups, (unsigned)items, 0, st>>>(c, (uint16_t *)a, (const uint16_t *)b, rows_a, rows_b); break;
-        case 4: transpose_twin_kernel<uint32_t><<<(unsigned)groups, (unsigned)items, 0, st>>>(c, (uint32_t *)a, (const uint32_t *)b, rows_a, rows_b); break;
-        case 8: transpose_twin_kernel<uint64_t><<<(unsigned)groups, (unsigned)items, 0, st>>>(c, (uint64_t *)a, (const uint64_t *)b, rows_a, rows_b); break;
+        case 1: transpose_twin_kernel<uint8_t><<<ka_grid, ka_block, 0, st>>>(c, (uint8_t *)a, (const uint8_t *)b, rows_a, rows_b); break;
+        case 2: transpose_twin_kernel<uint16_t><<<ka_grid, ka_block, 0, st>>>(c, (uint16_t *)a, (const uint16_t *)b, rows_a, rows_b); break;
+        case 4: transpose_twin_kernel<uint32_t><<<ka_grid, ka_block, 0, st>>>(c, (uint32_t *)a, (const uint32_t *)b, rows_a, rows_b); break;
+        case 8: transpose_twin_kernel<uint64_t><<<ka_grid, ka_block, 0, st>>>(c, (uint64_t *)a, (const uint64_t *)b, rows_a, rows_b); break;
         case 16:
             if ((((uintptr_t)a | (uintptr_t)b) & 15) != 0) return set_error(B200_ERR_UNSUPPORTED, "naive_transpose_kernel!: 16-byte elements need 16-byte aligned arrays");
-            transpose_twin_kernel<ulonglong2><<<(unsigned)groups, (unsigned)items, 0, st>>>(c, (ulonglong2 *)a, (const ulonglong2 *)b, rows_a, rows_b);
+            transpose_twin_kernel<ulonglong2><<<ka_grid, ka_block, 0, st>>>(c, (ulonglong2 *)a, (const ulonglong2 *)b, rows_a, rows_b);
             break;
         default: return set_error(B200_ERR_UNSUPPORTED, "naive_transpose_kernel!: element size %d not in {1,2,4,8,16}", elsize);
     }
@@ -115,9 +201,9 @@ int twin_matmul_naive(const KaCtx &c, void *out, const void *a, const void *b, l
                       cudaStream_t st) {
     KA_LAUNCH_1D(c, groups, items);
     if (is_f64)
-        matmul_naive_twin_kernel<double><<<(unsigned)groups, (unsigned)items, 0, st>>>(c, (double *)out, (const double *)a, (const double *)b, M, K);
+        matmul_naive_twin_kernel<double><<<ka_grid, ka_block, 0, st>>>(c, (double *)out, (const double *)a, (const double *)b, M, K);
     else
-        matmul_naive_twin_kernel<float><<<(unsigned)groups, (unsigned)items, 0, st>>>(c, (float *)out, (const float *)a, (const float *)b, M, K);
+        matmul_naive_twin_kernel<float><<<ka_grid, ka_block, 0, st>>>(c, (float *)out, (const float *)a, (const float *)b, M, K);
     B200_CHECK_LAUNCH("matmul_naive_twin_kernel");
     return B200_OK;
 }
@@ -126,9 +212,9 @@ int twin_matmul_naive(const KaCtx &c, void *out, const void *a, const void *b, l
 __global__ void localmem_twin_kernel(KaCtx c, int variant, long long *__restrict__ A, long long lenA) {
     extern __shared__ __align__(16) long long lmem[];  // @localmem Int (N,)  [x2 for many_localmem]
     const long long N = ka_groupsize_prod(c);           // N = @uniform prod(@groupsize()); N2 likewise
-    const long long i = ka_local_linear();
+    const long long i = ka_local_linear(c);
     if (variant == 2) {  // unsafe_indices = true: no guard, no region splitting (test/localmem.jl:37-48)
-        const long long gI = ka_group_linear();
+        const long long gI = ka_group_linear(c);
         lmem[i - 1] = i;
         __syncthreads();
         const long long I = (gI - 1) * N + i;
@@ -136,7 +222,7 @@ __global__ void localmem_twin_kernel(KaCtx c, int variant, long long *__restrict
         return;
     }
     const bool active = ka_valid(c);
-    const long long I = ka_global_linear();
+    const long long I = ka_global_linear(c);
     if (variant == 0) {
         if (active) lmem[i - 1] = i;
         __syncthreads();
@@ -161,7 +247,7 @@ __global__ void localmem_twin_kernel(KaCtx c, int variant, long long *__restrict
 int twin_localmem(const KaCtx &c, int variant, long long *A, long long lenA, cudaStream_t st) {
     KA_LAUNCH_1D(c, groups, items);
     size_t smem = (size_t)items * 8 * (variant == 3 ? 2 : 1);
-    localmem_twin_kernel<<<(unsigned)groups, (unsigned)items, smem, st>>>(c, variant, A, lenA);
+    localmem_twin_kernel<<<ka_grid, ka_block, smem, st>>>(c, variant, A, lenA);
     B200_CHECK_LAUNCH("localmem_twin_kernel");
     return B200_OK;
 }
@@ -177,18 +263,18 @@ __global__ void private_twin_kernel(KaCtx c, long long *__restrict__ A) {
     const long long N = ka_groupsize_prod(c);
     const bool active = ka_valid(c);
     long long priv[1];
-    const long long I = ka_global_linear(), i = ka_local_linear();
+    const long long I = ka_global_linear(c), i = ka_local_linear(c);
     if (active) priv[0] = N - i + 1;
     __syncthreads();
     if (active) A[I - 1] = priv[0];
 }
 __global__ void typetest_twin_kernel(KaCtx c, uint8_t *__restrict__ B) {
-    if (ka_valid(c)) B[ka_global_linear() - 1] = 1;  // eltype(priv) === eltype(A)
+    if (ka_valid(c)) B[ka_global_linear(c) - 1] = 1;  // eltype(priv) === eltype(A)
 }
 constexpr int FORLOOP_MAX_N = 128;
 __global__ void forloop_twin_kernel(KaCtx c, long long *__restrict__ A, long long rowsA, int N) {
     const bool active = ka_valid(c);
-    const long long I = ka_global_linear(), i = ka_local_linear();
+    const long long I = ka_global_linear(c), i = ka_local_linear(c);
     long long priv[FORLOOP_MAX_N];  // @private Int (N,)
     if (active) {
         for (int j = 1; j <= N; ++j) priv[j - 1] = A[(I - 1) + (long long)(j - 1) * rowsA];
@@ -216,19 +302,19 @@ __global__ void reduce_private_twin_kernel(KaCtx c, T *__restrict__ out, const T
 }
 int twin_stmt_form(const KaCtx &c, cudaStream_t st) {
     KA_LAUNCH_1D(c, groups, items);
-    stmt_form_twin_kernel<<<(unsigned)groups, (unsigned)items, 0, st>>>(c);
+    stmt_form_twin_kernel<<<ka_grid, ka_block, 0, st>>>(c);
     B200_CHECK_LAUNCH("stmt_form_twin_kernel");
     return B200_OK;
 }
 int twin_private(const KaCtx &c, long long *A, cudaStream_t st) {
     KA_LAUNCH_1D(c, groups, items);
-    private_twin_kernel<<<(unsigned)groups, (unsigned)items, 0, st>>>(c, A);
+    private_twin_kernel<<<ka_grid, ka_block, 0, st>>>(c, A);
     B200_CHECK_LAUNCH("private_twin_kernel");
     return B200_OK;
 }
 int twin_typetest(const KaCtx &c, uint8_t *B, cudaStream_t st) {
     KA_LAUNCH_1D(c, groups, items);
-    typetest_twin_kernel<<<(unsigned)groups, (unsigned)items, 0, st>>>(c, B);
+    typetest_twin_kernel<<<ka_grid, ka_block, 0, st>>>(c, B);
     B200_CHECK_LAUNCH("typetest_twin_kernel");
     return B200_OK;
 }
@@ -236,7 +322,7 @@ int twin_forloop(const KaCtx &c, long long *A, long long rowsA, long long N, cud
     KA_LAUNCH_1D(c, groups, items);
     if (N < 0 || N > FORLOOP_MAX_N)
         return set_error(B200_ERR_UNSUPPORTED, "forloop: Val(N) with N=%lld > %d private slots", N, FORLOOP_MAX_N);
-    forloop_twin_kernel<<<(unsigned)groups, (unsigned)items, 0, st>>>(c, A, rowsA, (int)N);
+    forloop_twin_kernel<<<ka_grid, ka_block, 0, st>>>(c, A, rowsA, (int)N);
     B200_CHECK_LAUNCH("forloop_twin_kernel");
     return B200_OK;
 }
@@ -244,9 +330,9 @@ int twin_reduce_private(const KaCtx &c, void *out, const void *A, long long n, l
                         cudaStream_t st) {
     KA_LAUNCH_1D(c, groups, items);
     if (is_f64)
-        reduce_private_twin_kernel<double><<<(unsigned)groups, (unsigned)items, 0, st>>>(c, (double *)out, (const double *)A, n, K);
+        reduce_private_twin_kernel<double><<<ka_grid, ka_block, 0, st>>>(c, (double *)out, (const double *)A, n, K);
     else
-        reduce_private_twin_kernel<float><<<(unsigned)groups, (unsigned)items, 0, st>>>(c, (float *)out, (const float *)A, n, K);
+        reduce_private_twin_kernel<float><<<ka_grid, ka_block, 0, st>>>(c, (float *)out, (const float *)A, n, K);
     B200_CHECK_LAUNCH("reduce_private_twin_kernel");
     return B200_OK;
 }
@@ -269,7 +355,7 @@ __global__ void unroll_twin_kernel(KaCtx c, int variant, float *__restrict__ a, 
     } else {
         const float va[3] = {1.f, 2.f, 3.f}, vb[3] = {3.f, 2.f, 1.f};  // @uniform MVectors
         float vc[9];
-        const long long I = ka_global_linear();
+        const long long I = ka_global_linear(c);
         for (int m = 1; m <= 3; ++m) {
             if (active) {
 #pragma unroll
@@ -284,7 +370,7 @@ __global__ void unroll_twin_kernel(KaCtx c, int variant, float *__restrict__ a, 
 }
 int twin_unroll(const KaCtx &c, int variant, float *a, long long N, cudaStream_t st) {
     KA_LAUNCH_1D(c, groups, items);
-    unroll_twin_kernel<<<(unsigned)groups, (unsigned)items, 0, st>>>(c, variant, a, (int)N);
+    unroll_twin_kernel<<<ka_grid, ka_block, 0, st>>>(c, variant, a, (int)N);
     B200_CHECK_LAUNCH("unroll_twin_kernel");
     return B200_OK;
 }
@@ -292,8 +378,8 @@ int twin_unroll(const KaCtx &c, int variant, float *a, long long N, cudaStream_t
 // ---- test/test.jl:46-73 index kernels, :216-230 kernel_val!/kernel_empty ----
 __global__ void index_linear_twin_kernel(KaCtx c, int which, long long *__restrict__ A) {
     if (ka_valid(c)) {
-        const long long I = ka_global_linear();
-        A[I - 1] = which == 0 ? I : (which == 1 ? ka_local_linear() : ka_group_linear());
+        const long long I = ka_global_linear(c);
+        A[I - 1] = which == 0 ? I : (which == 1 ? ka_local_linear(c) : ka_group_linear(c));
     }
 }
 __global__ void index_cartesian_twin_kernel(KaCtx c, int which, long long *__restrict__ A, int ndimA, long long d0,
@@ -324,32 +410,32 @@ __global__ void index_cartesian_twin_kernel(KaCtx c, int which, long long *__res
     }
 }
 __global__ void kernel_val_twin_kernel(KaCtx c, long long *__restrict__ a, long long m) {
-    if (ka_valid(c)) a[ka_global_linear() - 1] = m;
+    if (ka_valid(c)) a[ka_global_linear(c) - 1] = m;
 }
 __global__ void kernel_empty_twin_kernel(KaCtx c) { (void)ka_valid(c); }
 int twin_index_linear(const KaCtx &c, int which, long long *A, cudaStream_t st) {
     KA_LAUNCH_1D(c, groups, items);
-    index_linear_twin_kernel<<<(unsigned)groups, (unsigned)items, 0, st>>>(c, which, A);
+    index_linear_twin_kernel<<<ka_grid, ka_block, 0, st>>>(c, which, A);
     B200_CHECK_LAUNCH("index_linear_twin_kernel");
     return B200_OK;
 }
 int twin_index_cartesian(const KaCtx &c, int which, long long *A, int ndimA, const long long *dimsA, cudaStream_t st) {
     KA_LAUNCH_1D(c, groups, items);
     if (c.ndim > 3) return set_error(B200_ERR_UNSUPPORTED, "index_cartesian: more than 3 dims");
-    index_cartesian_twin_kernel<<<(unsigned)groups, (unsigned)items, 0, st>>>(
+    index_cartesian_twin_kernel<<<ka_grid, ka_block, 0, st>>>(
         c, which, A, ndimA, ndimA > 0 ? dimsA[0] : 1, ndimA > 1 ? dimsA[1] : 1, ndimA > 2 ? dimsA[2] : 1);
     B200_CHECK_LAUNCH("index_cartesian_twin_kernel");
     return B200_OK;
 }
 int twin_kernel_val(const KaCtx &c, long long *a, long long m, cudaStream_t st) {
     KA_LAUNCH_1D(c, groups, items);
-    kernel_val_twin_kernel<<<(unsigned)groups, (unsigned)items, 0, st>>>(c, a, m);
+    kernel_val_twin_kernel<<<ka_grid, ka_block, 0, st>>>(c, a, m);
     B200_CHECK_LAUNCH("kernel_val_twin_kernel");
     return B200_OK;
 }
 int twin_kernel_empty(const KaCtx &c, cudaStream_t st) {
     KA_LAUNCH_1D(c, groups, items);
-    kernel_empty_twin_kernel<<<(unsigned)groups, (unsigned)items, 0, st>>>(c);
+    kernel_empty_twin_kernel<<<ka_grid, ka_block, 0, st>>>(c);
     B200_CHECK_LAUNCH("kernel_empty_twin_kernel");
     return B200_OK;
 }
@@ -359,7 +445,7 @@ int twin_kernel_empty(const KaCtx &c, cudaStream_t st) {
 //       1: gpu_return_kernel!  if i <= length(x) / 2 { x[i] = 1; return }
 __global__ void misc_i64_twin_kernel(KaCtx c, int which, long long *__restrict__ a, long long len) {
     if (ka_valid(c)) {
-        const long long I = ka_global_linear();
+        const long long I = ka_global_linear(c);
         if (which == 0) {
             a[I - 1] = 1;
         } else if (I <= len / 2) {
@@ -370,7 +456,7 @@ __global__ void misc_i64_twin_kernel(KaCtx c, int which, long long *__restrict__
 }
 int twin_misc_i64(const KaCtx &c, int which, long long *a, long long len, cudaStream_t st) {
     KA_LAUNCH_1D(c, groups, items);
-    misc_i64_twin_kernel<<<(unsigned)groups, (unsigned)items, 0, st>>>(c, which, a, len);
+    misc_i64_twin_kernel<<<ka_grid, ka_block, 0, st>>>(c, which, a, len);
     B200_CHECK_LAUNCH("misc_i64_twin_kernel");
     return B200_OK;
 }
@@ -396,13 +482,12 @@ __global__ void unaliased_accumulate_twin_kernel(KaCtx c, T *output, const T *in
 int twin_unaliased_accumulate(const KaCtx &c, int local, void *output, const void *input, long long n,
                               long long rows_out, long long rows_in, int is_f64, cudaStream_t st) {
     KA_LAUNCH_1D(c, groups, items);
-    const unsigned g = (unsigned)groups, t = (unsigned)items;
     if (is_f64) {
-        if (local) unaliased_accumulate_twin_kernel<double, true><<<g, t, 0, st>>>(c, (double *)output, (const double *)input, n, rows_out, rows_in);
-        else unaliased_accumulate_twin_kernel<double, false><<<g, t, 0, st>>>(c, (double *)output, (const double *)input, n, rows_out, rows_in);
+        if (local) unaliased_accumulate_twin_kernel<double, true><<<ka_grid, ka_block, 0, st>>>(c, (double *)output, (const double *)input, n, rows_out, rows_in);
+        else unaliased_accumulate_twin_kernel<double, false><<<ka_grid, ka_block, 0, st>>>(c, (double *)output, (const double *)input, n, rows_out, rows_in);
     } else {
-        if (local) unaliased_accumulate_twin_kernel<float, true><<<g, t, 0, st>>>(c, (float *)output, (const float *)input, n, rows_out, rows_in);
-        else unaliased_accumulate_twin_kernel<float, false><<<g, t, 0, st>>>(c, (float *)output, (const float *)input, n, rows_out, rows_in);
+        if (local) unaliased_accumulate_twin_kernel<float, true><<<ka_grid, ka_block, 0, st>>>(c, (float *)output, (const float *)input, n, rows_out, rows_in);
+        else unaliased_accumulate_twin_kernel<float, false><<<ka_grid, ka_block, 0, st>>>(c, (float *)output, (const float *)input, n, rows_out, rows_in);
     }
     B200_CHECK_LAUNCH("unaliased_accumulate_twin_kernel");
     return B200_OK;
@@ -415,7 +500,7 @@ __device__ __forceinline__ T through_int(T x) { return (T)(I)x; }
 template <typename T>
 __global__ void convert_twin_kernel(KaCtx c, const T *__restrict__ A, T *__restrict__ B, long long rowsB) {
     if (ka_valid(c)) {
-        long long tid = ka_global_linear();
+        long long tid = ka_global_linear(c);
         tid = (long long)(int)tid;   // Int64(Int32(tid))
         const T a = A[tid - 1];
         const T v[3] = {(T)ceil((double)a), (T)floor((double)a), (T)rint((double)a)};
@@ -436,9 +521,9 @@ __global__ void convert_twin_kernel(KaCtx c, const T *__restrict__ A, T *__restr
 int twin_convert(const KaCtx &c, const void *A, void *B, long long rowsB, int is_f64, cudaStream_t st) {
     KA_LAUNCH_1D(c, groups, items);
     if (is_f64)
-        convert_twin_kernel<double><<<(unsigned)groups, (unsigned)items, 0, st>>>(c, (const double *)A, (double *)B, rowsB);
+        convert_twin_kernel<double><<<ka_grid, ka_block, 0, st>>>(c, (const double *)A, (double *)B, rowsB);
     else
-        convert_twin_kernel<float><<<(unsigned)groups, (unsigned)items, 0, st>>>(c, (const float *)A, (float *)B, rowsB);
+        convert_twin_kernel<float><<<ka_grid, ka_block, 0, st>>>(c, (const float *)A, (float *)B, rowsB);
     B200_CHECK_LAUNCH("convert_twin_kernel");
     return B200_OK;
 }
@@ -446,14 +531,14 @@ int twin_convert(const KaCtx &c, const void *A, void *B, long long rowsB, int is
 // ---- test/specialfunctions.jl:5-18 gamma_knl / erf_knl / erfc_knl (Float32; compared with isapprox upstream) ----
 __global__ void specialfn_twin_kernel(KaCtx c, int which, float *__restrict__ A, const float *__restrict__ B) {
     if (ka_valid(c)) {
-        const long long I = ka_global_linear();
+        const long long I = ka_global_linear(c);
         const float x = B[I - 1];
         A[I - 1] = which == 0 ? tgammaf(x) : (which == 1 ? erff(x) : erfcf(x));
     }
 }
 int twin_specialfn(const KaCtx &c, int which, float *A, const float *B, cudaStream_t st) {
     KA_LAUNCH_1D(c, groups, items);
-    specialfn_twin_kernel<<<(unsigned)groups, (unsigned)items, 0, st>>>(c, which, A, B);
+    specialfn_twin_kernel<<<ka_grid, ka_block, 0, st>>>(c, which, A, B);
     B200_CHECK_LAUNCH("specialfn_twin_kernel");
     return B200_OK;
 }
@@ -462,16 +547,60 @@ int twin_specialfn(const KaCtx &c, int which, float *A, const float *B, cudaStre
 template <typename T>
 __global__ void saxpy_twin_kernel(KaCtx c, T *__restrict__ Z, T a, const T *__restrict__ X, const T *__restrict__ Y) {
     if (ka_valid(c)) {
-        const long long I = ka_global_linear();
+        const long long I = ka_global_linear(c);
         Z[I - 1] = add_rn(mul_rn(a, X[I - 1]), Y[I - 1]);
+    }
+}
+// vectorised form (see copy_twin_vec_kernel): V = 16 / sizeof(T) work-items per 16-byte word, product and sum rounded separately
+template <typename T>
+__global__ void __launch_bounds__(256) saxpy_twin_vec_kernel(T *__restrict__ Z, T a, const T *__restrict__ X, const T *__restrict__ Y, long long nvec,
+                                                             long long n) {
+    constexpr int V = 16 / sizeof(T);
+    const long long v0 = (long long)blockIdx.x * (256 * KA_VEC_U) + threadIdx.x;
+    uint4 x[KA_VEC_U], y[KA_VEC_U];
+#pragma unroll
+    for (int u = 0; u < KA_VEC_U; ++u)
+        if (v0 + u * 256 < nvec) {
+            x[u] = ka_ldg16(X + V * (v0 + u * 256));
+            y[u] = ka_ldg16(Y + V * (v0 + u * 256));
+        }
+#pragma unroll
+    for (int u = 0; u < KA_VEC_U; ++u)
+        if (v0 + u * 256 < nvec) {
+            uint4 z;
+            const T *xs = reinterpret_cast<const T *>(&x[u]), *ys = reinterpret_cast<const T *>(&y[u]);
+            T *zs = reinterpret_cast<T *>(&z);
+#pragma unroll
+            for (int k = 0; k < V; ++k) zs[k] = add_rn(mul_rn(a, xs[k]), ys[k]);
+            ka_stg16(Z + V * (v0 + u * 256), z);
+        }
+    if (blockIdx.x == gridDim.x - 1) {      // the (< V) work-items behind the last whole word
+        const long long I = V * nvec + threadIdx.x;
+        if (I < n) Z[I] = add_rn(mul_rn(a, X[I]), Y[I]);
     }
 }
 int twin_saxpy(const KaCtx &c, void *Z, double a, const void *X, const void *Y, int is_f64, cudaStream_t st) {
     KA_LAUNCH_1D(c, groups, items);
+    long long n_valid = 0;
+    // in place (Z == Y, examples/numa_aware.jl:10-13) is fine: a work-item reads its own element before writing it; Z may not
+    // overlap X or Y in any other way (the registry checks X)
+    if (twin_vec_enabled() && ka_vectorisable(c, &n_valid) && ((((uintptr_t)Z | (uintptr_t)X | (uintptr_t)Y) & 15) == 0)) {
+        if (n_valid <= 0) return B200_OK;
+        const int V = is_f64 ? 2 : 4;
+        const long long nvec = n_valid / V;
+        const long long ctas = (nvec + 256 * KA_VEC_U - 1) / (256 * KA_VEC_U);
+        const unsigned g = (unsigned)(ctas < 1 ? 1 : ctas);
+        if (is_f64)
+            saxpy_twin_vec_kernel<double><<<g, 256, 0, st>>>((double *)Z, a, (const double *)X, (const double *)Y, nvec, n_valid);
+        else
+            saxpy_twin_vec_kernel<float><<<g, 256, 0, st>>>((float *)Z, (float)a, (const float *)X, (const float *)Y, nvec, n_valid);
+        B200_CHECK_LAUNCH("saxpy_twin_vec_kernel");
+        return B200_OK;
+    }
     if (is_f64)
-        saxpy_twin_kernel<double><<<(unsigned)groups, (unsigned)items, 0, st>>>(c, (double *)Z, a, (const double *)X, (const double *)Y);
+        saxpy_twin_kernel<double><<<ka_grid, ka_block, 0, st>>>(c, (double *)Z, a, (const double *)X, (const double *)Y);
     else
-        saxpy_twin_kernel<float><<<(unsigned)groups, (unsigned)items, 0, st>>>(c, (float *)Z, (float)a, (const float *)X, (const float *)Y);
+        saxpy_twin_kernel<float><<<ka_grid, ka_block, 0, st>>>(c, (float *)Z, (float)a, (const float *)X, (const float *)Y);
     B200_CHECK_LAUNCH("saxpy_twin_kernel");
     return B200_OK;
 }
@@ -533,11 +662,13 @@ __global__ void performance_twin_kernel(KaCtx c, T *__restrict__ output, const T
 template <typename T>
 static int launch_performance(const KaCtx &c, int which, T *out, const T *in, long long rows_out, long long rows_in,
                               long long bank, long long groups, long long items, cudaStream_t st) {
+    dim3 ka_grid, ka_block;
+    ka_launch_dims(c, &ka_grid, &ka_block);
     size_t smem = 0;
     if (which >= 2) smem = (size_t)(c.wgs[0] + bank) * (size_t)(which >= 4 ? c.wgs[0] : c.wgs[1]) * sizeof(T);
     if (smem > 48 * 1024) return set_error(B200_ERR_LAUNCH_DIMS, "performance kernel: %zu bytes of @localmem", smem);
 #define B200_PERF_CASE(W)                                                                                          \
-    case W: performance_twin_kernel<T, W><<<(unsigned)groups, (unsigned)items, smem, st>>>(c, out, in, rows_out,    \
+    case W: performance_twin_kernel<T, W><<<ka_grid, ka_block, smem, st>>>(c, out, in, rows_out,    \
                                                                                            rows_in, bank); break;
     switch (which) {
         B200_PERF_CASE(0) B200_PERF_CASE(1) B200_PERF_CASE(2) B200_PERF_CASE(3) B200_PERF_CASE(4) B200_PERF_CASE(5)

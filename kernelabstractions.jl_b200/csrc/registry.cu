@@ -567,6 +567,9 @@ extern "C" b200_status b200_launch(const char *name, const b200_launch_desc *des
             if (in && (desc->ndrange[d] < 0 || desc->wgs[d] < 1 || desc->blocks[d] < 0))
                 return set_error(B200_ERR_PARTITION, "invalid iteration space in dimension %d", d + 1);
         }
+        // choose the lowering of the index arithmetic (native grid / multiply-high / the reference's 64-bit divisions) and
+        // precompute its constants; `registry.ka_mode` forces one for A/B measurements
+        ka_ctx_finish(&L.ctx, tune_get("registry.ka_mode", -1));
     } else if (desc->kind == B200_LAUNCH_KI) {
         // KI.check_launch_args (reference src/intrinsics.jl:182-188): at most 3 dimensions -> ArgumentError
         if (desc->ndim < 1 || desc->ndim > 3)

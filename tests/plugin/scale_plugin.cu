@@ -10,13 +10,13 @@ using b200::KaCtx;
 
 __global__ void scale_kernel(KaCtx c, float *A, float s) {
     if (b200::ka_valid(c)) {
-        const long long I = b200::ka_global_linear();
+        const long long I = b200::ka_global_linear(c);
         A[I - 1] *= s;
     }
 }
 __global__ void rowsum_kernel(KaCtx c, double *out, const double *__restrict__ A, long long rows, long long cols) {
     if (b200::ka_valid(c)) {
-        const long long i = b200::ka_global_linear();
+        const long long i = b200::ka_global_linear(c);
         double s = 0.0;
         for (long long j = 0; j < cols; ++j) s += A[(i - 1) + j * rows];
         out[i - 1] = s;
@@ -29,7 +29,9 @@ extern "C" int32_t scale_handler(const b200_launch_desc *d, const b200_arg *a, i
     int32_t st = b200_plugin_ctx(d, &c, &groups, &items);
     if (st != B200_OK) return st;
     if (n != 2 || a[0].kind != B200_ARG_ARRAY || a[0].eltype != B200_T_F32 || a[1].kind != B200_ARG_SCALAR) return B200_ERR_BAD_ARGS;
-    if (groups) scale_kernel<<<(unsigned)groups, (unsigned)items, 0, (cudaStream_t)stream>>>(c, (float *)a[0].ptr, (float)a[1].fscalar);
+    dim3 grid, block;
+    b200::ka_launch_dims(c, &grid, &block);
+    if (groups) scale_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(c, (float *)a[0].ptr, (float)a[1].fscalar);
     if (user) ++*(long long *)user;   // call counter owned by the test
     return B200_OK;
 }
@@ -39,8 +41,8 @@ extern "C" int32_t rowsum_handler(const b200_launch_desc *d, const b200_arg *a, 
     int32_t st = b200_plugin_ctx(d, &c, &groups, &items);
     if (st != B200_OK) return st;
     if (n != 2 || a[0].eltype != B200_T_F64 || a[1].eltype != B200_T_F64 || a[1].ndim != 2 || a[0].dims[0] != a[1].dims[0]) return B200_ERR_BAD_ARGS;
-    if (groups)
-        rowsum_kernel<<<(unsigned)groups, (unsigned)items, 0, (cudaStream_t)stream>>>(c, (double *)a[0].ptr, (const double *)a[1].ptr, a[1].dims[0],
-                                                                                    a[1].dims[1]);
+    dim3 grid, block;
+    b200::ka_launch_dims(c, &grid, &block);
+    if (groups) rowsum_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(c, (double *)a[0].ptr, (const double *)a[1].ptr, a[1].dims[0], a[1].dims[1]);
     return B200_OK;
 }

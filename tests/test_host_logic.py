@@ -1,10 +1,14 @@
 """CPU-only: the host-side mirror of KA's launch logic against the reference's known answers and the oracle."""
+import os
+
 import numpy as np
 import pytest
 
 import b200ka as KA
 from b200ka.kernel import Kernel, check_launch_args
 from b200ka.ndrange import DYNAMIC, StaticSize
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 # ---- test/test.jl:14-44 "partition" ---------------------------------------------------------------
@@ -170,3 +174,85 @@ def test_histogram_slice_cuts_model():
         assert all((c + off) % 32 == 0 for c in cuts[1:-1] if c > 0)
         per = n4 / grid                                   # no slice grows by more than one line over its fair share
         assert all(b - a <= per + 32 for a, b in zip(cuts, cuts[1:]))
+
+
+# ---- strength-reduced NDRange -> grid lowering (csrc/ka_device.cuh, host half) ----------------------------------------------
+_MAGIC_HARNESS = r"""
+#include <cstdio>
+#include <cstdlib>
+#include "ka_device.cuh"
+using namespace b200;
+static unsigned umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a * b) >> 32); }
+static unsigned fastdiv(unsigned n, unsigned mul, unsigned shr) { return mul ? (umulhi(n, mul) >> shr) : n; }
+int main() {
+    // every divisor class: 1, powers of two, primes, 2^k +- 1, the largest legal values; dividends up to 2^31 - 1
+    unsigned long long bad = 0, checked = 0;
+    unsigned ds[] = {1, 2, 3, 4, 5, 7, 8, 16, 17, 31, 32, 33, 63, 64, 65, 255, 256, 257, 1000, 1023, 1024, 1025, 65535, 65536, 65537,
+                     1000003, 16777215, 16777216, 16777217, 0x3fffffff, 0x40000000, 0x40000001, 0x7ffffffe, 0x7fffffff};
+    unsigned long long x = 88172645463325252ull;
+    for (unsigned d : ds) {
+        unsigned mul, shr;
+        ka_magic(d, &mul, &shr);
+        unsigned ns[] = {0, 1, d - 1, d, d + 1, 2 * d - 1, 2 * d, 0x7fffffff, 0x7ffffffe, 0x40000000, 0x3fffffff};
+        for (unsigned n : ns) {
+            if (n > 0x7fffffffu) continue;
+            ++checked;
+            if (fastdiv(n, mul, shr) != n / d) ++bad;
+        }
+        for (int k = 0; k < 200000; ++k) {
+            x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+            const unsigned n = (unsigned)(x >> 33);           // < 2^31
+            ++checked;
+            if (fastdiv(n, mul, shr) != n / d) ++bad;
+        }
+    }
+    // random divisors
+    for (int k = 0; k < 300000; ++k) {
+        x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+        const unsigned d = (unsigned)((x >> 33) >> (x & 31)) | 1u;
+        x ^= x << 13; x ^= x >> 7; x ^= x << 17;
+        const unsigned n = (unsigned)(x >> 33);
+        unsigned mul, shr;
+        ka_magic(d, &mul, &shr);
+        ++checked;
+        if (fastdiv(n, mul, shr) != n / d) ++bad;
+    }
+    // lowering choice
+    KaCtx c = {};
+    c.ndim = 2; c.dynamic_check = 1;
+    c.ndrange[0] = 16384; c.ndrange[1] = 16384; c.wgs[0] = 256; c.wgs[1] = 1; c.blocks[0] = 64; c.blocks[1] = 16384;
+    ka_ctx_finish(&c);
+    printf("transpose mode=%d ragged=%d items=%u\n", c.mode, c.ragged, c.items);
+    c.ndrange[1] = 70000; c.blocks[1] = 70000;
+    ka_ctx_finish(&c);
+    printf("wide mode=%d ragged=%d\n", c.mode, c.ragged);
+    c.ndim = 4; c.ndrange[0] = 5; c.ndrange[1] = 3; c.ndrange[2] = 2; c.ndrange[3] = 3;
+    c.wgs[0] = 2; c.wgs[1] = 2; c.wgs[2] = 1; c.wgs[3] = 2; c.blocks[0] = 3; c.blocks[1] = 2; c.blocks[2] = 2; c.blocks[3] = 2;
+    ka_ctx_finish(&c);
+    printf("4d mode=%d ragged=%d items=%u\n", c.mode, c.ragged, c.items);
+    ka_ctx_finish(&c, KA_MODE_DIV64);
+    printf("forced mode=%d\n", c.mode);
+    printf("checked=%llu bad=%llu\n", checked, bad);
+    return bad != 0;
+}
+"""
+
+
+def test_magic_number_division_and_lowering_choice(tmp_path):
+    """q = umulhi(n, mul) >> shr equals n / d for every n < 2^31 (the bound ka_ctx_finish guarantees: group and item ids), and
+    the host picks the native grid where CUDA's limits allow it -- compiled from the real header with g++ (host half only)."""
+    import subprocess
+
+    src = tmp_path / "magic.cpp"
+    src.write_text(_MAGIC_HARNESS)
+    exe = tmp_path / "magic"
+    inc = os.path.join(ROOT, "kernelabstractions.jl_b200", "csrc")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-I", inc, "-x", "c++", str(src), "-o", str(exe)])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout
+    lines = out.stdout.strip().splitlines()
+    assert lines[0] == "transpose mode=0 ragged=0 items=256"     # native 2-d grid, nothing ragged: __validindex folds to true
+    assert lines[1] == "wide mode=1 ragged=0"                     # 70000 groups in y exceed the grid limit -> multiply-high
+    assert lines[2] == "4d mode=1 ragged=11 items=8"              # dims 1, 2 and 4 are ragged (5 % 2, 3 % 2, 3 % 2)
+    assert lines[3] == "forced mode=2"
+    assert lines[4].endswith("bad=0") and int(lines[4].split()[0].split("=")[1]) > 7_000_000
