@@ -257,6 +257,12 @@ b200_status b200_convert_f32_bf16(uint16_t *out, const float *in, int64_t rows, 
 b200_status b200_matmul_f32_via_bf16(float *C, const float *A, const float *B, int64_t M, int64_t K,
                                      int64_t N, int64_t lda, int64_t ldb, int64_t ldc, void *workspace);
 
+/* The same with B converted once and kept resident (Bbf = b200_convert_f32_bf16(B, K, N, ldb, transpose 0)): the sharded form --
+ * B is replicated at set-up, only the rank's A row panel is converted per call.  `workspace` must hold M*K * 2 bytes.
+ * Same bits as b200_matmul_f32_via_bf16. */
+b200_status b200_matmul_f32_bf16_resident_b(float *C, const float *A, const uint16_t *Bbf, int64_t M, int64_t K,
+                                            int64_t N, int64_t lda, int64_t ldc, void *workspace);
+
 /* ---- device-array conveniences: what Base / LinearAlgebra give a CPU() user for free on plain Arrays ----------------
  * (SURVEY.md 8(f)-4).  These return a VALUE, so they wait for the calling thread's stream.  Any element-aligned pointer
  * (unaligned views take a scalar prologue; two operands vectorise when they are equally misaligned).

@@ -159,6 +159,7 @@ SIGNATURES = {
     "b200_matmul_f32_tf32x3": (_I32, [_VP, _VP, _VP, _I64, _I64, _I64, _I64, _I64, _I64, _VP]),
     "b200_convert_f32_bf16": (_I32, [_VP, _VP, _I64, _I64, _I64, _I32]),
     "b200_matmul_f32_via_bf16": (_I32, [_VP, _VP, _VP, _I64, _I64, _I64, _I64, _I64, _I64, _VP]),
+    "b200_matmul_f32_bf16_resident_b": (_I32, [_VP, _VP, _VP, _I64, _I64, _I64, _I64, _I64, _VP]),
     "b200_reduce": (_I32, [_I32, _I32, _VP, _SZ, _VP]),
     "b200_count_mismatch": (_I32, [_VP, _VP, _SZ, _I32, _I32, _VP]),
     "b200_norms": (_I32, [_VP, _VP, _SZ, _I32, _VP]),

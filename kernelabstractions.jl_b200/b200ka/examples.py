@@ -133,6 +133,26 @@ def matmul_bf16_(C_: B200Array, A: B200Array, B: B200Array, workspace: B200Array
               C_.shape[0], C.c_void_p(ws.ptr))
 
 
+def prepare_bf16_b(B: B200Array) -> B200Array:
+    """B (K x N, FP32, column-major) -> its resident BF16 image for matmul_bf16_resident_b_ (converted once, e.g. after the
+    set-up broadcast that replicates B on every rank)."""
+    K, N = B.shape
+    out = allocate(B200Backend(), np.uint16, (K * N,))
+    _lib.call("b200_convert_f32_bf16", C.c_void_p(out.ptr), C.c_void_p(B.ptr), K, N, K, 0)
+    return out
+
+
+def matmul_bf16_resident_b_(C_: B200Array, A: B200Array, Bbf: B200Array, N: int, workspace: B200Array = None) -> None:
+    """C = A * B with FP32 A and C, BF16 tcgen05 arithmetic, B already converted (prepare_bf16_b): only the A (row panel) is
+    converted per call.  Same bits as matmul_bf16_."""
+    M, K = A.shape
+    if Bbf.size != K * N or C_.shape != (M, N):
+        raise _lib.ArgumentError("matmul_bf16_resident_b_: shapes do not conform")
+    ws = workspace if workspace is not None else allocate(B200Backend(), np.uint16, (M * K,))
+    _lib.call("b200_matmul_f32_bf16_resident_b", C.c_void_p(C_.ptr), C.c_void_p(A.ptr), C.c_void_p(Bbf.ptr), M, K, N, M, C_.shape[0],
+              C.c_void_p(ws.ptr))
+
+
 def matmul_tf32_(C_: B200Array, A: B200Array, B: B200Array) -> None:
     """Opt-in tensor-core path (no reference twin): tcgen05 kind::tf32 straight from the FP32 column-major operands --
     no conversion pass, no workspace; the tensor core uses the top 19 bits of every operand, FP32 accumulate."""

@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(T, 1) hist256_bytes_kernel(int32_t *__restrict
 template <int T, int P>
 __device__ __noinline__ void hist_count_phase(uint32_t *sh, uint32_t nbins, const int4 *__restrict__ in4, int64_t n4,
                                               const int32_t *__restrict__ tail, int ntail, int copies,
-                                              const int32_t *__restrict__ head = nullptr, int nhead = 0) {
+                                              const int32_t *__restrict__ head, int nhead, int interleave) {
     const int t = threadIdx.x, warp = t >> 5;
     // Programmatic dependent launch (see launch_pdl): the next kernel of the stream may be scheduled as SMs drain; our own set-up
     // runs before we wait for the previous kernel's memory.  Back-to-back steps on input shards hide ~2 us of the ~9 us a launch costs.
@@ -176,14 +176,34 @@ __device__ __noinline__ void hist_count_phase(uint32_t *sh, uint32_t nbins, cons
         uint32_t b = (uint32_t)v - 1u;
         if (b < nbins) atomicAdd(mine + b, 1u);
     };
-    const int64_t u0 = slice_cut(in4, n4, blockIdx.x), u1 = slice_cut(in4, n4, blockIdx.x + 1);
-    const int64_t nbatch = (u1 - u0 + (int64_t)P * T - 1) / ((int64_t)P * T);
+    // Which int4 units does this CTA count?  Two plans, same total:
+    //  * slices (interleave == 0): one contiguous slice per CTA, cut on 512-byte lines (slice_cut);
+    //  * interleaved (default): the input is dealt out in UNITS of T int4 (16 KiB for T = 1024, boundaries on 512-byte lines of
+    //    the address) round-robin over the CTAs -- unit u belongs to CTA u % grid.  Every CTA then walks the whole address range
+    //    at the same pace, sees the same mix of DRAM channels, and owns floor / ceil(units / grid) units: the slices finished up
+    //    to 6 us apart at 2^27 elements (b200_p2p_timeline), and the kernel ends with its slowest CTA.
+    const int64_t off = (int64_t)(((uintptr_t)in4 >> 4) & 31);
+    int64_t u0, u1, stride;
+    if (interleave) {
+        // position of this CTA's r-th unit: ((r * grid + b) * T - off); element index = that + t
+        u0 = (int64_t)blockIdx.x * T - off;
+        u1 = n4;
+        stride = (int64_t)gridDim.x * T;
+    } else {
+        u0 = slice_cut(in4, n4, blockIdx.x);
+        u1 = slice_cut(in4, n4, blockIdx.x + 1);
+        stride = T;
+    }
+    // loads r = 0, 1, ... of this CTA sit at u0 + r * stride + t and count if they fall into [max(u0, 0), u1)
+    const int64_t span = u1 - u0;
+    const int64_t nload = span > 0 ? (span + stride - 1) / stride : 0;
+    const int64_t nbatch = (nload + P - 1) / P;
     int4 cur[P], nxt[P];
     auto load_batch = [&](int64_t k, int4 *buf) {
 #pragma unroll
         for (int p = 0; p < P; ++p) {
-            int64_t u = u0 + (k * P + p) * (int64_t)T + t;
-            buf[p] = u < u1 ? ldg_stream_i4(in4 + u) : make_int4(0, 0, 0, 0);
+            const int64_t u = u0 + (k * P + p) * stride + t;
+            buf[p] = (u >= 0 && u < u1) ? ldg_stream_i4(in4 + u) : make_int4(0, 0, 0, 0);   // 0 is outside 1..nbins
         }
     };
     if (nbatch > 0) load_batch(0, cur);
@@ -207,10 +227,10 @@ __device__ __noinline__ void hist_count_phase(uint32_t *sh, uint32_t nbins, cons
 template <int T, int P>
 __global__ void __launch_bounds__(T) hist_atomic_kernel(int32_t *__restrict__ bins, uint32_t nbins,
                                                         const int4 *__restrict__ in4, int64_t n4,
-                                                        const int32_t *__restrict__ tail, int ntail, int copies) {
+                                                        const int32_t *__restrict__ tail, int ntail, int copies, int interleave) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t *sh = reinterpret_cast<uint32_t *>(smem_raw);
-    hist_count_phase<T, P>(sh, nbins, in4, n4, tail, ntail, copies);
+    hist_count_phase<T, P>(sh, nbins, in4, n4, tail, ntail, copies, nullptr, 0, interleave);
     for (uint32_t b = threadIdx.x; b < nbins; b += T) {
         uint32_t s = 0;
         for (int c = 0; c < copies; ++c) s += sh[(uint32_t)c * nbins + b];
@@ -376,12 +396,12 @@ template <int T, int P>
 __global__ void __launch_bounds__(T) hist_allreduce_kernel(int32_t *__restrict__ bins, uint32_t nbins,
                                                            const int4 *__restrict__ in4, int64_t n4,
                                                            const int32_t *__restrict__ tail, int ntail, int copies,
-                                                           const int32_t *__restrict__ head, int nhead,
+                                                           const int32_t *__restrict__ head, int nhead, int interleave,
                                                            const __grid_constant__ HistPeer peer) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t *sh = reinterpret_cast<uint32_t *>(smem_raw);
     if (blockIdx.x == 0 && threadIdx.x == 0) peer.stamps[5] = globaltimer_ns();          // first CTA resident
-    hist_count_phase<T, P>(sh, nbins, in4, n4, tail, ntail, copies, head, nhead);
+    hist_count_phase<T, P>(sh, nbins, in4, n4, tail, ntail, copies, head, nhead, interleave);
     fused_exchange<T>(sh, nbins, copies, bins, peer);
 }
 
@@ -432,7 +452,8 @@ static int launch_atomic(int32_t *bins, uint32_t nbins, const int4 *in4, int64_t
     if (smem > 48 * 1024)
         B200_CUDA(cudaFuncSetAttribute(hist_atomic_kernel<T, P>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem));
-    B200_TRY(launch_pdl(hist_atomic_kernel<T, P>, grid, T, smem, st, bins, nbins, in4, n4, tail, ntail, copies));
+    B200_TRY(launch_pdl(hist_atomic_kernel<T, P>, grid, T, smem, st, bins, nbins, in4, n4, tail, ntail, copies,
+                        tune_get("hist.interleave", 1)));
     B200_CHECK_LAUNCH("hist_atomic_kernel");
     return B200_OK;
 }
@@ -656,7 +677,7 @@ int histogram_allreduce_launch(P2P *h, int32_t *bins, int64_t nbins, const int32
     if (smem > 48 * 1024)
         B200_CUDA(cudaFuncSetAttribute(hist_allreduce_kernel<T, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     B200_TRY(launch_pdl(hist_allreduce_kernel<T, P>, grid, T, smem, st, bins, (uint32_t)nbins, reinterpret_cast<const int4 *>(body), n4,
-                        body + n4 * 4, tail_n, copies, input, (int)head, peer));
+                        body + n4 * 4, tail_n, copies, input, (int)head, tune_get("hist.interleave", 1), peer));
     B200_CHECK_LAUNCH("hist_allreduce_kernel");
     h->epoch++;
     return B200_OK;

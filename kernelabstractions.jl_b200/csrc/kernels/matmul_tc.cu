@@ -909,3 +909,17 @@ extern "C" b200_status b200_matmul_f32_via_bf16(float *C, const float *A, const 
     B200_TRY(convert_bf16_launch(bbf, B, K, N, ldb, 0, st));  // B: K x N col-major == N rows of K
     return gemm_bf16_launch(C, abf, bbf, M, K, N, ldc, st);
 }
+
+// The same product with B already converted and RESIDENT (b200_convert_f32_bf16(Bbf, B, K, N, ldb, 0), once): what a sharded
+// run does -- B is replicated at set-up and only the rank's A row panel changes per call.  workspace: M * K
+// bf16 for the converted panel.  Same bits as b200_matmul_f32_via_bf16 on the same operands.
+extern "C" b200_status b200_matmul_f32_bf16_resident_b(float *C, const float *A, const uint16_t *Bbf, int64_t M, int64_t K,
+                                                       int64_t N, int64_t lda, int64_t ldc, void *workspace) {
+    if (!C || !A || !Bbf || !workspace) return set_error(B200_ERR_INVALID_VALUE, "b200_matmul_f32_bf16_resident_b: NULL pointer");
+    if (lda < M || ldc < M) return set_error(B200_ERR_INVALID_VALUE, "b200_matmul_f32_bf16_resident_b: bad ld");
+    cudaStream_t st;
+    B200_TRY(current_stream(&st));
+    uint16_t *abf = (uint16_t *)workspace;
+    B200_TRY(convert_bf16_launch(abf, A, M, K, lda, 1, st));  // A: M x K col-major -> M rows of K
+    return gemm_bf16_launch(C, abf, Bbf, M, K, N, ldc, st);
+}

@@ -268,6 +268,19 @@ function matmul_bf16!(C::B200Array{Float32, 2}, A::B200Array{Float32, 2}, B::B20
     @b200 b200_matmul_f32_via_bf16 (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Int64, Int64, Int64, Int64, Ptr{Cvoid}) C.ptr A.ptr B.ptr M K N M K M workspace.ptr
     return C
 end
+# B converted once and kept resident (the sharded form: B is replicated at set-up, only the A row panel changes per call)
+function prepare_bf16_b(B::B200Array{Float32, 2})
+    out = B200Array{UInt16, 1}(undef, (length(B),))
+    @b200 b200_convert_f32_bf16 (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Int64, Int32) out.ptr B.ptr size(B, 1) size(B, 2) size(B, 1) Int32(0)
+    return out
+end
+function matmul_bf16_resident_b!(C::B200Array{Float32, 2}, A::B200Array{Float32, 2}, Bbf::B200Array{UInt16, 1};
+                                 workspace::B200Array{UInt16, 1} = B200Array{UInt16, 1}(undef, (length(A),)))
+    M, K, N = size(A, 1), size(A, 2), size(C, 2)
+    length(Bbf) == K * N || throw(DimensionMismatch("matmul_bf16_resident_b!"))
+    @b200 b200_matmul_f32_bf16_resident_b (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int64, Int64, Int64, Int64, Ptr{Cvoid}) C.ptr A.ptr Bbf.ptr M K N M M workspace.ptr
+    return C
+end
 Base.view(A::B200Array{T}, r::UnitRange{Int}) where {T} =
     B200Array{T, 1}(A.ptr + (first(r) - 1) * sizeof(T), (length(r),), A.unified, A)
 

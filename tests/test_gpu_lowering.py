@@ -36,7 +36,7 @@ def test_cartesian_indices_match_oracle_in_every_lowering(orc, mode, ndrange, wg
     if n > 3 and mode == "grid":
         pytest.skip("a 4-d space has no native grid (auto falls back to the multiply-high lowering)")
     for which, kern in [(0, K.index_cartesian_global), (1, K.index_cartesian_local), (2, K.index_cartesian_group)]:
-        A = KA.allocate(be, KA.CartesianIndex(n), *ndrange).fill_(0)
+        A = KA.to_device(np.zeros(ndrange, dtype=KA.CartesianIndex(n), order="F"))
         kern(be, wgs)(A, ndrange=ndrange)
         ref = np.zeros((n,) + tuple(ndrange), dtype=np.int64, order="F")
         orc.index_cartesian(which, ref, ndrange, ndrange, wgs)

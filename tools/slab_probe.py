@@ -49,13 +49,13 @@ def tune(k, v):
 
 
 n = 16384
-for G in (1, 2, 4, 8):
+for G in (1, 8):
     rb = n // G
     dB = KA.rand_uniform_(KA.allocate(be, np.float32, rb, n), 1235)
     dA = KA.zeros(be, np.float32, n, rb)
     ideal = 2 * 4 * n * rb / 6545.9e9 * 1e6
     for pdl in (0, 1):
-        for cps in (0, 6, 5, 4, 3, 2):
+        for cps in (0,):
             tune("transpose.pdl", pdl)
             tune("transpose.ctas_per_sm", cps)
             us = timed(lambda: EX.naive_transpose_(dA, dB))
@@ -75,6 +75,19 @@ for G in (1, 8):
             EX.mycopy_(dst[i], src[i])
     us = timed(cycle, steps=20) / npairs
     print(f"copy slab 1/{G} ({npairs} pairs rotated): {us:8.2f} us ({8 * ne / us / 1e3:7.1f} GB/s; at the measured peak {8 * ne / 6545.9e9 * 1e6:6.2f} us)", flush=True)
+    if G == 8:
+        for impl, kb, stages, cps in [(1, 8, 8, 1), (1, 8, 4, 2), (1, 16, 4, 2), (1, 8, 8, 2), (1, 32, 4, 1), (1, 16, 8, 1), (1, 4, 8, 2), (0, 0, 0, 0)]:
+            tune("copy.impl", impl)
+            if impl:
+                tune("copy.bulk_stage_kb", kb)
+                tune("copy.bulk_stages", stages)
+                tune("copy.bulk_ctas_per_sm", cps)
+            us = timed(cycle, steps=20) / npairs
+            print(f"   copy.impl={impl} stage_kb={kb} stages={stages} ctas_per_sm={cps}: {us:8.2f} us ({8 * ne / us / 1e3:7.1f} GB/s)", flush=True)
+        tune("copy.impl", 1)
+        tune("copy.bulk_stage_kb", 16)
+        tune("copy.bulk_stages", 4)
+        tune("copy.bulk_ctas_per_sm", 1)
     del src, dst
 
 peers = mg.PeerGroup(1, 0, lambda blob: [blob])
@@ -82,13 +95,16 @@ for G in (1, 8):
     ne = (1 << 30) // G
     d_in = KA.rand_bins_(KA.allocate(be, np.int32, ne), 1236, 256)
     bins = KA.zeros(be, np.int32, 256)
-    us_l = timed(lambda: EX.histogram_(bins, d_in), steps=100)
-    us_f = timed(lambda: peers.histogram_allreduce(bins, d_in), steps=100, graph=False)
-    print(f"histogram slab 1/{G}: local-only {us_l:8.2f} us, fused (1 rank) {us_f:8.2f} us; stream time at 7.25 TB/s {4 * ne / 7.25e12 * 1e6:7.2f} us", flush=True)
-    KA.synchronize(be)
-    for rep in range(3):
-        peers.timeline()
-        peers.histogram_allreduce(bins, d_in)
-        print("   fused timeline (ns, relative to the fastest CTA leaving the counting loop):", peers.timeline(), flush=True)
+    for inter in (0, 1):
+        tune("hist.interleave", inter)
+        us_l = timed(lambda: EX.histogram_(bins, d_in), steps=100)
+        us_f = timed(lambda: peers.histogram_allreduce(bins, d_in), steps=100, graph=False)
+        print(f"histogram slab 1/{G} interleave={inter}: local-only {us_l:8.2f} us, fused (1 rank) {us_f:8.2f} us; stream time at 7.25 TB/s {4 * ne / 7.25e12 * 1e6:7.2f} us", flush=True)
+        KA.synchronize(be)
+        for rep in range(3):
+            peers.timeline()
+            peers.histogram_allreduce(bins, d_in)
+            print("   fused timeline (ns, relative to the fastest CTA leaving the counting loop):", peers.timeline(), flush=True)
+    tune("hist.interleave", 1)
     del d_in
 peers.free()
