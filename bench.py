@@ -127,6 +127,51 @@ class ClockSampler:
                 "samples": len(self.samples)}
 
 
+class NvlinkCounter:
+    """Hardware NVLink byte counters of one GPU through NVML (NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX / _RX, summed over all links,
+    KiB): read before and after the timed steps, the difference is what actually crossed the links -- the proof that a fused
+    compute + collective kernel moved its bytes over NVLink and how many.  None when the driver does not expose the counters."""
+
+    def __init__(self, index):
+        self.h = None
+        try:
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.read()
+        except Exception:
+            self.h = None
+
+    def read(self):
+        nv = self.nv
+        vals = nv.nvmlDeviceGetFieldValues(self.h, [(nv.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX, 0xFFFFFFFF),
+                                                    (nv.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_RX, 0xFFFFFFFF)])
+        out = []
+        for v in vals:
+            if v.nvmlReturn != 0:
+                raise RuntimeError("NVLink counter not available")
+            out.append(int(v.value.ullVal) * 1024)
+        return tuple(out)
+
+    def delta_per_step(self, before, steps):
+        if self.h is None or before is None:
+            return None
+        try:
+            now = self.read()
+        except Exception:
+            return None
+        return {"tx_bytes": (now[0] - before[0]) / steps, "rx_bytes": (now[1] - before[1]) / steps}
+
+    def start(self):
+        if self.h is None:
+            return None
+        try:
+            return self.read()
+        except Exception:
+            return None
+
+
 # =================================================================================================
 # reference arm / cpu baseline: the oracle port of the reference CPU() algorithm
 # =================================================================================================
@@ -379,6 +424,33 @@ def main():
             barrier()
             return max_over_ranks(max(ms.value * 1e-3, wall)) / k   # device events and host clock agree; keep the larger
 
+        # ceiling of any host-array route on this host: the rank's slab h2d on one stream and d2h on another at the same time,
+        # no kernel (PCIe is full duplex; with several ranks on one host the host side is shared)
+        s2 = C.c_void_p()
+        _lib.call("b200_stream_create", C.byref(s2), 0)
+
+        def copy_only():
+            KA.copyto_(be, dB, h_in)
+            _lib.call("b200_set_stream", s2)
+            KA.copyto_(be, h_out, dA)
+            _lib.call("b200_set_stream", None)
+
+        def copy_only_wait():
+            KA.synchronize(be)
+            _lib.call("b200_set_stream", s2)
+            KA.synchronize(be)
+            _lib.call("b200_set_stream", None)
+
+        copy_only()
+        copy_only_wait()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            copy_only()
+        copy_only_wait()
+        dt_copy = max_over_ranks(time.perf_counter() - t0) / 3
+        _lib.call("b200_stream_destroy", s2)
+
         e2e_steps = max(1, min(args.e2e_steps, args.steps))
         dt_pipe = time_e2e(step_pipe, e2e_steps)
         h_out[...] = 0
@@ -394,6 +466,9 @@ def main():
         e2e = {"value": BYTES_T / best_dt / 1e9, "unit": "GB/s", "h2d_bytes_per_step": nbytes * world, "d2h_bytes_per_step": nbytes * world,
                "ms_per_step": best_dt * 1e3, "steps": e2e_steps, "result_checked": ok and ok_seq, "route": best_name,
                "pipelined_value": BYTES_T / dt_pipe / 1e9, "unpipelined_value": BYTES_T / dt_seq / 1e9,
+               "copy_only_duplex_value": BYTES_T / dt_copy / 1e9,
+               "limiter": "host <-> device copies: copy_only_duplex_value is the same slabs moved h2d and d2h concurrently with no kernel "
+                          "at all (the ceiling of any host-array route on this host; one NUMA node and no PCIe topology are exposed to the VM)",
                "path": "pipelined = EX.naive_transpose_host_ -> b200_transpose_host (pinned host in/out, 32 MiB slabs, h2d | kernel | d2h "
                        "overlapped); in-order = KA.copyto! in, naive_transpose!, KA.copyto! out on one stream; every rank moves its own "
                        "slab of the one matrix; bytes are whole-job totals"}
@@ -547,7 +622,7 @@ def run_suite(KA, _lib, EX, mg, orc, be, rank, world, dist, timed, graphed, all_
         gbs = 3 * 4 * n / (ms * 1e-3) / 1e9
         out["saxpy_2^26_f32"] = {"value": world * gbs, "unit": "GB/s", "ms_per_step": ms, "gpu_launches": launches,
                                  "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm"], "frac": gbs / peaks["hbm"],
-                                              "traffic": traffic_from_profiles("capture:saxpy"), "algorithmic_bytes_per_launch": 12 * n},
+                                              "traffic": traffic_from_profiles("saxpy_vec_kernel"), "algorithmic_bytes_per_launch": 12 * n},
                                  "scaling": "weak"}
         del X, Y, Z
         if cpu:
@@ -585,11 +660,16 @@ def run_suite(KA, _lib, EX, mg, orc, be, rank, world, dist, timed, graphed, all_
                     peer_ok = peer_ok and same
             del tmp, a_host
             ok, peer_ok = all_ranks(ok), all_ranks(peer_ok)
+            nvl = NvlinkCounter(env_int("LOCAL_RANK", 0))
+            nv0 = nvl.start()
             ms, launches = timed(step_dt, steps, warmup)
+            nv_meas = nvl.delta_per_step(nv0, steps + warmup)
             gbs = 2.0 * 4 * n * n / (ms * 1e-3) / 1e9
             out["distributed_transpose_16384_f32"] = {
                 "value": gbs, "unit": "GB/s", "ms_per_step": ms, "gpu_launches": launches, "scaling": "strong", "slab_checked": ok, "peer_block_checked": peer_ok,
                 "nvlink_egress_GBps_per_gpu": 4.0 * n * rb * (world - 1) / world / (ms * 1e-3) / 1e9,
+                "nvlink_expected_tx_bytes_per_step_per_gpu": 4.0 * n * rb * (world - 1) / world,
+                "nvlink_counters_per_step_rank0": nv_meas,   # NVML hardware counters (payload bytes, all links) around the same steps
                 "collective": "all-to-all fused into the transpose kernel's store phase (b200_transpose_alltoall: peer stores over NVLink + flag barrier), no NCCL",
                 "roofline": {"bound": "nvlink", "achieved": 4.0 * n * rb * (world - 1) / world / (ms * 1e-3) / 1e9, "peak": 900.0, "unit": "GB/s",
                              "frac": 4.0 * n * rb * (world - 1) / world / (ms * 1e-3) / 1e9 / 900.0, "peak_source": "NVLink 5 nominal, per direction"}}
@@ -632,13 +712,18 @@ def run_suite(KA, _lib, EX, mg, orc, be, rank, world, dist, timed, graphed, all_
         KA.synchronize(be)
         got = KA.Array(bins)
         check = bool(int(got.astype(np.int64).sum()) == n)  # every input lies in 1..256: counts must add up to n
+        nvl = NvlinkCounter(env_int("LOCAL_RANK", 0)) if world > 1 else None
+        nv0 = nvl.start() if nvl else None
         ms, launches = timed(step_hist, steps, warmup)
+        nv_meas = nvl.delta_per_step(nv0, steps + warmup) if nvl else None
         gbs = 4.0 * n / (ms * 1e-3) / 1e9  # whole job: all ranks' inputs / max time
         out["histogram_2^30_i32_256bins"] = {"value": gbs, "unit": "GB/s", "ms_per_step": ms, "gpu_launches": launches,
                                              "sum_conserved": check, "scaling": "strong",
+                                             "nvlink_counters_per_step_rank0": nv_meas,
+                                             "nvlink_expected_tx_bytes_per_step_per_gpu": (256 * 8 * (world - 1)) if world > 1 else None,
                                              "roofline": {"bound": "hbm", "achieved": gbs / world, "peak": peaks["hbm"],
                                                           "frac": gbs / world / peaks["hbm"],
-                                                          "traffic": traffic_from_profiles("capture:hist") if world == 1 else None,
+                                                          "traffic": traffic_from_profiles("hist_atomic_kernel", 1.0 / world),
                                                           "algorithmic_bytes_per_launch": 4 * (s1 - s0) + 1024,
                                                           "note": "read-only stream: the measured peak is a copy (mixed traffic); read-only ceiling "
                                                                   "7.2-7.5 TB/s (profiles/r04_hbm_stream.txt), so frac can exceed 1"},
@@ -789,6 +874,8 @@ def run_suite(KA, _lib, EX, mg, orc, be, rank, world, dist, timed, graphed, all_
         def step_tf32x3():
             EX.matmul_tf32x3_(dC, Ap, dBm, ws3)
 
+        tkey = {"matmul_bf16_tcgen05_8192": "gemm_tcgen05_kernel<bf16>", "matmul_tf32_tcgen05_8192": "gemm_tcgen05_kernel<tf32>",
+                "matmul_f32_tf32x3_tcgen05_8192": "gemm_tcgen05_kernel<tf32x3>"}
         for key, fn, peak, note, rtol in (
                 ("matmul_bf16_tcgen05_8192", step_tc, peaks["bf16"], "BF16 operands pre-converted (conversion pass excluded), FP32 accumulate/output", 1e-2),
                 ("matmul_bf16_tcgen05_8192_from_f32", step_tc_e2e, peaks["bf16"],
@@ -811,7 +898,11 @@ def run_suite(KA, _lib, EX, mg, orc, be, rank, world, dist, timed, graphed, all_
             tf = 2.0 * n * n * n / (ms * 1e-3) / 1e12
             out[key] = {"value": tf, "unit": "TFLOP/s", "ms_per_step": ms, "gpu_launches": launches, "scaling": "strong", "note": note,
                         "max_rel_err_sampled_vs_f64": err,
-                        "roofline": {"bound": "tensor", "achieved": tf / world, "peak": peak, "frac": tf / world / peak}}
+                        "roofline": {"bound": "tensor", "achieved": tf / world, "peak": peak, "frac": tf / world / peak,
+                                     "traffic": traffic_from_profiles(tkey[key], 1.0 / world) if key in tkey else None,
+                                     "peak_note": ("measured cuBLAS BF16 burst peak" if peak == peaks["bf16"] else
+                                                   "builder-defined: measured BF16 peak / 2 (TF32 runs at half the BF16 rate)" if peak == peaks["bf16"] / 2
+                                                   else "builder-defined: measured BF16 peak / 6 (three TF32 MMAs per k step at half the BF16 rate)")}}
     except Exception as ex:
         out["matmul_f32_8192"] = out.get("matmul_f32_8192", {"error": str(ex)[:300]})
     return out

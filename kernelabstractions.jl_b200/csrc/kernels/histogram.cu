@@ -19,6 +19,7 @@
 #include <cstring>
 
 #include "../common.cuh"
+#include "../tma_pipe.cuh"
 #include "../tune.h"
 
 namespace b200 {
@@ -158,67 +159,85 @@ __global__ void __launch_bounds__(T, 1) hist256_bytes_kernel(int32_t *__restrict
 // kernel, ptxas scheduled the four in-flight LDG.128 differently and the loop lost 13 % (745 us instead of 650 us for
 // 2^30 elements; profiles/r02_hist_fused_notes.md).
 // `tail`/`ntail`: the scalar leftovers, counted by CTA 0 -- the n % 4 elements behind the int4 body and, when the input is not
-// 16-byte aligned, the (< 4) head elements in front of it: both lie in ONE array of <= 6 words when head + body + tail are
-// contiguous, so the callers pass the head through `head`/`nhead`.
-template <int T, int P>
+// 16-byte aligned, the (< 4) head elements in front of it (`head`/`nhead`).
+//
+// Which int4 units does a CTA count?  Two plans (template parameter IL), same total:
+//  * slices (IL = false): one contiguous slice per CTA, cut on 512-byte lines of the address (slice_cut);
+//  * interleaved (IL = true): the input is dealt out in UNITS of T int4 (16 KiB for T = 1024) round-robin over the CTAs,
+//    unit u -> CTA u % grid, unit boundaries on 512-byte lines (the < 32 int4 in front of the first line are CTA 0's).
+//    Every CTA then walks the whole address range at the same pace, sees the same mix of DRAM channels and owns
+//    floor / ceil(units / grid) units; contiguous slices finished up to 6 us apart at 2^27 elements (b200_p2p_timeline,
+//    profiles/r05_slab_probe.txt), and a kernel ends with its slowest CTA.
+// The loop is issue-sensitive (16 shared atomics + their range tests per 4 loads keep the schedulers ~2/3 busy; a variant with
+// 25 % more integer instructions per batch ran 20 % slower, r05), so the main loop carries NO bounds predicates: `nfb` batches
+// of P loads per thread are complete by construction and ONE predicated batch follows for whatever is left.
+template <int T, int P, bool IL>
 __device__ __noinline__ void hist_count_phase(uint32_t *sh, uint32_t nbins, const int4 *__restrict__ in4, int64_t n4,
                                               const int32_t *__restrict__ tail, int ntail, int copies,
-                                              const int32_t *__restrict__ head, int nhead, int interleave) {
+                                              const int32_t *__restrict__ head, int nhead) {
     const int t = threadIdx.x, warp = t >> 5;
     // Programmatic dependent launch (see launch_pdl): the next kernel of the stream may be scheduled as SMs drain; our own set-up
     // runs before we wait for the previous kernel's memory.  Back-to-back steps on input shards hide ~2 us of the ~9 us a launch costs.
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    for (uint32_t i = t; i < nbins * (uint32_t)copies; i += T) sh[i] = 0;
+    const uint32_t nb1 = nbins + 1u;   // every private copy carries one extra counter: the sink of out-of-range values
+    for (uint32_t i = t; i < nb1 * (uint32_t)copies; i += T) sh[i] = 0;
     __syncthreads();
     asm volatile("griddepcontrol.wait;" ::: "memory");   // everything before us in the stream is complete and visible
-    uint32_t *mine = sh + (uint32_t)(warp % copies) * nbins;
-    auto bump = [&](int v) {
-        uint32_t b = (uint32_t)v - 1u;
-        if (b < nbins) atomicAdd(mine + b, 1u);
+    uint32_t *mine = sh + (uint32_t)(warp % copies) * nb1;
+    // Values outside 1..nbins are ignored by the reference's range test (examples/histogram.jl:45-46).  Here they are CLAMPED into
+    // the sink counter instead of branched around: (unsigned)(v - 1) >= nbins -> nbins.  One IADD + one unsigned MIN per element
+    // replace compare + branch + reconvergence in a loop whose limit is instruction issue (see below); the sink is never read.
+    auto bump = [&](int v) { atomicAdd(mine + min((uint32_t)v - 1u, nbins), 1u); };
+    auto bump4 = [&](const int4 &v) {
+        bump(v.x);
+        bump(v.y);
+        bump(v.z);
+        bump(v.w);
     };
-    // Which int4 units does this CTA count?  Two plans, same total:
-    //  * slices (interleave == 0): one contiguous slice per CTA, cut on 512-byte lines (slice_cut);
-    //  * interleaved (default): the input is dealt out in UNITS of T int4 (16 KiB for T = 1024, boundaries on 512-byte lines of
-    //    the address) round-robin over the CTAs -- unit u belongs to CTA u % grid.  Every CTA then walks the whole address range
-    //    at the same pace, sees the same mix of DRAM channels, and owns floor / ceil(units / grid) units: the slices finished up
-    //    to 6 us apart at 2^27 elements (b200_p2p_timeline), and the kernel ends with its slowest CTA.
-    const int64_t off = (int64_t)(((uintptr_t)in4 >> 4) & 31);
-    int64_t u0, u1, stride;
-    if (interleave) {
-        // position of this CTA's r-th unit: ((r * grid + b) * T - off); element index = that + t
-        u0 = (int64_t)blockIdx.x * T - off;
-        u1 = n4;
-        stride = (int64_t)gridDim.x * T;
+    // Round r of this CTA loads int4 number  first + r * rstride + t  (t = thread); rounds [0, nr) are complete (all T
+    // threads in range), then `extra` more int4 (< T) follow at round nr for the first `extra` threads.
+    int64_t first, rstride, nr, extra;
+    if (IL) {
+        const int64_t lead = min((int64_t)((32 - (((uintptr_t)in4 >> 4) & 31)) & 31), n4);   // int4 in front of the first 512-byte line
+        if (blockIdx.x == 0 && t < lead) bump4(ldg_stream_i4(in4 + t));
+        const int64_t m4 = n4 - lead, nu = m4 / T;                                            // whole units behind it
+        first = lead + (int64_t)blockIdx.x * T;
+        rstride = (int64_t)gridDim.x * T;
+        nr = nu > blockIdx.x ? (nu - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+        extra = (int64_t)(nu % gridDim.x) == (int64_t)blockIdx.x ? m4 - nu * T : 0;           // the partial last unit has one owner
     } else {
-        u0 = slice_cut(in4, n4, blockIdx.x);
-        u1 = slice_cut(in4, n4, blockIdx.x + 1);
-        stride = T;
+        const int64_t u0 = slice_cut(in4, n4, blockIdx.x), u1 = slice_cut(in4, n4, blockIdx.x + 1);
+        first = u0;
+        rstride = T;
+        nr = (u1 - u0) / T;
+        extra = (u1 - u0) - nr * T;
     }
-    // loads r = 0, 1, ... of this CTA sit at u0 + r * stride + t and count if they fall into [max(u0, 0), u1)
-    const int64_t span = u1 - u0;
-    const int64_t nload = span > 0 ? (span + stride - 1) / stride : 0;
-    const int64_t nbatch = (nload + P - 1) / P;
+    const int64_t nfb = nr / P;                      // complete batches
+    const int left = (int)(nr - nfb * P);            // complete rounds behind them (< P)
+    const int4 *ptr = in4 + first + t;
+    const int64_t bstep = rstride * P;
     int4 cur[P], nxt[P];
-    auto load_batch = [&](int64_t k, int4 *buf) {
+    if (nfb > 0) {
 #pragma unroll
-        for (int p = 0; p < P; ++p) {
-            const int64_t u = u0 + (k * P + p) * stride + t;
-            buf[p] = (u >= 0 && u < u1) ? ldg_stream_i4(in4 + u) : make_int4(0, 0, 0, 0);   // 0 is outside 1..nbins
-        }
-    };
-    if (nbatch > 0) load_batch(0, cur);
-    for (int64_t k = 0; k < nbatch; ++k) {
-        if (k + 1 < nbatch) load_batch(k + 1, nxt);
+        for (int p = 0; p < P; ++p) cur[p] = ldg_stream_i4(ptr + p * rstride);
+    }
+    for (int64_t k = 0; k < nfb; ++k) {
+        ptr += bstep;
+        if (k + 1 < nfb) {
 #pragma unroll
-        for (int p = 0; p < P; ++p) {
-            bump(cur[p].x);
-            bump(cur[p].y);
-            bump(cur[p].z);
-            bump(cur[p].w);
+            for (int p = 0; p < P; ++p) nxt[p] = ldg_stream_i4(ptr + p * rstride);
         }
+#pragma unroll
+        for (int p = 0; p < P; ++p) bump4(cur[p]);
 #pragma unroll
         for (int p = 0; p < P; ++p) cur[p] = nxt[p];
     }
+    // the one predicated batch: `left` complete rounds, then the partial round
+#pragma unroll
+    for (int p = 0; p < P; ++p)
+        cur[p] = (p < left || (p == left && t < extra)) ? ldg_stream_i4(ptr + p * rstride) : make_int4(0, 0, 0, 0);   // 0 is outside 1..nbins
+#pragma unroll
+    for (int p = 0; p < P; ++p) bump4(cur[p]);
     if (blockIdx.x == 0 && t < ntail) bump(tail[t]);
     if (blockIdx.x == 0 && t >= 32 && t < 32 + nhead) bump(head[t - 32]);
     __syncthreads();
@@ -228,13 +247,90 @@ template <int T, int P>
 __global__ void __launch_bounds__(T) hist_atomic_kernel(int32_t *__restrict__ bins, uint32_t nbins,
                                                         const int4 *__restrict__ in4, int64_t n4,
                                                         const int32_t *__restrict__ tail, int ntail, int copies, int interleave) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     uint32_t *sh = reinterpret_cast<uint32_t *>(smem_raw);
-    hist_count_phase<T, P>(sh, nbins, in4, n4, tail, ntail, copies, nullptr, 0, interleave);
+    if (interleave)
+        hist_count_phase<T, P, true>(sh, nbins, in4, n4, tail, ntail, copies, nullptr, 0);
+    else
+        hist_count_phase<T, P, false>(sh, nbins, in4, n4, tail, ntail, copies, nullptr, 0);
     for (uint32_t b = threadIdx.x; b < nbins; b += T) {
         uint32_t s = 0;
-        for (int c = 0; c < copies; ++c) s += sh[(uint32_t)c * nbins + b];
+        for (int c = 0; c < copies; ++c) s += sh[(uint32_t)c * (nbins + 1u) + b];
         if (s) atomicAdd(reinterpret_cast<unsigned int *>(bins) + b, s);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// impl 2 (A/B only, `hist.impl = 2`): the same counting with the input FED BY TMA -- one elected thread keeps a ring of
+// 16 KiB cp.async.bulk loads in flight (units dealt out round-robin like the interleaved plan), the 1024 threads read their
+// int4 from shared memory (LDS.128) instead of global memory and count it with the same shared atomics.  Measured against the
+// LDG feed in profiles/r05_hist_probe.txt; the LDG kernel stays the default unless this one wins.
+// ---------------------------------------------------------------------------------------------
+template <int T, int STAGES>
+__global__ void __launch_bounds__(T) hist_tma_kernel(int32_t *__restrict__ bins, uint32_t nbins, const int4 *__restrict__ in4, int64_t n4,
+                                                     const int32_t *__restrict__ tail, int ntail, int copies, uint32_t ring_off) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint32_t *sh = reinterpret_cast<uint32_t *>(smem_raw);
+    int4 *ring = reinterpret_cast<int4 *>(smem_raw + ring_off);                 // STAGES x T int4
+    __shared__ __align__(8) uint64_t full[STAGES], empty[STAGES];
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const uint32_t nb1 = nbins + 1u;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    for (uint32_t i = t; i < nb1 * (uint32_t)copies; i += T) sh[i] = 0;
+    if (t == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            pipe::mbar_init(&full[s], 1);
+            pipe::mbar_init(&empty[s], T / 32);
+        }
+        pipe::mbar_fence_init();
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    uint32_t *mine = sh + (uint32_t)(warp % copies) * nb1;
+    auto bump = [&](int v) { atomicAdd(mine + min((uint32_t)v - 1u, nbins), 1u); };
+    auto bump4 = [&](const int4 &v) {
+        bump(v.x);
+        bump(v.y);
+        bump(v.z);
+        bump(v.w);
+    };
+    const int64_t lead = min((int64_t)((32 - (((uintptr_t)in4 >> 4) & 31)) & 31), n4);
+    if (blockIdx.x == 0 && t < lead) bump4(ldg_stream_i4(in4 + t));
+    const int64_t m4 = n4 - lead, nu = m4 / T;
+    const int64_t first = lead + (int64_t)blockIdx.x * T, rstride = (int64_t)gridDim.x * T;
+    const int64_t nr = nu > blockIdx.x ? (nu - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int64_t extra = (int64_t)(nu % gridDim.x) == (int64_t)blockIdx.x ? m4 - nu * T : 0;
+    auto issue = [&](int64_t r) {                                               // thread 0
+        const int s = (int)(r % STAGES);
+        pipe::mbar_expect_tx(&full[s], T * 16);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         pipe::smem_u32(ring + (size_t)s * T)),
+                     "l"(in4 + first + r * rstride), "r"(T * 16), "r"(pipe::smem_u32(&full[s]))
+                     : "memory");
+    };
+    if (t == 0)
+        for (int64_t r = 0; r < nr && r < STAGES; ++r) issue(r);
+    for (int64_t r = 0; r < nr; ++r) {
+        const int s = (int)(r % STAGES);
+        const uint32_t parity = (uint32_t)((r / STAGES) & 1);
+        pipe::mbar_wait(&full[s], parity);
+        const int4 v = ring[(size_t)s * T + t];
+        __syncwarp();
+        if (lane == 0) pipe::mbar_arrive(&empty[s]);                            // this warp has read stage s
+        bump4(v);
+        if (t == 0 && r + STAGES < nr) {
+            pipe::mbar_wait(&empty[s], parity);                                 // every warp has: the stage may be refilled
+            issue(r + STAGES);
+        }
+    }
+    if (t < extra) bump4(ldg_stream_i4(in4 + first + nr * rstride + t));        // the partial last unit (one owner)
+    if (blockIdx.x == 0 && t < ntail) bump(tail[t]);
+    __syncthreads();
+    for (uint32_t b = t; b < nbins; b += T) {
+        uint32_t sum = 0;
+        for (int c = 0; c < copies; ++c) sum += sh[(uint32_t)c * nb1 + b];
+        if (sum) atomicAdd(reinterpret_cast<unsigned int *>(bins) + b, sum);
     }
 }
 
@@ -295,10 +391,10 @@ __device__ __noinline__ void fused_exchange(uint32_t *sh, uint32_t nbins, int co
     // Fold the private copies into copy 0.
     for (uint32_t b = t; b < nbins; b += T) {
         uint32_t s = 0;
-        for (int c = 0; c < copies; ++c) s += sh[(uint32_t)c * nbins + b];
+        for (int c = 0; c < copies; ++c) s += sh[(uint32_t)c * (nbins + 1u) + b];
         sh[b] = s;   // only thread (b mod T) touches column b
     }
-    uint32_t &ticket = sh[nbins * (uint32_t)copies];   // one spare word behind the private copies (dynamic smem)
+    uint32_t &ticket = sh[(nbins + 1u) * (uint32_t)copies];   // one spare word behind the private copies (dynamic smem)
     __syncthreads();
     // Draw the ticket FIRST (relaxed: it only orders the CTAs): the CTA that draws the last one keeps its counts in shared
     // memory, every other CTA publishes them (red.global) and then raises `published` with a release at device scope.
@@ -398,10 +494,13 @@ __global__ void __launch_bounds__(T) hist_allreduce_kernel(int32_t *__restrict__
                                                            const int32_t *__restrict__ tail, int ntail, int copies,
                                                            const int32_t *__restrict__ head, int nhead, int interleave,
                                                            const __grid_constant__ HistPeer peer) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     uint32_t *sh = reinterpret_cast<uint32_t *>(smem_raw);
     if (blockIdx.x == 0 && threadIdx.x == 0) peer.stamps[5] = globaltimer_ns();          // first CTA resident
-    hist_count_phase<T, P>(sh, nbins, in4, n4, tail, ntail, copies, head, nhead, interleave);
+    if (interleave)
+        hist_count_phase<T, P, true>(sh, nbins, in4, n4, tail, ntail, copies, head, nhead);
+    else
+        hist_count_phase<T, P, false>(sh, nbins, in4, n4, tail, ntail, copies, head, nhead);
     fused_exchange<T>(sh, nbins, copies, bins, peer);
 }
 
@@ -448,7 +547,7 @@ static int launch_bytes(int32_t *bins, uint32_t nbins, const int4 *in4, int64_t 
 template <int T, int P>
 static int launch_atomic(int32_t *bins, uint32_t nbins, const int4 *in4, int64_t n4, const int32_t *tail, int ntail,
                          int grid, int copies, cudaStream_t st) {
-    size_t smem = (size_t)nbins * copies * 4;
+    size_t smem = (size_t)(nbins + 1) * copies * 4;
     if (smem > 48 * 1024)
         B200_CUDA(cudaFuncSetAttribute(hist_atomic_kernel<T, P>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem));
@@ -486,6 +585,33 @@ int histogram_launch(int32_t *bins, int64_t nbins, const int32_t *input, int64_t
         B200_CHECK_LAUNCH("hist_global_kernel");
     }
     int grid = sms * tune_get("hist.ctas_per_sm", 1);
+    if (impl == 2) {   // A/B: TMA-fed counting (see hist_tma_kernel)
+        constexpr int T = 1024;
+        const int stages = tune_get("hist.tma_stages", 4);
+        int copies = (int)((48 * 1024) / ((nbins + 1) * 4));
+        if (copies > T / 32) copies = T / 32;
+        if (copies < 1) copies = 1;
+        grid = sms;
+        if ((int64_t)grid > (n4 + T - 1) / T) grid = (int)((n4 + T - 1) / T);
+        if (grid < 1) grid = 1;
+        const uint32_t ring_off = (uint32_t)((((size_t)(nbins + 1) * copies * 4) + 127) / 128 * 128);
+        const size_t smem = ring_off + (size_t)stages * T * 16;
+#define B200_HT(S)                                                                                                                 \
+    case S:                                                                                                                        \
+        B200_CUDA(cudaFuncSetAttribute(hist_tma_kernel<T, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));             \
+        B200_TRY(launch_pdl(hist_tma_kernel<T, S>, grid, T, smem, st, bins, (uint32_t)nbins, in4, n4, tailp, (int)tail_n, copies, ring_off)); \
+        break;
+        switch (stages) {
+            B200_HT(2)
+            B200_HT(4)
+            B200_HT(6)
+            B200_HT(8)
+            default: return set_error(B200_ERR_INVALID_VALUE, "hist.tma_stages must be 2, 4, 6 or 8");
+        }
+#undef B200_HT
+        B200_CHECK_LAUNCH("hist_tma_kernel");
+        return B200_OK;
+    }
     if (impl == 0) {
         int T = tune_get("hist.threads", 512), P = tune_get("hist.batch", 8), ILP = tune_get("hist.ilp", 2);
         int64_t min_units = (int64_t)T;  // do not launch more CTAs than there is work
@@ -509,7 +635,7 @@ int histogram_launch(int32_t *bins, int64_t nbins, const int32_t *input, int64_t
     {
         int T = tune_get("hist.atomic_threads", 1024), P = tune_get("hist.atomic_batch", 4);
         int warps = T / 32;
-        int copies = (int)((48 * 1024) / (nbins * 4));
+        int copies = (int)((48 * 1024) / ((nbins + 1) * 4));
         if (copies > warps) copies = warps;
         if (copies < 1) copies = 1;
         int cps = tune_get("hist.atomic_ctas_per_sm", 1);
@@ -541,7 +667,7 @@ template <int T, int P>
 __global__ void __launch_bounds__(T) hist64_atomic_kernel(long long *__restrict__ bins, uint32_t nbins,
                                                           const int4 *__restrict__ in4, int64_t n4,
                                                           const long long *__restrict__ tail, int ntail, int copies) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     uint32_t *sh = reinterpret_cast<uint32_t *>(smem_raw);
     const int t = threadIdx.x, warp = t >> 5;
     for (uint32_t i = t; i < nbins * (uint32_t)copies; i += T) sh[i] = 0;
@@ -667,13 +793,13 @@ int histogram_allreduce_launch(P2P *h, int32_t *bins, int64_t nbins, const int32
     const int64_t n4 = (n - head) / 4;
     const int tail_n = (int)((n - head) - n4 * 4);
     constexpr int T = 1024, P = 4;
-    int copies = (int)((48 * 1024 - 16) / (nbins * 4));
+    int copies = (int)((48 * 1024 - 16) / ((nbins + 1) * 4));
     if (copies > T / 32) copies = T / 32;
     if (copies < 1) copies = 1;
     int grid = sm_count();
     if ((int64_t)grid > (n4 + T - 1) / T) grid = (int)((n4 + T - 1) / T);
     if (grid < 1) grid = 1;   // n == 0 still takes part in the exchange
-    const size_t smem = (size_t)nbins * copies * 4 + 16;   // + the ticket word of fused_exchange
+    const size_t smem = (size_t)(nbins + 1) * copies * 4 + 16;   // + the ticket word of fused_exchange
     if (smem > 48 * 1024)
         B200_CUDA(cudaFuncSetAttribute(hist_allreduce_kernel<T, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     B200_TRY(launch_pdl(hist_allreduce_kernel<T, P>, grid, T, smem, st, bins, (uint32_t)nbins, reinterpret_cast<const int4 *>(body), n4,

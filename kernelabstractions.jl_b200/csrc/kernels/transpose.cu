@@ -18,6 +18,7 @@
 //
 // HBM bound: 2*elsize bytes of traffic per element; algorithmic bytes for 16384^2 F32 = 2^31.
 #include "../common.cuh"
+#include "../tma_pipe.cuh"
 #include "../tune.h"
 
 namespace b200 {
@@ -80,6 +81,125 @@ __global__ void __launch_bounds__(256) transpose64_f32_kernel(float *__restrict_
         float4 w = tile4[j * 16 + (ic ^ ((j >> 2) & 15))];
         stg_stream_f4(dst + (int64_t)(16 * s) * lda, w);
     }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// TMA variant of the fast path (`transpose.impl = 1`; A/B against the kernel above in profiles/r05_transpose_ab.txt).
+// The load side goes to the TMA engine: a 3-d tensor map over b with the columns i of a tile PERMUTED on the way in --
+// dimensions (j: contiguous, i_hi = i / 4: stride 4 ldb, i_lo = i % 4: stride ldb), box 32 x 16 x 4 -- so that shared-memory
+// row r = i_lo * 16 + i_hi holds the 128-byte segment b[j0 .. j0+32, i0 + 4 i_hi + i_lo], with the hardware's 128-byte swizzle
+// (16-byte chunk ^= row & 7).  Lane (ic = t & 15, jq = t >> 4) then reads its 4 x 4 block as four LDS.128 at rows i_lo * 16 + ic:
+// sixteen CONSECUTIVE rows per instruction, i.e. all eight swizzle phases -- conflict free (with the natural row order the
+// rows of a 4 x 4 register block are 4 apart and the hardware swizzle, which only knows row & 7, leaves an 8-way conflict).
+// After the register transpose the same lane mapping makes the stores coalesced: 16 lanes x float4 = 256 contiguous bytes of
+// one column of a.  Per 16 bytes: TMA + 1 LDS.128 + 1 STG.128 (the SIMT kernel: LDG + STS + LDS + STG), no second pass
+// through shared memory; persistent CTAs keep STAGES tiles of loads in flight behind an mbarrier ring.
+// ---------------------------------------------------------------------------------------------------------------------
+template <int STAGES>
+__global__ void __launch_bounds__(256) transpose64_tma_kernel(const __grid_constant__ CUtensorMap map_b, float *__restrict__ a, int tiles_i,
+                                                              int tiles_j, int64_t lda) {
+    extern __shared__ __align__(1024) unsigned char tma_smem_raw[];   // STAGES x (2 boxes x 64 rows x 128 B) + 1 KiB of slack
+    __shared__ __align__(8) uint64_t full[STAGES];
+    // the 128-byte swizzle is a function of the shared-memory ADDRESS: boxes must start on 1 KiB boundaries
+    unsigned char *tma_smem = tma_smem_raw + ((1024u - (pipe::smem_u32(tma_smem_raw) & 1023u)) & 1023u);
+    const int t = threadIdx.x;
+    const unsigned ntiles = (unsigned)tiles_i * (unsigned)tiles_j;
+    const unsigned mine = ntiles > blockIdx.x ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    auto tile_of = [&](unsigned k, int &ti, int &tj) {           // consecutive tiles walk j (b's contiguous dimension) first
+        const unsigned id = blockIdx.x + k * gridDim.x;
+        tj = (int)(id % (unsigned)tiles_j);
+        ti = (int)(id / (unsigned)tiles_j);
+    };
+    auto issue = [&](unsigned k) {                                // thread 0: both 32-column boxes of tile k
+        int ti, tj;
+        tile_of(k, ti, tj);
+        const int s = (int)(k % STAGES);
+        unsigned char *dst = tma_smem + (size_t)s * 16384;
+        pipe::mbar_expect_tx(&full[s], 16384);
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+            asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::
+                             "r"(pipe::smem_u32(dst + h * 8192)), "l"(&map_b), "r"(tj * 64 + h * 32), "r"(ti * 16), "r"(0),
+                         "r"(pipe::smem_u32(&full[s]))
+                         : "memory");
+    };
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (t == 0) {
+        pipe::tma_prefetch_desc(&map_b);
+        for (int s = 0; s < STAGES; ++s) pipe::mbar_init(&full[s], 1);
+        pipe::mbar_fence_init();
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (t == 0)
+        for (unsigned k = 0; k < mine && k < (unsigned)STAGES; ++k) issue(k);
+
+    const int ic = t & 15, jq = t >> 4;                           // i-chunk (4 rows of a) and j-chunk (4 columns of a) of the lane
+    const int half = jq >> 3, chunk = (jq & 7) ^ (ic & 7);        // box and swizzled 16-byte chunk inside the 128-byte row
+    for (unsigned k = 0; k < mine; ++k) {
+        const int s = (int)(k % STAGES);
+        pipe::mbar_wait(&full[s], (k / STAGES) & 1);
+        const float4 *box = reinterpret_cast<const float4 *>(tma_smem + (size_t)s * 16384 + half * 8192);
+        const float4 v0 = box[(0 * 16 + ic) * 8 + chunk];         // b[j0 + 4 jq .. +3, i0 + 4 ic + 0]
+        const float4 v1 = box[(1 * 16 + ic) * 8 + chunk];
+        const float4 v2 = box[(2 * 16 + ic) * 8 + chunk];
+        const float4 v3 = box[(3 * 16 + ic) * 8 + chunk];
+        __syncthreads();                                          // every lane has read stage s: it may be refilled
+        if (t == 0 && k + STAGES < mine) issue(k + STAGES);
+        int ti, tj;
+        tile_of(k, ti, tj);
+        float *dst = a + ((int64_t)ti * 64 + 4 * ic) + ((int64_t)tj * 64 + 4 * jq) * lda;
+        stg_stream_f4(dst, make_float4(v0.x, v1.x, v2.x, v3.x));
+        stg_stream_f4(dst + lda, make_float4(v0.y, v1.y, v2.y, v3.y));
+        stg_stream_f4(dst + 2 * lda, make_float4(v0.z, v1.z, v2.z, v3.z));
+        stg_stream_f4(dst + 3 * lda, make_float4(v0.w, v1.w, v2.w, v3.w));
+    }
+}
+
+static int transpose_tma_launch(float *a, const float *b, int64_t m, int64_t n, int64_t lda, int64_t ldb, cudaStream_t st) {
+    // b is n x m (ld ldb): dimensions (j, i_hi, i_lo) = (n, m / 4, 4), strides (4 ldb, ldb) elements
+    pipe::EncodeTiledFn enc = nullptr;
+    B200_TRY(pipe::get_encode_fn(&enc));
+    CUtensorMap map;
+    cuuint64_t gdim[3] = {(cuuint64_t)n, (cuuint64_t)(m / 4), 4};
+    cuuint64_t gstride[2] = {(cuuint64_t)ldb * 16, (cuuint64_t)ldb * 4};
+    cuuint32_t box[3] = {32, 16, 4};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(b), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(B200_ERR_CUDA, "transpose: cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    const int tiles_i = (int)(m / 64), tiles_j = (int)(n / 64);
+    const int stages = tune_get("transpose.tma_stages", 3);
+    const int cps = tune_get("transpose.tma_ctas_per_sm", 4);
+    int64_t grid = (int64_t)sm_count() * cps;
+    if (grid > (int64_t)tiles_i * tiles_j) grid = (int64_t)tiles_i * tiles_j;
+    const size_t smem = (size_t)stages * 16384 + 1024;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = tune_get("transpose.pdl", 1) != 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+#define B200_TT_CASE(S)                                                                                                         \
+    case S:                                                                                                                     \
+        B200_CUDA(cudaFuncSetAttribute(transpose64_tma_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
+        B200_CUDA(cudaLaunchKernelEx(&cfg, transpose64_tma_kernel<S>, map, a, tiles_i, tiles_j, lda));                           \
+        break;
+    switch (stages) {
+        B200_TT_CASE(2)
+        B200_TT_CASE(3)
+        B200_TT_CASE(4)
+        B200_TT_CASE(6)
+        default: return set_error(B200_ERR_INVALID_VALUE, "transpose.tma_stages must be 2, 3, 4 or 6");
+    }
+#undef B200_TT_CASE
+    B200_CHECK_LAUNCH("transpose64_tma_kernel");
+    return B200_OK;
 }
 
 // The same tile scheme for 4- AND 8-byte words and for ANY m, n (T = uint32_t / uint64_t, V = 16 / sizeof(T) words per
@@ -196,6 +316,8 @@ int transpose_launch(void *a, const void *b, int64_t m, int64_t n, int64_t lda, 
     const bool fast = elsize == 4 && (m % 64 == 0) && (n % 64 == 0) && (lda % 4 == 0) && (ldb % 4 == 0) &&
                       (((uintptr_t)a | (uintptr_t)b) & 15) == 0 && (m / 64) * (n / 64) < (int64_t)INT32_MAX &&
                       tune_get("transpose.force_generic", 0) == 0;
+    if (fast && tune_get("transpose.impl", 0) == 1 && n < (1LL << 31) && m < (1LL << 31))
+        return transpose_tma_launch((float *)a, (const float *)b, m, n, lda, ldb, st);
     if (fast) {
         int tiles_i = (int)(m / 64), tiles_j = (int)(n / 64);
         unsigned grid = (unsigned)((int64_t)tiles_i * tiles_j);

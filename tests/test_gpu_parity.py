@@ -31,9 +31,11 @@ def tune(**kv):
 @pytest.fixture(autouse=True)
 def _reset_tuning():
     yield
-    for k in ["registry.force_twins", "transpose.order", "transpose.force_generic"]:
+    _lib.call("b200_tune_set", b"transpose.tma_stages", 3)
+    _lib.call("b200_tune_set", b"transpose.tma_ctas_per_sm", 4)
+    for k in ["registry.force_twins", "transpose.order", "transpose.force_generic", "transpose.impl"]:
         _lib.call("b200_tune_set", k.encode(), 0)
-    for k, v in [("hist.impl", 1), ("copy.impl", 1), ("hist.threads", 512), ("hist.batch", 8), ("hist.ilp", 2), ("copy.unroll", 8),
+    for k, v in [("hist.impl", 1), ("hist.interleave", 1), ("hist.tma_stages", 4), ("copy.impl", 1), ("hist.threads", 512), ("hist.batch", 8), ("hist.ilp", 2), ("copy.unroll", 8),
                  ("copy.ctas_per_sm", 32), ("copy.bulk_stage_kb", 16), ("copy.bulk_stages", 4)]:
         _lib.call("b200_tune_set", k.encode(), v)
 
@@ -164,6 +166,31 @@ def test_transpose_matches_oracle(orc, shape, order):
     assert np.array_equal(KA.Array(dA).view(np.uint32), a_ref.view(np.uint32))
 
 
+@pytest.mark.parametrize("stages,cps", [(3, 4), (2, 1), (4, 3), (6, 2)])
+@pytest.mark.parametrize("shape", [(64, 64), (128, 64), (64, 128), (1024, 1024), (2048, 512), (4096, 192), (64, 9600)])
+def test_transpose_tma_variant_matches_oracle(orc, shape, stages, cps):
+    """transpose.impl = 1: TMA tensor loads with the tile's columns permuted on the way in (3-d map, 128-byte swizzle), register
+    transpose, coalesced stores -- same bits as the definition, for every ring depth / residency, incl. leading dimensions
+    larger than the matrix (views)."""
+    tune(transpose__impl=1, transpose__tma_stages=stages, transpose__tma_ctas_per_sm=cps)
+    m, n = shape
+    b = orc.gen_uniform_f32((n, m), 1235)
+    a_ref = F((m, n), np.float32)
+    orc.naive_transpose(a_ref, b)
+    dA = KA.zeros(be, np.float32, m, n)
+    EX.naive_transpose_(dA, KA.to_device(b))
+    KA.synchronize(be)
+    assert np.array_equal(KA.Array(dA).view(np.uint32), a_ref.view(np.uint32))
+    # leading dimensions larger than the shapes: the C entry point on sub-matrices of bigger arrays
+    big_b = orc.gen_uniform_f32((n + 64, m), 99)
+    dBig, dOut = KA.to_device(big_b), KA.allocate(be, np.float32, m + 128, n).fill_(-1.0)
+    _lib.call("b200_transpose", C.c_void_p(dOut.ptr + 4 * 64), C.c_void_p(dBig.ptr + 4 * 32), m, n, m + 128, n + 64, 4)
+    KA.synchronize(be)
+    got = KA.Array(dOut)
+    assert np.array_equal(got[64:64 + m, :], big_b[32:32 + n, :].T)
+    assert np.all(got[:64, :] == -1.0) and np.all(got[64 + m:, :] == -1.0)
+
+
 @pytest.mark.parametrize("dtype", [np.float32, np.float64, np.int64])
 @pytest.mark.parametrize("shape", [(132, 68), (68, 132), (1000, 1004), (4, 4), (2, 6), (64, 64), (192, 320), (100, 36), (2050, 130)])
 def test_transpose_any_shape_vector_path(shape, dtype):
@@ -289,7 +316,8 @@ def test_histogram_examples(orc):
                                  dict(hist__impl=0, hist__threads=512, hist__batch=4, hist__ilp=2),
                                  dict(hist__impl=0, hist__threads=768, hist__batch=4, hist__ilp=2),
                                  dict(hist__impl=0, hist__threads=256, hist__batch=8, hist__ilp=2),
-                                 dict(hist__impl=1)])
+                                 dict(hist__impl=1), dict(hist__impl=1, hist__interleave=0), dict(hist__impl=1, hist__interleave=1),
+                                 dict(hist__impl=2, hist__tma_stages=4), dict(hist__impl=2, hist__tma_stages=2)])
 @pytest.mark.parametrize("dist", ["uniform", "all_equal", "ramp", "out_of_range"])
 def test_histogram_variants_and_distributions(orc, cfg, dist):
     tune(**cfg)
@@ -307,6 +335,23 @@ def test_histogram_variants_and_distributions(orc, cfg, dist):
         inp[2::13] = 300
         inp[3::17] = np.iinfo(np.int32).min
     _hist_check(orc, inp, 256)
+
+
+@pytest.mark.parametrize("impl,interleave", [(1, 0), (1, 1), (2, 1)])
+@pytest.mark.parametrize("n,offset", [(1, 0), (3, 1), (5, 0), (127, 3), (1024 * 4, 0), (1024 * 4 + 1, 2), (148 * 4096 + 77, 1), (3 * (1 << 20) + 5, 3),
+                                      (1 << 22, 0), (100003, 2)])
+def test_histogram_unit_plans_sizes_and_alignments(orc, impl, interleave, n, offset):
+    """contiguous slices, interleaved 16 KiB units and the TMA-fed ring: every size class (less than one int4, less than one unit,
+    fewer units than CTAs, ragged last unit) and every misalignment of the input against 16 bytes / 512-byte lines."""
+    tune(hist__impl=impl, hist__interleave=interleave)
+    whole = orc.gen_bins_i32(n + offset, 77 + n % 13, 256)
+    d_all = EX.move(be, whole)
+    want = np.zeros(256, dtype=np.int32)
+    orc.histogram(want, np.ascontiguousarray(whole[offset:]), 256)
+    out = KA.zeros(be, np.int32, 256)
+    EX.histogram_(out, d_all.view(offset, (n,)))
+    KA.synchronize(be)
+    assert np.array_equal(KA.Array(out), want)
 
 
 def test_histogram_accumulates_and_other_bin_counts(orc):

@@ -15,15 +15,20 @@ $P tools/run_one.py sgemm 8192 1 20
 $P tools/run_one.py cublas_sgemm 8192 0 20
 $P tools/run_one.py tcgemm 8192 0 50
 $P tools/run_one.py tf32gemm 8192 0 20
-run_ncu sgemm sgemm_tma sgemm 4096 0 3
-run_ncu transpose transpose64 transpose 16384 0 3
+run_ncu sgemm sgemm_tma sgemm 8192 0 3
+run_ncu transpose transpose64_f32 transpose 16384 0 3
+B200_TUNE=transpose.impl=1 run_ncu transpose_tma transpose64_tma transpose 16384 0 3
 run_ncu hist hist_atomic hist 1073741824 0 3
+run_ncu hist_fused hist_allreduce hist_fused 134217728 0 3
 run_ncu copy copy_bulk copy 67108864 0 3
+run_ncu copy_twin_vec copy_twin_vec copy_twin 67108864 0 3
+run_ncu copy_twin_scalar copy_twin_kernel copy_twin 67108864 1 3
 run_ncu tcgemm gemm_tcgen05 tcgemm 8192 0 3
 run_ncu tf32gemm gemm_tcgen05 tf32gemm 8192 0 3
 run_ncu tf32x3gemm gemm_tcgen05 tf32x3gemm 8192 0 3
 run_ncu saxpy saxpy saxpy 67108864 0 3
-$P bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_plain.log 2>&1 && \
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
-    $P bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_ncu.log 2>&1
+# launch list: few steps per entry so that EVERY kernel of the suite (SGEMM and the tcgen05 GEMMs come last) fits under the cap
+$P bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_plain.log 2>&1 && \
+ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/launches.csv \
+    $P bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_ncu.log 2>&1
 echo "launch list rc=$?"; tail -c 600 gpurun_out/bench_plain.log

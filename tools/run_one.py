@@ -84,6 +84,16 @@ if kind == "copy":
     n = size or (1 << 26)
     s, d = KA.to_device(orc.gen_uniform_f32((n,), 1)), KA.zeros(be, np.float32, n)
     run(lambda: _lib.call("b200_copy", C.c_void_p(d.ptr), C.c_void_p(s.ptr), 4 * n), 8.0 * n, "GB/s")
+elif kind == "copy_twin":
+    # gpu_copy_kernel! through the generic NDRange lowering (registry.force_twins = 1): mode 0 = 128-bit vectorised twin,
+    # 1 = one work-item per thread (native-grid / multiply-high index arithmetic), 2 = one work-item per thread, Int64 div/mod
+    from b200ka import examples as EXc
+    n = size or (1 << 26)
+    s, d = KA.to_device(orc.gen_uniform_f32((n,), 1)), KA.zeros(be, np.float32, n)
+    _lib.call("b200_tune_set", b"registry.force_twins", 1)
+    _lib.call("b200_tune_set", b"registry.twin_vec", 1 if mode == 0 else 0)
+    _lib.call("b200_tune_set", b"registry.ka_mode", 2 if mode == 2 else -1)
+    run(lambda: EXc.mycopy_(d, s), 8.0 * n, "GB/s")
 elif kind == "transpose":
     n = size or 16384
     b_, a_ = KA.to_device(orc.gen_uniform_f32((n, n), 1235)), KA.zeros(be, np.float32, n, n)

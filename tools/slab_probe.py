@@ -62,6 +62,13 @@ for G in (1, 8):
             print(f"transpose slab 1/{G}: pdl={pdl} ctas_per_sm={cps or 8}: {us:8.2f} us  ({2 * 4 * n * rb / us / 1e3:7.1f} GB/s; at the measured peak {ideal:6.2f} us)", flush=True)
     tune("transpose.pdl", 1)
     tune("transpose.ctas_per_sm", 0)
+    tune("transpose.impl", 1)
+    for stages, cps in [(3, 4), (4, 3), (2, 6), (6, 2), (3, 2), (4, 2), (2, 4), (3, 3)]:
+        tune("transpose.tma_stages", stages)
+        tune("transpose.tma_ctas_per_sm", cps)
+        us = timed(lambda: EX.naive_transpose_(dA, dB))
+        print(f"transpose slab 1/{G}: TMA variant stages={stages} ctas_per_sm={cps}: {us:8.2f} us  ({2 * 4 * n * rb / us / 1e3:7.1f} GB/s)", flush=True)
+    tune("transpose.impl", 0)
     del dA, dB
 
 for G in (1, 8):

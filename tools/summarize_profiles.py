@@ -66,8 +66,10 @@ for f in sorted(os.listdir(GO)):
     if rd and wr:
         tot = float(rd[0].replace(",", "")) * UNIT_SCALE.get(rd[1], 1.0) + float(wr[0].replace(",", "")) * UNIT_SCALE.get(wr[1], 1.0)
         short = kname.split("(")[0].replace("void ", "").split("<")[0].split("::")[-1]
-        traffic[short] = tot
-        traffic[f"capture:{name}"] = tot   # keyed by capture too: both tensor-core GEMMs share one kernel template
+        # one kernel template serves three tensor-core products: key those by variant, never by the bare template name
+        variant = {"tcgemm": "<bf16>", "tf32gemm": "<tf32>", "tf32x3gemm": "<tf32x3>"}.get(name)
+        traffic[short + variant if variant else short] = tot
+        traffic[f"capture:{name}"] = tot
         dur = d.get("gpu__time_duration.sum", ("?", ""))
         summary_lines.append(f"| {name} | `{short}` | {dur[0]} {dur[1]} | {tot / 1e9:.3f} GB | "
                              f"{d.get('gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', ('?',))[0]} | "
@@ -108,7 +110,7 @@ with open(os.path.join(OUT, f"{rnd}_summary.md"), "w") as fo:
     fo.write("| capture | kernel | duration | DRAM read+write per launch | DRAM throughput % | FMA pipe % | tensor pipe % |\n|---|---|---|---|---|---|---|\n")
     fo.write("\n".join(summary_lines) + "\n\n")
     if share_lines:
-        fo.write("## Launch list of `python bench.py --steps 10 --warmup 3 --no-cpu-baseline`\n\n"
-                 "`ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv` (raw: `" + rnd + "_launches.csv`).\n\n")
+        fo.write("## Launch list of `python bench.py --steps 3 --warmup 3 --no-cpu-baseline`\n\n"
+                 "`ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv` (raw: `" + rnd + "_launches.csv`).\n\n")
         fo.write("| kernel | launches | avg us | total us | share |\n|---|---|---|---|---|\n" + "\n".join(share_lines) + "\n")
 print(open(os.path.join(OUT, f"{rnd}_summary.md")).read())
