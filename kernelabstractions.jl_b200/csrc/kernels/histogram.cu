@@ -544,6 +544,16 @@ static int launch_bytes(int32_t *bins, uint32_t nbins, const int4 *in4, int64_t 
     return B200_OK;
 }
 
+// Unit plan of the counting phase (`hist.interleave`: 0 slices, 1 interleaved, -1 = by size).  Measured on one B200
+// (profiles/r05_hist_probe.txt): 2^30 elements 587.7 us sliced / 593.1 interleaved, 2^29 297.0 / 298.5, 2^28 151.2 / 151.6,
+// 2^27 79.0 / 77.8 -- contiguous slices stream a little faster, interleaved units end closer together (4 us against 6 us between
+// the first and the last CTA), which is what counts once a launch is short.
+static int pick_interleave(int64_t n4) {
+    const int forced = tune_get("hist.interleave", -1);
+    if (forced == 0 || forced == 1) return forced;
+    return n4 * 16 < ((int64_t)768 << 20) ? 1 : 0;
+}
+
 template <int T, int P>
 static int launch_atomic(int32_t *bins, uint32_t nbins, const int4 *in4, int64_t n4, const int32_t *tail, int ntail,
                          int grid, int copies, cudaStream_t st) {
@@ -551,8 +561,7 @@ static int launch_atomic(int32_t *bins, uint32_t nbins, const int4 *in4, int64_t
     if (smem > 48 * 1024)
         B200_CUDA(cudaFuncSetAttribute(hist_atomic_kernel<T, P>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem));
-    B200_TRY(launch_pdl(hist_atomic_kernel<T, P>, grid, T, smem, st, bins, nbins, in4, n4, tail, ntail, copies,
-                        tune_get("hist.interleave", 1)));
+    B200_TRY(launch_pdl(hist_atomic_kernel<T, P>, grid, T, smem, st, bins, nbins, in4, n4, tail, ntail, copies, pick_interleave(n4)));
     B200_CHECK_LAUNCH("hist_atomic_kernel");
     return B200_OK;
 }
@@ -803,7 +812,7 @@ int histogram_allreduce_launch(P2P *h, int32_t *bins, int64_t nbins, const int32
     if (smem > 48 * 1024)
         B200_CUDA(cudaFuncSetAttribute(hist_allreduce_kernel<T, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     B200_TRY(launch_pdl(hist_allreduce_kernel<T, P>, grid, T, smem, st, bins, (uint32_t)nbins, reinterpret_cast<const int4 *>(body), n4,
-                        body + n4 * 4, tail_n, copies, input, (int)head, tune_get("hist.interleave", 1), peer));
+                        body + n4 * 4, tail_n, copies, input, (int)head, pick_interleave(n4), peer));
     B200_CHECK_LAUNCH("hist_allreduce_kernel");
     h->epoch++;
     return B200_OK;

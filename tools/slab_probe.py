@@ -112,6 +112,6 @@ for G in (1, 8):
             peers.timeline()
             peers.histogram_allreduce(bins, d_in)
             print("   fused timeline (ns, relative to the fastest CTA leaving the counting loop):", peers.timeline(), flush=True)
-    tune("hist.interleave", 1)
+    tune("hist.interleave", -1)
     del d_in
 peers.free()
