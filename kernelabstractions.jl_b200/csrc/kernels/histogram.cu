@@ -365,7 +365,15 @@ struct HistPeer {
     unsigned long long *slots[8];     // rank r's slot array: [2 halves][8 source ranks][nbins_max] x {count, tag}
     uint32_t *error_flag;             // pinned host word (zero-copy): set when the poll below gives up
     unsigned long long timeout_ns;    // 0 = wait for ever
+    unsigned long long *cta_slots;    // local [kLLMaxCtas][kLLMaxBins] x {count, tag}: the intra-GPU merge (nullptr: ticket + partial)
 };
+constexpr uint32_t kLLMaxBins = 1024, kLLMaxCtas = 160;
+__device__ __forceinline__ void st_slot_gpu(unsigned long long *p, uint32_t count, uint32_t tag) {
+    asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(count), "r"(tag) : "memory");
+}
+__device__ __forceinline__ void ld_slot_gpu(const unsigned long long *p, uint32_t &count, uint32_t &tag) {
+    asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(count), "=r"(tag) : "l"(p) : "memory");
+}
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
     unsigned long long v;
@@ -396,40 +404,97 @@ __device__ __noinline__ void fused_exchange(uint32_t *sh, uint32_t nbins, int co
     }
     uint32_t &ticket = sh[(nbins + 1u) * (uint32_t)copies];   // one spare word behind the private copies (dynamic smem)
     __syncthreads();
-    // Draw the ticket FIRST (relaxed: it only orders the CTAs): the CTA that draws the last one keeps its counts in shared
-    // memory, every other CTA publishes them (red.global) and then raises `published` with a release at device scope.
-    if (t == 0) ticket = atomicAdd(peer.counter, 1u);
-    __syncthreads();
-    const bool last = ticket == gridDim.x - 1;
-    uint32_t *published = peer.counter + 1;
-    if (!last) {
-        if (warp == 0) {
-            for (uint32_t b = t; b < nbins; b += 32) {
-                const uint32_t s = sh[b];
-                if (s) atomicAdd(peer.partial + b, s);
-            }
-            __threadfence();                           // every lane: its reds are performed before the count below is visible
-            __syncwarp();
-            if (t == 0) atomicAdd(published, 1u);
-        }
-        return;
-    }
-    // ---- last CTA of this GPU ----
-    if (t == 0) {
-        peer.stamps[1] = globaltimer_ns();                                               // local counting done (ticket drawn)
-        uint32_t seen;
-        do {
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(published) : "memory");
-        } while (seen != gridDim.x - 1);
-        peer.counter[0] = 0;                                                             // ready for the next launch
-        peer.counter[1] = 0;
-    }
-    __syncthreads();
     const uint32_t tag = peer.epoch + 1u;
+    if (peer.cta_slots != nullptr && nbins <= kLLMaxBins && gridDim.x <= kLLMaxCtas) {
+        // ---- intra-GPU merge, LL style (r05 A/B, opt-in).  Ticket + red.global + fence + counter cost the last CTA three dependent
+        // L2 round trips (~3 us, b200_p2p_timeline) after the slowest CTA left the counting loop.  Here every CTA stores its folded
+        // counts as {count, tag} words into its own row of a local slot array -- one 8-byte store carries data and "it is there",
+        // no fence, no atomic -- and CTA 0, the reducer, polls the rows and adds them up.  Measured slower (see the launcher).
+        if (blockIdx.x != 0) {
+            unsigned long long *row = peer.cta_slots + (size_t)blockIdx.x * kLLMaxBins;
+            for (uint32_t b = t; b < nbins; b += T) st_slot_gpu(row + b, sh[b], tag);
+            return;
+        }
+        // thread (part, b): rows part + 1, part + 1 + parts, ... of bin b; `parts` threads share a bin
+        uint32_t parts = (uint32_t)T / nbins;
+        if (parts > 16u) parts = 16u;
+        if (parts < 1u) parts = 1u;                       // nbins <= kLLMaxBins == T
+        const uint32_t part = (uint32_t)t / nbins, b = (uint32_t)t % nbins;
+        uint32_t acc = 0;
+        if (part < parts) {
+            for (uint32_t c0 = 1u + part; c0 < gridDim.x; c0 += 8u * parts) {            // 8 rows in flight per thread
+                uint32_t v[8], g[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const uint32_t c = c0 + (uint32_t)k * parts;
+                    v[k] = 0;
+                    g[k] = tag;
+                    if (c < gridDim.x) ld_slot_gpu(peer.cta_slots + (size_t)c * kLLMaxBins + b, v[k], g[k]);
+                }
+                while (true) {
+                    bool pending = false;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        if (g[k] != tag) {
+                            ld_slot_gpu(peer.cta_slots + (size_t)(c0 + (uint32_t)k * parts) * kLLMaxBins + b, v[k], g[k]);
+                            pending = pending || g[k] != tag;
+                        }
+                    if (!pending) break;
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) acc += v[k];
+            }
+        }
+        // combine the parts through shared memory (rows 1 .. parts of the private-copy area are free after the fold)
+        uint32_t *psum = sh + (nbins + 1u);
+        if (part < parts && part > 0) psum[(part - 1u) * nbins + b] = acc;
+        __syncthreads();
+        if (part == 0) {
+            for (uint32_t q = 1; q < parts; ++q) acc += psum[(q - 1u) * nbins + b];
+            sh[b] += acc;                                                                 // this GPU's total for bin b
+        }
+        __syncthreads();
+        if (t == 0) peer.stamps[1] = globaltimer_ns();                                   // every CTA's counts merged
+    } else {
+        // ---- ticket + partial (any nbins up to the shared-memory limit) ----
+        // Draw the ticket FIRST (relaxed: it only orders the CTAs): the CTA that draws the last one keeps its counts in shared
+        // memory, every other CTA publishes them (red.global) and then raises `published` with a release at device scope.
+        if (t == 0) ticket = atomicAdd(peer.counter, 1u);
+        __syncthreads();
+        const bool last = ticket == gridDim.x - 1;
+        uint32_t *published = peer.counter + 1;
+        if (!last) {
+            if (warp == 0) {
+                for (uint32_t b = t; b < nbins; b += 32) {
+                    const uint32_t s = sh[b];
+                    if (s) atomicAdd(peer.partial + b, s);
+                }
+                __threadfence();                           // every lane: its reds are performed before the count below is visible
+                __syncwarp();
+                if (t == 0) atomicAdd(published, 1u);
+            }
+            return;
+        }
+        // ---- last CTA of this GPU ----
+        if (t == 0) {
+            peer.stamps[1] = globaltimer_ns();                                           // local counting done (ticket drawn)
+            uint32_t seen;
+            do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(published) : "memory");
+            } while (seen != gridDim.x - 1);
+            peer.counter[0] = 0;                                                         // ready for the next launch
+            peer.counter[1] = 0;
+        }
+        __syncthreads();
+        for (uint32_t b = t; b < nbins; b += T) {
+            sh[b] += __ldcg(peer.partial + b);
+            peer.partial[b] = 0;
+        }
+        // (each thread reads back only the sh[b] it wrote)
+    }
     const size_t half = (size_t)(peer.epoch & 1u) * 8u * peer.nbins_max;
     for (uint32_t b = t; b < nbins; b += T) {
-        const uint32_t v = __ldcg(peer.partial + b) + sh[b];
-        peer.partial[b] = 0;
+        const uint32_t v = sh[b];
         for (int r = 0; r < peer.world; ++r) st_slot(peer.slots[r] + half + (size_t)peer.rank * peer.nbins_max + b, v, tag);
     }
     if (t == 0) peer.stamps[2] = globaltimer_ns();                                       // slots sent
@@ -761,7 +826,8 @@ int histogram64_launch(long long *bins, int64_t nbins, const long long *input, i
 constexpr uint32_t kP2PMaxBins = 14336;
 constexpr size_t kP2PCounterOff = 0 /* ticket, published */, kP2PStampsOff = 8 /* 8 x u64 */, kP2PPartialOff = 128;
 constexpr size_t kP2PSlotsOff = (kP2PPartialOff + (size_t)kP2PMaxBins * 4 + 255) / 256 * 256;
-constexpr size_t kP2PBytes = kP2PSlotsOff + 2 * 8 * (size_t)kP2PMaxBins * 8;
+constexpr size_t kP2PCtaSlotsOff = kP2PSlotsOff + 2 * 8 * (size_t)kP2PMaxBins * 8;
+constexpr size_t kP2PBytes = kP2PCtaSlotsOff + (size_t)kLLMaxCtas * kLLMaxBins * 8;
 
 struct P2P {
     void *local = nullptr;
@@ -792,6 +858,9 @@ int histogram_allreduce_launch(P2P *h, int32_t *bins, int64_t nbins, const int32
     peer.stamps = (unsigned long long *)((char *)h->local + kP2PStampsOff);
     peer.partial = (uint32_t *)((char *)h->local + kP2PPartialOff);
     peer.error_flag = h->error_dev;
+    // measured (profiles/r05_hist_probe2.txt, 2^27 elements, one rank): ticket + partial 82.2 us, per-CTA slot rows polled by CTA 0
+    // 84.9 us -- 147 x 256 slots are five dependent rounds of loads for one CTA; opt-in (`hist.fused_ll = 1`)
+    peer.cta_slots = tune_get("hist.fused_ll", 0) != 0 ? (unsigned long long *)((char *)h->local + kP2PCtaSlotsOff) : nullptr;
     peer.timeout_ns = (unsigned long long)tune_get("hist.fused_timeout_ms", 10000) * 1000000ull;
     for (int r = 0; r < 8; ++r)
         peer.slots[r] = r < h->world ? (unsigned long long *)((char *)h->peer[r] + kP2PSlotsOff) : nullptr;

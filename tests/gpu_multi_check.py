@@ -50,8 +50,8 @@ def main():
     peers = mg.PeerGroup(world, rank, mg.torch_gather(dist))
 
     # ---- histogram: both routes against the oracle, several steps back to back ----
-    sizes = [100003, 4 * 1000 * world, 17, 0, 5 * (1 << 20) + 4 * world, 999999]
-    nbins_list = [256, 256, 256, 256, 1000, 64]
+    sizes = [100003, 4 * 1000 * world, 17, 0, 5 * (1 << 20) + 4 * world, 999999, 3 * (1 << 20) + 1, 1 << 21]
+    nbins_list = [256, 256, 256, 256, 1000, 64, 2000, 1024]
     for step, (n, nbins) in enumerate(zip(sizes, nbins_list)):
         s0, s1 = mg.histogram_shard(n, world, rank)
         whole = orc.gen_bins_i32(max(n, 1), 4000 + step, nbins)[:n]
@@ -260,6 +260,9 @@ def main():
             out[f"hist_{name}_ms"] = ms
             out[f"hist_{name}_GBps"] = 4.0 * n / (ms * 1e-3) / 1e9
             if name == "fused":
+                peers.timeline()                      # reset the min / max stamps, then one more step
+                dist.barrier()
+                step_fused()
                 stamps = peers.timeline()
                 gathered = [None] * world
                 dist.all_gather_object(gathered, stamps)

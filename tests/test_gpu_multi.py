@@ -50,12 +50,16 @@ def test_exchange_single_rank():
     comm.destroy()
 
 
+@pytest.mark.parametrize("ll", [1, 0])
 @pytest.mark.parametrize("n,nbins,offset", [(100003, 256, 0), (17, 256, 0), (0, 256, 0), (5 * (1 << 20) + 3, 1000, 0), (999999, 64, 1),
-                                            (1 << 22, 256, 3), (2, 256, 2)])
-def test_fused_histogram_allreduce_single_rank(orc, n, nbins, offset):
+                                            (1 << 22, 256, 3), (2, 256, 2), (3 * (1 << 20), 1, 0), (3 * (1 << 20), 1024, 0), (1 << 21, 1025, 0),
+                                            (1 << 21, 5000, 1), (1 << 22, 7, 0)])
+def test_fused_histogram_allreduce_single_rank(orc, n, nbins, offset, ll):
     """b200_histogram_i32_allreduce with the rank as its only peer == the oracle; accumulates like the reference's +=; several
-    steps on one PeerGroup (slot parity / tags); unaligned inputs (offset elements off a 16-byte boundary)."""
+    steps on one PeerGroup (slot parity / tags); unaligned inputs (offset elements off a 16-byte boundary); both intra-GPU merges
+    (hist.fused_ll = 0, the default: ticket + partial; 1: per-CTA {count, tag} rows polled by CTA 0, for nbins <= 1024)."""
     be = KA.B200Backend()
+    _lib.call("b200_tune_set", b"hist.fused_ll", ll)
     peers = mg.PeerGroup(1, 0, _self_gather)
     try:
         for step in range(3):
@@ -70,8 +74,9 @@ def test_fused_histogram_allreduce_single_rank(orc, n, nbins, offset):
             KA.synchronize(be)
             assert np.array_equal(KA.Array(bins), want + np.arange(nbins, dtype=np.int32)), f"step {step}"
         t = peers.timeline()
-        assert t["all_summed"] >= t["slots_sent"] >= t["counts_merged"] >= 0
+        assert t["all_summed"] >= t["slots_sent"] >= t["counts_merged"]
     finally:
+        _lib.call("b200_tune_set", b"hist.fused_ll", 0)
         peers.free()
 
 

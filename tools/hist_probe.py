@@ -37,12 +37,13 @@ def tune(k, v):
 
 
 peers = mg.PeerGroup(1, 0, lambda blob: [blob])
-for G in (1, 2, 4, 8):
+for G in (1, 8):
     ne = (1 << 30) // G
     d_in = KA.rand_bins_(KA.allocate(be, np.int32, ne), 1236, 256)
     bins = KA.zeros(be, np.int32, 256)
-    for inter in (0, 1):
+    for inter, ll in ((0, 0), (1, 0), (1, 1)):
         tune("hist.interleave", inter)
+        tune("hist.fused_ll", ll)
         us_l = timed(lambda: EX.histogram_(bins, d_in))
         us_f = timed(lambda: peers.histogram_allreduce(bins, d_in))
         tl = []
@@ -52,7 +53,7 @@ for G in (1, 2, 4, 8):
             tl.append(peers.timeline())
         spread = [x["slowest_cta_done"] for x in tl]
         tail = [x["all_summed"] for x in tl]
-        print(f"histogram 2^30/{G} interleave={inter}: local-only {us_l:8.2f} us ({4 * ne / us_l / 1e3:6.0f} GB/s), fused 1 rank {us_f:8.2f} us; "
+        print(f"histogram 2^30/{G} interleave={inter} fused_ll={ll}: local-only {us_l:8.2f} us ({4 * ne / us_l / 1e3:6.0f} GB/s), fused 1 rank {us_f:8.2f} us; "
               f"stream time at 7.25 TB/s {4 * ne / 7.25e12 * 1e6:7.2f} us; fastest->slowest CTA {spread} ns, slowest CTA -> summed {tail} ns", flush=True)
     tune("hist.interleave", -1)
     for stages in (2, 4, 6):
@@ -63,4 +64,5 @@ for G in (1, 2, 4, 8):
         print(f"histogram 2^30/{G} TMA feed (hist.impl=2, {stages} x 16 KiB ring): local-only {us_t:8.2f} us ({4 * ne / us_t / 1e3:6.0f} GB/s)", flush=True)
     del d_in
 tune("hist.interleave", -1)
+tune("hist.fused_ll", 0)
 peers.free()
