@@ -327,6 +327,8 @@ b200_status b200_sendrecv(void *comm, const void *sendbuf, int32_t dst_rank, voi
 b200_status b200_sym_alloc(void **handle, size_t bytes);
 b200_status b200_sym_export(void *handle, void *ipc64);
 b200_status b200_sym_connect(void *handle, int32_t world, int32_t rank, const void *all_handles /* world x 64 bytes */);
+/* single-process form: the ranks are GPUs of one process, peers given as pointers (b200_sym_ptr(peer, -1)); enables peer access */
+b200_status b200_sym_connect_ptrs(void *handle, int32_t world, int32_t rank, void *const *peer_bufs);
 b200_status b200_sym_ptr(void *handle, int32_t rank, void **ptr);
 b200_status b200_sym_barrier(void *handle);
 b200_status b200_sym_free(void *handle);
@@ -344,6 +346,10 @@ b200_status b200_transpose_alltoall(void *a_sym, const void *b_local, int64_t N0
 b200_status b200_p2p_alloc(void **handle);
 b200_status b200_p2p_export(void *handle, void *ipc64);
 b200_status b200_p2p_connect(void *handle, int32_t world, int32_t rank, const void *all_handles /* world x 64 bytes */);
+/* single-process form of b200_p2p_connect: peers given as their b200_p2p handles (created while their GPU was current) */
+b200_status b200_p2p_connect_ptrs(void *handle, int32_t world, int32_t rank, void *const *peer_handles);
+/* profiling aid: store source rank `src`'s contribution to the NEXT fused step into this rank's slots (tools/nvlink_proof.py) */
+b200_status b200_p2p_debug_prefill(void *handle, int32_t src, const uint32_t *counts_host, int64_t nbins);
 b200_status b200_p2p_free(void *handle);
 /* diagnostic: four %globaltimer stamps (ns) of the last fused launch (slowest CTA left the counting loop, local counts
  * merged, slots sent, all ranks' slots summed) */

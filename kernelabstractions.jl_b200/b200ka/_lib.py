@@ -178,6 +178,9 @@ SIGNATURES = {
     "b200_p2p_export": (_I32, [_VP, _VP]),
     "b200_p2p_connect": (_I32, [_VP, _I32, _I32, _VP]),
     "b200_p2p_free": (_I32, [_VP]),
+    "b200_sym_connect_ptrs": (_I32, [_VP, _I32, _I32, C.POINTER(C.c_void_p)]),
+    "b200_p2p_connect_ptrs": (_I32, [_VP, _I32, _I32, C.POINTER(C.c_void_p)]),
+    "b200_p2p_debug_prefill": (_I32, [_VP, _I32, C.POINTER(C.c_uint32), _I64]),
     "b200_p2p_timeline": (_I32, [_VP, C.POINTER(C.c_uint64)]),
     "b200_p2p_debug": (_I32, [_VP, _VP]),
     "b200_histogram_i32_allreduce": (_I32, [_VP, _VP, _I64, _VP, _I64]),

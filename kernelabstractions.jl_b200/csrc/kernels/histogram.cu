@@ -17,6 +17,7 @@
 //   larger nbins: one red.global.add per in-range element.
 // Values outside 1..nbins are ignored, exactly like the reference's range test (:45-46).
 #include <cstring>
+#include <vector>
 
 #include "../common.cuh"
 #include "../tma_pipe.cuh"
@@ -180,9 +181,6 @@ __device__ __noinline__ void hist_count_phase(uint32_t *sh, uint32_t nbins, cons
     // runs before we wait for the previous kernel's memory.  Back-to-back steps on input shards hide ~2 us of the ~9 us a launch costs.
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const uint32_t nb1 = nbins + 1u;   // every private copy carries one extra counter: the sink of out-of-range values
-    for (uint32_t i = t; i < nb1 * (uint32_t)copies; i += T) sh[i] = 0;
-    __syncthreads();
-    asm volatile("griddepcontrol.wait;" ::: "memory");   // everything before us in the stream is complete and visible
     uint32_t *mine = sh + (uint32_t)(warp % copies) * nb1;
     // Values outside 1..nbins are ignored by the reference's range test (examples/histogram.jl:45-46).  Here they are CLAMPED into
     // the sink counter instead of branched around: (unsigned)(v - 1) >= nbins -> nbins.  One IADD + one unsigned MIN per element
@@ -196,10 +194,9 @@ __device__ __noinline__ void hist_count_phase(uint32_t *sh, uint32_t nbins, cons
     };
     // Round r of this CTA loads int4 number  first + r * rstride + t  (t = thread); rounds [0, nr) are complete (all T
     // threads in range), then `extra` more int4 (< T) follow at round nr for the first `extra` threads.
-    int64_t first, rstride, nr, extra;
+    int64_t first, rstride, nr, extra, lead = 0;
     if (IL) {
-        const int64_t lead = min((int64_t)((32 - (((uintptr_t)in4 >> 4) & 31)) & 31), n4);   // int4 in front of the first 512-byte line
-        if (blockIdx.x == 0 && t < lead) bump4(ldg_stream_i4(in4 + t));
+        lead = min((int64_t)((32 - (((uintptr_t)in4 >> 4) & 31)) & 31), n4);                 // int4 in front of the first 512-byte line
         const int64_t m4 = n4 - lead, nu = m4 / T;                                            // whole units behind it
         first = lead + (int64_t)blockIdx.x * T;
         rstride = (int64_t)gridDim.x * T;
@@ -217,10 +214,15 @@ __device__ __noinline__ void hist_count_phase(uint32_t *sh, uint32_t nbins, cons
     const int4 *ptr = in4 + first + t;
     const int64_t bstep = rstride * P;
     int4 cur[P], nxt[P];
+    asm volatile("griddepcontrol.wait;" ::: "memory");   // everything before us in the stream is complete and visible
+    // the first batch of loads goes out BEFORE the private copies are cleared: the clear runs under the loads' latency
     if (nfb > 0) {
 #pragma unroll
         for (int p = 0; p < P; ++p) cur[p] = ldg_stream_i4(ptr + p * rstride);
     }
+    for (uint32_t i = t; i < nb1 * (uint32_t)copies; i += T) sh[i] = 0;
+    __syncthreads();
+    if (IL && blockIdx.x == 0 && t < lead) bump4(ldg_stream_i4(in4 + t));
     for (int64_t k = 0; k < nfb; ++k) {
         ptr += bstep;
         if (k + 1 < nfb) {
@@ -243,6 +245,37 @@ __device__ __noinline__ void hist_count_phase(uint32_t *sh, uint32_t nbins, cons
     __syncthreads();
 }
 
+// Fold the private copies into copy 0 (sh[b], b < nbins); ends with the result visible to thread b only -- callers synchronise.
+// With few bins (nbins <= T / 4, the 256-bin case) four threads share a column: thread (b, q) sums the copies of group q into
+// the group's first copy (nobody else reads that column of those copies), then thread (b, 0) adds the four group sums: 8 + 4
+// dependent shared loads instead of 32 on the critical path of every CTA.
+template <int T>
+__device__ __forceinline__ void fold_copies(uint32_t *sh, uint32_t nbins, int copies) {
+    const int t = threadIdx.x;
+    const uint32_t nb1 = nbins + 1u;
+    if (nbins * 4u <= (uint32_t)T && copies >= 4) {
+        const uint32_t b = (uint32_t)t % nbins, q = (uint32_t)t / nbins;
+        const uint32_t per = ((uint32_t)copies + 3u) / 4u, c0 = q * per;
+        if (q < 4u && c0 < (uint32_t)copies) {
+            uint32_t s = 0;
+            for (uint32_t c = c0; c < c0 + per && c < (uint32_t)copies; ++c) s += sh[c * nb1 + b];
+            sh[c0 * nb1 + b] = s;
+        }
+        __syncthreads();
+        if (q == 0) {
+            uint32_t s = sh[b];
+            for (uint32_t g = 1; g < 4u && g * per < (uint32_t)copies; ++g) s += sh[g * per * nb1 + b];
+            sh[b] = s;
+        }
+    } else {
+        for (uint32_t b = t; b < nbins; b += T) {
+            uint32_t s = 0;
+            for (int c = 0; c < copies; ++c) s += sh[(uint32_t)c * nb1 + b];
+            sh[b] = s;   // only thread (b mod T) touches column b
+        }
+    }
+}
+
 template <int T, int P>
 __global__ void __launch_bounds__(T) hist_atomic_kernel(int32_t *__restrict__ bins, uint32_t nbins,
                                                         const int4 *__restrict__ in4, int64_t n4,
@@ -253,9 +286,9 @@ __global__ void __launch_bounds__(T) hist_atomic_kernel(int32_t *__restrict__ bi
         hist_count_phase<T, P, true>(sh, nbins, in4, n4, tail, ntail, copies, nullptr, 0);
     else
         hist_count_phase<T, P, false>(sh, nbins, in4, n4, tail, ntail, copies, nullptr, 0);
-    for (uint32_t b = threadIdx.x; b < nbins; b += T) {
-        uint32_t s = 0;
-        for (int c = 0; c < copies; ++c) s += sh[(uint32_t)c * (nbins + 1u) + b];
+    fold_copies<T>(sh, nbins, copies);
+    for (uint32_t b = threadIdx.x; b < nbins; b += T) {   // thread b reads back what it wrote
+        const uint32_t s = sh[b];
         if (s) atomicAdd(reinterpret_cast<unsigned int *>(bins) + b, s);
     }
 }
@@ -396,13 +429,9 @@ __device__ __noinline__ void fused_exchange(uint32_t *sh, uint32_t nbins, int co
         atomicMax(peer.stamps + 0, now);                                                 // slowest CTA leaves the counting loop
         atomicMin(peer.stamps + 4, now);                                                 // fastest CTA leaves the counting loop
     }
-    // Fold the private copies into copy 0.
-    for (uint32_t b = t; b < nbins; b += T) {
-        uint32_t s = 0;
-        for (int c = 0; c < copies; ++c) s += sh[(uint32_t)c * (nbins + 1u) + b];
-        sh[b] = s;   // only thread (b mod T) touches column b
-    }
-    uint32_t &ticket = sh[(nbins + 1u) * (uint32_t)copies];   // one spare word behind the private copies (dynamic smem)
+    fold_copies<T>(sh, nbins, copies);   // copy 0 <- sum of the private copies
+    const uint32_t nb1 = nbins + 1u;
+    uint32_t &ticket = sh[nb1 * (uint32_t)copies];   // one spare word behind the private copies (dynamic smem)
     __syncthreads();
     const uint32_t tag = peer.epoch + 1u;
     if (peer.cta_slots != nullptr && nbins <= kLLMaxBins && gridDim.x <= kLLMaxCtas) {
@@ -507,6 +536,7 @@ __device__ __noinline__ void fused_exchange(uint32_t *sh, uint32_t nbins, int co
     bool gave_up = false;
     for (uint32_t b0 = 0; b0 < nbins; b0 += 4 * (T / 8)) {       // 4 bins per thread and pass
         uint32_t v[4], g[4];
+        int32_t old[4];
         const unsigned long long *p[4];
         bool want[4];
 #pragma unroll
@@ -516,6 +546,8 @@ __device__ __noinline__ void fused_exchange(uint32_t *sh, uint32_t nbins, int co
             p[k] = mine + (size_t)src * peer.nbins_max + (want[k] ? b : 0);
             v[k] = 0;
             g[k] = tag;
+            // the value the sum is added to (`bins[b] +=`) is fetched NOW, under the slot poll, not after it
+            old[k] = (src == 0 && b < nbins) ? bins[b] : 0;
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k)
@@ -542,7 +574,7 @@ __device__ __noinline__ void fused_exchange(uint32_t *sh, uint32_t nbins, int co
             sum += __shfl_xor_sync(0xffffffffu, sum, 2);
             sum += __shfl_xor_sync(0xffffffffu, sum, 4);
             const uint32_t b = b0 + (uint32_t)k * (T / 8) + (uint32_t)(t >> 3);
-            if (src == 0 && b < nbins) bins[b] += (int32_t)sum;                          // accumulate like the reference's +=
+            if (src == 0 && b < nbins) bins[b] = old[k] + (int32_t)sum;                  // accumulate like the reference's +=
         }
     }
     if (gave_up) {
@@ -836,6 +868,7 @@ struct P2P {
     uint32_t epoch = 0;
     uint32_t *error_host = nullptr;   // pinned, mapped: the kernel's "a peer never arrived" flag
     uint32_t *error_dev = nullptr;
+    bool ipc = true;                  // peers mapped through cudaIpc (b200_p2p_connect) or plain pointers (b200_p2p_connect_ptrs)
 };
 
 int histogram_allreduce_launch(P2P *h, int32_t *bins, int64_t nbins, const int32_t *input, int64_t n, cudaStream_t st) {
@@ -940,6 +973,34 @@ extern "C" b200_status b200_p2p_connect(void *handle, int32_t world, int32_t ran
     return B200_OK;
 }
 
+// Single-process form of b200_p2p_connect (the ranks are GPUs of one process): peers as pointers to their b200_p2p buffers.
+extern "C" b200_status b200_p2p_connect_ptrs(void *handle, int32_t world, int32_t rank, void *const *peer_handles) {
+    if (!handle || !peer_handles) return set_error(B200_ERR_INVALID_VALUE, "NULL argument");
+    if (world < 1 || world > 8 || rank < 0 || rank >= world)
+        return set_error(B200_ERR_INVALID_VALUE, "b200_p2p_connect_ptrs: bad rank %d / world %d", rank, world);
+    B200_TRY(ensure_device());
+    P2P *h = (P2P *)handle;
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) {
+            h->peer[r] = h->local;
+            continue;
+        }
+        if (!peer_handles[r]) return set_error(B200_ERR_INVALID_VALUE, "b200_p2p_connect_ptrs: NULL handle for rank %d", r);
+        void *buf = ((P2P *)peer_handles[r])->local;
+        cudaPointerAttributes at;
+        B200_CUDA(cudaPointerGetAttributes(&at, buf));
+        cudaError_t e = cudaDeviceEnablePeerAccess(at.device, 0);
+        if (e == cudaErrorPeerAccessAlreadyEnabled) (void)cudaGetLastError();
+        else B200_CUDA(e);
+        h->peer[r] = buf;
+    }
+    h->world = world;
+    h->rank = rank;
+    h->epoch = 0;
+    h->ipc = false;
+    return B200_OK;
+}
+
 // Diagnostic: four %globaltimer stamps (ns) of the last fused launch: slowest CTA left the counting loop, local counting
 // merged (ticket), slots sent to all ranks, all ranks' slots summed.  Synchronises the calling thread's stream.
 extern "C" b200_status b200_p2p_debug(void *handle, uint64_t *stamps4) {
@@ -966,12 +1027,29 @@ extern "C" b200_status b200_p2p_timeline(void *handle, uint64_t *stamps6) {
     return B200_OK;
 }
 
+// Profiling aid (tools/nvlink_proof.py): store `counts` as source rank `src`'s contribution to the NEXT fused step into this
+// rank's own slot array, exactly as that peer's kernel would -- so that ONE rank of a multi-rank histogram can be replayed under
+// ncu (which serialises kernels: ranks polling each other would deadlock) while its slot stores still cross NVLink.
+extern "C" b200_status b200_p2p_debug_prefill(void *handle, int32_t src, const uint32_t *counts_host, int64_t nbins) {
+    if (!handle || !counts_host) return set_error(B200_ERR_INVALID_VALUE, "NULL argument");
+    P2P *h = (P2P *)handle;
+    if (src < 0 || src >= h->world || nbins < 1 || nbins > (int64_t)kP2PMaxBins) return set_error(B200_ERR_INVALID_VALUE, "b200_p2p_debug_prefill: bad src / nbins");
+    B200_TRY(ensure_device());
+    std::vector<unsigned long long> words((size_t)nbins);
+    const uint32_t tag = h->epoch + 1u;
+    for (int64_t b = 0; b < nbins; ++b) words[(size_t)b] = (unsigned long long)counts_host[b] | ((unsigned long long)tag << 32);
+    const size_t half = (size_t)(h->epoch & 1u) * 8u * kP2PMaxBins;
+    B200_CUDA(cudaMemcpy((char *)h->local + kP2PSlotsOff + (half + (size_t)src * kP2PMaxBins) * 8, words.data(), (size_t)nbins * 8,
+                         cudaMemcpyHostToDevice));
+    return B200_OK;
+}
+
 extern "C" b200_status b200_p2p_free(void *handle) {
     if (!handle) return B200_OK;
     P2P *h = (P2P *)handle;
     B200_CUDA(cudaDeviceSynchronize());
     for (int r = 0; r < h->world; ++r)
-        if (r != h->rank && h->peer[r]) (void)cudaIpcCloseMemHandle(h->peer[r]);
+        if (h->ipc && r != h->rank && h->peer[r]) (void)cudaIpcCloseMemHandle(h->peer[r]);
     if (h->local) (void)cudaFree(h->local);
     if (h->error_host) (void)cudaFreeHost(h->error_host);
     delete h;

@@ -34,6 +34,7 @@ struct Sym {
     void *peer[kSymMaxRanks] = {};
     unsigned long long epoch = 0;
     unsigned long long a2a_calls = 0;   // b200_transpose_alltoall calls so far (the value of the "ready" flags)
+    bool ipc = true;                    // peers mapped with cudaIpcOpenMemHandle (b200_sym_connect) or plain pointers (..._ptrs)
 };
 
 struct A2APeers {
@@ -238,6 +239,34 @@ extern "C" b200_status b200_sym_connect(void *handle, int32_t world, int32_t ran
     return B200_OK;
 }
 
+// Single-process form of b200_sym_connect: the ranks are GPUs of ONE process ("per-GPU kernels launched
+// concurrently from one process"), so the peers' buffers are handed over as pointers (b200_sym_ptr(peer_handle, -1) taken
+// while that GPU was current) instead of IPC handles; peer access is enabled here.
+extern "C" b200_status b200_sym_connect_ptrs(void *handle, int32_t world, int32_t rank, void *const *peer_bufs) {
+    if (!handle || !peer_bufs) return set_error(B200_ERR_INVALID_VALUE, "NULL argument");
+    if (world < 1 || world > kSymMaxRanks || rank < 0 || rank >= world)
+        return set_error(B200_ERR_INVALID_VALUE, "b200_sym_connect_ptrs: bad rank %d / world %d", rank, world);
+    B200_TRY(ensure_device());
+    Sym *h = (Sym *)handle;
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) {
+            h->peer[r] = h->local;
+            continue;
+        }
+        if (!peer_bufs[r]) return set_error(B200_ERR_INVALID_VALUE, "b200_sym_connect_ptrs: NULL buffer for rank %d", r);
+        cudaPointerAttributes at;
+        B200_CUDA(cudaPointerGetAttributes(&at, peer_bufs[r]));
+        cudaError_t e = cudaDeviceEnablePeerAccess(at.device, 0);
+        if (e == cudaErrorPeerAccessAlreadyEnabled) (void)cudaGetLastError();
+        else B200_CUDA(e);
+        h->peer[r] = peer_bufs[r];
+    }
+    h->world = world;
+    h->rank = rank;
+    h->ipc = false;
+    return B200_OK;
+}
+
 extern "C" b200_status b200_sym_ptr(void *handle, int32_t rank, void **ptr) {
     if (!handle || !ptr) return set_error(B200_ERR_INVALID_VALUE, "NULL argument");
     Sym *h = (Sym *)handle;
@@ -269,7 +298,7 @@ extern "C" b200_status b200_sym_free(void *handle) {
     Sym *h = (Sym *)handle;
     B200_CUDA(cudaDeviceSynchronize());
     for (int r = 0; r < h->world; ++r)
-        if (r != h->rank && h->peer[r]) (void)cudaIpcCloseMemHandle(h->peer[r]);
+        if (h->ipc && r != h->rank && h->peer[r]) (void)cudaIpcCloseMemHandle(h->peer[r]);
     if (h->local) (void)cudaFree(h->local);
     delete h;
     return B200_OK;
@@ -295,7 +324,11 @@ extern "C" b200_status b200_transpose_alltoall(void *a_sym, const void *b_local,
         peers.dst[r] = r < G ? h->peer[r] : nullptr;
         flags.dst[r] = r < G ? (char *)h->peer[r] + h->bytes : nullptr;
     }
-    const unsigned long long call = ++h->a2a_calls;
+    // `a2a.debug_no_sync` (profiling only): this rank's data kernel runs alone -- it neither waits for the peers' "ready" flags
+    // nor joins the trailing barrier -- so that ONE rank of a multi-rank transpose can be replayed under ncu (which serialises
+    // kernels: two ranks spinning for each other would deadlock) while its stores still cross NVLink (tools/nvlink_proof.py).
+    const bool no_sync = tune_get("a2a.debug_no_sync", 0) != 0;
+    const unsigned long long call = no_sync ? 0ull : ++h->a2a_calls;
     const int tiles_i = (int)(cols_blk / 64), tiles_j = (int)(rows_blk / 64);
     if ((int64_t)tiles_i * tiles_j * G > INT32_MAX) return set_error(B200_ERR_UNSUPPORTED, "b200_transpose_alltoall: too many tiles");
     const dim3 grid((unsigned)(tiles_i * tiles_j * G));
@@ -323,7 +356,7 @@ extern "C" b200_status b200_transpose_alltoall(void *a_sym, const void *b_local,
         else
             transpose_a2a_tma_kernel<uint64_t, 64, 64><<<g2, 256, 0, st>>>(maps, (const uint64_t *)b_local, N0, rows_blk, roff, (int)(cols_blk / TI), tj_n, h->rank, order, G, flags, call);
         B200_CHECK_LAUNCH("transpose_a2a_tma_kernel");
-        return b200_sym_barrier(a_sym);
+        return no_sync ? B200_OK : b200_sym_barrier(a_sym);
     }
     if (elsize == 4)
         transpose_a2a_kernel<uint32_t><<<grid, 256, 0, st>>>(peers, (const uint32_t *)b_local, N0, N1, rows_blk, (int64_t)h->rank * cols_blk,
@@ -332,5 +365,5 @@ extern "C" b200_status b200_transpose_alltoall(void *a_sym, const void *b_local,
         transpose_a2a_kernel<uint64_t><<<grid, 256, 0, st>>>(peers, (const uint64_t *)b_local, N0, N1, rows_blk, (int64_t)h->rank * cols_blk,
                                                             tiles_i, tiles_j, h->rank, order, G, flags, call);
     B200_CHECK_LAUNCH("transpose_a2a_kernel");
-    return b200_sym_barrier(a_sym);
+    return no_sync ? B200_OK : b200_sym_barrier(a_sym);
 }
