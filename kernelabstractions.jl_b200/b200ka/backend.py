@@ -10,6 +10,7 @@ from __future__ import annotations
 import ctypes as C
 import threading
 import time
+import weakref
 from typing import Optional, Sequence, Tuple
 
 import numpy as np
@@ -282,11 +283,35 @@ def pagelock_(backend, x: np.ndarray) -> None:
     """KA.pagelock! (reference src/KernelAbstractions.jl:166)"""
     if not (x.flags.f_contiguous or x.flags.c_contiguous):
         raise ArgumentError("pagelock!: host arrays must be contiguous")
-    call("b200_host_register", x.ctypes.data_as(C.c_void_p), C.c_size_t(x.nbytes))
+    addr = x.ctypes.data
+    call("b200_host_register", C.c_void_p(addr), C.c_size_t(x.nbytes))
+    # A registration that outlives the array poisons the address range: the allocator hands the pages to the next array, and a
+    # copy from a buffer that lies PARTLY inside a stale registration fails with "invalid argument" (seen as a flaky failure of
+    # whichever test came later).  Julia's pagelock! leaves this to the GC-owned Array; here the registration is dropped when the
+    # array that owns the memory is collected.
+    owner = x
+    while isinstance(getattr(owner, "base", None), np.ndarray):
+        owner = owner.base
+    if addr not in _pagelocked:
+        _pagelocked[addr] = weakref.finalize(owner, _unregister, addr)
+
+
+def _unregister(addr: int) -> None:
+    _pagelocked.pop(addr, None)
+    try:
+        lib().b200_host_unregister(C.c_void_p(addr))
+    except Exception:   # interpreter shutdown
+        pass
+
+
+_pagelocked: dict = {}
 
 
 def unpagelock_(backend, x: np.ndarray) -> None:
-    """Undo pagelock_ before the host array is freed (the registration outlives the Python object otherwise)."""
+    """Undo pagelock_ explicitly (it also happens when the array that owns the memory is collected)."""
+    fin = _pagelocked.pop(x.ctypes.data, None)
+    if fin is not None:
+        fin.detach()
     call("b200_host_unregister", x.ctypes.data_as(C.c_void_p))
 
 

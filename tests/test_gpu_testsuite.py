@@ -455,6 +455,18 @@ def test_priority_and_pagelock():
     KA.copyto_(be, D, h)
     KA.synchronize(be)
     assert np.array_equal(KA.Array(D), h)
+    # the registration goes away with the array (a stale one would poison the address range for whatever is allocated there next)
+    from b200ka import backend as B
+    addr = h.ctypes.data
+    assert addr in B._pagelocked
+    del h
+    import gc
+    gc.collect()
+    assert addr not in B._pagelocked
+    for _ in range(50):          # arrays that reuse the freed pages copy fine
+        g = np.arange(4096, dtype=np.float32)
+        KA.copyto_(be, D, g)
+        KA.synchronize(be)
 
 
 # ---- no JIT: unknown kernels and bad arguments fail loudly ---------------------------------------------------------------------------
