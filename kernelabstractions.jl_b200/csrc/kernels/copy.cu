@@ -108,7 +108,7 @@ __device__ __forceinline__ void bulk_wait_all() {
 template <int STAGES>
 __global__ void __launch_bounds__(32) copy_bulk_kernel(unsigned char *__restrict__ dst,
                                                        const unsigned char *__restrict__ src, size_t bytes16,
-                                                       uint32_t stage_bytes) {
+                                                       uint32_t stage_bytes, int prefetch) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ __align__(8) uint64_t full[STAGES];
     if (threadIdx.x != 0) return;
@@ -118,8 +118,6 @@ __global__ void __launch_bounds__(32) copy_bulk_kernel(unsigned char *__restrict
     for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    asm volatile("griddepcontrol.wait;" ::: "memory");   // everything before us in the stream is complete and visible
-
     const size_t nchunks = (bytes16 + stage_bytes - 1) / stage_bytes;
     const size_t mine = nchunks > blockIdx.x ? (nchunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     auto chunk_off = [&](size_t i) { return (blockIdx.x + i * (size_t)gridDim.x) * (size_t)stage_bytes; };
@@ -128,6 +126,14 @@ __global__ void __launch_bounds__(32) copy_bulk_kernel(unsigned char *__restrict
         size_t rem = bytes16 - off;
         return (uint32_t)(rem < stage_bytes ? rem : stage_bytes);
     };
+    // While the previous kernel of the stream drains, pull this CTA's first ring of chunks into L2.  A prefetch has no architectural
+    // effect -- L2 is the point of coherence, whatever the previous kernel still writes lands there too -- so it may run BEFORE
+    // the dependency wait; the ring's first loads then hit L2 instead of paying the DRAM ramp (~1.5 us of a 12 us 32 MiB copy).
+    if (prefetch)
+        for (size_t i = 0; i < mine && i < (size_t)STAGES; ++i)
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src + chunk_off(i)), "r"(chunk_len(i)) : "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");   // everything before us in the stream is complete and visible
+
     // prologue: fill the ring
     for (size_t i = 0; i < mine && i < (size_t)STAGES; ++i) {
         uint32_t len = chunk_len(i);
@@ -238,8 +244,13 @@ static int launch_vec16(unsigned char *d, const unsigned char *s, size_t n16, in
 
 static int launch_bulk(unsigned char *d, const unsigned char *s, size_t bytes16, cudaStream_t st) {
     int stage_kb = tune_get("copy.bulk_stage_kb", 16);
-    int stages = tune_get("copy.bulk_stages", 4);
+    // ring depth: 4 stages at large sizes (r01 sweeps); short copies (<= 64 MiB, e.g. the 8-GPU slab of the 2^26 copy) take 8 --
+    // the ring is also what a CTA prefetches into L2 before its dependency wait, and 8 x 16 KiB per CTA covers the DRAM ramp of
+    // a 12 us launch: 12.4 -> 10.3 us for 32 MiB (profiles/r05_slab_probe.txt).  `copy.bulk_stages` pins a value.
+    int stages = tune_get("copy.bulk_stages", 0);
+    if (stages == 0) stages = bytes16 <= ((size_t)64 << 20) ? 8 : 4;
     int ctas_per_sm = tune_get("copy.bulk_ctas_per_sm", 1);
+    const int prefetch = tune_get("copy.l2_prefetch", 1);
     uint32_t stage_bytes = (uint32_t)stage_kb * 1024u;
     size_t smem = (size_t)stage_bytes * stages;
     size_t nchunks = (bytes16 + stage_bytes - 1) / stage_bytes;
@@ -259,7 +270,7 @@ static int launch_bulk(unsigned char *d, const unsigned char *s, size_t bytes16,
     case S:                                                                                                     \
         B200_CUDA(cudaFuncSetAttribute(copy_bulk_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
                                        (int)smem));                                                             \
-        B200_CUDA(cudaLaunchKernelEx(&cfg, copy_bulk_kernel<S>, d, (const unsigned char *)s, bytes16, stage_bytes)); \
+        B200_CUDA(cudaLaunchKernelEx(&cfg, copy_bulk_kernel<S>, d, (const unsigned char *)s, bytes16, stage_bytes, prefetch)); \
         break;
     switch (stages) {
         B200_BULK_CASE(2)

@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(T, 1) hist256_bytes_kernel(int32_t *__restrict
 template <int T, int P, bool IL>
 __device__ __noinline__ void hist_count_phase(uint32_t *sh, uint32_t nbins, const int4 *__restrict__ in4, int64_t n4,
                                               const int32_t *__restrict__ tail, int ntail, int copies,
-                                              const int32_t *__restrict__ head, int nhead) {
+                                              const int32_t *__restrict__ head, int nhead, int npf) {
     const int t = threadIdx.x, warp = t >> 5;
     // Programmatic dependent launch (see launch_pdl): the next kernel of the stream may be scheduled as SMs drain; our own set-up
     // runs before we wait for the previous kernel's memory.  Back-to-back steps on input shards hide ~2 us of the ~9 us a launch costs.
@@ -214,6 +214,12 @@ __device__ __noinline__ void hist_count_phase(uint32_t *sh, uint32_t nbins, cons
     const int4 *ptr = in4 + first + t;
     const int64_t bstep = rstride * P;
     int4 cur[P], nxt[P];
+    // CTAs that become resident while the previous kernel of the stream is still in its tail (the fused kernel's exchange leaves
+    // HBM idle for ~5 us) pull their first rounds into L2 before the dependency wait.  A prefetch has no architectural effect --
+    // L2 is the point of coherence, anything the previous kernel still writes lands there too -- and the first loads then come
+    // from L2 instead of paying the DRAM ramp.  One thread per round: 16 KiB per instruction.
+    if (t < npf && (int64_t)t < nr)
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(in4 + first + (int64_t)t * rstride), "r"(T * 16) : "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");   // everything before us in the stream is complete and visible
     // the first batch of loads goes out BEFORE the private copies are cleared: the clear runs under the loads' latency
     if (nfb > 0) {
@@ -282,10 +288,10 @@ __global__ void __launch_bounds__(T) hist_atomic_kernel(int32_t *__restrict__ bi
                                                         const int32_t *__restrict__ tail, int ntail, int copies, int interleave) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint32_t *sh = reinterpret_cast<uint32_t *>(smem_raw);
-    if (interleave)
-        hist_count_phase<T, P, true>(sh, nbins, in4, n4, tail, ntail, copies, nullptr, 0);
+    if (interleave & 1)   // `interleave`: bit 0 = unit plan, bits 8.. = rounds to prefetch into L2 before the dependency wait
+        hist_count_phase<T, P, true>(sh, nbins, in4, n4, tail, ntail, copies, nullptr, 0, interleave >> 8);
     else
-        hist_count_phase<T, P, false>(sh, nbins, in4, n4, tail, ntail, copies, nullptr, 0);
+        hist_count_phase<T, P, false>(sh, nbins, in4, n4, tail, ntail, copies, nullptr, 0, interleave >> 8);
     fold_copies<T>(sh, nbins, copies);
     for (uint32_t b = threadIdx.x; b < nbins; b += T) {   // thread b reads back what it wrote
         const uint32_t s = sh[b];
@@ -594,10 +600,10 @@ __global__ void __launch_bounds__(T) hist_allreduce_kernel(int32_t *__restrict__
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint32_t *sh = reinterpret_cast<uint32_t *>(smem_raw);
     if (blockIdx.x == 0 && threadIdx.x == 0) peer.stamps[5] = globaltimer_ns();          // first CTA resident
-    if (interleave)
-        hist_count_phase<T, P, true>(sh, nbins, in4, n4, tail, ntail, copies, head, nhead);
+    if (interleave & 1)
+        hist_count_phase<T, P, true>(sh, nbins, in4, n4, tail, ntail, copies, head, nhead, interleave >> 8);
     else
-        hist_count_phase<T, P, false>(sh, nbins, in4, n4, tail, ntail, copies, head, nhead);
+        hist_count_phase<T, P, false>(sh, nbins, in4, n4, tail, ntail, copies, head, nhead, interleave >> 8);
     fused_exchange<T>(sh, nbins, copies, bins, peer);
 }
 
@@ -647,8 +653,9 @@ static int launch_bytes(int32_t *bins, uint32_t nbins, const int4 *in4, int64_t 
 // the first and the last CTA), which is what counts once a launch is short.
 static int pick_interleave(int64_t n4) {
     const int forced = tune_get("hist.interleave", -1);
-    if (forced == 0 || forced == 1) return forced;
-    return n4 * 16 < ((int64_t)768 << 20) ? 1 : 0;
+    const int npf = tune_get("hist.l2_prefetch_rounds", 16) << 8;   // rounds (16 KiB each) a CTA pulls into L2 before the dependency wait
+    if (forced == 0 || forced == 1) return forced | npf;
+    return (n4 * 16 < ((int64_t)768 << 20) ? 1 : 0) | npf;
 }
 
 template <int T, int P>

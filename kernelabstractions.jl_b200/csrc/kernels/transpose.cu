@@ -40,13 +40,12 @@ __device__ __forceinline__ void stg_stream_f4(float *p, const float4 &v) {
 // ORDER 0: consecutive CTAs walk j (b's contiguous dimension) first; ORDER 1: i (a's contiguous dim) first.
 template <int ORDER>
 __global__ void __launch_bounds__(256) transpose64_f32_kernel(float *__restrict__ a, const float *__restrict__ b,
-                                                              int tiles_i, int tiles_j, int64_t lda, int64_t ldb) {
+                                                              int tiles_i, int tiles_j, int64_t lda, int64_t ldb, int prefetch) {
     __shared__ __align__(16) float tile[64 * 64];  // [j][i], 16-byte chunk index XOR ((j >> 2) & 15)
     const int t = threadIdx.x;
     // Programmatic dependent launch (launch attribute set by transpose_launch): the next PDL-aware kernel of the stream may
     // become resident while this grid drains; nothing here touches global memory before the previous grid has completed.
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    asm volatile("griddepcontrol.wait;" ::: "memory");
     int ti, tj;
     if (ORDER == 0) {
         tj = blockIdx.x % tiles_j;
@@ -56,6 +55,15 @@ __global__ void __launch_bounds__(256) transpose64_f32_kernel(float *__restrict_
         tj = blockIdx.x / tiles_i;
     }
     const int64_t i0 = (int64_t)ti * 64, j0 = (int64_t)tj * 64;
+    // `transpose.l2_prefetch` (off: measured slower, 336.5 vs 327.8 us at 16384^2 and 45.2 vs 44.2 us on the 8-GPU slab,
+    // profiles/r05_slab_probe.txt): every CTA pulls its tile (64 columns x 256 bytes) into L2 before the dependency wait.  With
+    // 65536 short-lived CTAs the extra instruction and the doubled L2 fills cost more than the DRAM ramp of the first wave saves
+    // (the persistent copy and histogram kernels, which prefetch once per CTA, do gain).
+    if (prefetch && t < 128) {
+        const float *line = b + j0 + (i0 + (t >> 1)) * ldb + (t & 1) * 32;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(line));
+    }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     // ---- load: thread owns j = 4*jq .. 4*jq+3 and i = 4*iq .. 4*iq+3
     const int jq = t & 15, iq = t >> 4;
@@ -338,7 +346,7 @@ int transpose_launch(void *a, const void *b, int64_t m, int64_t n, int64_t lda, 
         attr[0].val.programmaticStreamSerializationAllowed = tune_get("transpose.pdl", 1) != 0;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        B200_CUDA(cudaLaunchKernelEx(&cfg, kern, (float *)a, (const float *)b, tiles_i, tiles_j, lda, ldb));
+        B200_CUDA(cudaLaunchKernelEx(&cfg, kern, (float *)a, (const float *)b, tiles_i, tiles_j, lda, ldb, tune_get("transpose.l2_prefetch", 0)));
         B200_CHECK_LAUNCH("transpose64_f32_kernel");
         return B200_OK;
     }

@@ -36,7 +36,7 @@ def _reset_tuning():
     for k in ["registry.force_twins", "transpose.order", "transpose.force_generic", "transpose.impl"]:
         _lib.call("b200_tune_set", k.encode(), 0)
     for k, v in [("hist.impl", 1), ("hist.interleave", -1), ("hist.tma_stages", 4), ("copy.impl", 1), ("hist.threads", 512), ("hist.batch", 8), ("hist.ilp", 2), ("copy.unroll", 8),
-                 ("copy.ctas_per_sm", 32), ("copy.bulk_stage_kb", 16), ("copy.bulk_stages", 4)]:
+                 ("copy.ctas_per_sm", 32), ("copy.bulk_stage_kb", 16), ("copy.bulk_stages", 0)]:
         _lib.call("b200_tune_set", k.encode(), v)
 
 

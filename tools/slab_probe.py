@@ -49,21 +49,21 @@ def tune(k, v):
 
 
 n = 16384
-for G in (1, 8):
+for G in (1, 2, 4, 8):
     rb = n // G
     dB = KA.rand_uniform_(KA.allocate(be, np.float32, rb, n), 1235)
     dA = KA.zeros(be, np.float32, n, rb)
     ideal = 2 * 4 * n * rb / 6545.9e9 * 1e6
-    for pdl in (0, 1):
-        for cps in (0,):
-            tune("transpose.pdl", pdl)
-            tune("transpose.ctas_per_sm", cps)
-            us = timed(lambda: EX.naive_transpose_(dA, dB))
-            print(f"transpose slab 1/{G}: pdl={pdl} ctas_per_sm={cps or 8}: {us:8.2f} us  ({2 * 4 * n * rb / us / 1e3:7.1f} GB/s; at the measured peak {ideal:6.2f} us)", flush=True)
+    for pdl, pf in ((0, 0), (1, 0), (1, 1)):
+        tune("transpose.pdl", pdl)
+        tune("transpose.l2_prefetch", pf)
+        us = timed(lambda: EX.naive_transpose_(dA, dB))
+        print(f"transpose slab 1/{G}: pdl={pdl} l2_prefetch={pf}: {us:8.2f} us  ({2 * 4 * n * rb / us / 1e3:7.1f} GB/s; at the measured peak {ideal:6.2f} us)", flush=True)
+    tune("transpose.l2_prefetch", 1)
     tune("transpose.pdl", 1)
     tune("transpose.ctas_per_sm", 0)
     tune("transpose.impl", 1)
-    for stages, cps in [(3, 4), (4, 3), (2, 6), (6, 2), (3, 2), (4, 2), (2, 4), (3, 3)]:
+    for stages, cps in [(3, 2)]:
         tune("transpose.tma_stages", stages)
         tune("transpose.tma_ctas_per_sm", cps)
         us = timed(lambda: EX.naive_transpose_(dA, dB))
@@ -71,7 +71,7 @@ for G in (1, 8):
     tune("transpose.impl", 0)
     del dA, dB
 
-for G in (1, 8):
+for G in (1, 2, 4, 8):
     ne = (1 << 26) // G
     npairs = max(2, (512 << 20) // (8 * ne))
     src = [KA.rand_uniform_(KA.allocate(be, np.float32, ne), 1 + i) for i in range(npairs)]
@@ -80,10 +80,14 @@ for G in (1, 8):
     def cycle():
         for i in range(npairs):
             EX.mycopy_(dst[i], src[i])
+    tune("copy.l2_prefetch", 0)
+    us0 = timed(cycle, steps=20) / npairs
+    tune("copy.l2_prefetch", 1)
+    print(f"copy slab 1/{G} without the L2 prefetch: {us0:8.2f} us", flush=True)
     us = timed(cycle, steps=20) / npairs
     print(f"copy slab 1/{G} ({npairs} pairs rotated): {us:8.2f} us ({8 * ne / us / 1e3:7.1f} GB/s; at the measured peak {8 * ne / 6545.9e9 * 1e6:6.2f} us)", flush=True)
-    if G == 8:
-        for impl, kb, stages, cps in [(1, 8, 8, 1), (1, 8, 4, 2), (1, 16, 4, 2), (1, 8, 8, 2), (1, 32, 4, 1), (1, 16, 8, 1), (1, 4, 8, 2), (0, 0, 0, 0)]:
+    if True:
+        for impl, kb, stages, cps in [(1, 16, 4, 1), (1, 16, 6, 1), (1, 16, 8, 1), (1, 32, 4, 1), (1, 32, 6, 1), (1, 8, 8, 1), (0, 0, 0, 0)]:
             tune("copy.impl", impl)
             if impl:
                 tune("copy.bulk_stage_kb", kb)
@@ -93,7 +97,7 @@ for G in (1, 8):
             print(f"   copy.impl={impl} stage_kb={kb} stages={stages} ctas_per_sm={cps}: {us:8.2f} us ({8 * ne / us / 1e3:7.1f} GB/s)", flush=True)
         tune("copy.impl", 1)
         tune("copy.bulk_stage_kb", 16)
-        tune("copy.bulk_stages", 4)
+        tune("copy.bulk_stages", 0)
         tune("copy.bulk_ctas_per_sm", 1)
     del src, dst
 
