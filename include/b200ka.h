@@ -354,8 +354,9 @@ b200_status b200_p2p_free(void *handle);
 /* diagnostic: four %globaltimer stamps (ns) of the last fused launch (slowest CTA left the counting loop, local counts
  * merged, slots sent, all ranks' slots summed) */
 b200_status b200_p2p_debug(void *handle, uint64_t *stamps4);
-/* the same plus [4] fastest CTA left the counting loop, [5] first CTA resident (six stamps) */
-b200_status b200_p2p_timeline(void *handle, uint64_t *stamps6);
+/* the same plus [4] fastest CTA left the counting loop, [5] first CTA resident, [6] every other CTA has published its counts,
+ * [7] the merged partial has been read back (eight stamps) */
+b200_status b200_p2p_timeline(void *handle, uint64_t *stamps8);
 b200_status b200_histogram_i32_allreduce(void *handle, int32_t *bins, int64_t nbins, const int32_t *input, int64_t n);
 
 #ifdef __cplusplus

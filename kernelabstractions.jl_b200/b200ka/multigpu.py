@@ -113,10 +113,11 @@ class PeerGroup:
 
     def timeline(self):
         """ns timeline of the last fused launch relative to the moment its FASTEST CTA left the counting loop (b200_p2p_timeline)."""
-        buf = (C.c_uint64 * 6)()
+        buf = (C.c_uint64 * 8)()
         _lib.call("b200_p2p_timeline", self.handle, buf)
         t0 = int(buf[4])
         return {"first_cta_resident": int(buf[5]) - t0, "slowest_cta_done": int(buf[0]) - t0, "counts_merged": int(buf[1]) - int(buf[0]),
+                "all_published": int(buf[6]) - int(buf[0]), "partial_read": int(buf[7]) - int(buf[0]),
                 "slots_sent": int(buf[2]) - int(buf[0]), "all_summed": int(buf[3]) - int(buf[0])}
 
     def free(self) -> None:

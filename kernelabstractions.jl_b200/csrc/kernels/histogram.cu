@@ -491,40 +491,36 @@ __device__ __noinline__ void fused_exchange(uint32_t *sh, uint32_t nbins, int co
         __syncthreads();
         if (t == 0) peer.stamps[1] = globaltimer_ns();                                   // every CTA's counts merged
     } else {
-        // ---- ticket + partial (any nbins up to the shared-memory limit) ----
-        // Draw the ticket FIRST (relaxed: it only orders the CTAs): the CTA that draws the last one keeps its counts in shared
-        // memory, every other CTA publishes them (red.global) and then raises `published` with a release at device scope.
-        if (t == 0) ticket = atomicAdd(peer.counter, 1u);
-        __syncthreads();
-        const bool last = ticket == gridDim.x - 1;
-        uint32_t *published = peer.counter + 1;
-        if (!last) {
-            if (warp == 0) {
-                for (uint32_t b = t; b < nbins; b += 32) {
-                    const uint32_t s = sh[b];
-                    if (s) atomicAdd(peer.partial + b, s);
-                }
-                __threadfence();                           // every lane: its reds are performed before the count below is visible
-                __syncwarp();
-                if (t == 0) atomicAdd(published, 1u);
+        // ---- publish + ticket (any nbins up to the shared-memory limit) ----
+        // Every CTA adds its folded counts to the device-local partial (red.global), fences, and only THEN draws its ticket: the
+        // CTA that draws the last one knows that every count -- its own included -- is in the partial.  Critical path after the
+        // slowest CTA leaves the counting loop (b200_p2p_timeline, 2^27 elements): fold 0.2 us, reds + fence ~1.0, ticket ~0.7,
+        // partial read-back 0.7.  (Drawing the ticket FIRST, so that the last CTA could keep its counts in shared memory, was
+        // tried in r05 and is slower: the last CTA then waits for the publish chains of the CTAs just ahead of it, 4.0 us in all.)
+        if (warp == 0) {
+            for (uint32_t b = t; b < nbins; b += 32) {
+                const uint32_t s = sh[b];
+                if (s) atomicAdd(peer.partial + b, s);
             }
-            return;
-        }
-        // ---- last CTA of this GPU ----
-        if (t == 0) {
-            peer.stamps[1] = globaltimer_ns();                                           // local counting done (ticket drawn)
-            uint32_t seen;
-            do {
-                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(published) : "memory");
-            } while (seen != gridDim.x - 1);
-            peer.counter[0] = 0;                                                         // ready for the next launch
-            peer.counter[1] = 0;
+            __threadfence();                               // every lane: its reds are performed before the ticket below is visible
+            __syncwarp();
+            if (t == 0) {
+                ticket = atomicAdd(peer.counter, 1u);
+                __threadfence();                           // ... and the reads of the partial below follow the ticket
+            }
         }
         __syncthreads();
+        if (ticket != gridDim.x - 1) return;   // only the last CTA of this GPU goes on
+        if (t == 0) {
+            peer.stamps[1] = globaltimer_ns();                                           // local counting merged (last ticket drawn)
+            peer.counter[0] = 0;                                                         // ready for the next launch
+            peer.stamps[6] = peer.stamps[1];
+        }
         for (uint32_t b = t; b < nbins; b += T) {
-            sh[b] += __ldcg(peer.partial + b);
+            sh[b] = __ldcg(peer.partial + b);
             peer.partial[b] = 0;
         }
+        if (t == 0) peer.stamps[7] = globaltimer_ns();                                   // partial read back
         // (each thread reads back only the sh[b] it wrote)
     }
     const size_t half = (size_t)(peer.epoch & 1u) * 8u * peer.nbins_max;
@@ -1022,13 +1018,14 @@ extern "C" b200_status b200_p2p_debug(void *handle, uint64_t *stamps4) {
     return B200_OK;
 }
 
-// Six stamps: [0..3] as b200_p2p_debug, [4] fastest CTA left the counting loop, [5] CTA 0 became resident.
+// Eight stamps: [0..3] as b200_p2p_debug, [4] fastest CTA left the counting loop, [5] CTA 0 became resident, [6] every other CTA
+// has published its counts (last CTA), [7] the partial has been read back.
 extern "C" b200_status b200_p2p_timeline(void *handle, uint64_t *stamps6) {
     if (!handle || !stamps6) return set_error(B200_ERR_INVALID_VALUE, "NULL argument");
     cudaStream_t st;
     B200_TRY(current_stream(&st));
     B200_CUDA(cudaStreamSynchronize(st));
-    B200_CUDA(cudaMemcpy(stamps6, (char *)((P2P *)handle)->local + kP2PStampsOff, 48, cudaMemcpyDeviceToHost));
+    B200_CUDA(cudaMemcpy(stamps6, (char *)((P2P *)handle)->local + kP2PStampsOff, 64, cudaMemcpyDeviceToHost));
     B200_CUDA(cudaMemset((char *)((P2P *)handle)->local + kP2PStampsOff, 0, 8));
     B200_CUDA(cudaMemset((char *)((P2P *)handle)->local + kP2PStampsOff + 4 * 8, 0xff, 8));
     return B200_OK;

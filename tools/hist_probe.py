@@ -54,6 +54,7 @@ for G in (1, 8):
             tl.append(peers.timeline())
         spread = [x["slowest_cta_done"] for x in tl]
         tail = [x["all_summed"] for x in tl]
+        print("   timelines:", tl)
         print(f"histogram 2^30/{G} interleave={inter} fused_ll={ll} l2_prefetch_rounds={npf}: local-only {us_l:8.2f} us ({4 * ne / us_l / 1e3:6.0f} GB/s), fused 1 rank {us_f:8.2f} us; "
               f"stream time at 7.25 TB/s {4 * ne / 7.25e12 * 1e6:7.2f} us; fastest->slowest CTA {spread} ns, slowest CTA -> summed {tail} ns", flush=True)
     tune("hist.interleave", -1)
@@ -62,6 +63,7 @@ for G in (1, 8):
         tune("hist.tma_stages", stages)
         us_t = timed(lambda: EX.histogram_(bins, d_in))
         tune("hist.impl", 1)
+        print("   timelines:", tl)
         print(f"histogram 2^30/{G} TMA feed (hist.impl=2, {stages} x 16 KiB ring): local-only {us_t:8.2f} us ({4 * ne / us_t / 1e3:6.0f} GB/s)", flush=True)
     del d_in
 tune("hist.interleave", -1)
