@@ -522,6 +522,10 @@ def main():
 
 def run_suite(KA, _lib, EX, mg, orc, be, rank, world, dist, timed, graphed, all_ranks, peaks, steps, warmup, barrier, cpu=False):
     out = {}
+    # Sub-millisecond kernels are timed over at least 100 steps: the ranks leave the host-side barrier tens of microseconds apart,
+    # a collective's first timed step absorbs that skew, and over 20 steps it would add 1-2 us to every step of an 85 us kernel
+    # (bench 84.8 us vs 83.2 us for the same fused histogram timed over 50 steps by tests/gpu_multi_check.py, r05).
+    steps_short = max(steps, 100)
 
     def cpu_time(fn, work, unit, scale, sample):
         """best of up to 3 passes of the oracle's work-group-vectorised restatement on the host cores (reported, not a target)"""
@@ -561,12 +565,12 @@ def run_suite(KA, _lib, EX, mg, orc, be, rank, world, dist, timed, graphed, all_
                 for _ in range(npairs):
                     step_copy()
             fn, keep = graphed(cycle)
-        k = max(1, steps // npairs) if world > 1 else steps
+        k = max(1, steps_short // npairs) if world > 1 else steps_short
         ms, launches = timed(fn, k, warmup)
         if world > 1:
             ms /= npairs
         gbs = 2 * 4 * n / (ms * 1e-3) / 1e9          # whole job: 2^26 elements / max-over-ranks time
-        out["copy_2^26_f32"] = {"value": gbs, "unit": "GB/s", "ms_per_step": ms, "gpu_launches": launches, "result_checked": ok,
+        out["copy_2^26_f32"] = {"value": gbs, "unit": "GB/s", "ms_per_step": ms, "gpu_launches": launches, "result_checked": ok, "steps": k * (npairs if world > 1 else 1),
                                 "roofline": {"bound": "hbm", "achieved": gbs / world, "peak": peaks["hbm"], "frac": gbs / world / peaks["hbm"],
                                              "traffic": traffic_from_profiles("copy_bulk_kernel", 1.0 / world),
                                              "algorithmic_bytes_per_launch": 8 * ns},
@@ -587,7 +591,7 @@ def run_suite(KA, _lib, EX, mg, orc, be, rank, world, dist, timed, graphed, all_
                 for k_, v_ in knobs.items():
                     _lib.call("b200_tune_set", k_.encode(), v_)
                 try:
-                    ms_t, _ = timed(step_copy, steps, warmup)
+                    ms_t, _ = timed(step_copy, steps_short, warmup)
                 finally:
                     _lib.call("b200_tune_set", b"registry.force_twins", 0)
                     _lib.call("b200_tune_set", b"registry.twin_vec", 1)
@@ -618,7 +622,7 @@ def run_suite(KA, _lib, EX, mg, orc, be, rank, world, dist, timed, graphed, all_
             kern(Z[i], np.float32(2.0), X[i], Y[i], ndrange=Z[i].shape)
             state["i"] += 1
 
-        ms, launches = timed(step_saxpy, steps, warmup)
+        ms, launches = timed(step_saxpy, steps_short, warmup)
         gbs = 3 * 4 * n / (ms * 1e-3) / 1e9
         out["saxpy_2^26_f32"] = {"value": world * gbs, "unit": "GB/s", "ms_per_step": ms, "gpu_launches": launches,
                                  "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm"], "frac": gbs / peaks["hbm"],
@@ -662,8 +666,8 @@ def run_suite(KA, _lib, EX, mg, orc, be, rank, world, dist, timed, graphed, all_
             ok, peer_ok = all_ranks(ok), all_ranks(peer_ok)
             nvl = NvlinkCounter(env_int("LOCAL_RANK", 0))
             nv0 = nvl.start()
-            ms, launches = timed(step_dt, steps, warmup)
-            nv_meas = nvl.delta_per_step(nv0, steps + warmup)
+            ms, launches = timed(step_dt, steps_short, warmup)
+            nv_meas = nvl.delta_per_step(nv0, steps_short + warmup)
             gbs = 2.0 * 4 * n * n / (ms * 1e-3) / 1e9
             out["distributed_transpose_16384_f32"] = {
                 "value": gbs, "unit": "GB/s", "ms_per_step": ms, "gpu_launches": launches, "scaling": "strong", "slab_checked": ok, "peer_block_checked": peer_ok,
@@ -714,11 +718,11 @@ def run_suite(KA, _lib, EX, mg, orc, be, rank, world, dist, timed, graphed, all_
         check = bool(int(got.astype(np.int64).sum()) == n)  # every input lies in 1..256: counts must add up to n
         nvl = NvlinkCounter(env_int("LOCAL_RANK", 0)) if world > 1 else None
         nv0 = nvl.start() if nvl else None
-        ms, launches = timed(step_hist, steps, warmup)
-        nv_meas = nvl.delta_per_step(nv0, steps + warmup) if nvl else None
+        ms, launches = timed(step_hist, steps_short, warmup)
+        nv_meas = nvl.delta_per_step(nv0, steps_short + warmup) if nvl else None
         gbs = 4.0 * n / (ms * 1e-3) / 1e9  # whole job: all ranks' inputs / max time
         out["histogram_2^30_i32_256bins"] = {"value": gbs, "unit": "GB/s", "ms_per_step": ms, "gpu_launches": launches,
-                                             "sum_conserved": check, "scaling": "strong",
+                                             "sum_conserved": check, "scaling": "strong", "steps": steps_short,
                                              "nvlink_counters_per_step_rank0": nv_meas,
                                              "nvlink_expected_tx_bytes_per_step_per_gpu": (256 * 8 * (world - 1)) if world > 1 else None,
                                              "roofline": {"bound": "hbm", "achieved": gbs / world, "peak": peaks["hbm"],
@@ -734,7 +738,7 @@ def run_suite(KA, _lib, EX, mg, orc, be, rank, world, dist, timed, graphed, all_
             step_hist_nccl()
             KA.synchronize(be)
             check2 = bool(np.array_equal(KA.Array(bins), got))
-            ms2, _ = timed(step_hist_nccl, steps, warmup)
+            ms2, _ = timed(step_hist_nccl, steps_short, warmup)
             out["histogram_2^30_i32_256bins"]["nccl_route"] = {"value": 4.0 * n / (ms2 * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": ms2,
                                                                 "same_bits_as_fused": check2,
                                                                 "collective": "b200_histogram_i32 + NCCL all-reduce of 256 x Int32 (2 launches)"}
