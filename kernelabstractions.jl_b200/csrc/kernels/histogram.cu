@@ -175,7 +175,8 @@ __global__ void __launch_bounds__(T, 1) hist256_bytes_kernel(int32_t *__restrict
 template <int T, int P, bool IL>
 __device__ __noinline__ void hist_count_phase(uint32_t *sh, uint32_t nbins, const int4 *__restrict__ in4, int64_t n4,
                                               const int32_t *__restrict__ tail, int ntail, int copies,
-                                              const int32_t *__restrict__ head, int nhead, int npf) {
+                                              const int32_t *__restrict__ head, int nhead, int npf,
+                                              uint32_t *dyn_ctr = nullptr, int dyn_rounds = 0) {
     const int t = threadIdx.x, warp = t >> 5;
     // Programmatic dependent launch (see launch_pdl): the next kernel of the stream may be scheduled as SMs drain; our own set-up
     // runs before we wait for the previous kernel's memory.  Back-to-back steps on input shards hide ~2 us of the ~9 us a launch costs.
@@ -195,13 +196,32 @@ __device__ __noinline__ void hist_count_phase(uint32_t *sh, uint32_t nbins, cons
     // Round r of this CTA loads int4 number  first + r * rstride + t  (t = thread); rounds [0, nr) are complete (all T
     // threads in range), then `extra` more int4 (< T) follow at round nr for the first `extra` threads.
     int64_t first, rstride, nr, extra, lead = 0;
+    // Work-stealing tail (IL plan, `dyn_ctr` given; opt-in A/B, `hist.dyn_rounds`): the last `dyn_rounds` rounds of units are not
+    // dealt out but CLAIMED, P units (one batch) at a time, from a global counter -- a CTA that runs ahead takes more of them.  It
+    // does what it should -- the CTAs end 2.0 us apart instead of 3.6 -- and still LOSES: the claimed batches stream slower than
+    // the static loop (two barriers per batch, no unrolling across batches): 2^27 elements, fused, one rank: 78.7 us without,
+    // 80.0 / 80.8 / 83.7 us with 4 / 16 / 32 rounds (profiles/r05_hist_probe3.txt).  dyn_first = first unit of that region.
+    int64_t dyn_first = 0, dyn_nu = 0, dyn_extra = 0;
+    uint32_t dyn_chunks = 0;
     if (IL) {
         lead = min((int64_t)((32 - (((uintptr_t)in4 >> 4) & 31)) & 31), n4);                 // int4 in front of the first 512-byte line
-        const int64_t m4 = n4 - lead, nu = m4 / T;                                            // whole units behind it
+        const int64_t m4 = n4 - lead;
+        int64_t nu = m4 / T;                                                                  // whole units behind it
         first = lead + (int64_t)blockIdx.x * T;
         rstride = (int64_t)gridDim.x * T;
-        nr = nu > blockIdx.x ? (nu - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-        extra = (int64_t)(nu % gridDim.x) == (int64_t)blockIdx.x ? m4 - nu * T : 0;           // the partial last unit has one owner
+        if (dyn_ctr != nullptr) {
+            int64_t s_rounds = nu / gridDim.x - dyn_rounds;                                   // rounds every CTA gets statically
+            if (s_rounds < 0) s_rounds = 0;
+            dyn_first = s_rounds * gridDim.x;
+            dyn_nu = nu;
+            dyn_extra = m4 - nu * T;
+            dyn_chunks = (uint32_t)((nu - dyn_first + (dyn_extra > 0 ? 1 : 0) + P - 1) / P);
+            nr = s_rounds;
+            extra = 0;
+        } else {
+            nr = nu > blockIdx.x ? (nu - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+            extra = (int64_t)(nu % gridDim.x) == (int64_t)blockIdx.x ? m4 - nu * T : 0;       // the partial last unit has one owner
+        }
     } else {
         const int64_t u0 = slice_cut(in4, n4, blockIdx.x), u1 = slice_cut(in4, n4, blockIdx.x + 1);
         first = u0;
@@ -246,6 +266,41 @@ __device__ __noinline__ void hist_count_phase(uint32_t *sh, uint32_t nbins, cons
         cur[p] = (p < left || (p == left && t < extra)) ? ldg_stream_i4(ptr + p * rstride) : make_int4(0, 0, 0, 0);   // 0 is outside 1..nbins
 #pragma unroll
     for (int p = 0; p < P; ++p) bump4(cur[p]);
+    if (IL && dyn_ctr != nullptr) {
+        // claimed batches: thread 0 keeps two claims ahead (the atomic's round trip runs under a batch of counting); the claims
+        // travel through two spare words behind the private copies
+        uint32_t *idx = sh + nb1 * (uint32_t)copies + 1;
+        if (t == 0) {
+            idx[0] = atomicAdd(dyn_ctr, 1u);
+            idx[1] = atomicAdd(dyn_ctr, 1u);
+        }
+        __syncthreads();
+        const int4 *dbase = in4 + lead + dyn_first * T + t;
+        auto load_chunk = [&](uint32_t c, int4 *buf) {
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                const int64_t u = dyn_first + (int64_t)c * P + p;
+                const bool valid = u < dyn_nu || (u == dyn_nu && t < dyn_extra);
+                buf[p] = valid ? ldg_stream_i4(dbase + ((int64_t)c * P + p) * T) : make_int4(0, 0, 0, 0);
+            }
+        };
+        uint32_t c = idx[0];
+        if (c < dyn_chunks) load_chunk(c, cur);
+        for (int k = 0; c < dyn_chunks; ++k) {
+            const uint32_t cn = idx[(k + 1) & 1];
+            if (cn < dyn_chunks) load_chunk(cn, nxt);
+            uint32_t fresh = 0;
+            if (t == 0) fresh = atomicAdd(dyn_ctr, 1u);
+#pragma unroll
+            for (int p = 0; p < P; ++p) bump4(cur[p]);
+#pragma unroll
+            for (int p = 0; p < P; ++p) cur[p] = nxt[p];
+            __syncthreads();                 // every thread has read both claims
+            if (t == 0) idx[k & 1] = fresh;
+            __syncthreads();
+            c = cn;
+        }
+    }
     if (blockIdx.x == 0 && t < ntail) bump(tail[t]);
     if (blockIdx.x == 0 && t >= 32 && t < 32 + nhead) bump(head[t - 32]);
     __syncthreads();
@@ -489,7 +544,10 @@ __device__ __noinline__ void fused_exchange(uint32_t *sh, uint32_t nbins, int co
             sh[b] += acc;                                                                 // this GPU's total for bin b
         }
         __syncthreads();
-        if (t == 0) peer.stamps[1] = globaltimer_ns();                                   // every CTA's counts merged
+        if (t == 0) {
+            peer.stamps[1] = globaltimer_ns();                                           // every CTA's counts merged
+            peer.counter[1] = 0;                                                         // the work-stealing claims of this launch
+        }
     } else {
         // ---- publish + ticket (any nbins up to the shared-memory limit) ----
         // Every CTA adds its folded counts to the device-local partial (red.global), fences, and only THEN draws its ticket: the
@@ -514,6 +572,7 @@ __device__ __noinline__ void fused_exchange(uint32_t *sh, uint32_t nbins, int co
         if (t == 0) {
             peer.stamps[1] = globaltimer_ns();                                           // local counting merged (last ticket drawn)
             peer.counter[0] = 0;                                                         // ready for the next launch
+            peer.counter[1] = 0;                                                         // (the work-stealing claims too)
             peer.stamps[6] = peer.stamps[1];
         }
         for (uint32_t b = t; b < nbins; b += T) {
@@ -596,8 +655,10 @@ __global__ void __launch_bounds__(T) hist_allreduce_kernel(int32_t *__restrict__
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint32_t *sh = reinterpret_cast<uint32_t *>(smem_raw);
     if (blockIdx.x == 0 && threadIdx.x == 0) peer.stamps[5] = globaltimer_ns();          // first CTA resident
+    // `interleave`: bit 0 = unit plan, bits 1-7 = rounds of the work-stealing tail (0: none), bits 8.. = rounds to prefetch
     if (interleave & 1)
-        hist_count_phase<T, P, true>(sh, nbins, in4, n4, tail, ntail, copies, head, nhead, interleave >> 8);
+        hist_count_phase<T, P, true>(sh, nbins, in4, n4, tail, ntail, copies, head, nhead, interleave >> 8,
+                                     ((interleave >> 1) & 127) ? peer.counter + 1 : nullptr, (interleave >> 1) & 127);
     else
         hist_count_phase<T, P, false>(sh, nbins, in4, n4, tail, ntail, copies, head, nhead, interleave >> 8);
     fused_exchange<T>(sh, nbins, copies, bins, peer);
@@ -917,7 +978,8 @@ int histogram_allreduce_launch(P2P *h, int32_t *bins, int64_t nbins, const int32
     if (smem > 48 * 1024)
         B200_CUDA(cudaFuncSetAttribute(hist_allreduce_kernel<T, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     B200_TRY(launch_pdl(hist_allreduce_kernel<T, P>, grid, T, smem, st, bins, (uint32_t)nbins, reinterpret_cast<const int4 *>(body), n4,
-                        body + n4 * 4, tail_n, copies, input, (int)head, pick_interleave(n4), peer));
+                        body + n4 * 4, tail_n, copies, input, (int)head,
+                        pick_interleave(n4) | ((tune_get("hist.dyn_rounds", 0) & 127) << 1), peer));
     B200_CHECK_LAUNCH("hist_allreduce_kernel");
     h->epoch++;
     return B200_OK;

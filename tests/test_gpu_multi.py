@@ -50,16 +50,17 @@ def test_exchange_single_rank():
     comm.destroy()
 
 
-@pytest.mark.parametrize("ll", [1, 0])
+@pytest.mark.parametrize("ll,dyn", [(0, 16), (0, 0), (0, 1), (0, 127), (1, 16)])
 @pytest.mark.parametrize("n,nbins,offset", [(100003, 256, 0), (17, 256, 0), (0, 256, 0), (5 * (1 << 20) + 3, 1000, 0), (999999, 64, 1),
                                             (1 << 22, 256, 3), (2, 256, 2), (3 * (1 << 20), 1, 0), (3 * (1 << 20), 1024, 0), (1 << 21, 1025, 0),
-                                            (1 << 21, 5000, 1), (1 << 22, 7, 0)])
-def test_fused_histogram_allreduce_single_rank(orc, n, nbins, offset, ll):
+                                            (1 << 21, 5000, 1), (1 << 22, 7, 0), ((1 << 25) + 12345, 256, 1), (148 * 4096 * 20 + 5, 256, 0)])
+def test_fused_histogram_allreduce_single_rank(orc, n, nbins, offset, ll, dyn):
     """b200_histogram_i32_allreduce with the rank as its only peer == the oracle; accumulates like the reference's +=; several
     steps on one PeerGroup (slot parity / tags); unaligned inputs (offset elements off a 16-byte boundary); both intra-GPU merges
     (hist.fused_ll = 0, the default: ticket + partial; 1: per-CTA {count, tag} rows polled by CTA 0, for nbins <= 1024)."""
     be = KA.B200Backend()
     _lib.call("b200_tune_set", b"hist.fused_ll", ll)
+    _lib.call("b200_tune_set", b"hist.dyn_rounds", dyn)     # rounds of the work-stealing tail (0: every unit dealt out statically)
     peers = mg.PeerGroup(1, 0, _self_gather)
     try:
         for step in range(3):
@@ -77,6 +78,7 @@ def test_fused_histogram_allreduce_single_rank(orc, n, nbins, offset, ll):
         assert t["all_summed"] >= t["slots_sent"] >= t["counts_merged"]
     finally:
         _lib.call("b200_tune_set", b"hist.fused_ll", 0)
+        _lib.call("b200_tune_set", b"hist.dyn_rounds", 0)
         peers.free()
 
 

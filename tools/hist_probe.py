@@ -41,10 +41,11 @@ for G in (1, 8):
     ne = (1 << 30) // G
     d_in = KA.rand_bins_(KA.allocate(be, np.int32, ne), 1236, 256)
     bins = KA.zeros(be, np.int32, 256)
-    for inter, ll, npf in ((0, 0, 8), (1, 0, 0), (1, 0, 4), (1, 0, 8), (1, 0, 16), (1, 0, 32)):
+    for inter, ll, npf, dyn in ((0, 0, 16, 0), (1, 0, 0, 0), (1, 0, 16, 0), (1, 0, 16, 4), (1, 0, 16, 8), (1, 0, 16, 16), (1, 0, 16, 32), (1, 0, 16, 64)):
         tune("hist.interleave", inter)
         tune("hist.fused_ll", ll)
         tune("hist.l2_prefetch_rounds", npf)
+        tune("hist.dyn_rounds", dyn)
         us_l = timed(lambda: EX.histogram_(bins, d_in))
         us_f = timed(lambda: peers.histogram_allreduce(bins, d_in))
         tl = []
@@ -54,8 +55,7 @@ for G in (1, 8):
             tl.append(peers.timeline())
         spread = [x["slowest_cta_done"] for x in tl]
         tail = [x["all_summed"] for x in tl]
-        print("   timelines:", tl)
-        print(f"histogram 2^30/{G} interleave={inter} fused_ll={ll} l2_prefetch_rounds={npf}: local-only {us_l:8.2f} us ({4 * ne / us_l / 1e3:6.0f} GB/s), fused 1 rank {us_f:8.2f} us; "
+        print(f"histogram 2^30/{G} interleave={inter} fused_ll={ll} l2_prefetch_rounds={npf} dyn_rounds={dyn}: local-only {us_l:8.2f} us ({4 * ne / us_l / 1e3:6.0f} GB/s), fused 1 rank {us_f:8.2f} us; "
               f"stream time at 7.25 TB/s {4 * ne / 7.25e12 * 1e6:7.2f} us; fastest->slowest CTA {spread} ns, slowest CTA -> summed {tail} ns", flush=True)
     tune("hist.interleave", -1)
     for stages in (2, 4, 6):
@@ -63,10 +63,10 @@ for G in (1, 8):
         tune("hist.tma_stages", stages)
         us_t = timed(lambda: EX.histogram_(bins, d_in))
         tune("hist.impl", 1)
-        print("   timelines:", tl)
         print(f"histogram 2^30/{G} TMA feed (hist.impl=2, {stages} x 16 KiB ring): local-only {us_t:8.2f} us ({4 * ne / us_t / 1e3:6.0f} GB/s)", flush=True)
     del d_in
 tune("hist.interleave", -1)
 tune("hist.fused_ll", 0)
 tune("hist.l2_prefetch_rounds", 16)
+tune("hist.dyn_rounds", 0)
 peers.free()
