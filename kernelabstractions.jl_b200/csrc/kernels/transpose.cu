@@ -55,11 +55,12 @@ __global__ void __launch_bounds__(256) transpose64_f32_kernel(float *__restrict_
         tj = blockIdx.x / tiles_i;
     }
     const int64_t i0 = (int64_t)ti * 64, j0 = (int64_t)tj * 64;
-    // `transpose.l2_prefetch` (off: measured slower, 336.5 vs 327.8 us at 16384^2 and 45.2 vs 44.2 us on the 8-GPU slab,
-    // profiles/r05_slab_probe.txt): every CTA pulls its tile (64 columns x 256 bytes) into L2 before the dependency wait.  With
-    // 65536 short-lived CTAs the extra instruction and the doubled L2 fills cost more than the DRAM ramp of the first wave saves
-    // (the persistent copy and histogram kernels, which prefetch once per CTA, do gain).
-    if (prefetch && t < 128) {
+    // The first `prefetch` CTAs -- the ones that become resident while the previous kernel of the stream drains -- pull their tile
+    // (64 columns x 256 bytes) into L2 before the dependency wait; a prefetch has no architectural effect (L2 is the point of
+    // coherence).  Measured (profiles/r05_slab_probe.txt, leading 16 x 148 CTAs): 44.3 -> 43.0 us on the 8-GPU slab (8192 tiles),
+    // 85.7 -> 84.7 on the 4-GPU slab, but 327.8 -> 335.5 us at 16384^2 (and 338 when every CTA does it): a long launch keeps HBM
+    // busy to its very end, so the prefetches only compete.  Hence: launches of <= 16384 tiles only (`transpose.l2_prefetch`).
+    if (blockIdx.x < (unsigned)prefetch && t < 128) {   // `prefetch` = number of leading CTAs that do it (0: none)
         const float *line = b + j0 + (i0 + (t >> 1)) * ldb + (t & 1) * 32;
         asm volatile("prefetch.global.L2 [%0];" ::"l"(line));
     }
@@ -346,7 +347,10 @@ int transpose_launch(void *a, const void *b, int64_t m, int64_t n, int64_t lda, 
         attr[0].val.programmaticStreamSerializationAllowed = tune_get("transpose.pdl", 1) != 0;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        B200_CUDA(cudaLaunchKernelEx(&cfg, kern, (float *)a, (const float *)b, tiles_i, tiles_j, lda, ldb, tune_get("transpose.l2_prefetch", 0)));
+        // leading CTAs that pull their tile into L2 before the dependency wait: only worth it for SHORT launches (see the kernel)
+        int pf = tune_get("transpose.l2_prefetch", -1);
+        if (pf < 0) pf = grid <= 16384u ? 16 : 0;
+        B200_CUDA(cudaLaunchKernelEx(&cfg, kern, (float *)a, (const float *)b, tiles_i, tiles_j, lda, ldb, pf * sm_count()));
         B200_CHECK_LAUNCH("transpose64_f32_kernel");
         return B200_OK;
     }

@@ -54,7 +54,7 @@ for G in (1, 2, 4, 8):
     dB = KA.rand_uniform_(KA.allocate(be, np.float32, rb, n), 1235)
     dA = KA.zeros(be, np.float32, n, rb)
     ideal = 2 * 4 * n * rb / 6545.9e9 * 1e6
-    for pdl, pf in ((0, 0), (1, 0), (1, 1)):
+    for pdl, pf in ((1, 0), (1, 4), (1, 8), (1, 16), (1, 100000)):
         tune("transpose.pdl", pdl)
         tune("transpose.l2_prefetch", pf)
         us = timed(lambda: EX.naive_transpose_(dA, dB))
