@@ -607,6 +607,34 @@ def run_suite(KA, _lib, EX, mg, orc, be, rank, world, dist, timed, graphed, all_
     except Exception as ex:
         out["copy_2^26_f32"] = {"error": str(ex)[:300]}
 
+    # ---- the N-d index arithmetic itself: naive_transpose_kernel! 8192^2 through its LITERAL twin (one work-item per thread,
+    # ---- `i, j = @index(Global, NTuple)`, reads strided by a column as in the reference) under the three lowerings ----
+    if world == 1:
+        try:
+            nt = 8192
+            tb = KA.rand_uniform_(KA.allocate(be, np.float32, nt, nt), 99)
+            ta = KA.zeros(be, np.float32, nt, nt)
+            res = {}
+            for name, mode in (("native_grid", 0), ("multiply_high", 1), ("div64_reference", 2)):
+                _lib.call("b200_tune_set", b"registry.force_twins", 1)
+                _lib.call("b200_tune_set", b"registry.ka_mode", mode)
+                try:
+                    ms_t, _ = timed(lambda: EX.naive_transpose_(ta, tb), max(5, steps // 4), 3)
+                finally:
+                    _lib.call("b200_tune_set", b"registry.force_twins", 0)
+                    _lib.call("b200_tune_set", b"registry.ka_mode", -1)
+                res[name] = {"value": 2.0 * 4 * nt * nt / (ms_t * 1e-3) / 1e9, "ms_per_step": ms_t}
+            ok_t = bool(np.array_equal(KA.Array(ta)[:64, :64], KA.Array(tb)[:64, :64].T))
+            out["naive_transpose_8192_literal_twin"] = {
+                "value": res["native_grid"]["value"], "unit": "GB/s", "ms_per_step": res["native_grid"]["ms_per_step"], "scaling": "strong",
+                "lowerings": res, "result_checked": ok_t,
+                "note": "registry.force_twins=1: the reference's access pattern (32-byte sector per 4-byte element read), so far from the "
+                        "tiled kernel by construction; the three entries differ only in how (i, j) is recovered per work-item",
+                "roofline": {"bound": "hbm", "achieved": res["native_grid"]["value"], "peak": peaks["hbm"], "frac": res["native_grid"]["value"] / peaks["hbm"]}}
+            del ta, tb
+        except Exception as ex:
+            out["naive_transpose_8192_literal_twin"] = {"error": str(ex)[:300]}
+
     # ---- SAXPY 2^26 F32 (benchmark/benchmarks.jl:29-70 kernel at a size beyond L2): 12 bytes per element ----
     try:
         n = N_COPY
