@@ -330,7 +330,13 @@ KA.functional(::B200Backend) = begin
     n = Ref{Int32}(0)
     ccall((:b200_device_count, libb200ka), Int32, (Ptr{Int32},), n) == B200_OK && n[] > 0
 end
-KA.pagelock!(::B200Backend, x::Array) = (@b200 b200_host_register (Ptr{Cvoid}, Csize_t) pointer(x) sizeof(x); nothing)
+# The registration is dropped together with the array: a stale one would poison the address range for whatever the allocator
+# puts there next (a later copy from a buffer lying PARTLY inside it fails with "invalid argument").
+function KA.pagelock!(::B200Backend, x::Array)
+    GC.@preserve x @b200 b200_host_register (Ptr{Cvoid}, Csize_t) pointer(x) sizeof(x)
+    finalizer(a -> ccall((:b200_host_unregister, libb200ka), Int32, (Ptr{Cvoid},), pointer(a)), x)
+    return nothing
+end
 KA.get_backend(::B200Array) = B200Backend()
 KA.supports_float64(::B200Backend) = true
 KA.supports_atomics(::B200Backend) = true
