@@ -414,3 +414,32 @@ def test_runtime_state_is_task_local():
     # async host copies keep both arrays alive for the enqueue
     for head in [r"function KA\.copyto!\(::B200Backend, A::B200Array\{T\}, B::Array\{T\}\)", r"function KA\.copyto!\(::B200Backend, A::Array\{T\}, B::B200Array\{T\}\)"]:
         assert "GC.@preserve A B" in method_bodies(src, head)[0]
+
+
+# ------------------------------------------------------------------------------------------------------------
+# 7. shallow syntax check: block openers and `end`s balance, brackets balance (nothing here can parse Julia properly, but an
+#    unbalanced edit is the most likely slip in a file that is never executed)
+# ------------------------------------------------------------------------------------------------------------
+def test_julia_blocks_and_brackets_balance():
+    src = strip_jl_comments(open(JL).read())
+    src = re.sub(r'"(?:\\.|[^"\\])*"', '""', src)                      # string literals out of the way
+    depth_paren = depth_brack = depth_brace = 0
+    for ch in src:
+        depth_paren += ch == "("
+        depth_paren -= ch == ")"
+        depth_brack += ch == "["
+        depth_brack -= ch == "]"
+        depth_brace += ch == "{"
+        depth_brace -= ch == "}"
+        assert depth_paren >= 0 and depth_brack >= 0 and depth_brace >= 0
+    assert (depth_paren, depth_brack, depth_brace) == (0, 0, 0)
+    no_index = src
+    while True:                                                          # `a[end]` is not a block end, a comprehension's `for` no opener
+        nxt = re.sub(r"\[[^\[\]]*\]", "<>", no_index)
+        if nxt == no_index:
+            break
+        no_index = nxt
+    openers = len(re.findall(r"(?<![\w.:@])(?:function|if|for|while|let|begin|try|quote|struct|macro|module|do)\b(?!\s*=)", no_index))
+    openers -= len(re.findall(r"\bmutable\s+struct\b", no_index)) * 0  # `mutable struct` counts once (matched at `struct`)
+    ends = len(re.findall(r"(?<![\w.:])end\b", no_index))
+    assert openers == ends, f"{openers} block openers vs {ends} `end`s"
