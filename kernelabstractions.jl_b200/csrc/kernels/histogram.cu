@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(T, 1) hist256_bytes_kernel(int32_t *__restrict
 // The loop is issue-sensitive (16 shared atomics + their range tests per 4 loads keep the schedulers ~2/3 busy; a variant with
 // 25 % more integer instructions per batch ran 20 % slower, r05), so the main loop carries NO bounds predicates: `nfb` batches
 // of P loads per thread are complete by construction and ONE predicated batch follows for whatever is left.
-template <int T, int P, bool IL>
+template <int T, int P, bool IL, bool I64 = false>
 __device__ __noinline__ void hist_count_phase(uint32_t *sh, uint32_t nbins, const int4 *__restrict__ in4, int64_t n4,
                                               const int32_t *__restrict__ tail, int ntail, int copies,
                                               const int32_t *__restrict__ head, int nhead, int npf,
@@ -187,11 +187,21 @@ __device__ __noinline__ void hist_count_phase(uint32_t *sh, uint32_t nbins, cons
     // the sink counter instead of branched around: (unsigned)(v - 1) >= nbins -> nbins.  One IADD + one unsigned MIN per element
     // replace compare + branch + reconvergence in a loop whose limit is instruction issue (see below); the sink is never read.
     auto bump = [&](int v) { atomicAdd(mine + min((uint32_t)v - 1u, nbins), 1u); };
+    // Int64 values (I64: two per int4, `lo` / `hi` halves): the same clamp in 64 bits
+    auto bump64 = [&](int lo, int hi) {
+        const unsigned long long b = (((unsigned long long)(uint32_t)hi << 32) | (uint32_t)lo) - 1ull;
+        atomicAdd(mine + (uint32_t)min(b, (unsigned long long)nbins), 1u);
+    };
     auto bump4 = [&](const int4 &v) {
-        bump(v.x);
-        bump(v.y);
-        bump(v.z);
-        bump(v.w);
+        if (I64) {
+            bump64(v.x, v.y);
+            bump64(v.z, v.w);
+        } else {
+            bump(v.x);
+            bump(v.y);
+            bump(v.z);
+            bump(v.w);
+        }
     };
     // Round r of this CTA loads int4 number  first + r * rstride + t  (t = thread); rounds [0, nr) are complete (all T
     // threads in range), then `extra` more int4 (< T) follow at round nr for the first `extra` threads.
@@ -301,8 +311,15 @@ __device__ __noinline__ void hist_count_phase(uint32_t *sh, uint32_t nbins, cons
             c = cn;
         }
     }
-    if (blockIdx.x == 0 && t < ntail) bump(tail[t]);
-    if (blockIdx.x == 0 && t >= 32 && t < 32 + nhead) bump(head[t - 32]);
+    if (I64) {
+        if (blockIdx.x == 0 && t < ntail) {
+            const unsigned long long v = reinterpret_cast<const unsigned long long *>(tail)[t];
+            bump64((int)(uint32_t)v, (int)(uint32_t)(v >> 32));
+        }
+    } else {
+        if (blockIdx.x == 0 && t < ntail) bump(tail[t]);
+        if (blockIdx.x == 0 && t >= 32 && t < 32 + nhead) bump(head[t - 32]);
+    }
     __syncthreads();
 }
 
@@ -836,43 +853,18 @@ int histogram_launch(int32_t *bins, int64_t nbins, const int32_t *input, int64_t
 template <int T, int P>
 __global__ void __launch_bounds__(T) hist64_atomic_kernel(long long *__restrict__ bins, uint32_t nbins,
                                                           const int4 *__restrict__ in4, int64_t n4,
-                                                          const long long *__restrict__ tail, int ntail, int copies) {
+                                                          const long long *__restrict__ tail, int ntail, int copies, int plan) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint32_t *sh = reinterpret_cast<uint32_t *>(smem_raw);
-    const int t = threadIdx.x, warp = t >> 5;
-    for (uint32_t i = t; i < nbins * (uint32_t)copies; i += T) sh[i] = 0;
-    __syncthreads();
-    uint32_t *mine = sh + (uint32_t)(warp % copies) * nbins;
-    auto bump = [&](int lo, int hi) {   // value = hi:lo, 1-based bin
-        const unsigned long long b = (((unsigned long long)(uint32_t)hi << 32) | (uint32_t)lo) - 1ull;
-        if (b < (unsigned long long)nbins) atomicAdd(mine + (uint32_t)b, 1u);
-    };
-    const int64_t u0 = slice_cut(in4, n4, blockIdx.x), u1 = slice_cut(in4, n4, blockIdx.x + 1);
-    const int64_t nbatch = (u1 - u0 + (int64_t)P * T - 1) / ((int64_t)P * T);
-    int4 cur[P], nxt[P];
-    auto load_batch = [&](int64_t k, int4 *buf) {
-#pragma unroll
-        for (int p = 0; p < P; ++p) {
-            int64_t u = u0 + (k * P + p) * (int64_t)T + t;
-            buf[p] = u < u1 ? ldg_stream_i4(in4 + u) : make_int4(0, 0, 0, 0);   // 0 is outside 1..nbins
-        }
-    };
-    if (nbatch > 0) load_batch(0, cur);
-    for (int64_t k = 0; k < nbatch; ++k) {
-        if (k + 1 < nbatch) load_batch(k + 1, nxt);
-#pragma unroll
-        for (int p = 0; p < P; ++p) {
-            bump(cur[p].x, cur[p].y);
-            bump(cur[p].z, cur[p].w);
-        }
-#pragma unroll
-        for (int p = 0; p < P; ++p) cur[p] = nxt[p];
-    }
-    if (blockIdx.x == 0 && t < ntail) bump((int)(uint32_t)tail[t], (int)(uint32_t)((unsigned long long)tail[t] >> 32));
-    __syncthreads();
-    for (uint32_t b = t; b < nbins; b += T) {
-        uint32_t sum = 0;
-        for (int c = 0; c < copies; ++c) sum += sh[(uint32_t)c * nbins + b];
+    // the counting phase of the Int32 kernel with 64-bit values (two per 128-bit load): branch-free clamp into the sink counter,
+    // unpredicated main loop, unit plan by size, L2 prefetch under the dependency wait (`plan` as in hist_atomic_kernel)
+    if (plan & 1)
+        hist_count_phase<T, P, true, true>(sh, nbins, in4, n4, reinterpret_cast<const int32_t *>(tail), ntail, copies, nullptr, 0, plan >> 8);
+    else
+        hist_count_phase<T, P, false, true>(sh, nbins, in4, n4, reinterpret_cast<const int32_t *>(tail), ntail, copies, nullptr, 0, plan >> 8);
+    fold_copies<T>(sh, nbins, copies);
+    for (uint32_t b = threadIdx.x; b < nbins; b += T) {
+        const uint32_t sum = sh[b];
         if (sum) atomicAdd(reinterpret_cast<unsigned long long *>(bins) + b, (unsigned long long)sum);
     }
 }
@@ -901,17 +893,17 @@ int histogram64_launch(long long *bins, int64_t nbins, const long long *input, i
     const long long *body = input + head;
     const int64_t n4 = (n - head) / 2, tail_n = (n - head) - 2 * n4;
     constexpr int T = 1024, P = 4;
-    int copies = (int)((48 * 1024) / (nbins * 4));
+    int copies = (int)((48 * 1024) / ((nbins + 1) * 4));
     if (copies > T / 32) copies = T / 32;
     if (copies < 1) copies = 1;
     int grid = sms;
     if ((int64_t)grid > (n4 + T - 1) / T) grid = (int)((n4 + T - 1) / T);
     if (grid < 1) grid = 1;
-    const size_t smem = (size_t)nbins * copies * 4;
+    const size_t smem = (size_t)(nbins + 1) * copies * 4;
     if (smem > 48 * 1024)
         B200_CUDA(cudaFuncSetAttribute(hist64_atomic_kernel<T, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    hist64_atomic_kernel<T, P><<<grid, T, smem, st>>>(bins, (uint32_t)nbins, reinterpret_cast<const int4 *>(body), n4, body + 2 * n4,
-                                                      (int)tail_n, copies);
+    B200_TRY(launch_pdl(hist64_atomic_kernel<T, P>, grid, T, smem, st, bins, (uint32_t)nbins, reinterpret_cast<const int4 *>(body), n4,
+                        body + 2 * n4, (int)tail_n, copies, pick_interleave(n4)));
     B200_CHECK_LAUNCH("hist64_atomic_kernel");
     return B200_OK;
 }

@@ -538,8 +538,11 @@ def test_matmul_bf16_tensor_core():
     assert r.returncode == 0, "tensor-core GEMM check failed:\n" + r.stdout[-2000:] + r.stderr[-2000:]
 
 
-@pytest.mark.parametrize("n,nbins", [(1000, 128), (1, 1), (2, 7), (100003, 256), (1 << 20, 1000), (50000, 14336), (50000, 20000), ((1 << 22) + 1, 256)])
-def test_histogram_int64_matches_int32_oracle(orc, n, nbins):
+@pytest.mark.parametrize("plan", [-1, 0, 1])
+@pytest.mark.parametrize("n,nbins", [(1000, 128), (1, 1), (2, 7), (100003, 256), (1 << 20, 1000), (50000, 14336), (50000, 20000), ((1 << 22) + 1, 256),
+                                     (148 * 2048 * 3 + 7, 256)])
+def test_histogram_int64_matches_int32_oracle(orc, n, nbins, plan):
+    tune(hist__interleave=plan)      # unit plan of the counting phase shared with the Int32 kernel: by size / slices / interleaved
     # histogram_kernel! is generic in the element type (examples/histogram.jl:18); Julia's `rand(1:128, n)` is Int64.
     # The Int64 path must give the counts of the pinned Int32 oracle on the same values, incl. out-of-range ones.
     inp32 = orc.gen_bins_i32(n, 99, nbins + 3) - 1          # values 0 .. nbins+2: 0 and > nbins are ignored
