@@ -462,9 +462,8 @@ __global__ void __launch_bounds__(T) hist_tma_kernel(int32_t *__restrict__ bins,
 // The poll used to walk the 8 sources of a bin one after the other, every step a dependent ~0.7 us system-scope load: ~5 us
 // for 8 ranks.  Now the (bin, source) pairs are spread over all threads of the CTA -- 8 consecutive lanes hold the 8 sources of
 // one bin, every thread has all its slot loads in flight at once, and the sources are summed with three shuffles -- so the
-// poll costs one round trip (plus re-polls of slots that have not landed).  The last CTA also skips the round trip of its own
-// counts through the partial (they are still in its shared memory) and the ticket is taken with one acq_rel atomic instead of
-// atomic + two fences.
+// poll costs one round trip (plus re-polls of slots that have not landed); the value the sum is added to (`bins[b] +=`) is
+// fetched under the poll, and the fold of the private copies is four-way parallel.  Timeline of a step: DESIGN.md section 6.
 struct HistPeer {
     int world;
     int rank;
@@ -912,7 +911,7 @@ int histogram64_launch(long long *bins, int64_t nbins, const long long *input, i
 // symmetric peer buffers (cudaIpc) for the fused histogram + all-reduce
 // ---------------------------------------------------------------------------------------------
 constexpr uint32_t kP2PMaxBins = 14336;
-constexpr size_t kP2PCounterOff = 0 /* ticket, published */, kP2PStampsOff = 8 /* 8 x u64 */, kP2PPartialOff = 128;
+constexpr size_t kP2PCounterOff = 0 /* [0] ticket, [1] work-stealing claims */, kP2PStampsOff = 8 /* 8 x u64 */, kP2PPartialOff = 128;
 constexpr size_t kP2PSlotsOff = (kP2PPartialOff + (size_t)kP2PMaxBins * 4 + 255) / 256 * 256;
 constexpr size_t kP2PCtaSlotsOff = kP2PSlotsOff + 2 * 8 * (size_t)kP2PMaxBins * 8;
 constexpr size_t kP2PBytes = kP2PCtaSlotsOff + (size_t)kLLMaxCtas * kLLMaxBins * 8;
