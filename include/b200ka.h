@@ -323,6 +323,8 @@ b200_status b200_sendrecv(void *comm, const void *sendbuf, int32_t dst_rank, voi
  * straight into the destination slabs, then b200_sym_barrier.  N0, N1 multiples of 64 x world; elsize 4 or 8.
  * Back-to-back calls are safe without a barrier in between: every rank announces at the start of its call that its slab
  * may be overwritten (its stream has finished whatever read the previous result) and stores into a slab wait for that.
+ * Every wait for a peer inside these kernels is bounded (`a2a.timeout_ms` tuning knob, default 10 s): a rank that never makes
+ * the matching call makes its peers' NEXT call on the buffer fail with B200_ERR_CUDA instead of hanging their GPUs.
  * (the all-to-all the reference-style formulation would need, examples/mpi.jl:24-39 being its only exchange.) */
 b200_status b200_sym_alloc(void **handle, size_t bytes);
 b200_status b200_sym_export(void *handle, void *ipc64);

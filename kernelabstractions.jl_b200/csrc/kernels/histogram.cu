@@ -1045,9 +1045,13 @@ extern "C" b200_status b200_p2p_connect_ptrs(void *handle, int32_t world, int32_
         void *buf = ((P2P *)peer_handles[r])->local;
         cudaPointerAttributes at;
         B200_CUDA(cudaPointerGetAttributes(&at, buf));
-        cudaError_t e = cudaDeviceEnablePeerAccess(at.device, 0);
-        if (e == cudaErrorPeerAccessAlreadyEnabled) (void)cudaGetLastError();
-        else B200_CUDA(e);
+        int cur = -1;
+        B200_CUDA(cudaGetDevice(&cur));
+        if (at.device != cur) {   // (a "peer" on the same GPU needs no enabling: used by the single-GPU tests)
+            cudaError_t e = cudaDeviceEnablePeerAccess(at.device, 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) (void)cudaGetLastError();
+            else B200_CUDA(e);
+        }
         h->peer[r] = buf;
     }
     h->world = world;

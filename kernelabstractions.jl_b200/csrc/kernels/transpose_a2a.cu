@@ -35,7 +35,40 @@ struct Sym {
     unsigned long long epoch = 0;
     unsigned long long a2a_calls = 0;   // b200_transpose_alltoall calls so far (the value of the "ready" flags)
     bool ipc = true;                    // peers mapped with cudaIpcOpenMemHandle (b200_sym_connect) or plain pointers (..._ptrs)
+    uint32_t *error_host = nullptr;     // pinned, mapped: set by a kernel whose wait for a peer timed out
+    uint32_t *error_dev = nullptr;
 };
+
+// Every wait for a peer inside a kernel is BOUNDED (`a2a.timeout_ms`, default 10 s): a rank that never makes the matching call
+// (failed validation, crashed process) must turn into an error on its peers' next call, not into a GPU that spins for ever.
+struct A2ACtl {
+    unsigned long long timeout_ns;      // 0 = wait for ever
+    uint32_t *error;                    // host-visible flag
+};
+__device__ __forceinline__ unsigned long long a2a_now_ns() {
+    unsigned long long v;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v));
+    return v;
+}
+// spin until *p >= want; false (and the error flag raised) when the budget runs out
+__device__ __forceinline__ bool a2a_spin_until(const unsigned long long *p, unsigned long long want, const A2ACtl &ctl) {
+    unsigned long long v;
+    unsigned spins = 0;
+    unsigned long long t0 = 0;
+    while (true) {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+        if (v >= want) return true;
+        if (ctl.timeout_ns && (++spins & 1023u) == 0) {
+            const unsigned long long now = a2a_now_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > ctl.timeout_ns) {
+                *reinterpret_cast<volatile uint32_t *>(ctl.error) = 1u;
+                __threadfence_system();
+                return false;
+            }
+        }
+    }
+}
 
 struct A2APeers {
     void *dst[kSymMaxRanks];
@@ -63,14 +96,8 @@ __device__ __forceinline__ void a2a_post_ready(const A2APeers &flags, int world,
         asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(theirs), "l"(call) : "memory");
     }
 }
-__device__ __forceinline__ void a2a_wait_ready(const A2APeers &flags, int rank, int h, unsigned long long call) {
-    if (threadIdx.x == 0) {
-        const unsigned long long *mine = reinterpret_cast<const unsigned long long *>(flags.dst[rank]) + 8 + h;
-        unsigned long long v;
-        do {
-            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
-        } while (v < call);
-    }
+__device__ __forceinline__ void a2a_wait_ready(const A2APeers &flags, int rank, int h, unsigned long long call, const A2ACtl &ctl) {
+    if (threadIdx.x == 0) a2a_spin_until(reinterpret_cast<const unsigned long long *>(flags.dst[rank]) + 8 + h, call, ctl);
 }
 
 // Rank g's data kernel.  src block for destination h: b_local + h * rows_blk (rows_blk = N0/G rows of every local column);
@@ -79,7 +106,7 @@ __device__ __forceinline__ void a2a_wait_ready(const A2APeers &flags, int rank, 
 template <typename T>
 __global__ void __launch_bounds__(256) transpose_a2a_kernel(A2APeers peers, const T *__restrict__ b_local, int64_t ld_src, int64_t ld_dst,
                                                             int64_t rows_blk, int64_t row_off, int tiles_i, int tiles_j, int first_dst, int order, int world,
-                                                            A2APeers flags, unsigned long long call) {
+                                                            A2APeers flags, unsigned long long call, A2ACtl ctl) {
     constexpr int V = 16 / sizeof(T), CH = 64 / V, PASSES = CH * CH / 256, ROWS_PER_PASS = 256 / CH;
     __shared__ V16<T> tile[64 * CH];
     const int t = threadIdx.x;
@@ -111,7 +138,7 @@ __global__ void __launch_bounds__(256) transpose_a2a_kernel(A2APeers peers, cons
             tile[(V * jq + c) * CH + (iq ^ jq)] = w;
         }
     }
-    a2a_wait_ready(flags, first_dst, h, call);   // thread 0, before the barrier: nobody stores into h's slab earlier
+    a2a_wait_ready(flags, first_dst, h, call, ctl);   // thread 0, before the barrier: nobody stores into h's slab earlier
     __syncthreads();
     const int ic = t % CH, jr = t / CH;
 #pragma unroll
@@ -137,7 +164,7 @@ struct A2AMaps {
 template <typename T, int TI, int TJ>
 __global__ void __launch_bounds__(256) transpose_a2a_tma_kernel(const __grid_constant__ A2AMaps maps, const T *__restrict__ b_local,
                                                                 int64_t ld_src, int64_t rows_blk, int row_off, int tiles_i, int tiles_j, int first_dst,
-                                                                int order, int world, A2APeers flags, unsigned long long call) {
+                                                                int order, int world, A2APeers flags, unsigned long long call, A2ACtl ctl) {
     constexpr int V = 16 / sizeof(T), CI = TI / V, CJ = TJ / V, PASSES = CI * CJ / 256;
     static_assert(CI * CJ % 256 == 0 && 256 % CJ == 0, "tile must be a whole number of passes of 256 threads");
     __shared__ __align__(128) V16<T> tile[TJ * CI];   // [j][chunk of i], dense: exactly the box the tensor map describes
@@ -165,7 +192,7 @@ __global__ void __launch_bounds__(256) transpose_a2a_tma_kernel(const __grid_con
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the bulk engine
     __syncthreads();
-    a2a_wait_ready(flags, first_dst, h, call);
+    a2a_wait_ready(flags, first_dst, h, call, ctl);
     if (t == 0) {
         asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(&maps.m[h]),
                      "r"(row_off + (int)i0), "r"((int)j0), "r"(pipe::smem_u32(tile))
@@ -177,18 +204,28 @@ __global__ void __launch_bounds__(256) transpose_a2a_tma_kernel(const __grid_con
 
 // One CTA: make everything this GPU wrote before visible system-wide, raise `epoch` in every peer's flag word for this rank,
 // wait until every peer has raised its word here.
-__global__ void sym_barrier_kernel(A2APeers flags, int world, int rank, unsigned long long epoch) {
+__global__ void sym_barrier_kernel(A2APeers flags, int world, int rank, unsigned long long epoch, A2ACtl ctl) {
     __threadfence_system();
     const int r = threadIdx.x;
     if (r < world) {
         unsigned long long *theirs = reinterpret_cast<unsigned long long *>(flags.dst[r]) + rank;
         asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(theirs), "l"(epoch) : "memory");
-        const unsigned long long *mine = reinterpret_cast<const unsigned long long *>(flags.dst[rank]) + r;
-        unsigned long long v;
-        do {
-            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
-        } while (v < epoch);
+        a2a_spin_until(reinterpret_cast<const unsigned long long *>(flags.dst[rank]) + r, epoch, ctl);
     }
+}
+
+static A2ACtl make_ctl(const Sym *h) {
+    A2ACtl c;
+    c.timeout_ns = (unsigned long long)tune_get("a2a.timeout_ms", 10000) * 1000000ull;
+    c.error = h->error_dev;
+    if (!c.error) c.timeout_ns = 0;
+    return c;
+}
+static int check_sym_error(const Sym *h, const char *who) {
+    if (h->error_host && *h->error_host != 0)
+        return set_error(B200_ERR_CUDA, "%s: an earlier call on this symmetric buffer timed out waiting for a peer (a rank skipped the "
+                         "collective or its launch failed); the ranks are out of step -- free the buffer and connect again", who);
+    return B200_OK;
 }
 
 }  // namespace b200
@@ -207,6 +244,9 @@ extern "C" b200_status b200_sym_alloc(void **handle, size_t bytes) {
         return set_error(B200_ERR_OOM, "b200_sym_alloc: cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
     }
     B200_CUDA(cudaMemset((char *)h->local + h->bytes, 0, kSymFlagBytes));
+    B200_CUDA(cudaHostAlloc((void **)&h->error_host, 64, cudaHostAllocMapped | cudaHostAllocPortable));
+    *h->error_host = 0;
+    B200_CUDA(cudaHostGetDevicePointer((void **)&h->error_dev, h->error_host, 0));
     *handle = h;
     return B200_OK;
 }
@@ -256,9 +296,13 @@ extern "C" b200_status b200_sym_connect_ptrs(void *handle, int32_t world, int32_
         if (!peer_bufs[r]) return set_error(B200_ERR_INVALID_VALUE, "b200_sym_connect_ptrs: NULL buffer for rank %d", r);
         cudaPointerAttributes at;
         B200_CUDA(cudaPointerGetAttributes(&at, peer_bufs[r]));
-        cudaError_t e = cudaDeviceEnablePeerAccess(at.device, 0);
-        if (e == cudaErrorPeerAccessAlreadyEnabled) (void)cudaGetLastError();
-        else B200_CUDA(e);
+        int cur = -1;
+        B200_CUDA(cudaGetDevice(&cur));
+        if (at.device != cur) {   // (a "peer" on the same GPU needs no enabling: used by the single-GPU tests)
+            cudaError_t e = cudaDeviceEnablePeerAccess(at.device, 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) (void)cudaGetLastError();
+            else B200_CUDA(e);
+        }
         h->peer[r] = peer_bufs[r];
     }
     h->world = world;
@@ -288,7 +332,8 @@ extern "C" b200_status b200_sym_barrier(void *handle) {
     B200_TRY(current_stream(&st));
     A2APeers flags;
     for (int r = 0; r < kSymMaxRanks; ++r) flags.dst[r] = r < h->world ? (char *)h->peer[r] + h->bytes : nullptr;
-    sym_barrier_kernel<<<1, 32, 0, st>>>(flags, h->world, h->rank, ++h->epoch);
+    B200_TRY(check_sym_error(h, "b200_sym_barrier"));
+    sym_barrier_kernel<<<1, 32, 0, st>>>(flags, h->world, h->rank, ++h->epoch, make_ctl(h));
     B200_CHECK_LAUNCH("sym_barrier_kernel");
     return B200_OK;
 }
@@ -300,6 +345,7 @@ extern "C" b200_status b200_sym_free(void *handle) {
     for (int r = 0; r < h->world; ++r)
         if (h->ipc && r != h->rank && h->peer[r]) (void)cudaIpcCloseMemHandle(h->peer[r]);
     if (h->local) (void)cudaFree(h->local);
+    if (h->error_host) (void)cudaFreeHost(h->error_host);
     delete h;
     return B200_OK;
 }
@@ -316,6 +362,8 @@ extern "C" b200_status b200_transpose_alltoall(void *a_sym, const void *b_local,
     if ((size_t)(N1 * (N0 / G)) * (size_t)elsize > h->bytes)
         return set_error(B200_ERR_INVALID_VALUE, "b200_transpose_alltoall: the symmetric output slab is smaller than N1 x N0/world elements");
     if (((uintptr_t)b_local & 15) != 0) return set_error(B200_ERR_UNSUPPORTED, "b200_transpose_alltoall: b must be 16-byte aligned");
+    B200_TRY(check_sym_error(h, "b200_transpose_alltoall"));
+    const A2ACtl ctl = make_ctl(h);
     cudaStream_t st;
     B200_TRY(current_stream(&st));
     const int64_t rows_blk = N0 / G, cols_blk = N1 / G;   // a block of b_local: rows_blk x cols_blk; its transpose: cols_blk x rows_blk
@@ -348,22 +396,22 @@ extern "C" b200_status b200_transpose_alltoall(void *a_sym, const void *b_local,
         const dim3 g2((unsigned)((cols_blk / TI) * tj_n * G));
         const int roff = (int)(h->rank * cols_blk);
         if (elsize == 4 && wide)
-            transpose_a2a_tma_kernel<uint32_t, 256, 16><<<g2, 256, 0, st>>>(maps, (const uint32_t *)b_local, N0, rows_blk, roff, (int)(cols_blk / TI), tj_n, h->rank, order, G, flags, call);
+            transpose_a2a_tma_kernel<uint32_t, 256, 16><<<g2, 256, 0, st>>>(maps, (const uint32_t *)b_local, N0, rows_blk, roff, (int)(cols_blk / TI), tj_n, h->rank, order, G, flags, call, ctl);
         else if (elsize == 4)
-            transpose_a2a_tma_kernel<uint32_t, 64, 64><<<g2, 256, 0, st>>>(maps, (const uint32_t *)b_local, N0, rows_blk, roff, (int)(cols_blk / TI), tj_n, h->rank, order, G, flags, call);
+            transpose_a2a_tma_kernel<uint32_t, 64, 64><<<g2, 256, 0, st>>>(maps, (const uint32_t *)b_local, N0, rows_blk, roff, (int)(cols_blk / TI), tj_n, h->rank, order, G, flags, call, ctl);
         else if (wide)
-            transpose_a2a_tma_kernel<uint64_t, 256, 16><<<g2, 256, 0, st>>>(maps, (const uint64_t *)b_local, N0, rows_blk, roff, (int)(cols_blk / TI), tj_n, h->rank, order, G, flags, call);
+            transpose_a2a_tma_kernel<uint64_t, 256, 16><<<g2, 256, 0, st>>>(maps, (const uint64_t *)b_local, N0, rows_blk, roff, (int)(cols_blk / TI), tj_n, h->rank, order, G, flags, call, ctl);
         else
-            transpose_a2a_tma_kernel<uint64_t, 64, 64><<<g2, 256, 0, st>>>(maps, (const uint64_t *)b_local, N0, rows_blk, roff, (int)(cols_blk / TI), tj_n, h->rank, order, G, flags, call);
+            transpose_a2a_tma_kernel<uint64_t, 64, 64><<<g2, 256, 0, st>>>(maps, (const uint64_t *)b_local, N0, rows_blk, roff, (int)(cols_blk / TI), tj_n, h->rank, order, G, flags, call, ctl);
         B200_CHECK_LAUNCH("transpose_a2a_tma_kernel");
         return no_sync ? B200_OK : b200_sym_barrier(a_sym);
     }
     if (elsize == 4)
         transpose_a2a_kernel<uint32_t><<<grid, 256, 0, st>>>(peers, (const uint32_t *)b_local, N0, N1, rows_blk, (int64_t)h->rank * cols_blk,
-                                                            tiles_i, tiles_j, h->rank, order, G, flags, call);
+                                                            tiles_i, tiles_j, h->rank, order, G, flags, call, ctl);
     else
         transpose_a2a_kernel<uint64_t><<<grid, 256, 0, st>>>(peers, (const uint64_t *)b_local, N0, N1, rows_blk, (int64_t)h->rank * cols_blk,
-                                                            tiles_i, tiles_j, h->rank, order, G, flags, call);
+                                                            tiles_i, tiles_j, h->rank, order, G, flags, call, ctl);
     B200_CHECK_LAUNCH("transpose_a2a_kernel");
     return no_sync ? B200_OK : b200_sym_barrier(a_sym);
 }

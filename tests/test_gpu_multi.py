@@ -106,6 +106,65 @@ def test_transpose_alltoall_single_rank(N0, N1, dt):
         a_sym.free()
 
 
+def test_missing_peer_times_out_instead_of_hanging():
+    """Rank 0 of a 2-rank job whose peer never makes the matching call: every wait inside the kernels is bounded
+    (`a2a.timeout_ms`, `hist.fused_timeout_ms`), the call returns, and the NEXT call on the handle reports the lost step."""
+    import ctypes as C
+    import time
+
+    be = KA.B200Backend()
+    # two symmetric buffers on the one GPU, connected as ranks 0 and 1 of a single-process job; only rank 0 ever calls
+    N0 = N1 = 256
+    hs = []
+    for _ in range(2):
+        h = C.c_void_p()
+        _lib.call("b200_sym_alloc", C.byref(h), C.c_size_t(N1 * (N0 // 2) * 4))
+        hs.append(h)
+    ptrs = (C.c_void_p * 2)()
+    for r in range(2):
+        p = C.c_void_p()
+        _lib.call("b200_sym_ptr", hs[r], -1, C.byref(p))
+        ptrs[r] = p.value
+    for r in range(2):
+        _lib.call("b200_sym_connect_ptrs", hs[r], 2, r, ptrs)
+    b_loc = KA.rand_uniform_(KA.allocate(be, np.float32, N0, N1 // 2), 5)
+    _lib.call("b200_tune_set", b"a2a.timeout_ms", 30)
+    try:
+        t0 = time.perf_counter()
+        _lib.call("b200_transpose_alltoall", hs[0], C.c_void_p(b_loc.ptr), N0, N1, 4)
+        KA.synchronize(be)
+        assert time.perf_counter() - t0 < 5.0
+        with pytest.raises(_lib.B200Error, match="timed out waiting for a peer"):
+            _lib.call("b200_transpose_alltoall", hs[0], C.c_void_p(b_loc.ptr), N0, N1, 4)
+    finally:
+        _lib.call("b200_tune_set", b"a2a.timeout_ms", 10000)
+        for h in hs:
+            _lib.call("b200_sym_free", h)
+    # the fused histogram: rank 0 of 2, the peer's slots never arrive
+    ps = []
+    for _ in range(2):
+        h = C.c_void_p()
+        _lib.call("b200_p2p_alloc", C.byref(h))
+        ps.append(h)
+    harr = (C.c_void_p * 2)(*[h.value for h in ps])
+    for r in range(2):
+        _lib.call("b200_p2p_connect_ptrs", ps[r], 2, r, harr)
+    d_in = KA.rand_bins_(KA.allocate(be, np.int32, 1 << 16), 1, 256)
+    bins = KA.zeros(be, np.int32, 256)
+    _lib.call("b200_tune_set", b"hist.fused_timeout_ms", 30)
+    try:
+        t0 = time.perf_counter()
+        _lib.call("b200_histogram_i32_allreduce", ps[0], C.c_void_p(bins.ptr), 256, C.c_void_p(d_in.ptr), d_in.size)
+        KA.synchronize(be)
+        assert time.perf_counter() - t0 < 5.0
+        with pytest.raises(_lib.B200Error, match="timed out waiting for a peer"):
+            _lib.call("b200_histogram_i32_allreduce", ps[0], C.c_void_p(bins.ptr), 256, C.c_void_p(d_in.ptr), d_in.size)
+    finally:
+        _lib.call("b200_tune_set", b"hist.fused_timeout_ms", 10000)
+        for h in ps:
+            _lib.call("b200_p2p_free", h)
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
