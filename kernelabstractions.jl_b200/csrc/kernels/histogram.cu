@@ -578,10 +578,9 @@ __device__ __noinline__ void fused_exchange(uint32_t *sh, uint32_t nbins, int co
             }
             __threadfence();                               // every lane: its reds are performed before the ticket below is visible
             __syncwarp();
-            if (t == 0) {
-                ticket = atomicAdd(peer.counter, 1u);
-                __threadfence();                           // ... and the reads of the partial below follow the ticket
-            }
+            // (no fence behind the ticket: the last CTA reads the partial with ld.global.cg -- L2, where the reds were performed --
+            // and those loads depend on the ticket's value through the branch below)
+            if (t == 0) ticket = atomicAdd(peer.counter, 1u);
         }
         __syncthreads();
         if (ticket != gridDim.x - 1) return;   // only the last CTA of this GPU goes on
