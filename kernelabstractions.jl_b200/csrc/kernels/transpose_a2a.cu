@@ -25,7 +25,8 @@ namespace b200 {
 
 constexpr int kSymMaxRanks = 8;
 constexpr size_t kSymFlagBytes = 256;   // words [0..7]: arrival flags of b200_sym_barrier, [8..15]: "slab may be overwritten" flags
-                                        // of b200_transpose_alltoall -- written by the peers, one 8-byte word per source rank
+                                        // of b200_transpose_alltoall -- written by the peers, one 8-byte word per source rank;
+                                        // words [16..]: LOCAL 32-bit counters of the fused completion (done per destination, all)
 
 struct Sym {
     void *local = nullptr;      // user bytes, then kSymFlagBytes of flags
@@ -106,9 +107,10 @@ __device__ __forceinline__ void a2a_wait_ready(const A2APeers &flags, int rank, 
 template <typename T>
 __global__ void __launch_bounds__(256) transpose_a2a_kernel(A2APeers peers, const T *__restrict__ b_local, int64_t ld_src, int64_t ld_dst,
                                                             int64_t rows_blk, int64_t row_off, int tiles_i, int tiles_j, int first_dst, int order, int world,
-                                                            A2APeers flags, unsigned long long call, A2ACtl ctl) {
+                                                            A2APeers flags, unsigned long long call, A2ACtl ctl, unsigned long long epoch) {
     constexpr int V = 16 / sizeof(T), CH = 64 / V, PASSES = CH * CH / 256, ROWS_PER_PASS = 256 / CH;
     __shared__ V16<T> tile[64 * CH];
+    __shared__ unsigned s_last;
     const int t = threadIdx.x;
     a2a_post_ready(flags, world, first_dst, call);
     // Destinations are INTERLEAVED over consecutive CTAs (a 1-d grid of world x tiles): the local tiles run at HBM speed, the
@@ -149,6 +151,33 @@ __global__ void __launch_bounds__(256) transpose_a2a_kernel(A2APeers peers, cons
         T *p = dst + (i0 + V * ic) + (j0 + jl) * ld_dst;
         asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(r.x), "r"(r.y), "r"(r.z), "r"(r.w) : "memory");
     }
+    if (epoch == 0) return;   // completion is signalled by the separate barrier kernel (a2a.fused_signal = 0)
+    // ---- completion, inside the data kernel (a2a.fused_signal, r05 A/B -- measured slower, see the launcher): ONE launch does
+    // transpose, all-to-all and barrier.
+    // Each CTA makes its tile visible system-wide (barrier, then ONE system-scope fence by thread 0: cumulative over the CTA's
+    // stores) and counts itself done for its destination h on a LOCAL counter; the CTA that completes a destination raises this
+    // rank's arrival flag at rank h (the same words b200_sym_barrier uses).  The fences of different CTAs overlap with each
+    // other and with the data phase; only the last tile's fence is exposed, where the barrier kernel paid a launch and a fence
+    // over everything.  The CTA that finishes last overall then waits for every peer's arrival flag, so that the kernel's
+    // completion still means "my slab is complete" -- the contract of the two-launch form.
+    __syncthreads();
+    if (t == 0) {
+        unsigned long long *local = reinterpret_cast<unsigned long long *>(flags.dst[first_dst]);   // first_dst == this rank
+        __threadfence_system();
+        const unsigned per_dst = gridDim.x / (unsigned)world;
+        unsigned *done = reinterpret_cast<unsigned *>(local + 16);                                     // done[h], h < 8; [8] = all
+        if (atomicAdd(done + h, 1u) == per_dst - 1) {
+            done[h] = 0;
+            unsigned long long *theirs = reinterpret_cast<unsigned long long *>(flags.dst[h]) + first_dst;
+            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(theirs), "l"(epoch) : "memory");
+        }
+        __threadfence();
+        s_last = atomicAdd(done + 8, 1u) == gridDim.x - 1;
+        if (s_last) done[8] = 0;
+    }
+    __syncthreads();
+    if (s_last && t < world)
+        a2a_spin_until(reinterpret_cast<const unsigned long long *>(flags.dst[first_dst]) + t, epoch, ctl);
 }
 
 // The same data kernel with the store phase handed to TMA (opt-in, `a2a.tma_store`): the transposed tile is laid out densely and
@@ -406,12 +435,18 @@ extern "C" b200_status b200_transpose_alltoall(void *a_sym, const void *b_local,
         B200_CHECK_LAUNCH("transpose_a2a_tma_kernel");
         return no_sync ? B200_OK : b200_sym_barrier(a_sym);
     }
+    // a2a.fused_signal = 1: completion signalled inside the data kernel (one launch) instead of by the barrier kernel (two).
+    // Measured on 2 GPUs, 16384^2 Float32 (r05): 0.632 ms against 0.394 ms -- a system-scope fence per CTA makes every CTA wait
+    // for the NVLink acknowledgements of its own tile, and 8192 such waits cost far more than the one fence + one launch of the
+    // barrier kernel.  Opt-in, parity-tested.
+    const bool fused = !no_sync && tune_get("a2a.fused_signal", 0) != 0;
+    const unsigned long long ep = fused ? ++h->epoch : 0ull;
     if (elsize == 4)
         transpose_a2a_kernel<uint32_t><<<grid, 256, 0, st>>>(peers, (const uint32_t *)b_local, N0, N1, rows_blk, (int64_t)h->rank * cols_blk,
-                                                            tiles_i, tiles_j, h->rank, order, G, flags, call, ctl);
+                                                            tiles_i, tiles_j, h->rank, order, G, flags, call, ctl, ep);
     else
         transpose_a2a_kernel<uint64_t><<<grid, 256, 0, st>>>(peers, (const uint64_t *)b_local, N0, N1, rows_blk, (int64_t)h->rank * cols_blk,
-                                                            tiles_i, tiles_j, h->rank, order, G, flags, call, ctl);
+                                                            tiles_i, tiles_j, h->rank, order, G, flags, call, ctl, ep);
     B200_CHECK_LAUNCH("transpose_a2a_kernel");
-    return no_sync ? B200_OK : b200_sym_barrier(a_sym);
+    return (no_sync || fused) ? B200_OK : b200_sym_barrier(a_sym);
 }

@@ -93,8 +93,9 @@ def test_transpose_alltoall_single_rank(N0, N1, dt):
     try:
         a_view = a_sym.array(dt, (N1, N0))
         keep = KA.allocate(be, dt, N1, N0)
-        for tma in (0, 1, 0):
+        for tma, fused in ((0, 0), (1, 0), (0, 1), (0, 0)):
             _lib.call("b200_tune_set", b"a2a.tma_store", tma)
+            _lib.call("b200_tune_set", b"a2a.fused_signal", fused)     # completion inside the data kernel (opt-in A/B)
             whole = np.asfortranarray((rng.standard_normal((N0, N1)) * 100).astype(dt))
             b_loc = KA.to_device(whole)
             mg.transpose_alltoall_(a_sym, b_loc, N0, N1)
@@ -103,6 +104,7 @@ def test_transpose_alltoall_single_rank(N0, N1, dt):
             assert np.array_equal(KA.Array(keep), whole.T)
     finally:
         _lib.call("b200_tune_set", b"a2a.tma_store", 0)
+        _lib.call("b200_tune_set", b"a2a.fused_signal", 0)
         a_sym.free()
 
 
