@@ -62,3 +62,51 @@ def test_concurrent_host_threads_have_private_streams_and_correct_results():
     assert not errors, errors
     assert len(set(streams)) == nthreads, "every host thread must get its own stream"
     _lib.call("b200_device_synchronize")
+
+
+def test_task_style_streams_bind_create_destroy():
+    """What the Julia layer does per task (reference keeps queue + device in task_local_storage, src/pocl/pocl.jl:12-41): own
+    stream handles (b200_stream_create), bound together with the device before every call (b200_bind), from WHICHEVER OS thread
+    the task happens to run on -- here two "tasks" whose calls alternate between two OS threads."""
+    dev = C.c_int32()
+    _lib.call("b200_get_device", C.byref(dev))
+    streams = []
+    for prio in (0, 1):
+        s = C.c_void_p()
+        _lib.call("b200_stream_create", C.byref(s), prio)
+        streams.append(s)
+    assert streams[0].value != streams[1].value
+    n = 1 << 20
+    src = [KA.to_device(np.full(n, k + 1, dtype=np.float32)) for k in range(2)]
+    dst = [KA.zeros(be, np.float32, n) for _ in range(2)]
+    KA.synchronize(be)
+    errors = []
+
+    def step(task, thread_tag):
+        try:
+            _lib.call("b200_bind", dev.value, streams[task])                  # the task's state -> this OS thread
+            got = C.c_void_p()
+            _lib.call("b200_get_stream", C.byref(got))
+            assert got.value == streams[task].value
+            _lib.call("b200_copy", C.c_void_p(dst[task].ptr), C.c_void_p(src[task].ptr), C.c_size_t(4 * n))
+        except BaseException as ex:  # noqa: BLE001
+            errors.append((task, thread_tag, repr(ex)))
+
+    for rnd in range(4):             # task 0 and task 1 swap OS threads every round
+        ts = [threading.Thread(target=step, args=((rnd + k) % 2, k)) for k in range(2)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+    assert not errors, errors
+    for task in range(2):            # cooperative wait on the TASK's stream, from the main thread
+        _lib.call("b200_bind", dev.value, streams[task])
+        while _lib.lib().b200_stream_query() == _lib.B200_NOT_READY:
+            pass
+        assert np.all(KA.Array(dst[task]) == task + 1)
+    _lib.call("b200_bind", dev.value, None)                                    # back to the thread's own stream
+    for s in streams:
+        _lib.call("b200_stream_destroy", s)
+    with pytest.raises(_lib.B200Error):
+        bad = C.c_void_p()
+        _lib.call("b200_stream_create", C.byref(bad), 7)                       # priority out of range
